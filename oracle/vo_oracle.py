@@ -1,0 +1,197 @@
+"""CPU ORACLE (test infrastructure, NOT product code): plain PyTorch fp32 restatement of the
+reference's visual-odometry CNN and RL visual encoder, as pure functions of a reference-format
+state_dict.  This is the "torch fp32 reference" the floating-point CUDA kernels are compared with.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product path never does.
+
+Parity status: PINNED against the unmodified reference modules executed in the build container
+(tests/golden/make_golden.py -> tests/golden/vo_*.npz, tests/test_oracle_golden.py): outputs, running
+statistics after a training-mode forward, and parameter gradients.
+
+Reference (paths relative to /root/reference/pointnav_vo):
+  assemble_input       vo/models/vo_cnn.py:110-174   (NHWC->NCHW, rgb/255, prev|cur interleave)
+  running_mean_var     model_utils/running_mean_and_var.py:22-63
+  resnet_forward       model_utils/visual_encoders/resnet.py:29-55,95-120,153-223
+  vo_forward           vo/models/vo_cnn.py:82-95,176-179,216-233 ; vo_cnn_act_embed.py:65-75
+  rl_encoder_forward   rl/policies/resnet_policy.py:146-174
+  vo_losses            vo/engine/vo_cnn_engine.py:135-198 ; vo_cnn_regression_geo_invariance_engine.py:367-449
+"""
+import torch
+import torch.nn.functional as F
+
+RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet50": ("bottleneck", [3, 4, 6, 3]),
+                 "resnet101": ("bottleneck", [3, 4, 23, 3])}
+
+OBS_ORDER = ("rgb", "depth", "discretized_depth", "top_down_view")  # vo_cnn.py:114-166 append order
+
+
+def assemble_input(obs, observation_space):
+    """vo_cnn.py:110-174 -> [B, C, H, W] fp32, channels [prev_rgb, prev_d, prev_dd, prev_td, cur_...]."""
+    pairs = []
+    for k in OBS_ORDER:
+        if k not in observation_space:
+            continue
+        x = obs[k].permute(0, 3, 1, 2)
+        if k == "rgb":
+            x = x / 255.0
+        n = x.shape[1] // 2
+        pairs.append((x[:, :n], x[:, n:]))
+    prev = [p[0] for p in pairs]
+    cur = [p[1] for p in pairs]
+    return torch.cat(prev + cur, dim=1)
+
+
+def running_mean_var(x, mean, var, count, training=False):
+    """running_mean_and_var.py:22-63 (single process).  Returns (normalised x, mean, var, count)."""
+    if training:
+        new_mean = F.adaptive_avg_pool2d(x, 1).sum(0, keepdim=True)
+        new_count = torch.full_like(count, x.size(0))
+        new_mean = new_mean / new_count
+        new_var = F.adaptive_avg_pool2d((x - new_mean).pow(2), 1).sum(0, keepdim=True)
+        new_var = new_var / new_count
+        m_a = var * count
+        m_b = new_var * new_count
+        M2 = m_a + m_b + (new_mean - mean).pow(2) * count * new_count / (count + new_count)
+        var = M2 / (count + new_count)
+        mean = (count * mean + new_count * new_mean) / (count + new_count)
+        count = count + new_count
+    stdev = torch.sqrt(torch.max(var, torch.full_like(var, 1e-2)))
+    return (x - mean) / stdev, mean, var, count
+
+
+def _gn(x, sd, key, groups):
+    return F.group_norm(x, groups, sd[key + ".weight"], sd[key + ".bias"], 1e-5)
+
+
+def _basic_block(x, sd, p, ngroups, stride, has_down):
+    """resnet.py:29-55"""
+    out = F.conv2d(x, sd[p + ".convs.0.weight"], None, stride, 1)
+    out = F.relu(_gn(out, sd, p + ".convs.1", ngroups))
+    out = F.conv2d(out, sd[p + ".convs.3.weight"], None, 1, 1)
+    out = _gn(out, sd, p + ".convs.4", ngroups)
+    res = x
+    if has_down:
+        res = _gn(F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0), sd, p + ".downsample.1", ngroups)
+    return F.relu(out + res)
+
+
+def _bottleneck(x, sd, p, ngroups, stride, has_down):
+    """resnet.py:58-120"""
+    out = F.conv2d(x, sd[p + ".convs.0.weight"])
+    out = F.relu(_gn(out, sd, p + ".convs.1", ngroups))
+    out = F.conv2d(out, sd[p + ".convs.3.weight"], None, stride, 1)
+    out = F.relu(_gn(out, sd, p + ".convs.4", ngroups))
+    out = F.conv2d(out, sd[p + ".convs.6.weight"])
+    out = _gn(out, sd, p + ".convs.7", ngroups)
+    res = x
+    if has_down:
+        res = _gn(F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0), sd, p + ".downsample.1", ngroups)
+    return F.relu(out + res)
+
+
+def resnet_forward(x, sd, prefix, backbone, ngroups, taps=None):
+    """resnet.py:214-223.  taps (optional dict) receives named intermediate activations (NCHW)."""
+    kind, layers = RESNET_LAYERS[backbone]
+    block = _basic_block if kind == "basic" else _bottleneck
+    x = F.conv2d(x, sd[prefix + ".conv1.0.weight"], None, 2, 3)
+    if taps is not None:
+        taps["conv1_raw"] = x
+    x = F.relu(_gn(x, sd, prefix + ".conv1.1", ngroups))
+    x = F.max_pool2d(x, 3, 2, 1)
+    if taps is not None:
+        taps["pool"] = x
+    for li, nblocks in enumerate(layers, start=1):
+        for b in range(nblocks):
+            p = f"{prefix}.layer{li}.{b}"
+            has_down = (p + ".downsample.0.weight") in sd
+            stride = 2 if (b == 0 and li > 1) else 1
+            x = block(x, sd, p, ngroups, stride, has_down)
+        if taps is not None:
+            taps[f"layer{li}"] = x
+    return x
+
+
+def encoder_tail(x, sd, prefix):
+    """compression: conv3x3 -> GroupNorm(1, C) -> ReLU (vo_cnn.py:85-95)."""
+    x = F.conv2d(x, sd[prefix + ".compression.0.weight"], None, 1, 1)
+    x = F.group_norm(x, 1, sd[prefix + ".compression.1.weight"], sd[prefix + ".compression.1.bias"], 1e-5)
+    return F.relu(x)
+
+
+def vo_forward(obs, sd, observation_space, backbone="resnet18", ngroups=16, training=False,
+               actions=None, taps=None):
+    """Full VO model forward (dropout_p = 0 semantics; eval mode == reference eval mode).
+
+    Returns (out [B, output_dim], new_running_stats or None).  sd: reference-named tensors
+    (vo_cnn.py state_dict keys).  actions: LongTensor[B] for the act-embed variant."""
+    pfx = "visual_encoder"
+    x = assemble_input(obs, observation_space)
+    stats = None
+    if (pfx + ".running_mean_and_var._mean") in sd:
+        x, m, v, c = running_mean_var(x, sd[pfx + ".running_mean_and_var._mean"],
+                                      sd[pfx + ".running_mean_and_var._var"],
+                                      sd[pfx + ".running_mean_and_var._count"], training)
+        stats = (m, v, c)
+    if taps is not None:
+        taps["input"] = x
+    x = resnet_forward(x, sd, pfx + ".backbone", backbone, ngroups, taps)
+    x = encoder_tail(x, sd, pfx)
+    if taps is not None:
+        taps["compression"] = x
+    feat = x.contiguous().view(x.size(0), -1)  # Flatten over NCHW (misc_utils.py:45-47)
+    if "action_embedding.weight" in sd:
+        emb = F.embedding(actions, sd["action_embedding.weight"])
+        feat = torch.cat((feat, emb), dim=1)
+        h = F.relu(F.linear(feat, sd["hidden_generator.1.weight"], sd["hidden_generator.1.bias"]))
+    else:
+        h = F.relu(F.linear(feat, sd["visual_fc.2.weight"], sd["visual_fc.2.bias"]))
+    out = F.linear(h, sd["output_head.1.weight"], sd["output_head.1.bias"])
+    return out, stats
+
+
+def rl_encoder_forward(obs, sd, prefix="net.visual_encoder", backbone="resnet18", ngroups=16,
+                       use_rgb=False, use_depth=True, taps=None):
+    """rl/policies/resnet_policy.py:146-174 (obs_transform=None, normalize_visual_inputs=False)."""
+    inp = []
+    if use_rgb:
+        inp.append(obs["rgb"].permute(0, 3, 1, 2).contiguous() / 255.0)
+    if use_depth:
+        inp.append(obs["depth"].permute(0, 3, 1, 2).contiguous())
+    x = torch.cat(inp, dim=1)
+    x = F.avg_pool2d(x, 2)
+    if taps is not None:
+        taps["input"] = x
+    x = resnet_forward(x, sd, prefix + ".backbone", backbone, ngroups, taps)
+    return encoder_tail(x, sd, prefix)
+
+
+def vo_losses(pred, target, loss_weights=(1.0, 1.0, 1.0), dz_regress_masks=None):
+    """vo_cnn_engine.py:135-198: per-delta mean((gt - pred)^2 * w); returns (loss_dx, loss_dz, loss_dyaw)."""
+    out = []
+    for i in range(3):
+        diff = (target[:, i:i + 1] - pred[:, i:i + 1]) ** 2
+        if i == 1 and dz_regress_masks is not None:
+            diff = dz_regress_masks * diff
+        out.append(torch.mean(diff * loss_weights[i]))
+    return tuple(out)
+
+
+def geo_invariance_inverse_loss(deltas, actions, move_forward=1):
+    """vo_cnn_regression_geo_invariance_engine.py:367-449; deltas interleaved [a0, b0, a1, b1, ...]
+    (a = cur_rel_to_prev, b = prev_rel_to_cur); actions has one entry per row of deltas."""
+    a = deltas[0::2]
+    b = deltas[1::2]
+    act = actions[0::2]
+    rot = (a[:, 2] + b[:, 2]) ** 2
+    loss_rot = torch.mean(rot)
+    yaw = b[:, 2]
+    R = torch.stack((torch.cos(yaw), torch.sin(yaw), -1 * torch.sin(yaw), torch.cos(yaw)), dim=1).reshape(-1, 2, 2)
+    pred = torch.matmul(R, a[:, :2].unsqueeze(-1)).squeeze(-1)
+    pos = (b[:, :2] + pred) ** 2
+    fwd = torch.nonzero(act == move_forward, as_tuple=True)[0]
+    if fwd.numel() != 0:
+        mask = torch.ones_like(pos)
+        mask[fwd, 1] = 0.0
+        pos = mask * pos
+    return loss_rot + torch.mean(pos)

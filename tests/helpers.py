@@ -1,0 +1,83 @@
+"""Shared test helpers: the same seeded inputs / weights the golden generator used (numpy only)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import preproc_oracle as po
+from pointnav_vo_b200.utils import synth
+
+VO_CASES = {
+    "r18_30ch": ("vo_cnn_rgb_d_dd_top_down", ["rgb", "depth", "discretized_depth", "top_down_view"], "resnet18",
+                 dict(discretized_depth_channels=10)),
+    "r18_8ch": ("vo_cnn", ["rgb", "depth"], "resnet18", {}),
+    "r50_8ch": ("base", ["rgb", "depth"], "resnet50", {}),
+    "r18_8ch_act_embed": ("vo_cnn_act_embed", ["rgb", "depth"], "resnet18", {}),
+}
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def edge_depth_frames():
+    """Must mirror tests/golden/make_golden.py:edge_depth_frames."""
+    D = synth.depth_frames(24, seed=1)
+    D[0] = 0
+    D[1] = 0
+    D[1, 100, 200] = 0.5
+    D[2] = 1.0
+    D[3, :90] = 0
+    D[4, :, :170] = 0
+    D[5] = np.float32(1e-6)
+    D[6, :, 1:] = 0
+    D[7, 1:, :] = 0
+    return D
+
+
+def edge_values():
+    h = np.arange(0, 0x3C01, dtype=np.uint16).view(np.float16).astype(np.float32)
+    th = np.array(po.discretize_end_vals(10), dtype=np.float32)
+    lo = np.nextafter(th, np.float32(-1)).astype(np.float32)
+    hi = np.nextafter(th, np.float32(2)).astype(np.float32)
+    return np.clip(np.concatenate([h, th, lo, hi]), 0, 1).astype(np.float32)
+
+
+def golden_topdown(pre, i):
+    a, b = pre["td_ptr"][i], pre["td_ptr"][i + 1]
+    out = np.zeros(192 * 341, dtype=np.float32)
+    out[pre["td_idx"][a:b]] = pre["td_val"][a:b]
+    return out.reshape(192, 341)
+
+
+def vo_inputs_np(B, seed, observation_space):
+    """Mirror of make_golden.vo_inputs (dd / top-down channels derived by the pinned oracle)."""
+    rgb = synth.rgb_frames(2 * B, seed=seed).reshape(B, 2, synth.H, synth.W, 3)
+    rgb = np.concatenate([rgb[:, 0], rgb[:, 1]], axis=-1).astype(np.float32)
+    dep = synth.depth_frames(2 * B, seed=seed + 100).reshape(B, 2, synth.H, synth.W)
+    obs = {"rgb": rgb, "depth": np.stack([dep[:, 0], dep[:, 1]], axis=-1)}
+    if "discretized_depth" in observation_space:
+        oh = po.discretize_depth_onehot(dep)
+        obs["discretized_depth"] = np.concatenate([oh[:, 0], oh[:, 1]], axis=-1)
+    if "top_down_view" in observation_space:
+        orc = po.TopDownOracle()
+        obs["top_down_view"] = np.stack(
+            [np.stack([orc.gen_top_down_view(dep[b, j])[..., 0] for j in range(2)], -1) for b in range(B)])
+    return {k: np.ascontiguousarray(v) for k, v in obs.items() if k in observation_space}
+
+
+def vo_inputs(B, seed, observation_space, device="cpu"):
+    return {k: torch.from_numpy(v).to(device) for k, v in vo_inputs_np(B, seed, observation_space).items()}
+
+
+def vo_state_dict(case, seed=7, device="cpu"):
+    """Reference-format state_dict filled by synth.fill_state_dict in the golden key order."""
+    g = np.load(os.path.join(GOLDEN, f"vo_{case}.npz"))
+    shapes = vo_state_shapes(case)
+    keys = [str(k) for k in g["keys"]]
+    proto = {k: np.empty(shapes[k], dtype=np.float32) for k in keys}
+    sd = synth.fill_state_dict(proto, seed=seed)
+    return {k: torch.from_numpy(v).to(device) for k, v in sd.items()}
+
+
+def vo_state_shapes(case):
+    from pointnav_vo_b200.vo.models.shapes import vo_state_dict_shapes
+    name, space, backbone, kw = VO_CASES[case]
+    return vo_state_dict_shapes(space, backbone, act_embed="act_embed" in case, **kw)
