@@ -1,0 +1,132 @@
+/*
+ * pnvo.h -- C ABI of libpnvo.so: the B200 (sm_100a) kernels behind PointNav-VO's data-parallel hot path.
+ *
+ * The reference (Xiaoming-Zhao/PointNav-VO) is 100% Python/PyTorch and has no native/FFI boundary
+ * (SURVEY.md section 8b); these entry points are what a ctypes binding of its hot path binds.  Each
+ * one cites the reference code it replaces.  Conventions:
+ *   - plain pointers and sizes only; every buffer is caller-allocated DEVICE memory (the library
+ *     never owns memory and keeps no global state besides the last-error string);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value 0 = launched; negative = error, text via pnvo_last_error();
+ *   - kernels are asynchronous with respect to the host.
+ */
+#ifndef PNVO_H_
+#define PNVO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNVO_ABI_VERSION 1
+
+const char* pnvo_last_error(void);
+int pnvo_abi_version(void);
+/* compute capability check: returns 0 when the current device is sm_100 (B200), <0 otherwise. */
+int pnvo_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7  depth discretisation -- BaseRLTrainerWithVO._discretize_depth_func
+ *     (pointnav_vo/rl/common/base_trainer_with_vo.py:135-167; NumPy twin
+ *     pointnav_vo/vo/dataset/regression_iter_dataset.py:32-69).
+ * depth: n_pix fp32 in [0,1].  edges: n_channels+1 fp32 bin edges on the device (float(i/n), last 1.0).
+ * onehot (nullable): fp32, element (p, c) written at onehot[p*onehot_stride + c], c < n_channels.
+ * index (nullable): uint8 bin per pixel (255 = outside [0,1], which the reference asserts against).
+ * err_count (nullable): int32 device counter incremented per out-of-range pixel.
+ */
+int pnvo_discretize_depth(const float* depth, int64_t n_pix, const float* edges, int n_channels,
+                          float* onehot, int64_t onehot_stride, uint8_t* index, int32_t* err_count,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8  egocentric top-down projection -- NormalizedDepth2TopDownViewHabitatTorch.gen_top_down_view
+ *     (pointnav_vo/utils/geometry_utils.py:491-721), fp32 variant, batched over frames.
+ * depth: [n_frames, H, W] fp32 (frame stride in_stride floats).  out: [n_frames, H, W] fp32 written at
+ * out[f*out_frame_stride + (r*W + c)*out_pix_stride].  count (nullable): int32 [n_frames, H, W] raw
+ * per-cell point counts (the bit-exact index map).  ray: W fp32 = (Kinv @ [u+.5, ., 1])[0].
+ * consts: {min_x, x_den, z_den, depth_scale, depth_off} as produced by the host mirror of
+ * geometry_utils.py:558-583,678-682.
+ */
+typedef struct {
+  float min_x, x_den, z_den, depth_scale, depth_off;
+  int rows_around_center; /* 50 */
+  int center_crop;        /* 1 */
+} pnvo_topdown_consts;
+
+int pnvo_topdown_project(const float* depth, int64_t in_stride, int n_frames, int H, int W,
+                         const float* ray, const pnvo_topdown_consts* consts, float* out,
+                         int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a13 GAE / discounted returns -- RolloutStorage.compute_returns
+ *     (pointnav_vo/rl/common/rollout_storage.py:102-120).
+ * rewards [T,N], value_preds [T+1,N] (row T is overwritten with next_value when use_gae, as the reference
+ * does), masks [T+1,N], next_value [N], returns [T+1,N].  mode 0: one lane per env, sequential in t,
+ * same rounding order as the reference (bit-exact); mode 1: warp-scan over t (affine-map composition,
+ * equal within fp32 rounding).
+ */
+int pnvo_gae_scan(const float* rewards, float* value_preds, const float* masks, const float* next_value,
+                  float* returns, int T, int N, int use_gae, float gamma, float gamma_tau, int mode,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10 batched goal update -- compute_goal_pos (pointnav_vo/utils/geometry_utils.py:115-144), fp64.
+ * goal_xyz [n,3] f64 in/out (cartesian), delta [n,3] f32 (dx, dz, dyaw), polar [n,2] f32 out (rho, -phi).
+ */
+int pnvo_goal_update(double* goal_xyz, const float* delta, float* polar, int n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The CNN path (a1-a6, a11): a flat program of ops executed in order on one stream.  The host mirror
+ * of the reference modules (pointnav_vo_b200/vo/models, rl/policies) builds the program once per
+ * (architecture, batch) and replays it; per-op wrappers below take the same struct.
+ *   reference: vo/models/vo_cnn.py:110-233, model_utils/visual_encoders/resnet.py:29-223,
+ *   model_utils/running_mean_and_var.py:22-63, rl/policies/resnet_policy.py:146-174.
+ */
+enum pnvo_opcode {
+  PNVO_OP_ZERO = 1,           /* p0 <- 0 (i0 bytes) */
+  PNVO_OP_ASSEMBLE = 2,       /* NHWC fp32 sources -> normalised fp16 NHWC (vo_cnn.py:110-176) */
+  PNVO_OP_INPUT_STATS = 3,    /* RunningMeanAndVar batch statistics (running_mean_and_var.py:24-38) */
+  PNVO_OP_RMV_UPDATE = 4,     /* RunningMeanAndVar Chan merge + scale/shift (:41-63) */
+  PNVO_OP_CONV = 5,           /* implicit-GEMM conv (fprop or dgrad) + GroupNorm partial sums, tcgen05 */
+  PNVO_OP_WGRAD = 6,          /* weight gradient, tcgen05, split over pixels */
+  PNVO_OP_GN_APPLY = 7,       /* GroupNorm affine (+residual) (+ReLU)  (resnet.py:39-55) */
+  PNVO_OP_GN_POOL = 8,        /* GroupNorm + ReLU + MaxPool 3x3/s2/p1 (resnet.py:165-168) */
+  PNVO_OP_GN_BWD_REDUCE = 9,  /* sum dy, sum dy*xhat per (sample, channel) */
+  PNVO_OP_GN_BWD_APPLY = 10,  /* dx of GroupNorm(+ReLU) */
+  PNVO_OP_GN_POOL_BWD = 11,   /* gradient through MaxPool+ReLU to the GN output, reduce + apply share it */
+  PNVO_OP_PACK_W = 12,        /* OIHW fp32 -> [Cout][R][S][Cin_pad] fp16 (+ flipped/transposed for dgrad) */
+  PNVO_OP_UNPACK_DW = 13,     /* packed fp32 dW -> OIHW fp32 grad */
+  PNVO_OP_HEAD_FWD = 14,      /* Linear(hidden, out_dim) with warp-shuffle dot products (vo_cnn.py:223-227) */
+  PNVO_OP_HEAD_BWD = 15,
+  PNVO_OP_BIAS_RELU = 16,     /* fc bias (+ReLU) fwd on fp32 GEMM output */
+  PNVO_OP_BIAS_RELU_BWD = 17,
+  PNVO_OP_MSE_LOSS = 18,      /* vo_cnn_engine.py:135-198 losses + d(loss)/d(pred) */
+  PNVO_OP_ADAM = 19,          /* Adam step over a flat fp32 bucket */
+  PNVO_OP_AVGPOOL2 = 20,      /* F.avg_pool2d(x, 2) -> fp16 NHWC (resnet_policy.py:168) */
+  PNVO_OP_GN_PARAM_GRAD = 21, /* dgamma/dbeta from the per-(sample,channel) sums */
+  PNVO_OP_CAST = 22,          /* fp32 <-> fp16 copies with channel padding */
+  PNVO_OP_MAX = 23
+};
+
+typedef struct {
+  int32_t code;
+  int32_t i[27];
+  float f[4];
+  void* p[10];
+} pnvo_op;
+
+/* Executes ops[0..n_ops) in order on `stream`.  `ops` is HOST memory. */
+int pnvo_run_ops(const pnvo_op* ops, int n_ops, void* stream);
+
+/* Dynamic shared memory / TMEM columns / grid the conv op would use (for tests and DESIGN.md tables). */
+int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, int32_t* smem_bytes,
+                          int32_t* tmem_cols, int32_t* stages);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t pnvo_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNVO_H_ */

@@ -1,0 +1,239 @@
+// C ABI of libpnvo.so (include/pnvo.h): error plumbing and the op-program interpreter.
+// Field layout of every op (i = int slots, f = float slots, p = pointer slots) is mirrored by
+// pointnav_vo_b200/lib.py, which is the only producer of pnvo_op records.
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+
+#include "common.cuh"
+#include "elem.cuh"
+#include "ops.cuh"
+
+namespace pnvo {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+static int run_op(const pnvo_op& op, cudaStream_t st) {
+  const int32_t* i = op.i;
+  const float* f = op.f;
+  void* const* p = op.p;
+  switch (op.code) {
+    case PNVO_OP_ZERO:
+      // p0 = buffer; i0|i1 = byte count (lo, hi)
+      return zero_launch(p[0], (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), st);
+    case PNVO_OP_ASSEMBLE:
+    case PNVO_OP_INPUT_STATS: {
+      // p0..p3 = sources, p4 = scale, p5 = shift, p6 = out (assemble) / fp64 stats (input_stats)
+      // i0 = n_src, i1..i4 = nch, i5 = C, i6 = Cpad, i7|i8 = n_pix, i9..i16 = packed LUT (4 x int8 per word:
+      // 8 words of src_idx<<4|... see below), f0..f3 = pre_scale
+      AssembleArgs a{};
+      a.n_src = i[0];
+      for (int t = 0; t < 4; ++t) {
+        a.src[t] = static_cast<const float*>(p[t]);
+        a.nch[t] = i[1 + t];
+        a.pre_scale[t] = f[t];
+      }
+      a.C = i[5];
+      a.Cpad = i[6];
+      a.n_pix = (static_cast<int64_t>(static_cast<uint32_t>(i[8])) << 32) | static_cast<uint32_t>(i[7]);
+      PNVO_REQUIRE(a.C >= 1 && a.C <= kMaxInC, "assemble: C=%d", a.C);
+      for (int c = 0; c < kMaxInC; ++c) {
+        // word 9 + c/2: two channels per word, each 16 bits = (src_idx << 8) | src_ch
+        const uint32_t w = static_cast<uint32_t>(i[9 + c / 2]);
+        const uint32_t h = (c & 1) ? (w >> 16) : (w & 0xffff);
+        a.src_idx[c] = static_cast<signed char>(h >> 8);
+        a.src_ch[c] = static_cast<signed char>(h & 0xff);
+        if (c < a.C) PNVO_REQUIRE(a.src_idx[c] >= 0 && a.src_idx[c] < a.n_src && a.src_ch[c] < a.nch[a.src_idx[c]],
+                                  "assemble: bad LUT entry for channel %d", c);
+      }
+      a.scale = static_cast<const float*>(p[4]);
+      a.shift = static_cast<const float*>(p[5]);
+      if (op.code == PNVO_OP_ASSEMBLE) {
+        a.out = static_cast<__half*>(p[6]);
+        return assemble_launch(a, st);
+      }
+      return input_stats_launch(a, static_cast<double*>(p[6]), st);
+    }
+    case PNVO_OP_RMV_UPDATE:
+      // p0 = fp64 stats, p1 = _mean, p2 = _var, p3 = _count, p4 = scale, p5 = shift
+      // i0 = C, i1 = update, i2 = have_rmv; f0 = batch samples (all ranks), f1 = pixels per sample
+      return rmv_update_launch(static_cast<const double*>(p[0]), f[0], f[1], static_cast<float*>(p[1]),
+                               static_cast<float*>(p[2]), static_cast<float*>(p[3]), i[0], i[1], i[2],
+                               static_cast<float*>(p[4]), static_cast<float*>(p[5]), st);
+    case PNVO_OP_CONV: {
+      // p0 = x, p1 = w, p2 = y, p3 = add, p4 = stats
+      ConvArgs a{};
+      a.x = static_cast<const __half*>(p[0]);
+      a.w = static_cast<const __half*>(p[1]);
+      a.y = p[2];
+      a.add = static_cast<const __half*>(p[3]);
+      a.stats = static_cast<float*>(p[4]);
+      a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
+      a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];
+      a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18];
+      return conv_launch(a, st);
+    }
+    case PNVO_OP_WGRAD: {
+      // p0 = x, p1 = dy, p2 = dw (packed fp32)
+      WgradArgs a{};
+      a.x = static_cast<const __half*>(p[0]);
+      a.dy = static_cast<const __half*>(p[1]);
+      a.dw = static_cast<float*>(p[2]);
+      a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
+      a.mul = i[8]; a.pad = i[9]; a.w_ld = i[11]; a.n_total = i[12]; a.ld_dy = i[14]; a.pad_w = i[18];
+      return wgrad_launch(a, st);
+    }
+    case PNVO_OP_GN_APPLY:
+    case PNVO_OP_GN_POOL: {
+      // p0 = x, p1 = stats, p2 = gamma, p3 = beta, p4 = res, p5 = y, p6 = argmax
+      // i0 = B, i1 = C, i2 = G, i3 = cpg, i4 = HW, i5 = relu, i6 = x_fp32, i7..i10 = H, W, PH, PW; f0 = cnt, f1 = eps
+      GnArgs a{};
+      a.x = p[0]; a.stats = static_cast<const float*>(p[1]); a.gamma = static_cast<const float*>(p[2]);
+      a.beta = static_cast<const float*>(p[3]); a.res = static_cast<const __half*>(p[4]);
+      a.y = static_cast<__half*>(p[5]);
+      a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.relu = i[5]; a.x_fp32 = i[6]; a.C_real = i[11];
+      a.cnt = f[0]; a.eps = f[1];
+      if (op.code == PNVO_OP_GN_APPLY) return gn_apply_launch(a, i[0], st);
+      return gn_pool_launch(a, i[0], i[7], i[8], i[9], i[10], static_cast<uint8_t*>(p[6]), st);
+    }
+    case PNVO_OP_GN_POOL_BWD:
+      // p0 = g (pooled grad), p1 = pooled output, p2 = argmax, p3 = dy out; i0 = B, i1 = C, i7..i10 = H, W, PH, PW
+      return pool_bwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),
+                             static_cast<const uint8_t*>(p[2]), static_cast<__half*>(p[3]), i[0], i[7], i[8], i[9],
+                             i[10], i[1], st);
+    case PNVO_OP_GN_BWD_REDUCE:
+    case PNVO_OP_GN_BWD_APPLY: {
+      // p0 = g, p1 = relu_ref, p2 = x, p3 = stats, p4 = gamma, p5 = sums, p6 = dx, p7 = dy_out
+      GnBwdArgs a{};
+      a.g = static_cast<const __half*>(p[0]); a.relu_ref = static_cast<const __half*>(p[1]); a.x = p[2];
+      a.stats = static_cast<const float*>(p[3]); a.gamma = static_cast<const float*>(p[4]);
+      a.sums = static_cast<float*>(p[5]); a.dx = static_cast<__half*>(p[6]); a.dy_out = static_cast<__half*>(p[7]);
+      a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.x_fp32 = i[6]; a.C_real = i[11];
+      a.cnt = f[0]; a.eps = f[1];
+      if (op.code == PNVO_OP_GN_BWD_REDUCE) return gn_bwd_reduce_launch(a, i[0], st);
+      return gn_bwd_apply_launch(a, i[0], st);
+    }
+    case PNVO_OP_GN_PARAM_GRAD:
+      // p0 = sums, p1 = dgamma, p2 = dbeta; i0 = B, i1 = C, i2 = C_real, i3 = accumulate
+      return gn_param_grad_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], static_cast<float*>(p[1]),
+                                  static_cast<float*>(p[2]), i[3], st);
+    case PNVO_OP_PACK_W:
+      // p0 = w (OIHW fp32), p1 = wp, p2 = wt; i0..i3 = Cout, Cin, R, S; i4 = cin_pad, i5 = ld_p, i6 = cout_pad, i7 = ld_t,
+      // i8 = t_mode (0: conv dgrad layout, 1: plain transpose of wp)
+      return pack_w_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], static_cast<__half*>(p[1]), i[4],
+                           i[5], static_cast<__half*>(p[2]), i[6], i[7], i[8], st);
+    case PNVO_OP_UNPACK_DW:
+      // p0 = dwp, p1 = grad; i0..i3 = Cout, Cin, R, S; i4 = cin_pad, i5 = ld_p, i6 = accumulate
+      return unpack_dw_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], i[4], i[5],
+                              static_cast<float*>(p[1]), i[6], st);
+    case PNVO_OP_BIAS_RELU:
+      // p0 = z, p1 = bias, p2 = h32, p3 = h16; i0 = B, i1 = N, i2 = relu
+      return bias_relu_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]), i[0], i[1], i[2],
+                              static_cast<float*>(p[2]), static_cast<__half*>(p[3]), st);
+    case PNVO_OP_HEAD_FWD:
+      // p0 = h, p1 = W, p2 = bias, p3 = out; i0 = B, i1 = K, i2 = O
+      return head_fwd_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
+                             static_cast<const float*>(p[2]), i[0], i[1], i[2], static_cast<float*>(p[3]), st);
+    case PNVO_OP_HEAD_BWD:
+      // p0 = dout, p1 = h, p2 = W, p3 = dW, p4 = db2, p5 = dz16, p6 = db1; i0 = B, i1 = K, i2 = O, i3 = accumulate
+      return head_bwd_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
+                             static_cast<const float*>(p[2]), i[0], i[1], i[2], static_cast<float*>(p[3]),
+                             static_cast<float*>(p[4]), static_cast<__half*>(p[5]), static_cast<float*>(p[6]), i[3], st);
+    case PNVO_OP_ADAM:
+      // p0 = param, p1 = grad, p2 = m, p3 = v; i0|i1 = n, i2 = step; f0 = lr, f1 = beta1, f2 = beta2, f3 = eps
+      return adam_launch(static_cast<float*>(p[0]), static_cast<const float*>(p[1]), static_cast<float*>(p[2]),
+                         static_cast<float*>(p[3]),
+                         (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), f[0],
+                         f[1], f[2], f[3], i[2], 1.0f, st);
+    case PNVO_OP_AVGPOOL2:
+      // p0 = src fp32 NHWC, p1 = out fp16; i0 = B, i1 = H, i2 = W, i3 = C, i4 = Cpad, i5 = coff; f0 = pre_scale
+      return avgpool2_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], f[0], static_cast<__half*>(p[1]),
+                             i[4], i[5], st);
+    default:
+      set_error("run_ops: unknown opcode %d", op.code);
+      return -3;
+  }
+}
+
+}  // namespace pnvo
+
+using namespace pnvo;
+
+extern "C" const char* pnvo_last_error(void) { return g_err; }
+extern "C" int pnvo_abi_version(void) { return PNVO_ABI_VERSION; }
+extern "C" int64_t pnvo_launch_count(void) { return g_launches.load(); }
+
+extern "C" int pnvo_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  if (prop.major != 10) {
+    set_error("libpnvo is built for sm_100a (B200); device %d is sm_%d%d", dev, prop.major, prop.minor);
+    return -2;
+  }
+  return 0;
+}
+
+extern "C" int pnvo_run_ops(const pnvo_op* ops, int n_ops, void* stream) {
+  PNVO_REQUIRE(ops || n_ops == 0, "run_ops: null program");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int k = 0; k < n_ops; ++k) {
+    const int rc = run_op(ops[k], st);
+    if (rc != 0) {
+      char tmp[400];
+      snprintf(tmp, sizeof(tmp), "%s", g_err);
+      set_error("op %d (code %d): %s", k, ops[k].code, tmp);
+      return rc;
+    }
+  }
+  return 0;
+}
+
+extern "C" int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, int32_t* smem_bytes,
+                                     int32_t* tmem_cols, int32_t* stages) {
+  PNVO_REQUIRE(op && (op->code == PNVO_OP_CONV || op->code == PNVO_OP_WGRAD), "conv_launch_info: not a conv op");
+  const int32_t* i = op->i;
+  if (op->code == PNVO_OP_CONV) {
+    ConvArgs a{};
+    a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
+    a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];
+    a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18];
+    a.stats = static_cast<float*>(op->p[4]);
+    if (conv_plan(a)) return -1;
+    *grid_x = a.grid_x; *grid_y = a.grid_y; *smem_bytes = a.smem_bytes; *tmem_cols = a.tmem_cols; *stages = a.stages;
+  } else {
+    WgradArgs a{};
+    a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
+    a.mul = i[8]; a.pad = i[9]; a.w_ld = i[11]; a.n_total = i[12]; a.ld_dy = i[14]; a.pad_w = i[18];
+    if (wgrad_plan(a)) return -1;
+    *grid_x = a.grid_x * a.grid_y; *grid_y = a.grid_z; *smem_bytes = a.smem_bytes; *tmem_cols = a.tmem_cols;
+    *stages = a.stages;
+  }
+  return 0;
+}

@@ -1,0 +1,79 @@
+// Argument structs + launchers of the elementwise / reduction kernels (norm_pool.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pnvo {
+
+static constexpr int kMaxInC = 32;  // input channels of the first conv (30 for the default VO model)
+
+struct AssembleArgs {
+  const float* src[4];  // NHWC fp32 sources (rgb, depth, discretized_depth, top_down_view)
+  int nch[4];           // channels per pixel of each source
+  float pre_scale[4];   // 1/255 for rgb, 1 otherwise (vo_cnn.py:117-118)
+  int n_src;
+  int C, Cpad;             // real / padded channel count of the assembled tensor
+  signed char src_idx[kMaxInC];  // output channel -> source tensor
+  signed char src_ch[kMaxInC];   // output channel -> channel inside that source
+  const float* scale;      // per output channel (nullable = 1)
+  const float* shift;      // per output channel (nullable = 0)
+  __half* out;             // [n_pix][Cpad]
+  int64_t n_pix;
+};
+int assemble_launch(const AssembleArgs& a, cudaStream_t st);
+int input_stats_launch(const AssembleArgs& a, double* stats, cudaStream_t st);
+int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample, float* mean, float* var,
+                      float* count, int C, int update, int have_rmv, float* scale, float* shift, cudaStream_t st);
+int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
+                    cudaStream_t st);
+int zero_launch(void* p, int64_t bytes, cudaStream_t st);
+
+struct GnArgs {
+  const void* x;       // raw conv output [B*HW][C] fp16 (or fp32 when x_fp32)
+  int x_fp32;
+  const float* stats;  // [B][G][2]
+  const float* gamma;  // [C] (padded channels: 0)
+  const float* beta;   // [C]
+  const __half* res;   // optional residual [B*HW][C]
+  __half* y;           // [B*HW][C] (or pooled)
+  int C, C_real, G, cpg, HW;
+  float cnt;           // elements per group = cpg_real * HW
+  float eps;
+  int relu;
+};
+int gn_apply_launch(const GnArgs& a, int B, cudaStream_t st);
+int gn_pool_launch(const GnArgs& a, int B, int H, int W, int PH, int PW, uint8_t* argmax, cudaStream_t st);
+int pool_bwd_launch(const __half* g, const __half* pooled, const uint8_t* argmax, __half* dy, int B, int H, int W,
+                    int PH, int PW, int C, cudaStream_t st);
+
+struct GnBwdArgs {
+  const __half* g;         // gradient w.r.t. the GN(+ReLU) output [B*HW][C]
+  const __half* relu_ref;  // saved post-ReLU output (mask = relu_ref > 0); null = no ReLU
+  const void* x;           // raw conv output (GN input)
+  int x_fp32;
+  const float* stats;
+  const float* gamma;
+  float* sums;             // [B][C][2] (sum dy, sum dy*xhat), pre-zeroed for the reduce pass
+  __half* dx;              // apply pass: gradient w.r.t. the raw conv output
+  __half* dy_out;          // apply pass, optional: masked g (identity-branch gradient)
+  int C, C_real, G, cpg, HW;
+  float cnt, eps;
+};
+int gn_bwd_reduce_launch(const GnBwdArgs& a, int B, cudaStream_t st);
+int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st);
+int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dgamma, float* dbeta, int accumulate,
+                         cudaStream_t st);
+
+int pack_w_launch(const float* w, int Cout, int Cin, int R, int S, __half* wp, int cin_pad, int ld_p, __half* wt,
+                  int cout_pad, int ld_t, int t_mode, cudaStream_t st);
+int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p, float* grad,
+                     int accumulate, cudaStream_t st);
+int bias_relu_launch(const float* z, const float* bias, int B, int N, int relu, float* h32, __half* h16,
+                     cudaStream_t st);
+int head_fwd_launch(const float* h, const float* W, const float* bias, int B, int K, int O, float* out,
+                    cudaStream_t st);
+int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,
+                    __half* dz16, float* db1, int accumulate, cudaStream_t st);
+int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                int step, float grad_scale, cudaStream_t st);
+
+}  // namespace pnvo

@@ -1,0 +1,774 @@
+// HBM-bound elementwise / reduction kernels around the tensor-core convolutions (sm_100a):
+// input assembly + RunningMeanAndVar (vo_cnn.py:110-176, running_mean_and_var.py:22-63), GroupNorm apply
+// with fused ReLU / residual / 3x3-s2 max-pool (resnet.py:39-55,165-168), GroupNorm backward, weight
+// (un)packing, the tiny regression head (vo_cnn.py:216-227) and a flat-bucket Adam.
+// All activation tensors are NHWC fp16 with the channel count padded to a multiple of 8, so every
+// thread moves 16-byte vectors.
+#include "common.cuh"
+#include "elem.cuh"
+
+namespace pnvo {
+
+// ------------------------------------------------------------------------------------------------
+// zero fill
+// ------------------------------------------------------------------------------------------------
+__global__ void zero_kernel(uint4* __restrict__ p, int64_t n16, unsigned char* tail, int ntail) {
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = i0; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
+  if (i0 < ntail) tail[i0] = 0;
+}
+int zero_launch(void* p, int64_t bytes, cudaStream_t st) {
+  if (bytes <= 0) return 0;
+  PNVO_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "zero: pointer not 16-byte aligned");
+  const int64_t n16 = bytes / 16;
+  const int ntail = static_cast<int>(bytes - n16 * 16);
+  const int blocks = static_cast<int>(std::min<int64_t>(std::max<int64_t>(1, ceil_div64(n16, 256)), 148 * 8));
+  zero_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(p), n16, reinterpret_cast<unsigned char*>(p) + n16 * 16,
+                                      ntail);
+  count_launch();
+  return check_launch("zero");
+}
+
+// ------------------------------------------------------------------------------------------------
+// input assembly: up to 4 NHWC fp32 sources whose channels are [prev | cur] -> one NHWC fp16 tensor
+// with channels [prev of every source ..., cur of every source ..., zero pad], normalised per channel.
+// A block stages 256 pixels of every source in shared memory with coalesced float4 loads (the
+// per-pixel channel runs of the sources are 8..80 bytes, too short for direct vector access), then
+// one thread per pixel picks its channels through a constant LUT and stores 16-byte vectors.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kAsmPix = 256;
+
+__device__ __forceinline__ void stage_sources(const AssembleArgs& a, int64_t pix0, int npix, float* s_src,
+                                              int* s_base) {
+  int off = 0;
+  for (int t = 0; t < a.n_src; ++t) {
+    const int nch = a.nch[t];
+    const int64_t f0 = pix0 * nch;           // first float of this block in source t
+    const int nfl = npix * nch;              // floats to stage
+    const float* __restrict__ g = a.src[t] + f0;
+    float* d = s_src + off;
+    if (threadIdx.x == 0) s_base[t] = off;
+    // pix0 is a multiple of 256 so f0*4 is 16-byte aligned for every nch
+    const int n4 = nfl >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+      reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < nfl; i += blockDim.x) d[i] = __ldg(g + i);
+    off += kAsmPix * nch;
+  }
+}
+
+__device__ __forceinline__ void pick_pixel(const AssembleArgs& a, const float* s_src, const int* s_base, int lp,
+                                           float* v) {
+#pragma unroll
+  for (int c = 0; c < kMaxInC; ++c) {
+    v[c] = 0.f;
+    if (c < a.C) {
+      const int t = a.src_idx[c];
+      v[c] = s_src[s_base[t] + lp * a.nch[t] + a.src_ch[c]] * a.pre_scale[t];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAsmPix) assemble_kernel(const AssembleArgs a) {
+  extern __shared__ __align__(16) float s_src[];
+  __shared__ float s_scale[kMaxInC], s_shift[kMaxInC];
+  __shared__ int s_base[4];
+  if (threadIdx.x < kMaxInC) {
+    const int c = threadIdx.x;
+    s_scale[c] = (c < a.C) ? (a.scale ? a.scale[c] : 1.f) : 0.f;
+    s_shift[c] = (c < a.C && a.shift) ? a.shift[c] : 0.f;
+  }
+  const int64_t pix0 = static_cast<int64_t>(blockIdx.x) * kAsmPix;
+  const int npix = static_cast<int>(min(static_cast<int64_t>(kAsmPix), a.n_pix - pix0));
+  stage_sources(a, pix0, npix, s_src, s_base);
+  __syncthreads();
+  const int lp = threadIdx.x;
+  if (lp >= npix) return;
+  float v[kMaxInC];
+  pick_pixel(a, s_src, s_base, lp, v);
+  __half* __restrict__ out = a.out + (pix0 + lp) * a.Cpad;
+#pragma unroll
+  for (int q = 0; q < kMaxInC / 8; ++q) {
+    if (q * 8 < a.Cpad) {
+      uint4 u;
+      __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = q * 8 + 2 * e;
+        h2[e] = __floats2half2_rn(fmaf(v[c], s_scale[c], s_shift[c]), fmaf(v[c + 1], s_scale[c + 1], s_shift[c + 1]));
+      }
+      *reinterpret_cast<uint4*>(out + q * 8) = u;
+    }
+  }
+}
+
+// per-channel sum / sum of squares of the assembled (un-normalised) input: fp32 per-thread partials over
+// kStatsTiles pixels, fp64 from the warp reduction upwards
+static constexpr int kStatsTiles = 8;
+__global__ void __launch_bounds__(kAsmPix) input_stats_kernel(const AssembleArgs a, double* __restrict__ stats) {
+  extern __shared__ __align__(16) float s_src[];
+  __shared__ double s_acc[2 * kMaxInC];
+  __shared__ int s_base[4];
+  if (threadIdx.x < 2 * kMaxInC) s_acc[threadIdx.x] = 0.0;
+  float s[kMaxInC], q[kMaxInC];
+#pragma unroll
+  for (int c = 0; c < kMaxInC; ++c) s[c] = q[c] = 0.f;
+  for (int it = 0; it < kStatsTiles; ++it) {
+    const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kStatsTiles + it) * kAsmPix;
+    if (pix0 >= a.n_pix) break;
+    const int npix = static_cast<int>(min(static_cast<int64_t>(kAsmPix), a.n_pix - pix0));
+    __syncthreads();
+    stage_sources(a, pix0, npix, s_src, s_base);
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < npix) {
+      float v[kMaxInC];
+      pick_pixel(a, s_src, s_base, threadIdx.x, v);
+#pragma unroll
+      for (int c = 0; c < kMaxInC; ++c) {
+        s[c] += v[c];
+        q[c] = fmaf(v[c], v[c], q[c]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < kMaxInC; ++c) {
+    double ds = s[c], dq = q[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if (lane == 0 && c < a.C) {
+      atomicAdd(&s_acc[2 * c], ds);
+      atomicAdd(&s_acc[2 * c + 1], dq);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * a.C) atomicAdd(stats + threadIdx.x, s_acc[threadIdx.x]);
+}
+
+// RunningMeanAndVar (running_mean_and_var.py:22-63): optional Chan merge of the batch statistics into
+// the running buffers (training), then scale = 1/sqrt(max(var, 1e-2)), shift = -mean*scale.
+// stats: [2C] fp64 (sum, sumsq interleaved) + stats[2*kMaxInC] = sample count (all ranks), n_per_sample pixels.
+__global__ void rmv_update_kernel(const double* __restrict__ stats, double n_batch, double pix_per_sample,
+                                  float* __restrict__ mean, float* __restrict__ var, float* __restrict__ count, int C,
+                                  int update, int have_rmv, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = threadIdx.x;
+  const float cnt = have_rmv ? *count : 0.f;
+  __syncthreads();
+  if (c < C) {
+    float m = have_rmv ? mean[c] : 0.f, v = have_rmv ? var[c] : 1.f;
+    if (update && have_rmv) {
+      const double n = n_batch * pix_per_sample;
+      const double mu = stats[2 * c] / n;
+      double va = stats[2 * c + 1] / n - mu * mu;
+      if (va < 0) va = 0;
+      const float new_mean = static_cast<float>(mu), new_var = static_cast<float>(va);
+      const float new_count = static_cast<float>(n_batch);
+      const float m_a = v * cnt, m_b = new_var * new_count;
+      const float d = new_mean - m;
+      const float M2 = m_a + m_b + d * d * cnt * new_count / (cnt + new_count);
+      v = M2 / (cnt + new_count);
+      m = (cnt * m + new_count * new_mean) / (cnt + new_count);
+      mean[c] = m;
+      var[c] = v;
+    }
+    if (have_rmv) {
+      const float sd = sqrtf(fmaxf(v, 1e-2f));
+      scale[c] = 1.0f / sd;
+      shift[c] = -m / sd;
+    } else {
+      scale[c] = 1.f;
+      shift[c] = 0.f;
+    }
+  }
+  if (c == 0 && update && have_rmv) *count = cnt + static_cast<float>(n_batch);
+}
+
+int assemble_launch(const AssembleArgs& a, cudaStream_t st) {
+  PNVO_REQUIRE(a.C <= kMaxInC && a.Cpad <= kMaxInC && a.Cpad % 8 == 0 && a.C <= a.Cpad, "assemble: bad channel counts");
+  PNVO_REQUIRE(a.n_src >= 1 && a.n_src <= 4, "assemble: n_src");
+  int tot_ch = 0;
+  for (int t = 0; t < a.n_src; ++t) tot_ch += a.nch[t];
+  PNVO_REQUIRE(tot_ch * kAsmPix * 4 <= 48 * 1024, "assemble: %d source channels exceed the staging tile", tot_ch);
+  if (a.n_pix <= 0) return 0;
+  int tot = 0;
+  for (int t = 0; t < a.n_src; ++t) tot += a.nch[t];
+  assemble_kernel<<<static_cast<int>(ceil_div64(a.n_pix, kAsmPix)), kAsmPix, tot * kAsmPix * sizeof(float), st>>>(a);
+  count_launch();
+  return check_launch("assemble");
+}
+int input_stats_launch(const AssembleArgs& a, double* stats, cudaStream_t st) {
+  PNVO_REQUIRE(a.C <= kMaxInC, "input_stats: too many channels");
+  if (a.n_pix <= 0) return 0;
+  int tot = 0;
+  for (int t = 0; t < a.n_src; ++t) tot += a.nch[t];
+  input_stats_kernel<<<static_cast<int>(ceil_div64(a.n_pix, kAsmPix * kStatsTiles)), kAsmPix,
+                       tot * kAsmPix * sizeof(float), st>>>(a, stats);
+  count_launch();
+  return check_launch("input_stats");
+}
+int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample, float* mean, float* var,
+                      float* count, int C, int update, int have_rmv, float* scale, float* shift, cudaStream_t st) {
+  PNVO_REQUIRE(C <= kMaxInC, "rmv_update: too many channels");
+  rmv_update_kernel<<<1, 64, 0, st>>>(stats, n_batch, pix_per_sample, mean, var, count, C, update, have_rmv, scale,
+                                      shift);
+  count_launch();
+  return check_launch("rmv_update");
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 average pool of fp32 NHWC sources -> fp16 NHWC (policy encoder, resnet_policy.py:146-168)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ src, int B, int H, int W, int C,
+                                                       float pre_scale, __half* __restrict__ out, int Cpad, int coff) {
+  const int OH = H / 2, OW = W / 2;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW;
+  if (idx >= total) return;
+  const int ow = static_cast<int>(idx % OW);
+  const int oh = static_cast<int>((idx / OW) % OH);
+  const int b = static_cast<int>(idx / (static_cast<int64_t>(OW) * OH));
+  const float* p = src + ((static_cast<int64_t>(b) * H + 2 * oh) * W + 2 * ow) * C;
+  for (int c = 0; c < C; ++c) {
+    // F.avg_pool2d sums the window then multiplies by 1/4
+    const float s = ((p[c] + p[C + c]) + p[static_cast<int64_t>(W) * C + c]) + p[static_cast<int64_t>(W) * C + C + c];
+    out[idx * Cpad + coff + c] = __float2half_rn(s * 0.25f * pre_scale);
+  }
+}
+int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
+                    cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+  if (total <= 0) return 0;
+  avgpool2_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, st>>>(src, B, H, W, C, pre_scale, out, Cpad, coff);
+  count_launch();
+  return check_launch("avgpool2");
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm helpers.  stats[b][g] = (sum, sumsq) over the group's cpg_real*HW elements (fp32 partials
+// accumulated by the conv epilogue).  Per block (one sample) the affine per channel is put in smem:
+//   y = x * a_c + b_c,  a_c = gamma_c * rstd_g,  b_c = beta_c - mean_g * a_c
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group_mean_rstd(const float* stats, int b, int G, int g, float cnt, float eps,
+                                                float& mean, float& rstd) {
+  const float s = stats[(static_cast<int64_t>(b) * G + g) * 2], q = stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
+  mean = s / cnt;
+  const float var = fmaxf(q / cnt - mean * mean, 0.f);
+  rstd = 1.0f / sqrtf(var + eps);
+}
+
+__device__ __forceinline__ void load8(const void* base, int64_t idx8, int is_fp32, float* v) {
+  if (is_fp32) {
+    const float4* p = reinterpret_cast<const float4*>(base) + idx8 * 2;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base) + idx8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      v[2 * e] = f.x;
+      v[2 * e + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void store8h(__half* base, int64_t idx8, const float* v) {
+  uint4 u;
+  __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+  reinterpret_cast<uint4*>(base)[idx8] = u;
+}
+
+// y = [relu]( GN(x) [+ res] )
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
+  extern __shared__ float s_ab[];  // a_c [C], b_c [C]
+  const int b = blockIdx.y;
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    group_mean_rstd(a.stats, b, a.G, c / a.cpg, a.cnt, a.eps, mean, rstd);
+    const float ga = (c < a.C_real) ? a.gamma[c] * rstd : 0.f;
+    s_ab[c] = ga;
+    s_ab[C + c] = (c < a.C_real) ? a.beta[c] - mean * ga : 0.f;
+  }
+  __syncthreads();
+  const int c8 = C >> 3;
+  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
+  const int64_t base = static_cast<int64_t>(b) * per_sample;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8) * 8;
+    float v[8];
+    load8(a.x, base + i, a.x_fp32, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_ab[cc + e], s_ab[C + cc + e]);
+    if (a.res) {
+      float r[8];
+      load8(a.res, base + i, 0, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    store8h(a.y, base + i, v);
+  }
+}
+
+// GN + ReLU + MaxPool 3x3 / stride 2 / pad 1; also records the arg-max tap (0..8) for the backward pass
+__global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int W, int PH, int PW,
+                                                      uint8_t* __restrict__ argmax) {
+  extern __shared__ float s_ab[];
+  const int b = blockIdx.y;
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    group_mean_rstd(a.stats, b, a.G, c / a.cpg, a.cnt, a.eps, mean, rstd);
+    const float ga = (c < a.C_real) ? a.gamma[c] * rstd : 0.f;
+    s_ab[c] = ga;
+    s_ab[C + c] = (c < a.C_real) ? a.beta[c] - mean * ga : 0.f;
+  }
+  __syncthreads();
+  const int c8 = C >> 3;
+  const int64_t per_sample = static_cast<int64_t>(PH) * PW * c8;
+  const int64_t in_base = static_cast<int64_t>(b) * H * W * c8;
+  const int64_t out_base = static_cast<int64_t>(b) * per_sample;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % c8);
+    const int cc = q * 8;
+    const int pw = static_cast<int>((i / c8) % PW);
+    const int ph = static_cast<int>(i / (static_cast<int64_t>(c8) * PW));
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ph - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * pw - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load8(a.x, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, a.x_fp32, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float y = fmaxf(fmaf(v[e], s_ab[cc + e], s_ab[C + cc + e]), 0.f);
+          if (y > best[e]) { best[e] = y; arg[e] = r * 3 + s; }
+        }
+      }
+    }
+    store8h(a.y, out_base + i, best);
+    if (argmax) {
+      uint2 u;
+      u.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      u.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      reinterpret_cast<uint2*>(argmax)[out_base + i] = u;
+    }
+  }
+}
+
+// gradient of MaxPool(ReLU(.)) routed back to the GN output: dy[h,w,c] = sum of g[ph,pw,c] over the
+// windows whose arg-max is (h,w) and whose pooled value is > 0
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const __half* __restrict__ g, const __half* __restrict__ pooled,
+                                                       const uint8_t* __restrict__ argmax, __half* __restrict__ dy,
+                                                       int H, int W, int PH, int PW, int C) {
+  const int b = blockIdx.y;
+  const int c8 = C >> 3;
+  const int64_t per_sample = static_cast<int64_t>(H) * W * c8;
+  const int64_t out_base = static_cast<int64_t>(b) * per_sample;
+  const int64_t p_base = static_cast<int64_t>(b) * PH * PW * c8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % c8);
+    const int w = static_cast<int>((i / c8) % W);
+    const int h = static_cast<int>(i / (static_cast<int64_t>(c8) * W));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int ph = max(0, h / 2); ph <= min(PH - 1, (h + 1) / 2); ++ph) {
+      const int r = h - (2 * ph - 1);
+      for (int pw = max(0, w / 2); pw <= min(PW - 1, (w + 1) / 2); ++pw) {
+        const int s = w - (2 * pw - 1);
+        const int tap = r * 3 + s;
+        const int64_t pi = p_base + (static_cast<int64_t>(ph) * PW + pw) * c8 + q;
+        const uint2 am = __ldg(reinterpret_cast<const uint2*>(argmax) + pi);
+        float gv[8], pv[8];
+        load8(g, pi, 0, gv);
+        load8(pooled, pi, 0, pv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int t = ((e < 4 ? am.x : am.y) >> (8 * (e & 3))) & 0xff;
+          if (t == tap && pv[e] > 0.f) acc[e] += gv[e];
+        }
+      }
+    }
+    store8h(dy, out_base + i, acc);
+  }
+}
+
+// GN backward, pass 1: per (sample, channel) sums of dy and dy*xhat, dy = g * [relu_ref > 0]
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
+  extern __shared__ float s_mem[];  // mean_g [G], rstd_g [G], acc [2C]
+  const int b = blockIdx.y;
+  const int C = a.C, G = a.G;
+  float* s_mean = s_mem;
+  float* s_rstd = s_mem + G;
+  float* s_acc = s_mem + 2 * G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) group_mean_rstd(a.stats, b, G, g, a.cnt, a.eps, s_mean[g], s_rstd[g]);
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_acc[c] = 0.f;
+  __syncthreads();
+  const int c8 = C >> 3;
+  // thread -> fixed channel chunk, strided over pixels (requires blockDim % c8 == 0 or c8 % blockDim == 0)
+  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
+  const int64_t base = static_cast<int64_t>(b) * per_sample;
+  const int64_t start = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if (stride % c8 == 0) {
+    const int cc = static_cast<int>(start % c8) * 8;
+    float sd[8], sx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sd[e] = sx[e] = 0.f;
+    for (int64_t i = start; i < per_sample; i += stride) {
+      float g[8], x[8];
+      load8(a.g, base + i, 0, g);
+      load8(a.x, base + i, a.x_fp32, x);
+      if (a.relu_ref) {
+        float y[8];
+        load8(a.relu_ref, base + i, 0, y);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int grp = (cc + e) / a.cpg;
+        const float xh = (x[e] - s_mean[grp]) * s_rstd[grp];
+        sd[e] += g[e];
+        sx[e] = fmaf(g[e], xh, sx[e]);
+      }
+    }
+    if (start < per_sample) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_acc[2 * (cc + e)], sd[e]);
+        atomicAdd(&s_acc[2 * (cc + e) + 1], sx[e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x)
+    atomicAdd(a.sums + static_cast<int64_t>(b) * 2 * C + c, s_acc[c]);
+}
+
+// GN backward, pass 2: dx = rstd*(gamma*dy - (S1 + xhat*S2)/cnt); optionally also writes dy (masked g)
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
+  extern __shared__ float s_mem[];  // mean [G], rstd [G], k1 [G], k2 [G], ga [C]
+  const int b = blockIdx.y;
+  const int C = a.C, G = a.G;
+  float* s_mean = s_mem;
+  float* s_rstd = s_mem + G;
+  float* s_k1 = s_mem + 2 * G;
+  float* s_k2 = s_mem + 3 * G;
+  float* s_ga = s_mem + 4 * G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float mean, rstd;
+    group_mean_rstd(a.stats, b, G, g, a.cnt, a.eps, mean, rstd);
+    float S1 = 0.f, S2 = 0.f;
+    for (int c = g * a.cpg; c < (g + 1) * a.cpg && c < a.C_real; ++c) {
+      const float gm = a.gamma[c];
+      S1 = fmaf(gm, a.sums[(static_cast<int64_t>(b) * C + c) * 2], S1);
+      S2 = fmaf(gm, a.sums[(static_cast<int64_t>(b) * C + c) * 2 + 1], S2);
+    }
+    s_mean[g] = mean;
+    s_rstd[g] = rstd;
+    s_k1[g] = rstd * S1 / a.cnt;
+    s_k2[g] = rstd * S2 / a.cnt;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_ga[c] = (c < a.C_real) ? a.gamma[c] : 0.f;
+  __syncthreads();
+  const int c8 = C >> 3;
+  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
+  const int64_t base = static_cast<int64_t>(b) * per_sample;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8) * 8;
+    float g[8], x[8], dx[8];
+    load8(a.g, base + i, 0, g);
+    load8(a.x, base + i, a.x_fp32, x);
+    if (a.relu_ref) {
+      float y[8];
+      load8(a.relu_ref, base + i, 0, y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int grp = (cc + e) / a.cpg;
+      const float xh = (x[e] - s_mean[grp]) * s_rstd[grp];
+      dx[e] = s_rstd[grp] * s_ga[cc + e] * g[e] - s_k1[grp] - xh * s_k2[grp];
+    }
+    store8h(a.dx, base + i, dx);
+    if (a.dy_out) store8h(a.dy_out, base + i, g);
+  }
+}
+
+// dgamma[c] = sum_b sums[b][c][1], dbeta[c] = sum_b sums[b][c][0]
+__global__ void gn_param_grad_kernel(const float* __restrict__ sums, int B, int C, int C_real,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C_real) return;
+  float dg = 0.f, db = 0.f;
+  for (int b = 0; b < B; ++b) {
+    db += sums[(static_cast<int64_t>(b) * C + c) * 2];
+    dg += sums[(static_cast<int64_t>(b) * C + c) * 2 + 1];
+  }
+  if (accumulate) { dgamma[c] += dg; dbeta[c] += db; }
+  else { dgamma[c] = dg; dbeta[c] = db; }
+}
+
+static int gn_grid_x(int64_t per_sample_items, int B, int c8) {
+  // enough CTAs for ~4 waves of 148 SMs x 8 CTAs, multiple of c8-friendly stride handled by the kernel
+  int64_t want = std::max<int64_t>(1, (148 * 8 * 2) / std::max(1, B));
+  int64_t maxb = std::max<int64_t>(1, ceil_div64(per_sample_items, 256));
+  (void)c8;
+  return static_cast<int>(std::min(want, maxb));
+}
+
+int gn_apply_launch(const GnArgs& a, int B, cudaStream_t st) {
+  PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 4096, "gn_apply: C=%d", a.C);
+  if (B <= 0 || a.HW <= 0) return 0;
+  const int gx = gn_grid_x(static_cast<int64_t>(a.HW) * (a.C / 8), B, a.C / 8);
+  gn_apply_kernel<<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a);
+  count_launch();
+  return check_launch("gn_apply");
+}
+int gn_pool_launch(const GnArgs& a, int B, int H, int W, int PH, int PW, uint8_t* argmax, cudaStream_t st) {
+  PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 4096, "gn_pool: C=%d", a.C);
+  if (B <= 0) return 0;
+  const int gx = gn_grid_x(static_cast<int64_t>(PH) * PW * (a.C / 8), B, a.C / 8);
+  gn_pool_kernel<<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a, H, W, PH, PW, argmax);
+  count_launch();
+  return check_launch("gn_pool");
+}
+int pool_bwd_launch(const __half* g, const __half* pooled, const uint8_t* argmax, __half* dy, int B, int H, int W,
+                    int PH, int PW, int C, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int gx = gn_grid_x(static_cast<int64_t>(H) * W * (C / 8), B, C / 8);
+  pool_bwd_kernel<<<dim3(gx, B), 256, 0, st>>>(g, pooled, argmax, dy, H, W, PH, PW, C);
+  count_launch();
+  return check_launch("pool_bwd");
+}
+int gn_bwd_reduce_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
+  PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 2048, "gn_bwd_reduce: C=%d", a.C);
+  if (B <= 0 || a.HW <= 0) return 0;
+  const int c8 = a.C / 8;
+  PNVO_REQUIRE(256 % c8 == 0 || c8 % 256 == 0, "gn_bwd_reduce: C/8=%d must divide or be a multiple of 256", c8);
+  int gx = gn_grid_x(static_cast<int64_t>(a.HW) * c8, B, c8);
+  if (c8 > 256) gx = ((gx + c8 / 256 - 1) / (c8 / 256)) * (c8 / 256);  // keep gridDim.x*256 a multiple of c8
+  gn_bwd_reduce_kernel<<<dim3(gx, B), 256, (2 * a.G + 2 * a.C) * sizeof(float), st>>>(a);
+  count_launch();
+  return check_launch("gn_bwd_reduce");
+}
+int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
+  PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 2048, "gn_bwd_apply: C=%d", a.C);
+  if (B <= 0 || a.HW <= 0) return 0;
+  const int gx = gn_grid_x(static_cast<int64_t>(a.HW) * (a.C / 8), B, a.C / 8);
+  gn_bwd_apply_kernel<<<dim3(gx, B), 256, (4 * a.G + a.C) * sizeof(float), st>>>(a);
+  count_launch();
+  return check_launch("gn_bwd_apply");
+}
+int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dgamma, float* dbeta, int accumulate,
+                         cudaStream_t st) {
+  gn_param_grad_kernel<<<ceil_div(C_real, 128), 128, 0, st>>>(sums, B, C, C_real, dgamma, dbeta, accumulate);
+  count_launch();
+  return check_launch("gn_param_grad");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> [n][ (r*S+s)*Cin_pad + c ] fp16 (fprop / wgrad layout), and the dgrad
+// layout [c][ ((R-1-r)*S + (S-1-s))*Cout_pad + n ].  Destination buffers are zero-initialised once; pad
+// entries are never written.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, __half* __restrict__ wp,
+                              int cin_pad, int ld_p, __half* __restrict__ wt, int cout_pad, int ld_t, int t_mode) {
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i % S);
+    const int r = static_cast<int>((i / S) % R);
+    const int c = static_cast<int>((i / (static_cast<int64_t>(S) * R)) % Cin);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(S) * R * Cin));
+    const __half h = __float2half_rn(w[i]);
+    if (wp) wp[static_cast<int64_t>(n) * ld_p + (r * S + s) * cin_pad + c] = h;
+    if (wt) {
+      if (t_mode == 0) wt[static_cast<int64_t>(c) * ld_t + ((R - 1 - r) * S + (S - 1 - s)) * cout_pad + n] = h;
+      else wt[static_cast<int64_t>((r * S + s) * cin_pad + c) * ld_t + n] = h;
+    }
+  }
+}
+__global__ void unpack_dw_kernel(const float* __restrict__ dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p,
+                                 float* __restrict__ grad, int accumulate) {
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i % S);
+    const int r = static_cast<int>((i / S) % R);
+    const int c = static_cast<int>((i / (static_cast<int64_t>(S) * R)) % Cin);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(S) * R * Cin));
+    const float v = dwp[static_cast<int64_t>(n) * ld_p + (r * S + s) * cin_pad + c];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+int pack_w_launch(const float* w, int Cout, int Cin, int R, int S, __half* wp, int cin_pad, int ld_p, __half* wt,
+                  int cout_pad, int ld_t, int t_mode, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
+  if (total <= 0) return 0;
+  pack_w_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 4)), 256, 0, st>>>(
+      w, Cout, Cin, R, S, wp, cin_pad, ld_p, wt, cout_pad, ld_t, t_mode);
+  count_launch();
+  return check_launch("pack_w");
+}
+int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p, float* grad,
+                     int accumulate, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
+  if (total <= 0) return 0;
+  unpack_dw_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 4)), 256, 0, st>>>(
+      dwp, Cout, Cin, R, S, cin_pad, ld_p, grad, accumulate);
+  count_launch();
+  return check_launch("unpack_dw");
+}
+
+// ------------------------------------------------------------------------------------------------
+// regression head (vo_cnn.py:216-227).  fc1 runs on the tensor cores as a 6x11 "convolution"; here:
+//   bias_relu   : h = relu(z + b1) (fp32 z from the GEMM) -> fp32 h and fp16 h
+//   head_fwd    : out[b][o] = <h[b], W2[o]> + b2[o], one warp per (b, o), shuffle reduction
+//   head_bwd    : dW2, db2 (reduction over the batch), dz = (W2^T dout) * [h > 0] -> fp16, db1
+// ------------------------------------------------------------------------------------------------
+__global__ void bias_relu_kernel(const float* __restrict__ z, const float* __restrict__ bias, int B, int N, int relu,
+                                 float* __restrict__ h32, __half* __restrict__ h16) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(B) * N) return;
+  float v = z[i] + bias[i % N];
+  if (relu) v = fmaxf(v, 0.f);
+  if (h32) h32[i] = v;
+  if (h16) h16[i] = __float2half_rn(v);
+}
+__global__ void head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ bias,
+                                int B, int K, int O, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * O) return;
+  const int b = warp / O, o = warp % O;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(h[static_cast<int64_t>(b) * K + k], W[static_cast<int64_t>(o) * K + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[b * O + o] = acc + bias[o];
+}
+// one block per hidden unit k: dW2[o][k], db1[k]; dz[b][k]
+__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ h,
+                                                       const float* __restrict__ W, int B, int K, int O,
+                                                       float* __restrict__ dW, float* __restrict__ db2,
+                                                       __half* __restrict__ dz16, float* __restrict__ db1,
+                                                       int accumulate) {
+  const int k = blockIdx.x;
+  __shared__ float s_red[4][9];
+  float accW[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) accW[o] = 0.f;
+  float accb1 = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float hv = h[static_cast<int64_t>(b) * K + k];
+    float dh = 0.f;
+    for (int o = 0; o < O; ++o) {
+      const float d = dout[b * O + o];
+      accW[o] = fmaf(d, hv, accW[o]);
+      dh = fmaf(d, W[static_cast<int64_t>(o) * K + k], dh);
+    }
+    const float dzv = hv > 0.f ? dh : 0.f;
+    dz16[static_cast<int64_t>(b) * K + k] = __float2half_rn(dzv);
+    accb1 += dzv;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = 0; o < O; ++o) accW[o] = warp_sum(accW[o]);
+  accb1 = warp_sum(accb1);
+  if (lane == 0) {
+    for (int o = 0; o < O; ++o) s_red[warp][o] = accW[o];
+    s_red[warp][8] = accb1;
+  }
+  __syncthreads();
+  if (threadIdx.x <= O || threadIdx.x == 8) {
+    const int o = threadIdx.x;
+    if (o < O) {
+      const float v = s_red[0][o] + s_red[1][o] + s_red[2][o] + s_red[3][o];
+      float* dst = dW + static_cast<int64_t>(o) * K + k;
+      *dst = accumulate ? *dst + v : v;
+    } else if (o == 8) {
+      const float v = s_red[0][8] + s_red[1][8] + s_red[2][8] + s_red[3][8];
+      db1[k] = accumulate ? db1[k] + v : v;
+    }
+  }
+  if (k == 0 && threadIdx.x < O) {
+    float v = 0.f;
+    for (int b = 0; b < B; ++b) v += dout[b * O + threadIdx.x];
+    db2[threadIdx.x] = accumulate ? db2[threadIdx.x] + v : v;
+  }
+}
+int bias_relu_launch(const float* z, const float* bias, int B, int N, int relu, float* h32, __half* h16,
+                     cudaStream_t st) {
+  if (B * N <= 0) return 0;
+  bias_relu_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(z, bias, B, N, relu, h32, h16);
+  count_launch();
+  return check_launch("bias_relu");
+}
+int head_fwd_launch(const float* h, const float* W, const float* bias, int B, int K, int O, float* out,
+                    cudaStream_t st) {
+  if (B * O <= 0) return 0;
+  head_fwd_kernel<<<ceil_div(B * O * 32, 128), 128, 0, st>>>(h, W, bias, B, K, O, out);
+  count_launch();
+  return check_launch("head_fwd");
+}
+int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,
+                    __half* dz16, float* db1, int accumulate, cudaStream_t st) {
+  PNVO_REQUIRE(O <= 8, "head_bwd: output_dim %d > 8", O);
+  if (B <= 0) return 0;
+  head_bwd_kernel<<<K, 128, 0, st>>>(dout, h, W, B, K, O, dW, db2, dz16, db1, accumulate);
+  count_launch();
+  return check_launch("head_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam over a flat fp32 bucket (torch.optim.Adam semantics, weight_decay = 0, amsgrad = False)
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float grad_scale) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                int step, float grad_scale, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+  adam_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 148 * 8)), 256, 0, st>>>(
+      p, g, m, v, n, lr, b1, b2, eps, bc1, sqrtf(bc2), grad_scale);
+  count_launch();
+  return check_launch("adam");
+}
+
+}  // namespace pnvo

@@ -1,0 +1,40 @@
+// Internal argument structs + launchers shared by the op dispatcher (api.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace pnvo {
+
+struct ConvArgs {
+  const __half* x;    // input NHWC [B, IH, IW, Cin] fp16
+  const __half* w;    // packed weights [n_total][w_ld] fp16, K-major, zero padded
+  void* y;            // output [M][ldo] fp16 (or fp32 when out_fp32)
+  const __half* add;  // optional [M][ldo] fp16 added before the store (dgrad accumulation)
+  float* stats;       // optional GroupNorm partial sums [B][G][2] (sum, sum of squares), pre-zeroed
+  int B, IH, IW, Cin;
+  int OH, OW;
+  int R, S, mul, pad, pad_w, div;  // t = o*mul - pad + r; tap valid iff t >= 0, t % div == 0, t/div < I
+  int w_ld;
+  int n_total, n_store, ldo;
+  int cpg, G;
+  int out_fp32;
+  // derived by conv_plan
+  int cin_log2, cmask, M, K, nkb, N, tmem_cols, stages, smem_bytes, grid_x, grid_y;
+};
+int conv_plan(ConvArgs& a);
+int conv_launch(ConvArgs a, cudaStream_t st);
+
+struct WgradArgs {
+  const __half* x;   // conv input NHWC [B, IH, IW, Cin] fp16
+  const __half* dy;  // gradient of the conv output [M][ld_dy] fp16 (M = B*OH*OW)
+  float* dw;         // packed fp32 gradient [n_total][w_ld], accumulated with atomics (pre-zeroed)
+  int B, IH, IW, Cin;
+  int OH, OW;
+  int R, S, mul, pad, pad_w;
+  int w_ld, n_total, ld_dy;
+  // derived
+  int cin_log2, cmask, M, K, n_mtiles, mt, N, n_ntiles, tmem_cols, stages, smem_bytes, grid_x, grid_y, grid_z, chunks_per_split;
+};
+int wgrad_plan(WgradArgs& a);
+int wgrad_launch(WgradArgs a, cudaStream_t st);
+
+}  // namespace pnvo

@@ -1,0 +1,392 @@
+// HBM-bound preprocessing kernels of the PointNav-VO hot path (sm_100a):
+//   depth discretisation (a7), egocentric top-down projection (a8), GAE / return scan (a13),
+//   batched goal update (a10).  All arithmetic that feeds an index map uses explicit round-to-nearest
+//   intrinsics (no FMA contraction) so the maps are bit-identical to the reference's fp32 torch path.
+#include "common.cuh"
+
+namespace pnvo {
+
+// ------------------------------------------------------------------------------------------------
+// a7: depth discretisation (base_trainer_with_vo.py:135-167)
+//   bin i  <=>  d >= e_i && d < e_{i+1}; the last bin is closed at e_n = 1.0.  For d in [0,1] this is
+//   idx = #{ i in 1..n-1 : d >= e_i }.  One warp handles 32 consecutive pixels; the one-hot rows are
+//   written with lanes striding over the 32*n_ch contiguous floats (bin index fetched by shuffle).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) discretize_kernel(const float* __restrict__ depth, int64_t n_pix,
+                                                         const float* __restrict__ edges, int n_ch,
+                                                         float* __restrict__ onehot, int64_t stride,
+                                                         uint8_t* __restrict__ index, int32_t* err_count) {
+  __shared__ float s_edges[65];
+  for (int i = threadIdx.x; i <= n_ch; i += blockDim.x) s_edges[i] = edges[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float lo = s_edges[0], hi = s_edges[n_ch];
+  for (int64_t p0 = warp_global * 32; p0 < n_pix; p0 += n_warps * 32) {
+    const int64_t p = p0 + lane;
+    int idx = 255;
+    if (p < n_pix) {
+      const float d = __ldg(depth + p);
+      if (d >= lo && d <= hi) {
+        idx = 0;
+        for (int i = 1; i < n_ch; ++i) idx += (d >= s_edges[i]) ? 1 : 0;
+      } else if (err_count) {
+        atomicAdd(err_count, 1);
+      }
+      if (index) index[p] = static_cast<uint8_t>(idx);
+    }
+    if (onehot) {
+      const int n_valid = static_cast<int>(min(static_cast<int64_t>(32), n_pix - p0));
+      if (stride == n_ch) {
+        // fully contiguous rows: coalesced stores over the 32*n_ch floats of this warp
+        float* base = onehot + p0 * stride;
+        for (int f = lane; f < 32 * n_ch; f += 32) {
+          const int pp = f / n_ch;
+          const int c = f - pp * n_ch;
+          const int bin = __shfl_sync(0xffffffffu, idx, pp);
+          if (pp < n_valid) base[f] = (bin == c) ? 1.0f : 0.0f;
+        }
+      } else {
+        for (int f = lane; f < 32 * n_ch; f += 32) {
+          const int pp = f / n_ch;
+          const int c = f - pp * n_ch;
+          const int bin = __shfl_sync(0xffffffffu, idx, pp);
+          if (pp < n_valid) onehot[(p0 + pp) * stride + c] = (bin == c) ? 1.0f : 0.0f;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8: top-down projection (geometry_utils.py:516-721, Torch fp32 variant), one CTA per frame.
+//   phase 1: bounding box of non-zero depth (rows/cols with any element > 0), float4 loads + smem flags
+//   phase 2: 3x3 blur (cv2 GaussianBlur ksize 3, sigma 0, zero border: ((a+c)*.25 + b*.5), rows first),
+//            only for the <=100 centre rows of the crop; unproject; histogram in shared memory
+//            (uint16 pairs packed in uint32 words, 192*341*2 B = 131 KB)
+//   phase 3: block max, out = count / max (fp32 division), coalesced store
+//   Values outside the crop are zero by construction of the bbox, so zero padding at the crop edge ==
+//   reading the frame itself with zero padding at the frame edge.
+// ------------------------------------------------------------------------------------------------
+struct TopDownArgs {
+  const float* depth;
+  int64_t in_stride;
+  int H, W;
+  const float* ray;
+  pnvo_topdown_consts k;
+  float* out;
+  int64_t out_frame_stride, out_pix_stride;
+  int32_t* count;
+};
+
+__device__ __forceinline__ float blur_h(const float* row, int c, int W) {
+  const float a = (c > 0) ? row[c - 1] : 0.0f;
+  const float b = row[c];
+  const float d = (c + 1 < W) ? row[c + 1] : 0.0f;
+  return __fadd_rn(__fmul_rn(__fadd_rn(a, d), 0.25f), __fmul_rn(b, 0.5f));
+}
+
+__global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = a.H, W = a.W;
+  const int n_cells = H * W;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);       // (n_cells+1)/2 words
+  const int hist_words = (n_cells + 1) >> 1;
+  int* s_row_any = reinterpret_cast<int*>(hist + hist_words);   // H
+  int* s_col_any = s_row_any + H;                               // W
+  __shared__ int s_bbox[4];
+  __shared__ int s_max;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float* __restrict__ D = a.depth + static_cast<int64_t>(blockIdx.x) * a.in_stride;
+
+  for (int i = tid; i < hist_words; i += nt) hist[i] = 0u;
+  for (int i = tid; i < H + W; i += nt) s_row_any[i] = 0;
+  if (tid == 0) {
+    s_bbox[0] = H; s_bbox[1] = -1; s_bbox[2] = W; s_bbox[3] = -1;
+    s_max = 0;
+  }
+  __syncthreads();
+  // phase 1: any(depth > 0) per row / column (depth >= 0, so fp32 sum > 0 <=> any element > 0)
+  for (int i = tid; i < n_cells; i += nt) {
+    const float d = __ldg(D + i);
+    if (d > 0.0f) {
+      const int r = i / W;
+      const int c = i - r * W;
+      if (!s_row_any[r]) s_row_any[r] = 1;
+      if (!s_col_any[c]) s_col_any[c] = 1;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < H; i += nt)
+    if (s_row_any[i]) { atomicMin(&s_bbox[0], i); atomicMax(&s_bbox[1], i); }
+  for (int i = tid; i < W; i += nt)
+    if (s_col_any[i]) { atomicMin(&s_bbox[2], i); atomicMax(&s_bbox[3], i); }
+  __syncthreads();
+  const int r0 = s_bbox[0], r1 = s_bbox[1], c0 = s_bbox[2], c1 = s_bbox[3];
+  float* __restrict__ out = a.out + static_cast<int64_t>(blockIdx.x) * a.out_frame_stride;
+  int32_t* cnt_out = a.count ? a.count + static_cast<int64_t>(blockIdx.x) * n_cells : nullptr;
+  if (r1 < 0) {  // geometry_utils.py:519-525: empty frame -> all-zero map
+    for (int i = tid; i < n_cells; i += nt) {
+      out[static_cast<int64_t>(i) * a.out_pix_stride] = 0.0f;
+      if (cnt_out) cnt_out[i] = 0;
+    }
+    return;
+  }
+  // phase 2: rows of the crop that are projected (:608-620)
+  const int h = r1 - r0 + 1, w = c1 - c0 + 1;
+  int ra, rb;
+  if (a.k.center_crop) {
+    const int c = (h + 1) >> 1;  // ceil(h / 2)
+    ra = max(0, c - a.k.rows_around_center);
+    rb = min(h, c + a.k.rows_around_center);
+  } else {
+    ra = 0;
+    rb = min(a.k.rows_around_center * 2, h);
+  }
+  const int n_pts = (rb - ra) * w;
+  const float fH = static_cast<float>(H), fW = static_cast<float>(W);
+  for (int i = tid; i < n_pts; i += nt) {
+    const int rr = i / w;
+    const int cc = i - rr * w;
+    const int r = r0 + ra + rr;  // frame row
+    const int c = c0 + cc;       // frame column
+    // horizontal pass on rows r-1, r, r+1 (zero outside the crop == zero outside the frame / bbox)
+    const float hm = (r > r0) ? blur_h(D + static_cast<int64_t>(r - 1) * W, c, W) : 0.0f;
+    const float h0 = blur_h(D + static_cast<int64_t>(r) * W, c, W);
+    const float hp = (r < r1) ? blur_h(D + static_cast<int64_t>(r + 1) * W, c, W) : 0.0f;
+    const float v = __fadd_rn(__fmul_rn(__fadd_rn(hm, hp), 0.25f), __fmul_rn(h0, 0.5f));
+    const float z = __fadd_rn(__fmul_rn(v, a.k.depth_scale), a.k.depth_off);  // :558-560
+    const float x = __fmul_rn(__ldg(a.ray + c), z);                            // :656
+    const float nx = __fdiv_rn(__fsub_rn(x, a.k.min_x), a.k.x_den);            // :679
+    const float nz = __fdiv_rn(__fsub_rn(z, a.k.depth_off), a.k.z_den);        // :680
+    const float frow = __fsub_rn(fH, ceilf(__fmul_rn(fH, nz)));                // :689-691
+    const float fcol = floorf(__fmul_rn(fW, nx));                              // :692
+    if (frow >= 0.0f && frow < fH && fcol >= 0.0f && fcol < fW) {              // :706-711
+      const int cell = static_cast<int>(frow) * W + static_cast<int>(fcol);
+      atomicAdd(&hist[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+    }
+  }
+  __syncthreads();
+  // phase 3: max + normalise
+  int m = 0;
+  for (int i = tid; i < hist_words; i += nt) {
+    const uint32_t wv = hist[i];
+    m = max(m, static_cast<int>(max(wv & 0xFFFFu, wv >> 16)));
+  }
+  m = warp_max_i(m);
+  if ((tid & 31) == 0) atomicMax(&s_max, m);
+  __syncthreads();
+  const int mx = s_max;
+  const float fm = static_cast<float>(mx);
+  for (int i = tid; i < n_cells; i += nt) {
+    const uint32_t wv = hist[i >> 1];
+    const int c = (i & 1) ? static_cast<int>(wv >> 16) : static_cast<int>(wv & 0xFFFFu);
+    float o = 0.0f;
+    if (mx > 0) o = fminf(__fdiv_rn(static_cast<float>(c), fm), 1.0f);
+    out[static_cast<int64_t>(i) * a.out_pix_stride] = o;
+    if (cnt_out) cnt_out[i] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a13: GAE / discounted returns (rollout_storage.py:102-120)
+// mode 0: lanes = envs (coalesced along N), time loop sequential with the reference's rounding order:
+//   delta = (r + (g*V[t+1])*m[t+1]) - V[t];  gae = delta + ((g*tau)*m[t+1])*gae;  ret = gae + V[t]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gae_seq_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+                                                      const float* __restrict__ masks,
+                                                      const float* __restrict__ next_value,
+                                                      float* __restrict__ returns, int T, int N, int use_gae, float g,
+                                                      float gt) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float nv = next_value[n];
+  if (use_gae) {
+    values[static_cast<int64_t>(T) * N + n] = nv;
+    returns[static_cast<int64_t>(T) * N + n] = 0.0f;
+    float gae = 0.0f;
+    float v_next = nv;
+    // software-pipelined: loads of step t-1 are independent of the recurrence
+    float r = rewards[static_cast<int64_t>(T - 1) * N + n];
+    float m = masks[static_cast<int64_t>(T) * N + n];
+    float v = values[static_cast<int64_t>(T - 1) * N + n];
+    for (int t = T - 1; t >= 0; --t) {
+      float r_n = 0.f, m_n = 0.f, v_n = 0.f;
+      if (t > 0) {
+        r_n = rewards[static_cast<int64_t>(t - 1) * N + n];
+        m_n = masks[static_cast<int64_t>(t) * N + n];
+        v_n = values[static_cast<int64_t>(t - 1) * N + n];
+      }
+      float delta = __fadd_rn(r, __fmul_rn(__fmul_rn(g, v_next), m));
+      delta = __fsub_rn(delta, v);
+      gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gt, m), gae));
+      returns[static_cast<int64_t>(t) * N + n] = __fadd_rn(gae, v);
+      v_next = v;
+      r = r_n; m = m_n; v = v_n;
+    }
+  } else {
+    float ret = nv;
+    returns[static_cast<int64_t>(T) * N + n] = nv;
+    for (int t = T - 1; t >= 0; --t) {
+      const float m = masks[static_cast<int64_t>(t + 1) * N + n];
+      const float r = rewards[static_cast<int64_t>(t) * N + n];
+      ret = __fadd_rn(__fmul_rn(__fmul_rn(ret, g), m), r);
+      returns[static_cast<int64_t>(t) * N + n] = ret;
+    }
+  }
+}
+
+// mode 1: warp-scan over time.  The recurrence y_t = b_t + a_t * y_{t+1} is the composition of affine
+// maps f_t(y) = a_t*y + b_t; one warp owns one env, lane l owns the contiguous time chunk
+// [l*C, (l+1)*C), composes its chunk locally, then a reversed inclusive shuffle scan composes across
+// lanes.  Same result as mode 0 up to fp32 re-association.
+__global__ void __launch_bounds__(128) gae_scan_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+                                                       const float* __restrict__ masks,
+                                                       const float* __restrict__ next_value,
+                                                       float* __restrict__ returns, int T, int N, int use_gae,
+                                                       float g, float gt) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const float nv = next_value[n];
+  const int C = (T + 31) / 32;
+  const int t_lo = lane * C, t_hi = min(T, t_lo + C);
+  if (lane == 0) {
+    if (use_gae) {
+      values[static_cast<int64_t>(T) * N + n] = nv;
+      returns[static_cast<int64_t>(T) * N + n] = 0.0f;
+    } else {
+      returns[static_cast<int64_t>(T) * N + n] = nv;
+    }
+  }
+  // local composition over the chunk, from t_hi-1 down to t_lo: y_{t_lo} = A * y_{t_hi} + Bc
+  float A = 1.0f, Bc = 0.0f;
+  for (int t = t_hi - 1; t >= t_lo; --t) {
+    const float m = masks[static_cast<int64_t>(t + 1) * N + n];
+    float a_t, b_t;
+    if (use_gae) {
+      const float vn = (t + 1 == T) ? nv : values[static_cast<int64_t>(t + 1) * N + n];
+      a_t = gt * m;
+      b_t = rewards[static_cast<int64_t>(t) * N + n] + g * vn * m - values[static_cast<int64_t>(t) * N + n];
+    } else {
+      a_t = g * m;
+      b_t = rewards[static_cast<int64_t>(t) * N + n];
+    }
+    Bc = b_t + a_t * Bc;
+    A = a_t * A;
+  }
+  // suffix scan across lanes: after it, (A, Bc) of lane l maps y_T-side boundary of lane 31 to y_{t_lo(l)}
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float A2 = __shfl_down_sync(0xffffffffu, A, o);
+    const float B2 = __shfl_down_sync(0xffffffffu, Bc, o);
+    if (lane + o < 32) {
+      Bc = Bc + A * B2;
+      A = A * A2;
+    }
+  }
+  // boundary value entering this lane's chunk = y at t_hi = result of lane+1's suffix map applied to y_T
+  const float yT = use_gae ? 0.0f : nv;
+  float y_in = __shfl_down_sync(0xffffffffu, Bc + A * yT, 1);
+  if (lane == 31) y_in = yT;
+  float y = y_in;
+  for (int t = t_hi - 1; t >= t_lo; --t) {
+    const float m = masks[static_cast<int64_t>(t + 1) * N + n];
+    if (use_gae) {
+      const float vn = (t + 1 == T) ? nv : values[static_cast<int64_t>(t + 1) * N + n];
+      const float v = values[static_cast<int64_t>(t) * N + n];
+      const float delta = rewards[static_cast<int64_t>(t) * N + n] + g * vn * m - v;
+      y = delta + gt * m * y;
+      returns[static_cast<int64_t>(t) * N + n] = y + v;
+    } else {
+      y = y * g * m + rewards[static_cast<int64_t>(t) * N + n];
+      returns[static_cast<int64_t>(t) * N + n] = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10: goal update (geometry_utils.py:115-144), fp64 like the reference's numpy-quaternion path
+// ------------------------------------------------------------------------------------------------
+__global__ void goal_update_kernel(double* __restrict__ goal, const float* __restrict__ delta,
+                                   float* __restrict__ polar, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double dx = delta[3 * i + 0], dz = delta[3 * i + 1], dyaw = delta[3 * i + 2];
+  const double vx = goal[3 * i + 0] - dx, vy = goal[3 * i + 1], vz = goal[3 * i + 2] - dz;
+  const double c = cos(dyaw), s = sin(dyaw);
+  const double x = c * vx - s * vz, z = s * vx + c * vz;
+  goal[3 * i + 0] = x;
+  goal[3 * i + 1] = vy;
+  goal[3 * i + 2] = z;
+  polar[2 * i + 0] = static_cast<float>(hypot(-z, x));
+  polar[2 * i + 1] = static_cast<float>(-atan2(x, -z));
+}
+
+}  // namespace pnvo
+
+using namespace pnvo;
+
+extern "C" int pnvo_discretize_depth(const float* depth, int64_t n_pix, const float* edges, int n_channels,
+                                     float* onehot, int64_t onehot_stride, uint8_t* index, int32_t* err_count,
+                                     void* stream) {
+  PNVO_REQUIRE(depth && edges, "discretize_depth: null input");
+  PNVO_REQUIRE(n_channels >= 1 && n_channels <= 64, "discretize_depth: n_channels %d not in [1,64]", n_channels);
+  PNVO_REQUIRE(!onehot || onehot_stride >= n_channels, "discretize_depth: onehot_stride < n_channels");
+  if (n_pix <= 0) return 0;
+  const int threads = 256;
+  int64_t warps = ceil_div64(n_pix, 32);
+  int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(warps, threads / 32), 148 * 8));
+  discretize_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(depth, n_pix, edges, n_channels, onehot,
+                                                                               onehot_stride, index, err_count);
+  count_launch();
+  return check_launch("discretize_depth");
+}
+
+extern "C" int pnvo_topdown_project(const float* depth, int64_t in_stride, int n_frames, int H, int W,
+                                    const float* ray, const pnvo_topdown_consts* consts, float* out,
+                                    int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream) {
+  PNVO_REQUIRE(depth && ray && consts && out, "topdown_project: null argument");
+  PNVO_REQUIRE(H > 0 && W > 0 && static_cast<int64_t>(H) * W <= 110000, "topdown_project: frame %dx%d too large", H, W);
+  PNVO_REQUIRE(consts->rows_around_center * 2 * W < 65535, "topdown_project: too many points for uint16 counts");
+  if (n_frames <= 0) return 0;
+  TopDownArgs a;
+  a.depth = depth; a.in_stride = in_stride; a.H = H; a.W = W; a.ray = ray; a.k = *consts;
+  a.out = out; a.out_frame_stride = out_frame_stride; a.out_pix_stride = out_pix_stride; a.count = count;
+  const size_t smem = static_cast<size_t>((H * W + 1) / 2) * 4 + static_cast<size_t>(H + W) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(topdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  topdown_kernel<<<n_frames, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  return check_launch("topdown_project");
+}
+
+extern "C" int pnvo_gae_scan(const float* rewards, float* value_preds, const float* masks, const float* next_value,
+                             float* returns, int T, int N, int use_gae, float gamma, float gamma_tau, int mode,
+                             void* stream) {
+  PNVO_REQUIRE(rewards && value_preds && masks && next_value && returns, "gae_scan: null argument");
+  PNVO_REQUIRE(T >= 0 && N >= 0, "gae_scan: negative size");
+  if (N == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 0) {
+    gae_seq_kernel<<<ceil_div(N, 128), 128, 0, st>>>(rewards, value_preds, masks, next_value, returns, T, N, use_gae,
+                                                     gamma, gamma_tau);
+  } else {
+    gae_scan_kernel<<<ceil_div(N * 32, 128), 128, 0, st>>>(rewards, value_preds, masks, next_value, returns, T, N,
+                                                           use_gae, gamma, gamma_tau);
+  }
+  count_launch();
+  return check_launch("gae_scan");
+}
+
+extern "C" int pnvo_goal_update(double* goal_xyz, const float* delta, float* polar, int n, void* stream) {
+  PNVO_REQUIRE(goal_xyz && delta && polar, "goal_update: null argument");
+  if (n <= 0) return 0;
+  goal_update_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(goal_xyz, delta, polar, n);
+  count_launch();
+  return check_launch("goal_update");
+}

@@ -1,0 +1,416 @@
+"""Builds and replays the op programs (libpnvo `pnvo_op` lists) of the GroupNorm-ResNet encoders.
+
+One `EncoderPlan` per (architecture, batch size, device): it owns every activation / gradient /
+workspace buffer (torch tensors used purely as device memory), the packed fp16 weights, and three
+programs -- pack (weights -> kernel layouts), forward, backward -- that each run with a single C call.
+
+Reference semantics: vo/models/vo_cnn.py:110-233 (ResNetEncoder + VisualOdometryCNNBase),
+model_utils/visual_encoders/resnet.py:29-223 (BasicBlock / Bottleneck / ResNet),
+rl/policies/resnet_policy.py:61-174 (RL ResNetEncoder).
+Data layout: activations NHWC fp16 (channels padded to a multiple of 8, conv outputs to 32), raw conv
+outputs fp16 (fp32 accumulate / GroupNorm statistics), weights [Cout][R][S][Cin] fp16.
+"""
+import math
+
+import torch
+
+from . import lib as L
+
+RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet50": ("bottleneck", [3, 4, 6, 3]),
+                 "resnet101": ("bottleneck", [3, 4, 23, 3])}
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+def _pow2(x):
+    p = 8
+    while p < x:
+        p *= 2
+    return p
+
+
+class ConvLayer:
+    """Geometry + packed-weight buffers of one convolution (or Linear seen as a 1x1 convolution)."""
+
+    def __init__(self, key, Cin, Cout, R, S, stride, pad, IH, IW, need_dgrad=True, src_shape=None, cin_pad=None):
+        self.key, self.Cin, self.Cout, self.R, self.S, self.stride, self.pad = key, Cin, Cout, R, S, stride, pad
+        self.IH, self.IW = IH, IW
+        self.OH = (IH + 2 * pad - R) // stride + 1
+        self.OW = (IW + 2 * pad - S) // stride + 1
+        if cin_pad is None:
+            cin_pad = _ru(Cin, 8) if R * S == 1 else _pow2(Cin)
+        self.cin_pad = cin_pad
+        self.cout_pad = _ru(Cout, 32)
+        self.K = R * S * self.cin_pad
+        self.w_ld = _ru(self.K, 64)
+        self.need_dgrad = need_dgrad
+        # dgrad runs the same kernel with Cin' = cout_pad (must be a power of two unless 1x1)
+        self.Kt = R * S * self.cout_pad
+        self.wt_ld = _ru(self.Kt, 64)
+        self.nt_total = _ru(self.cin_pad, 16)
+        # how the OIHW source is viewed by the pack kernel (Linear layers: [Cout, C, H, W] of the flatten)
+        self.src_shape = src_shape or (Cout, Cin, R, S)
+        self.wp = self.wt = self.dwp = None
+
+    def alloc(self, dev, training):
+        self.wp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
+        if self.need_dgrad and training:
+            self.wt = torch.zeros(self.nt_total, self.wt_ld, dtype=torch.float16, device=dev)
+        if training:
+            self.dwp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float32, device=dev)
+
+    def flops(self, B):
+        return 2.0 * B * self.OH * self.OW * self.Cout * self.Cin * self.R * self.S
+
+    # ---- op builders ----
+    def op_pack(self, w):
+        return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld,
+                           self.cout_pad, self.wt_ld, 0)
+
+    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False):
+        return L.op_conv(x, self.wp, y, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
+                         self.stride, self.pad, 1, self.w_ld, self.cout_pad, self.cout_pad, self.cout_pad, None, stats,
+                         cpg, G, out_fp32)
+
+    def op_dgrad(self, dy, gx, B, add=None):
+        # gx[b, h, w, c] = sum_{r,s,n} dy[b, (h + pad - r)/stride, (w + pad - s)/stride, n] * W[n, c, r, s]
+        return L.op_conv(dy, self.wt, gx, B, self.OH, self.OW, self.cout_pad, self.IH, self.IW, self.R, self.S, 1,
+                         self.R - 1 - self.pad, self.stride, self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, add,
+                         None, 0, 0, False, pad_w=self.S - 1 - self.pad)
+
+    def op_wgrad(self, x, dy, B):
+        return L.op_wgrad(x, dy, self.dwp, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
+                          self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad)
+
+    def op_unpack(self, grad):
+        return L.op_unpack_dw(self.dwp, grad, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld)
+
+
+class LinearLayer(ConvLayer):
+    """nn.Linear over an NCHW-flattened [C, H, W] feature map == 1x1 conv over the NHWC-flattened map
+    (weight columns permuted by the pack kernel; vo_cnn.py:216-221, misc_utils.py:45-47)."""
+
+    def __init__(self, key, C, H, W, c_pad, Cout):
+        super().__init__(key, H * W * c_pad, Cout, 1, 1, 1, 0, 1, 1, True, cin_pad=H * W * c_pad)
+        self.fC, self.fH, self.fW, self.c_pad = C, H, W, c_pad
+
+    def op_pack(self, w):
+        # source viewed as OIHW [Cout, C, H, W]; packed column (h*W + w)*c_pad + c; wt = plain transpose
+        return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld,
+                           self.cout_pad, self.wt_ld, 1)
+
+    def op_unpack(self, grad):
+        return L.op_unpack_dw(self.dwp, grad, self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld)
+
+
+class GNLayer:
+    def __init__(self, key, C, G):
+        self.key, self.C_real, self.G = key, C, G
+        self.C = _ru(C, 32)
+        self.cpg_real = C // G
+        self.cpg = self.C // G
+
+
+class EncoderPlan:
+    """Programs for: input assembly -> ResNet(GroupNorm) -> compression -> [fc -> ReLU -> head]."""
+
+    def __init__(self, *, params, buffers, B, H, W, in_channels, sources, backbone, baseplanes, ngroups,
+                 compression_channels, prefix, head=None, training=True, avgpool_input=False, device="cuda",
+                 world_size=1, raw_fp32=False):
+        """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
+        sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
+        head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim)."""
+        self.P, self.Bf = params, buffers
+        self.B, self.H, self.W = B, H, W
+        self.dev = torch.device(device)
+        self.training = training
+        self.prefix = prefix
+        self.sources = sources
+        self.in_channels = in_channels
+        self.avgpool_input = avgpool_input
+        self.world_size = world_size
+        self.raw_fp32 = raw_fp32
+        self.head = head
+        self.grads = {}
+        self._build_layers(backbone, baseplanes, ngroups, compression_channels)
+        self._alloc()
+        self._build_programs()
+
+    # ------------------------------------------------------------------------------------------
+    def _build_layers(self, backbone, baseplanes, ngroups, comp_ch):
+        kind, nblocks = RESNET_LAYERS[backbone]
+        pfx = self.prefix + ".backbone"
+        H, W = (self.H // 2, self.W // 2) if self.avgpool_input else (self.H, self.W)
+        self.inH, self.inW = H, W
+        self.cin_pad = _pow2(self.in_channels)
+        self.convs, self.gns = {}, {}
+        c1 = ConvLayer(pfx + ".conv1.0.weight", self.in_channels, baseplanes, 7, 7, 2, 3, H, W, need_dgrad=False,
+                       cin_pad=self.cin_pad)
+        self.conv1, self.gn1 = c1, GNLayer(pfx + ".conv1.1", baseplanes, ngroups)
+        self.PH, self.PW = (c1.OH + 2 - 3) // 2 + 1, (c1.OW + 2 - 3) // 2 + 1
+        h, w, inpl = self.PH, self.PW, baseplanes
+        self.blocks = []
+        exp = 1 if kind == "basic" else 4
+        for li, nb in enumerate(nblocks, start=1):
+            planes = baseplanes * (2 ** (li - 1))
+            for b in range(nb):
+                stride = 2 if (b == 0 and li > 1) else 1
+                p = f"{pfx}.layer{li}.{b}"
+                blk = {"name": p, "convs": [], "gns": [], "down": None, "IH": h, "IW": w, "Cin": inpl}
+                if kind == "basic":
+                    ca = ConvLayer(p + ".convs.0.weight", inpl, planes, 3, 3, stride, 1, h, w)
+                    cb = ConvLayer(p + ".convs.3.weight", planes, planes, 3, 3, 1, 1, ca.OH, ca.OW)
+                    blk["convs"] = [ca, cb]
+                    blk["gns"] = [GNLayer(p + ".convs.1", planes, ngroups), GNLayer(p + ".convs.4", planes, ngroups)]
+                else:
+                    ca = ConvLayer(p + ".convs.0.weight", inpl, planes, 1, 1, 1, 0, h, w)
+                    cb = ConvLayer(p + ".convs.3.weight", planes, planes, 3, 3, stride, 1, h, w)
+                    cc = ConvLayer(p + ".convs.6.weight", planes, planes * exp, 1, 1, 1, 0, cb.OH, cb.OW)
+                    blk["convs"] = [ca, cb, cc]
+                    blk["gns"] = [GNLayer(p + ".convs.1", planes, ngroups), GNLayer(p + ".convs.4", planes, ngroups),
+                                  GNLayer(p + ".convs.7", planes * exp, ngroups)]
+                outc = planes * exp
+                last = blk["convs"][-1]
+                if b == 0 and (stride != 1 or inpl != outc):
+                    blk["down"] = (ConvLayer(p + ".downsample.0.weight", inpl, outc, 1, 1, stride, 0, h, w),
+                                   GNLayer(p + ".downsample.1", outc, ngroups))
+                blk["OH"], blk["OW"], blk["Cout"] = last.OH, last.OW, outc
+                self.blocks.append(blk)
+                h, w, inpl = last.OH, last.OW, outc
+        self.fH, self.fW, self.final_channels = h, w, inpl
+        self.comp = ConvLayer(self.prefix + ".compression.0.weight", inpl, comp_ch, 3, 3, 1, 1, h, w)
+        self.gnc = GNLayer(self.prefix + ".compression.1", comp_ch, 1)
+        self.comp_ch = comp_ch
+        if self.head is not None:
+            self.fc = LinearLayer(self.head["fc_w"], comp_ch, h, w, self.comp.cout_pad, self.head["hidden"])
+
+    def all_convs(self):
+        out = [self.conv1]
+        for blk in self.blocks:
+            out += blk["convs"]
+            if blk["down"]:
+                out.append(blk["down"][0])
+        out.append(self.comp)
+        if self.head is not None:
+            out.append(self.fc)
+        return out
+
+    def all_gns(self):
+        out = [self.gn1]
+        for blk in self.blocks:
+            out += blk["gns"]
+            if blk["down"]:
+                out.append(blk["down"][1])
+        out.append(self.gnc)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _act(self, B, H, W, C, dtype=torch.float16):
+        return torch.empty(B, H, W, C, dtype=dtype, device=self.dev)
+
+    def _alloc(self):
+        B, dev, tr = self.B, self.dev, self.training
+        for c in self.all_convs():
+            c.alloc(dev, tr)
+        gns = self.all_gns()
+        # one contiguous fp32 region for all GroupNorm partial sums -> a single ZERO op per forward
+        tot = sum(B * g.G * 2 for g in gns)
+        self.stats_all = torch.zeros(_ru(tot, 4), dtype=torch.float32, device=dev)
+        off = 0
+        for g in gns:
+            g.stats = self.stats_all[off:off + B * g.G * 2]
+            off += B * g.G * 2
+        if tr:
+            tot = sum(B * g.C * 2 for g in gns)
+            self.sums_all = torch.zeros(_ru(tot, 4), dtype=torch.float32, device=dev)
+            off = 0
+            for g in gns:
+                g.sums = self.sums_all[off:off + B * g.C * 2]
+                off += B * g.C * 2
+        raw_dt = torch.float32 if self.raw_fp32 else torch.float16
+        self.x0 = self._act(B, self.inH, self.inW, self.cin_pad)
+        if self.avgpool_input:
+            self.x0.zero_()  # pad channels stay zero (avgpool writes only the real ones)
+        self.in_stats = torch.zeros(2 * 32 + 2, dtype=torch.float64, device=dev)
+        self.in_scale = torch.ones(32, dtype=torch.float32, device=dev)
+        self.in_shift = torch.zeros(32, dtype=torch.float32, device=dev)
+        c1 = self.conv1
+        self.raw1 = self._act(B, c1.OH, c1.OW, c1.cout_pad, raw_dt)
+        self.pool = self._act(B, self.PH, self.PW, c1.cout_pad)
+        self.argmax = torch.empty(B, self.PH, self.PW, c1.cout_pad, dtype=torch.uint8, device=dev) if tr else None
+        for blk in self.blocks:
+            blk["raw"] = [self._act(B, c.OH, c.OW, c.cout_pad, raw_dt) for c in blk["convs"]]
+            blk["mid"] = [self._act(B, c.OH, c.OW, c.cout_pad) for c in blk["convs"][:-1]]
+            blk["y"] = self._act(B, blk["OH"], blk["OW"], blk["convs"][-1].cout_pad)
+            if blk["down"]:
+                d = blk["down"][0]
+                blk["raw_d"] = self._act(B, d.OH, d.OW, d.cout_pad, raw_dt)
+                blk["res_d"] = self._act(B, d.OH, d.OW, d.cout_pad)
+        self.raw_c = self._act(B, self.fH, self.fW, self.comp.cout_pad, raw_dt)
+        self.feat = self._act(B, self.fH, self.fW, self.comp.cout_pad)
+        if self.head is not None:
+            hid, od = self.head["hidden"], self.head["out_dim"]
+            self.z = torch.empty(B, self.fc.cout_pad, dtype=torch.float32, device=dev)
+            self.h32 = torch.empty(B, hid, dtype=torch.float32, device=dev)
+            self.h16 = torch.empty(B, hid, dtype=torch.float16, device=dev)
+            self.out = torch.empty(B, od, dtype=torch.float32, device=dev)
+        if tr:
+            # gradient buffers (w.r.t. post-activation tensors, fp16) and raw-gradient scratch
+            self.g_feat = torch.empty_like(self.feat)
+            self.dx_c = torch.empty_like(self.feat)
+            for blk in self.blocks:
+                blk["g_y"] = torch.empty_like(blk["y"])
+                blk["dy_last"] = torch.empty_like(blk["y"])
+                blk["dx"] = [torch.empty(r.shape, dtype=torch.float16, device=dev) for r in blk["raw"]]
+                blk["g_mid"] = [torch.empty_like(m) for m in blk["mid"]]
+                if blk["down"]:
+                    blk["dx_d"] = torch.empty(blk["raw_d"].shape, dtype=torch.float16, device=dev)
+            self.g_pool = torch.empty_like(self.pool)
+            self.dy1 = torch.empty(self.raw1.shape, dtype=torch.float16, device=dev)
+            self.dx1 = torch.empty(self.raw1.shape, dtype=torch.float16, device=dev)
+            if self.head is not None:
+                self.dout = torch.zeros(B, self.head["out_dim"], dtype=torch.float32, device=dev)
+                self.dz16 = torch.zeros(B, self.fc.cout_pad, dtype=torch.float16, device=dev)
+            else:
+                self.g_feat_in = self.g_feat
+            # flat gradient bucket: one fp32 buffer, per-parameter views (the DDP all-reduce payload)
+            names = self.param_names()
+            n = sum(self.P[k].numel() for k in names)
+            self.grad_flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            off = 0
+            for k in names:
+                m = self.P[k].numel()
+                self.grads[k] = self.grad_flat[off:off + m].view(self.P[k].shape)
+                off += m
+
+    def param_names(self):
+        names = []
+        for c in self.all_convs():
+            names.append(c.key)
+        for g in self.all_gns():
+            names += [g.key + ".weight", g.key + ".bias"]
+        if self.head is not None:
+            names += [self.head["fc_b"], self.head["out_w"], self.head["out_b"]]
+        return names
+
+    # ------------------------------------------------------------------------------------------
+    def _gn_apply(self, g, x, y, HW, relu=True, res=None):
+        B = self.B
+        return L.op_gn_apply(x, g.stats, self.P[g.key + ".weight"], self.P[g.key + ".bias"], y, B, g.C, g.G, g.cpg, HW,
+                             float(g.cpg_real * HW), relu, res, self.raw_fp32, 1e-5, g.C_real)
+
+    def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW):
+        return L.op_gn_bwd(reduce, gin, relu_ref, x, g.stats, self.P[g.key + ".weight"], g.sums, dx, dy_out, self.B,
+                           g.C, g.G, g.cpg, HW, float(g.cpg_real * HW), self.raw_fp32, 1e-5, g.C_real)
+
+    def _gn_bwd_all(self, ops, g, gin, relu_ref, x, dx, dy_out, HW):
+        ops.append(self._gn_bwd(True, g, gin, relu_ref, x, dx, dy_out, HW))
+        ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B, g.C,
+                                      g.C_real))
+        ops.append(self._gn_bwd(False, g, gin, relu_ref, x, dx, dy_out, HW))
+
+    def _build_programs(self):
+        B = self.B
+        # ---- pack ----
+        self.pack_prog = L.Program([c.op_pack(self.P[c.key]) for c in self.all_convs()])
+        # ---- forward (after the input tensor x0 has been produced) ----
+        ops = [L.op_zero(self.stats_all)]
+        c1, g1 = self.conv1, self.gn1
+        ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32))
+        ops.append(L.op_gn_pool(self.raw1, g1.stats, self.P[g1.key + ".weight"], self.P[g1.key + ".bias"], self.pool,
+                                self.argmax, B, g1.C, g1.G, g1.cpg, c1.OH, c1.OW, self.PH, self.PW,
+                                float(g1.cpg_real * c1.OH * c1.OW), self.raw_fp32, 1e-5, g1.C_real))
+        x = self.pool
+        for blk in self.blocks:
+            convs, gns = blk["convs"], blk["gns"]
+            res = x
+            if blk["down"]:
+                d, gd = blk["down"]
+                ops.append(d.op_fwd(x, blk["raw_d"], B, gd.stats, gd.cpg, gd.G, self.raw_fp32))
+                ops.append(self._gn_apply(gd, blk["raw_d"], blk["res_d"], d.OH * d.OW, relu=False))
+                res = blk["res_d"]
+            cur = x
+            for k, (c, g) in enumerate(zip(convs, gns)):
+                ops.append(c.op_fwd(cur, blk["raw"][k], B, g.stats, g.cpg, g.G, self.raw_fp32))
+                if k < len(convs) - 1:
+                    ops.append(self._gn_apply(g, blk["raw"][k], blk["mid"][k], c.OH * c.OW, relu=True))
+                    cur = blk["mid"][k]
+                else:
+                    ops.append(self._gn_apply(g, blk["raw"][k], blk["y"], c.OH * c.OW, relu=True, res=res))
+            blk["x_in"] = x
+            x = blk["y"]
+        cc, gc = self.comp, self.gnc
+        ops.append(cc.op_fwd(x, self.raw_c, B, gc.stats, gc.cpg, gc.G, self.raw_fp32))
+        ops.append(self._gn_apply(gc, self.raw_c, self.feat, self.fH * self.fW, relu=True))
+        if self.head is not None:
+            hd = self.head
+            feat_flat = self.feat  # [B, 1, 1, fH*fW*c_pad] as far as the 1x1 "conv" is concerned
+            ops.append(self.fc.op_fwd(feat_flat, self.z, B, None, 0, 0, True))
+            ops.append(L.op_bias_relu(self.z, self.P[hd["fc_b"]], self.h32, self.h16, B, hd["hidden"], True))
+            ops.append(L.op_head_fwd(self.h32, self.P[hd["out_w"]], self.P[hd["out_b"]], self.out, B, hd["hidden"],
+                                     hd["out_dim"]))
+        self.fwd_ops = ops
+        self.fwd_prog = L.Program(ops)
+        if not self.training:
+            return
+        # ---- backward ----
+        ops = [L.op_zero(self.sums_all)]
+        for c in self.all_convs():
+            ops.append(L.op_zero(c.dwp))
+        if self.head is not None:
+            hd = self.head
+            ops.append(L.op_head_bwd(self.dout, self.h32, self.P[hd["out_w"]], self.grads[hd["out_w"]],
+                                     self.grads[hd["out_b"]], self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"],
+                                     hd["out_dim"]))
+            ops.append(self.fc.op_wgrad(self.feat, self.dz16, B))
+            ops.append(self.fc.op_dgrad(self.dz16, self.g_feat, B))
+        HWf = self.fH * self.fW
+        self._gn_bwd_all(ops, gc, self.g_feat, self.feat, self.raw_c, self.dx_c, None, HWf)
+        ops.append(cc.op_wgrad(x, self.dx_c, B))
+        ops.append(cc.op_dgrad(self.dx_c, self.blocks[-1]["g_y"], B))
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[bi]
+            convs, gns = blk["convs"], blk["gns"]
+            g_in = blk["g_y"]                                  # gradient w.r.t. the block output
+            g_x = self.blocks[bi - 1]["g_y"] if bi > 0 else self.g_pool  # gradient w.r.t. the block input
+            n = len(convs)
+            # last GN (+ residual + ReLU): relu mask from the saved block output
+            c, g = convs[-1], gns[-1]
+            self._gn_bwd_all(ops, g, g_in, blk["y"], blk["raw"][-1], blk["dx"][-1], blk["dy_last"], c.OH * c.OW)
+            add = blk["dy_last"]  # identity-branch gradient
+            if blk["down"]:
+                d, gd = blk["down"]
+                self._gn_bwd_all(ops, gd, blk["dy_last"], None, blk["raw_d"], blk["dx_d"], None, d.OH * d.OW)
+                ops.append(d.op_wgrad(blk["x_in"], blk["dx_d"], B))
+                ops.append(d.op_dgrad(blk["dx_d"], g_x, B))
+                add = g_x
+            for k in range(n - 1, -1, -1):
+                c, g = convs[k], gns[k]
+                xin = blk["x_in"] if k == 0 else blk["mid"][k - 1]
+                ops.append(c.op_wgrad(xin, blk["dx"][k], B))
+                if k > 0:
+                    ops.append(c.op_dgrad(blk["dx"][k], blk["g_mid"][k - 1], B))
+                    cp, gp = convs[k - 1], gns[k - 1]
+                    self._gn_bwd_all(ops, gp, blk["g_mid"][k - 1], blk["mid"][k - 1], blk["raw"][k - 1],
+                                     blk["dx"][k - 1], None, cp.OH * cp.OW)
+                else:
+                    ops.append(c.op_dgrad(blk["dx"][0], g_x, B, add=add))
+        # stem: max-pool + ReLU routing, GN, conv1 weight gradient (no data gradient: the input is data)
+        ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
+        self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
+        ops.append(c1.op_wgrad(self.x0, self.dx1, B))
+        for c in self.all_convs():
+            ops.append(c.op_unpack(self.grads[c.key]))
+        self.bwd_ops = ops
+        self.bwd_prog = L.Program(ops)
+
+    # ------------------------------------------------------------------------------------------
+    def conv_flops(self, backward=False):
+        f = sum(c.flops(self.B) for c in self.all_convs())
+        if self.head is not None:
+            f += 2.0 * self.B * self.head["hidden"] * self.head["out_dim"]
+        if backward:
+            f = 3 * f - self.conv1.flops(self.B)
+        return f

@@ -1,0 +1,231 @@
+"""ctypes binding of libpnvo.so (include/pnvo.h) and builders for `pnvo_op` records.
+
+There is NO fallback: if the library is missing, or a CUDA tensor is handed to an op on a device
+that is not sm_100, the call raises.  PyTorch is used only to own device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
+
+# opcodes (include/pnvo.h: enum pnvo_opcode)
+OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
+OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST = range(16, 23)
+
+
+class PnvoOp(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int32), ("i", ctypes.c_int32 * 27), ("f", ctypes.c_float * 4),
+                ("p", ctypes.c_void_p * 10)]
+
+
+class TopdownConsts(ctypes.Structure):
+    _fields_ = [("min_x", ctypes.c_float), ("x_den", ctypes.c_float), ("z_den", ctypes.c_float),
+                ("depth_scale", ctypes.c_float), ("depth_off", ctypes.c_float),
+                ("rows_around_center", ctypes.c_int), ("center_crop", ctypes.c_int)]
+
+
+class PnvoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_discretize_depth",
+           "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
+           "pnvo_launch_count"]
+
+
+def load():
+    """Loads libpnvo.so (building is __graft_entry__.build()'s job); raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PnvoError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU / PyTorch fallback for the CUDA path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    lib.pnvo_last_error.restype = ctypes.c_char_p
+    lib.pnvo_abi_version.restype = i32
+    lib.pnvo_check_device.restype = i32
+    lib.pnvo_launch_count.restype = i64
+    lib.pnvo_discretize_depth.argtypes = [vp, i64, vp, i32, vp, i64, vp, vp, vp]
+    lib.pnvo_topdown_project.argtypes = [vp, i64, i32, i32, i32, vp, ctypes.POINTER(TopdownConsts), vp, i64, i64, vp, vp]
+    lib.pnvo_gae_scan.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
+    lib.pnvo_goal_update.argtypes = [vp, vp, vp, i32, vp]
+    lib.pnvo_run_ops.argtypes = [ctypes.POINTER(PnvoOp), i32, vp]
+    lib.pnvo_conv_launch_info.argtypes = [ctypes.POINTER(PnvoOp)] + [ctypes.POINTER(ctypes.c_int32)] * 5
+    for n in ("pnvo_discretize_depth", "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops",
+              "pnvo_conv_launch_info"):
+        getattr(lib, n).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PnvoError(load().pnvo_last_error().decode())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PnvoError("libpnvo ops need CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(load().pnvo_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# op record builders
+# ------------------------------------------------------------------------------------------------
+def _op(code, ints=(), floats=(), ptrs=()):
+    op = PnvoOp()
+    op.code = code
+    for k, v in enumerate(ints):
+        op.i[k] = int(v)
+    for k, v in enumerate(floats):
+        op.f[k] = float(v)
+    for k, v in enumerate(ptrs):
+        op.p[k] = (v.data_ptr() if isinstance(v, torch.Tensor) else (v or 0)) or None
+    return op
+
+
+def _lohi(n):
+    n = int(n)
+    lo, hi = n & 0xFFFFFFFF, (n >> 32) & 0xFFFFFFFF
+    return (lo - (1 << 32) if lo >= (1 << 31) else lo), (hi - (1 << 32) if hi >= (1 << 31) else hi)
+
+
+def op_zero(t):
+    lo, hi = _lohi(t.numel() * t.element_size())
+    return _op(OP_ZERO, [lo, hi], (), [t])
+
+
+def _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix):
+    ints = [len(srcs)] + list(nch) + [0] * (4 - len(nch)) + [C, Cpad, *_lohi(n_pix)]
+    words = []
+    for c in range(0, 32, 2):
+        h = []
+        for cc in (c, c + 1):
+            si, sc = lut[cc] if cc < len(lut) else (0, 0)
+            h.append(((si & 0xFF) << 8) | (sc & 0xFF))
+        w = h[0] | (h[1] << 16)
+        words.append(w - (1 << 32) if w >= (1 << 31) else w)
+    return ints + words, list(pre_scale) + [1.0] * (4 - len(pre_scale))
+
+
+def op_assemble(srcs, nch, pre_scale, lut, C, Cpad, n_pix, scale, shift, out):
+    ints, fl = _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix)
+    return _op(OP_ASSEMBLE, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [scale, shift, out])
+
+
+def op_input_stats(srcs, nch, pre_scale, lut, C, Cpad, n_pix, stats_f64):
+    ints, fl = _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix)
+    return _op(OP_INPUT_STATS, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [None, None, stats_f64])
+
+
+def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv, n_batch, pix_per_sample):
+    return _op(OP_RMV_UPDATE, [C, int(update), int(have_rmv)], [n_batch, pix_per_sample],
+               [stats_f64, mean, var, count, scale, shift])
+
+
+def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, add=None, stats=None,
+            cpg=0, G=0, out_fp32=False, pad_w=None):
+    return _op(OP_CONV, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, cpg, G,
+                         int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats])
+
+
+def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None):
+    return _op(OP_WGRAD, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, 1, w_ld, n_total, 0, ld_dy, 0, 0, 0,
+                          pad if pad_w is None else pad_w], (), [x, dy, dw])
+
+
+def op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, cnt, relu=True, res=None, x_fp32=False, eps=1e-5,
+                C_real=None):
+    return _op(OP_GN_APPLY, [B, C, G, cpg, HW, int(relu), int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real],
+               [cnt, eps], [x, stats, gamma, beta, res, y])
+
+
+def op_gn_pool(x, stats, gamma, beta, y, argmax, B, C, G, cpg, H, W, PH, PW, cnt, x_fp32=False, eps=1e-5,
+               C_real=None):
+    return _op(OP_GN_POOL, [B, C, G, cpg, H * W, 1, int(x_fp32), H, W, PH, PW, C if C_real is None else C_real],
+               [cnt, eps],
+               [x, stats, gamma, beta, None, y, argmax])
+
+
+def op_pool_bwd(g, pooled, argmax, dy, B, C, H, W, PH, PW):
+    return _op(OP_GN_POOL_BWD, [B, C, 0, 0, 0, 0, 0, H, W, PH, PW], (), [g, pooled, argmax, dy])
+
+
+def op_gn_bwd(reduce, g, relu_ref, x, stats, gamma, sums, dx, dy_out, B, C, G, cpg, HW, cnt, x_fp32=False, eps=1e-5,
+              C_real=None):
+    return _op(OP_GN_BWD_REDUCE if reduce else OP_GN_BWD_APPLY,
+               [B, C, G, cpg, HW, 0, int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real], [cnt, eps],
+               [g, relu_ref, x, stats, gamma, sums, dx, dy_out])
+
+
+def op_gn_param_grad(sums, dgamma, dbeta, B, C, C_real, accumulate=False):
+    return _op(OP_GN_PARAM_GRAD, [B, C, C_real, int(accumulate)], (), [sums, dgamma, dbeta])
+
+
+def op_pack_w(w, wp, wt, Cout, Cin, R, S, cin_pad, ld_p, cout_pad=0, ld_t=0, t_mode=0):
+    return _op(OP_PACK_W, [Cout, Cin, R, S, cin_pad, ld_p, cout_pad, ld_t, t_mode], (), [w, wp, wt])
+
+
+def op_unpack_dw(dwp, grad, Cout, Cin, R, S, cin_pad, ld_p, accumulate=False):
+    return _op(OP_UNPACK_DW, [Cout, Cin, R, S, cin_pad, ld_p, int(accumulate)], (), [dwp, grad])
+
+
+def op_bias_relu(z, bias, h32, h16, B, N, relu=True):
+    return _op(OP_BIAS_RELU, [B, N, int(relu)], (), [z, bias, h32, h16])
+
+
+def op_head_fwd(h, W, bias, out, B, K, O):
+    return _op(OP_HEAD_FWD, [B, K, O], (), [h, W, bias, out])
+
+
+def op_head_bwd(dout, h, W, dW, db2, dz16, db1, B, K, O, accumulate=False):
+    return _op(OP_HEAD_BWD, [B, K, O, int(accumulate)], (), [dout, h, W, dW, db2, dz16, db1])
+
+
+def op_adam(p, g, m, v, n, step, lr, beta1, beta2, eps):
+    lo, hi = _lohi(n)
+    return _op(OP_ADAM, [lo, hi, step], [lr, beta1, beta2, eps], [p, g, m, v])
+
+
+def op_avgpool2(src, out, B, H, W, C, Cpad, coff, pre_scale=1.0):
+    return _op(OP_AVGPOOL2, [B, H, W, C, Cpad, coff], [pre_scale], [src, out])
+
+
+class Program:
+    """A list of pnvo_op records packed into one ctypes array, replayed with a single C call."""
+
+    def __init__(self, ops):
+        self.n = len(ops)
+        self.arr = (PnvoOp * max(1, self.n))(*ops)
+
+    def run(self, device=None):
+        if self.n:
+            check(load().pnvo_run_ops(self.arr, self.n, stream_ptr(device)))
+
+
+def run_ops(ops, device=None):
+    Program(list(ops)).run(device)
+
+
+def conv_launch_info(op):
+    vals = [ctypes.c_int32() for _ in range(5)]
+    check(load().pnvo_conv_launch_info(ctypes.byref(op), *[ctypes.byref(v) for v in vals]))
+    return dict(zip(("grid_x", "grid_y", "smem_bytes", "tmem_cols", "stages"), (v.value for v in vals)))

@@ -1,0 +1,281 @@
+"""Visual-odometry regression networks with the reference's nn.Module surface
+(pointnav_vo/vo/models/vo_cnn.py:16-561): same constructor keywords, registry names, state_dict keys
+and forward signature -- `model(observation_pairs: dict[str, NHWC fp32 tensor]) -> [B, output_dim]`.
+
+The arithmetic runs in libpnvo (hand-written sm_100a kernels) through an `EncoderPlan` op program;
+this file only owns parameters, the autograd boundary and the plan cache.  CUDA only: a CPU tensor or
+a missing library raises (no fallback).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import lib as L
+from ...engine import EncoderPlan
+from ...model_utils import resnet
+from ...model_utils.running_mean_and_var import RunningMeanAndVar
+from ...utils.baseline_registry import baseline_registry
+from ..common.common_vars import (DEFAULT_DELTA_STATE_SIZE, DEPTH_PAIR_CHANNEL, RGB_PAIR_CHANNEL,
+                                  TOP_DOWN_VIEW_PAIR_CHANNEL)
+
+OBS_ORDER = ("rgb", "depth", "discretized_depth", "top_down_view")  # vo_cnn.py:114-166 append order
+
+
+class Flatten(nn.Module):
+    def forward(self, x):
+        return x.contiguous().view(x.size(0), -1)
+
+
+class ResNetEncoder(nn.Module):
+    """vo_cnn.py:16-179.  Holds the backbone / compression parameters and the input bookkeeping."""
+
+    def __init__(self, *, observation_space, observation_size, baseplanes=32, ngroups=32, spatial_size_w=128,
+                 spatial_size_h=128, make_backbone=None, normalize_visual_inputs=False,
+                 after_compression_flat_size=2048, rgb_pair_channel=RGB_PAIR_CHANNEL,
+                 depth_pair_channel=DEPTH_PAIR_CHANNEL, discretized_depth_channels=0,
+                 top_down_view_pair_channel=TOP_DOWN_VIEW_PAIR_CHANNEL):
+        super().__init__()
+        n = {"rgb": rgb_pair_channel, "depth": depth_pair_channel,
+             "discretized_depth": discretized_depth_channels * 2, "top_down_view": top_down_view_pair_channel}
+        self._sources = []
+        for k in OBS_ORDER:
+            if k in observation_space:
+                spatial_size_w, spatial_size_h = observation_size
+                self._sources.append((k, n[k], 1.0 / 255.0 if k == "rgb" else 1.0))
+        self._n_input_rgb = n["rgb"] if "rgb" in observation_space else 0
+        self._n_input_depth = n["depth"] if "depth" in observation_space else 0
+        self._n_input_discretized_depth = n["discretized_depth"] if "discretized_depth" in observation_space else 0
+        self._n_input_top_down_view = n["top_down_view"] if "top_down_view" in observation_space else 0
+        input_channels = sum(s[1] for s in self._sources)
+        assert input_channels > 0  # visual odometry must not be blind (vo_cnn.py:67-68)
+        self.input_channels = input_channels
+        self.spatial_size = (spatial_size_h, spatial_size_w)
+        self.baseplanes, self.ngroups = baseplanes, ngroups
+        if normalize_visual_inputs:
+            self.running_mean_and_var = RunningMeanAndVar(input_channels)
+        else:
+            self.running_mean_and_var = nn.Sequential()
+        self.backbone = make_backbone(input_channels, baseplanes, ngroups)
+        final_w = int(np.ceil(spatial_size_w * self.backbone.final_spatial_compress))
+        final_h = int(np.ceil(spatial_size_h * self.backbone.final_spatial_compress))
+        num_compression_channels = int(round(after_compression_flat_size / (final_w * final_h)))
+        self.compression = nn.Sequential(
+            nn.Conv2d(self.backbone.final_channels, num_compression_channels, kernel_size=3, padding=1, bias=False),
+            nn.GroupNorm(1, num_compression_channels), nn.ReLU(True))
+        self.output_shape = (num_compression_channels, final_h, final_w)
+
+    def layer_init(self):
+        for layer in self.modules():
+            if isinstance(layer, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(layer.weight, nn.init.calculate_gain("relu"))
+                if layer.bias is not None:
+                    nn.init.constant_(layer.bias, val=0)
+
+    def forward(self, observation_pairs):
+        raise RuntimeError("ResNetEncoder is executed as part of its owner's op program (libpnvo)")
+
+
+class _VOFunction(torch.autograd.Function):
+    """Autograd boundary: forward/backward are libpnvo op programs; parameters enter as inputs so that
+    torch optimisers, .grad accumulation and DDP-style hooks see ordinary leaf gradients."""
+
+    @staticmethod
+    def forward(ctx, model, obs, training, need_grad, *params):
+        plan = model._plan_for(obs, need_grad)
+        model._run_forward(plan, obs, training)
+        ctx.model, ctx.plan = model, plan
+        return plan.out.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, plan = ctx.model, ctx.plan
+        if not plan.training:
+            raise RuntimeError("backward through a plan built without gradient buffers")
+        plan.dout.copy_(grad_out)
+        plan.bwd_prog.run(plan.dev)
+        flat = plan.grad_flat.clone()  # detach from the plan's reusable bucket
+        grads, off = [], 0
+        by_name = {}
+        for k in plan.param_names():
+            m = plan.P[k].numel()
+            by_name[k] = flat[off:off + m].view(plan.P[k].shape)
+            off += m
+        for k in model._param_order:
+            grads.append(by_name.get(k))
+        return (None, None, None, None, *grads)
+
+
+class VisualOdometryCNNBase(nn.Module):
+    """vo_cnn.py:182-233."""
+
+    def __init__(self, *, observation_space, observation_size, hidden_size=512, resnet_baseplanes=32,
+                 backbone="resnet18", normalize_visual_inputs=False, output_dim=DEFAULT_DELTA_STATE_SIZE,
+                 dropout_p=0.2, after_compression_flat_size=2048, rgb_pair_channel=RGB_PAIR_CHANNEL,
+                 depth_pair_channel=DEPTH_PAIR_CHANNEL, discretized_depth_channels=0,
+                 top_down_view_pair_channel=TOP_DOWN_VIEW_PAIR_CHANNEL):
+        super().__init__()
+        self.visual_encoder = ResNetEncoder(
+            observation_space=observation_space, observation_size=observation_size, baseplanes=resnet_baseplanes,
+            ngroups=resnet_baseplanes // 2, make_backbone=resnet.make_backbone(backbone),
+            normalize_visual_inputs=normalize_visual_inputs, after_compression_flat_size=after_compression_flat_size,
+            rgb_pair_channel=rgb_pair_channel, depth_pair_channel=depth_pair_channel,
+            discretized_depth_channels=discretized_depth_channels,
+            top_down_view_pair_channel=top_down_view_pair_channel)
+        self.visual_fc = nn.Sequential(Flatten(), nn.Dropout(dropout_p),
+                                       nn.Linear(int(np.prod(self.visual_encoder.output_shape)), hidden_size),
+                                       nn.ReLU(True))
+        self.output_head = nn.Sequential(nn.Dropout(dropout_p), nn.Linear(hidden_size, output_dim))
+        nn.init.orthogonal_(self.output_head[1].weight)
+        nn.init.constant_(self.output_head[1].bias, 0)
+        self._backbone_name = backbone
+        self._hidden_size, self._output_dim, self._dropout_p = hidden_size, output_dim, dropout_p
+        self._plans = {}
+        self._packed_version = None
+        self._ptr_sig = None
+        self._param_order = [k for k, _ in self.named_parameters()]
+        self._fc_keys = dict(fc_w="visual_fc.2.weight", fc_b="visual_fc.2.bias", out_w="output_head.1.weight",
+                             out_b="output_head.1.bias")
+        self.raw_fp32 = False  # store pre-GroupNorm conv outputs in fp32 instead of fp16
+
+    # ---------------------------------------------------------------- runtime
+    def _tensors(self):
+        P = {k: p.data for k, p in self.named_parameters()}
+        Bf = {k: b for k, b in self.named_buffers()}
+        return P, Bf
+
+    def _signature(self):
+        return tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers())
+
+    def _plan_for(self, obs, need_grad):
+        enc = self.visual_encoder
+        first = obs[enc._sources[0][0]]
+        if not first.is_cuda:
+            raise L.PnvoError("VO model inputs must be CUDA tensors: the B200 path has no CPU fallback")
+        L.load()
+        sig = self._signature()
+        if sig != self._ptr_sig:  # parameters moved (.to(), load with assign, ...): plans hold raw pointers
+            self._plans.clear()
+            self._ptr_sig = sig
+            self._packed_version = None
+        B, H, W = first.shape[0], first.shape[1], first.shape[2]
+        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32)
+        plan = self._plans.get(key)
+        if plan is None:
+            P, Bf = self._tensors()
+            for p in P.values():
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise L.PnvoError("parameters must be contiguous fp32 CUDA tensors")
+            world = 1
+            rmv = enc.running_mean_and_var
+            if isinstance(rmv, RunningMeanAndVar) and rmv._distributed:
+                world = torch.distributed.get_world_size()
+            head = dict(self._fc_keys, hidden=self._hidden_size, out_dim=self._output_dim)
+            plan = EncoderPlan(params=P, buffers=Bf, B=B, H=H, W=W, in_channels=enc.input_channels,
+                               sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
+                               ngroups=enc.ngroups, compression_channels=enc.output_shape[0],
+                               prefix="visual_encoder", head=head, training=bool(need_grad), device=first.device,
+                               world_size=world, raw_fp32=self.raw_fp32)
+            self._plans[key] = plan
+        return plan
+
+    def _weights_version(self):
+        return sum(p._version for p in self.parameters())
+
+    def _run_forward(self, plan, obs, training):
+        enc = self.visual_encoder
+        dev = plan.dev
+        srcs, nch, pre, lut_prev, lut_cur = [], [], [], [], []
+        for si, (k, n, scale) in enumerate(enc._sources):
+            t = obs[k]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            assert t.shape[-1] == n, f"{k}: expected {n} channels, got {t.shape[-1]}"
+            srcs.append(t)
+            nch.append(n)
+            pre.append(scale)
+            lut_prev += [(si, c) for c in range(n // 2)]
+            lut_cur += [(si, c) for c in range(n // 2, n)]
+        lut = lut_prev + lut_cur  # [prev of every source..., cur of every source...] (vo_cnn.py:169-174)
+        C = enc.input_channels
+        n_pix = plan.B * plan.H * plan.W
+        rmv = enc.running_mean_and_var
+        have_rmv = isinstance(rmv, RunningMeanAndVar)
+        ops = []
+        if have_rmv:
+            if training:
+                ops.append(L.op_zero(plan.in_stats))
+                ops.append(L.op_input_stats(srcs, nch, pre, lut, C, plan.cin_pad, n_pix, plan.in_stats))
+                L.run_ops(ops, dev)
+                ops = []
+                if plan.world_size > 1:
+                    torch.distributed.all_reduce(plan.in_stats)
+            ops.append(L.op_rmv_update(plan.in_stats, rmv._mean, rmv._var, rmv._count, plan.in_scale, plan.in_shift, C,
+                                       training, True, plan.B * plan.world_size, plan.H * plan.W))
+            scale, shift = plan.in_scale, plan.in_shift
+        else:
+            scale = shift = None
+        ops.append(L.op_assemble(srcs, nch, pre, lut, C, plan.cin_pad, n_pix, scale, shift, plan.x0))
+        L.run_ops(ops, dev)
+        ver = self._weights_version()
+        if ver != self._packed_version or plan is not getattr(self, "_packed_plan", None):
+            plan.pack_prog.run(dev)
+            self._packed_version, self._packed_plan = ver, plan
+        plan.fwd_prog.run(dev)
+
+    def forward(self, observation_pairs):
+        if self.training and self._dropout_p > 0:
+            raise NotImplementedError("training-mode dropout is not implemented on the B200 path yet; "
+                                      "construct the model with dropout_p=0.0")
+        params = [p for _, p in self.named_parameters()]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _VOFunction.apply(self, observation_pairs, self.training, need_grad, *params)
+
+
+def _variant(name, required=(), forbidden=(), backbone="resnet18", widen=1, no_dd=False):
+    """Builds one of the registered subclasses (vo_cnn.py:236-561); they differ only in their asserts
+    and in the encoder width."""
+
+    def __init__(self, *, observation_space, observation_size, hidden_size=512, resnet_baseplanes=32,
+                 backbone="resnet18", normalize_visual_inputs=False, output_dim=DEFAULT_DELTA_STATE_SIZE,
+                 dropout_p=0.2, discretized_depth_channels=0, top_down_view_pair_channel=TOP_DOWN_VIEW_PAIR_CHANNEL):
+        assert backbone == self._required_backbone
+        if self._no_dd:
+            assert discretized_depth_channels == 0
+        for k in self._required:
+            assert k in observation_space
+        for k in self._forbidden:
+            assert k not in observation_space
+        VisualOdometryCNNBase.__init__(
+            self, observation_space=observation_space, observation_size=observation_size, hidden_size=hidden_size,
+            resnet_baseplanes=resnet_baseplanes * self._widen, backbone=backbone,
+            normalize_visual_inputs=normalize_visual_inputs, output_dim=output_dim, dropout_p=dropout_p,
+            discretized_depth_channels=discretized_depth_channels,
+            top_down_view_pair_channel=top_down_view_pair_channel)
+
+    return type(name, (VisualOdometryCNNBase,), dict(
+        __init__=__init__, _required=tuple(required), _forbidden=tuple(forbidden), _required_backbone=backbone,
+        _widen=widen, _no_dd=no_dd, __doc__=f"registered VO variant {name} (vo_cnn.py:236-561)"))
+
+
+DD, TD = "discretized_depth", "top_down_view"
+VisualOdometryCNN = baseline_registry.register_vo_model(name="vo_cnn")(
+    _variant("VisualOdometryCNN", forbidden=(DD, TD), no_dd=True))
+VisualOdometryCNNRGB = baseline_registry.register_vo_model(name="vo_cnn_rgb")(
+    _variant("VisualOdometryCNNRGB", forbidden=("depth", DD, TD), no_dd=True))
+VisualOdometryCNNWider = baseline_registry.register_vo_model(name="vo_cnn_wider")(
+    _variant("VisualOdometryCNNWider", forbidden=(DD, TD), widen=2, no_dd=True))
+VisualOdometryCNNDeeper = baseline_registry.register_vo_model(name="vo_cnn_deeper")(
+    _variant("VisualOdometryCNNDeeper", forbidden=(DD, TD), backbone="resnet101", no_dd=True))
+VisualOdometryCNNDiscretizedDepth = baseline_registry.register_vo_model(name="vo_cnn_rgb_d_dd")(
+    _variant("VisualOdometryCNNDiscretizedDepth", required=(DD,), forbidden=(TD,)))
+VisualOdometryCNN_RGB_D_TopDownView = baseline_registry.register_vo_model(name="vo_cnn_rgb_d_top_down")(
+    _variant("VisualOdometryCNN_RGB_D_TopDownView", required=("rgb", "depth", TD), forbidden=(DD,)))
+VisualOdometryCNN_RGB_DD_TopDownView = baseline_registry.register_vo_model(name="vo_cnn_rgb_dd_top_down")(
+    _variant("VisualOdometryCNN_RGB_DD_TopDownView", required=("rgb", DD, TD), forbidden=("depth",)))
+VisualOdometryCNN_D_DD_TopDownView = baseline_registry.register_vo_model(name="vo_cnn_d_dd_top_down")(
+    _variant("VisualOdometryCNN_D_DD_TopDownView", required=("depth", DD, TD), forbidden=("rgb",)))
+VisualOdometryCNNDiscretizedDepthTopDownView = baseline_registry.register_vo_model(name="vo_cnn_rgb_d_dd_top_down")(
+    _variant("VisualOdometryCNNDiscretizedDepthTopDownView", required=(DD, TD)))
+LegacyVisualOdometryCNNDiscretizedDepthTopDownView = baseline_registry.register_vo_model(
+    name="vo_cnn_discretize_depth_top_down")(
+    type("LegacyVisualOdometryCNNDiscretizedDepthTopDownView", (VisualOdometryCNNDiscretizedDepthTopDownView,), {}))
