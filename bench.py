@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the VO hot path (BASELINE.json metric: VO frame-pairs/s, 341x192 RGB-D, batch 256 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one training step (forward + backward + Adam) of the shipped default VO model
+(vo_cnn_rgb_d_dd_top_down, GroupNorm-ResNet-18, 30 input channels) on a batch of 256 synthetic frame
+pairs per GPU (BASELINE configs[1]).  `value` times the step with the model inputs already resident in
+HBM; `e2e` times the same step from pinned HOST buffers (uint8 rgb + fp32 depth), including the H2D
+copies, the on-device derivation of the discretised-depth / top-down channels, and a D2H read of the loss.
+`--impl reference` times the reference algorithm's CPU path (oracle/vo_oracle.py: the plain-PyTorch fp32
+restatement pinned against the unmodified reference) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W = 192, 341
+GFLOP_FWD, GFLOP_FWDBWD = 2.6845, 6.509  # per pair, BASELINE.md section 2
+METRIC = "VO frame-pairs/sec (341x192 RGB-D, bs256 per GPU, ResNet-18 fwd+bwd+Adam)"
+SPACE = ["rgb", "depth", "discretized_depth", "top_down_view"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for n, v in zip(names, r[5:9]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(n)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def synth_batch(B, seed):
+    from pointnav_vo_b200.utils import synth
+
+    rgb = synth.rgb_frames(2 * B, seed=seed).reshape(B, 2, H, W, 3)
+    rgb = np.ascontiguousarray(np.concatenate([rgb[:, 0], rgb[:, 1]], axis=-1))  # [B,H,W,6] uint8
+    base = synth.depth_frames(32, seed=seed + 100)  # 32 distinct frames, tiled (generation is host-bound)
+    idx = np.arange(2 * B) % 32
+    dep = base[idx].reshape(B, 2, H, W)
+    dep = np.ascontiguousarray(np.stack([dep[:, 0], dep[:, 1]], axis=-1))  # [B,H,W,2] fp32
+    tgt = np.random.default_rng(seed).normal(0, 0.1, size=(B, 3)).astype(np.float32)
+    return rgb, dep, tgt
+
+
+def build_model(device, dropout_p=0.0):
+    from pointnav_vo_b200.vo.models import vo_cnn
+
+    torch.manual_seed(0)
+    m = vo_cnn.baseline_registry.get_vo_model("vo_cnn_rgb_d_dd_top_down")(
+        observation_space=SPACE, observation_size=(W, H), hidden_size=512, backbone="resnet18",
+        normalize_visual_inputs=True, output_dim=3, dropout_p=dropout_p, discretized_depth_channels=10)
+    return m.to(device).train()
+
+
+class DevicePreproc:
+    """uint8 rgb + fp32 depth (as shipped from the host) -> the model's four NHWC fp32 inputs, on device."""
+
+    def __init__(self, B, device):
+        from pointnav_vo_b200.utils import geometry_utils as gu
+
+        self.gu = gu
+        self.td = gu.NormalizedDepth2TopDownViewHabitatTorch(0.1, 10.0, H, W, 70)
+        self.dd = torch.empty(B, H, W, 20, dtype=torch.float32, device=device)
+        self.tdv = torch.empty(B, H, W, 2, dtype=torch.float32, device=device)
+        self.rgbf = torch.empty(B, H, W, 6, dtype=torch.float32, device=device)
+        self.B = B
+
+    def __call__(self, rgb_u8, depth):
+        self.rgbf.copy_(rgb_u8)  # dtype cast on device
+        dprev = depth[..., 0].contiguous()
+        dcur = depth[..., 1].contiguous()
+        self.gu.discretize_depth(dprev, 10, check=False, out=self.dd[..., :10])
+        self.gu.discretize_depth(dcur, 10, check=False, out=self.dd[..., 10:])
+        self.td.gen_top_down_view(dprev, out=self.tdv[..., 0:1])
+        self.td.gen_top_down_view(dcur, out=self.tdv[..., 1:2])
+        return {"rgb": self.rgbf, "depth": depth, "discretized_depth": self.dd, "top_down_view": self.tdv}
+
+
+def run_b200(args):
+    from pointnav_vo_b200 import lib as L
+    from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    L.check(L.load().pnvo_check_device())
+    B = args.batch
+    model = build_model(dev)
+    trainer = FusedVOTrainStep(model)
+    rgb, dep, tgt = synth_batch(B, seed=1 + rank)
+    h_rgb = torch.from_numpy(rgb).pin_memory()
+    h_dep = torch.from_numpy(dep).pin_memory()
+    h_tgt = torch.from_numpy(tgt).pin_memory()
+    d_rgb = torch.empty_like(h_rgb, device=dev)
+    d_dep = torch.empty_like(h_dep, device=dev)
+    d_tgt = torch.empty_like(h_tgt, device=dev)
+    pre = DevicePreproc(B, dev)
+
+    def e2e_step():
+        d_rgb.copy_(h_rgb, non_blocking=True)
+        d_dep.copy_(h_dep, non_blocking=True)
+        d_tgt.copy_(h_tgt, non_blocking=True)
+        obs = pre(d_rgb, d_dep)
+        loss = trainer.step(obs, d_tgt)
+        return float(loss.item())  # D2H read of the step's result
+
+    # resident inputs for the device-only measurement
+    d_rgb.copy_(h_rgb)
+    d_dep.copy_(h_dep)
+    d_tgt.copy_(h_tgt)
+    obs = {k: v.clone() for k, v in pre(d_rgb, d_dep).items()}
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        sync_all()
+        return ms
+
+    for _ in range(args.warmup):
+        trainer.step(obs, d_tgt)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = L.launch_count()
+    ms = timed(lambda: trainer.step(obs, d_tgt), args.steps)
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    loss_val = float(trainer._loss.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    t_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B / (t_e2e / args.steps * 1e-3)
+    h2d = h_rgb.numel() * h_rgb.element_size() + h_dep.numel() * 4 + h_tgt.numel() * 4
+    if rank != 0:
+        return
+
+    # dominant kernel: the stem convolution (57 % of the forward FLOPs), timed alone with CUDA events
+    plan = trainer._plan
+    pk, how = peaks()
+    conv_op = plan.fwd_ops[1]
+    prog = L.Program([conv_op])
+    for _ in range(3):
+        prog.run(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 10
+    for _ in range(reps):
+        prog.run(dev)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps
+    k_flop = plan.conv1.flops(B)
+    achieved = k_flop / (k_ms * 1e-3) / 1e12
+    roofline = {"kernel": "conv_igemm_kernel (conv1 7x7/s2 30->32, B=%d)" % B, "bound": "tensor",
+                "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None, "peak_source": how + " (burst)",
+                "launch_ms": round(k_ms, 4), "flop_per_launch": k_flop,
+                "step_tflops": round(world * B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12, 2),
+                "step_frac_of_sustained": round(B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12
+                                                / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), 4)}
+    cpu = cpu_baseline(seconds=args.cpu_seconds) if world == 1 and not args.no_cpu else None
+    out = {"metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+           "config": {"workload": "VO ResNet-18 (vo_cnn_rgb_d_dd_top_down, 30 ch) forward+backward+Adam, "
+                                  "batch 256 per GPU, 341x192 RGB-D pairs (BASELINE configs[1])",
+                      "global_batch": world * B, "parallelism": f"dp{world}",
+                      "l2": "inputs (2.0 GB / step) exceed the 126 MB L2; no flush needed"},
+           "e2e": {"value": round(e2e_value, 1), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": 4, "ms_per_step": round(t_e2e / args.steps, 3),
+                   "path": "pinned uint8 rgb + fp32 depth -> H2D -> discretise + top-down on device -> train step -> loss"},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val}
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(seconds=15.0, batch=4, threads=None):
+    """The reference algorithm on the host cores: oracle/vo_oracle.py (fp32 PyTorch-CPU restatement pinned
+    against the unmodified reference), forward + backward + Adam on batches of 4 pairs."""
+    from oracle import preproc_oracle as po  # noqa: F401  (checker-side import, allowed in bench's cpu leg)
+    from oracle import vo_oracle as vo
+    from pointnav_vo_b200.vo.models.shapes import vo_state_dict_shapes
+    from pointnav_vo_b200.utils import synth
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    shapes = vo_state_dict_shapes(SPACE, "resnet18", discretized_depth_channels=10)
+    sd = synth.fill_state_dict({k: np.empty(s, np.float32) for k, s in shapes.items()}, seed=7)
+    sd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if "running" not in k]
+    opt = torch.optim.Adam(params, lr=2.5e-4, eps=1e-8)
+    rng = np.random.default_rng(0)
+    obs = {"rgb": torch.from_numpy(rng.integers(0, 256, size=(batch, H, W, 6)).astype(np.float32)),
+           "depth": torch.rand(batch, H, W, 2), "discretized_depth": torch.zeros(batch, H, W, 20),
+           "top_down_view": torch.rand(batch, H, W, 2)}
+    obs["discretized_depth"][..., 3] = 1
+    obs["discretized_depth"][..., 13] = 1
+    tgt = torch.randn(batch, 3) * 0.1
+
+    def step():
+        opt.zero_grad()
+        y, _ = vo.vo_forward(obs, sd, SPACE, "resnet18", training=True)
+        sum(vo.vo_losses(y, tgt)).backward()
+        opt.step()
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": round(n * batch / dt, 2), "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{n} fwd+bwd+Adam steps of batch {batch} (same model, 341x192, fp32 PyTorch-CPU oracle), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    vals = []
+    t0 = time.perf_counter()
+    cb = None
+    for _ in range(args.warmup + args.steps):
+        cb = cpu_baseline(seconds=max(2.0, min(10.0, 60.0 / (args.warmup + args.steps))))
+        vals.append(cb["value"])
+    vals = vals[args.warmup:]
+    v = float(np.mean(vals))
+    cb["value"] = round(v, 2)
+    out = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": "pairs/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(256 / v * 1e3, 1),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "VO ResNet-18 (vo_cnn_rgb_d_dd_top_down, 30 ch) forward+backward+Adam on the host "
+                                  "CPU, batch 4 samples of the batch-256 workload (BASELINE configs[0]/[1])"},
+           "cpu_baseline": cb, "e2e": {"value": round(v, 2), "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                                       "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1)}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(3, args.warmup)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,22 @@ RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet50": ("bottleneck",
 
 OBS_ORDER = ("rgb", "depth", "discretized_depth", "top_down_view")  # vo_cnn.py:114-166 append order
 
+# Optional emulation of the CUDA path's storage precision (fp16 activations / weights, fp32 accumulate):
+# with QUANT[0] = True every tensor the kernels keep in fp16 is rounded through fp16 here too (straight-
+# through in autograd).  This separates "is the kernel logic right" (tight tolerance against the
+# quantised oracle) from "what does fp16 storage cost" (looser tolerance against the fp32 oracle).
+QUANT = [False]
+
+
+def _q(x):
+    if not QUANT[0]:
+        return x
+    return x + (x.half().float() - x).detach()
+
+
+def _conv(x, w, stride=1, pad=0):
+    return _q(F.conv2d(x, _q(w), None, stride, pad))
+
 
 def assemble_input(obs, observation_space):
     """vo_cnn.py:110-174 -> [B, C, H, W] fp32, channels [prev_rgb, prev_d, prev_dd, prev_td, cur_...]."""
@@ -66,38 +82,38 @@ def _gn(x, sd, key, groups):
 
 def _basic_block(x, sd, p, ngroups, stride, has_down):
     """resnet.py:29-55"""
-    out = F.conv2d(x, sd[p + ".convs.0.weight"], None, stride, 1)
-    out = F.relu(_gn(out, sd, p + ".convs.1", ngroups))
-    out = F.conv2d(out, sd[p + ".convs.3.weight"], None, 1, 1)
+    out = _conv(x, sd[p + ".convs.0.weight"], stride, 1)
+    out = _q(F.relu(_gn(out, sd, p + ".convs.1", ngroups)))
+    out = _conv(out, sd[p + ".convs.3.weight"], 1, 1)
     out = _gn(out, sd, p + ".convs.4", ngroups)
     res = x
     if has_down:
-        res = _gn(F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0), sd, p + ".downsample.1", ngroups)
-    return F.relu(out + res)
+        res = _q(_gn(_conv(x, sd[p + ".downsample.0.weight"], stride, 0), sd, p + ".downsample.1", ngroups))
+    return _q(F.relu(out + res))
 
 
 def _bottleneck(x, sd, p, ngroups, stride, has_down):
     """resnet.py:58-120"""
-    out = F.conv2d(x, sd[p + ".convs.0.weight"])
-    out = F.relu(_gn(out, sd, p + ".convs.1", ngroups))
-    out = F.conv2d(out, sd[p + ".convs.3.weight"], None, stride, 1)
-    out = F.relu(_gn(out, sd, p + ".convs.4", ngroups))
-    out = F.conv2d(out, sd[p + ".convs.6.weight"])
+    out = _conv(x, sd[p + ".convs.0.weight"])
+    out = _q(F.relu(_gn(out, sd, p + ".convs.1", ngroups)))
+    out = _conv(out, sd[p + ".convs.3.weight"], stride, 1)
+    out = _q(F.relu(_gn(out, sd, p + ".convs.4", ngroups)))
+    out = _conv(out, sd[p + ".convs.6.weight"])
     out = _gn(out, sd, p + ".convs.7", ngroups)
     res = x
     if has_down:
-        res = _gn(F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0), sd, p + ".downsample.1", ngroups)
-    return F.relu(out + res)
+        res = _q(_gn(_conv(x, sd[p + ".downsample.0.weight"], stride, 0), sd, p + ".downsample.1", ngroups))
+    return _q(F.relu(out + res))
 
 
 def resnet_forward(x, sd, prefix, backbone, ngroups, taps=None):
     """resnet.py:214-223.  taps (optional dict) receives named intermediate activations (NCHW)."""
     kind, layers = RESNET_LAYERS[backbone]
     block = _basic_block if kind == "basic" else _bottleneck
-    x = F.conv2d(x, sd[prefix + ".conv1.0.weight"], None, 2, 3)
+    x = _conv(x, sd[prefix + ".conv1.0.weight"], 2, 3)
     if taps is not None:
         taps["conv1_raw"] = x
-    x = F.relu(_gn(x, sd, prefix + ".conv1.1", ngroups))
+    x = _q(F.relu(_gn(x, sd, prefix + ".conv1.1", ngroups)))
     x = F.max_pool2d(x, 3, 2, 1)
     if taps is not None:
         taps["pool"] = x
@@ -114,9 +130,9 @@ def resnet_forward(x, sd, prefix, backbone, ngroups, taps=None):
 
 def encoder_tail(x, sd, prefix):
     """compression: conv3x3 -> GroupNorm(1, C) -> ReLU (vo_cnn.py:85-95)."""
-    x = F.conv2d(x, sd[prefix + ".compression.0.weight"], None, 1, 1)
+    x = _conv(x, sd[prefix + ".compression.0.weight"], 1, 1)
     x = F.group_norm(x, 1, sd[prefix + ".compression.1.weight"], sd[prefix + ".compression.1.bias"], 1e-5)
-    return F.relu(x)
+    return _q(F.relu(x))
 
 
 def vo_forward(obs, sd, observation_space, backbone="resnet18", ngroups=16, training=False,
@@ -133,6 +149,7 @@ def vo_forward(obs, sd, observation_space, backbone="resnet18", ngroups=16, trai
                                       sd[pfx + ".running_mean_and_var._var"],
                                       sd[pfx + ".running_mean_and_var._count"], training)
         stats = (m, v, c)
+    x = _q(x)
     if taps is not None:
         taps["input"] = x
     x = resnet_forward(x, sd, pfx + ".backbone", backbone, ngroups, taps)
@@ -145,7 +162,7 @@ def vo_forward(obs, sd, observation_space, backbone="resnet18", ngroups=16, trai
         feat = torch.cat((feat, emb), dim=1)
         h = F.relu(F.linear(feat, sd["hidden_generator.1.weight"], sd["hidden_generator.1.bias"]))
     else:
-        h = F.relu(F.linear(feat, sd["visual_fc.2.weight"], sd["visual_fc.2.bias"]))
+        h = F.relu(F.linear(feat, _q(sd["visual_fc.2.weight"]), sd["visual_fc.2.bias"]))
     out = F.linear(h, sd["output_head.1.weight"], sd["output_head.1.bias"])
     return out, stats
 
@@ -159,7 +176,7 @@ def rl_encoder_forward(obs, sd, prefix="net.visual_encoder", backbone="resnet18"
     if use_depth:
         inp.append(obs["depth"].permute(0, 3, 1, 2).contiguous())
     x = torch.cat(inp, dim=1)
-    x = F.avg_pool2d(x, 2)
+    x = _q(F.avg_pool2d(x, 2))
     if taps is not None:
         taps["input"] = x
     x = resnet_forward(x, sd, prefix + ".backbone", backbone, ngroups, taps)

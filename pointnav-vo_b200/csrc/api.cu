@@ -156,6 +156,12 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       return head_bwd_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
                              static_cast<const float*>(p[2]), i[0], i[1], i[2], static_cast<float*>(p[3]),
                              static_cast<float*>(p[4]), static_cast<__half*>(p[5]), static_cast<float*>(p[6]), i[3], st);
+    case PNVO_OP_MSE_LOSS:
+      // p0 = pred, p1 = target, p2 = dz mask (nullable), p3 = dout (nullable), p4 = loss; i0 = B, i1 = O;
+      // f0..f2 = loss weights, f3 = gradient scale
+      return mse_loss_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
+                             static_cast<const float*>(p[2]), i[0], i[1], f[0], f[1], f[2], f[3],
+                             static_cast<float*>(p[3]), static_cast<float*>(p[4]), st);
     case PNVO_OP_ADAM:
       // p0 = param, p1 = grad, p2 = m, p3 = v; i0|i1 = n, i2 = step; f0 = lr, f1 = beta1, f2 = beta2, f3 = eps
       return adam_launch(static_cast<float*>(p[0]), static_cast<const float*>(p[1]), static_cast<float*>(p[2]),

@@ -73,6 +73,8 @@ int head_fwd_launch(const float* h, const float* W, const float* bias, int B, in
                     cudaStream_t st);
 int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,
                     __half* dz16, float* db1, int accumulate, cudaStream_t st);
+int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, int B, int O, float w0, float w1,
+                    float w2, float grad_scale, float* dout, float* loss, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 int step, float grad_scale, cudaStream_t st);
 

@@ -744,6 +744,42 @@ int head_bwd_launch(const float* dout, const float* h, const float* W, int B, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// VO regression loss (vo_cnn_engine.py:135-198): loss = sum_i w_i * mean_b (t_bi - p_bi)^2 (dz optionally
+// masked), and its gradient dout_bi = 2 w_i mask_bi (p_bi - t_bi) / B (scaled by grad_scale, e.g. 1/world).
+// One block; B is a few hundred.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                       const float* __restrict__ dz_mask, int B, int O, float w0,
+                                                       float w1, float w2, float grad_scale, float* __restrict__ dout,
+                                                       float* __restrict__ loss) {
+  __shared__ float s_part[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B * O; i += blockDim.x) {
+    const int b = i / O, o = i - b * O;
+    float w = (o == 0) ? w0 : ((o == 1) ? w1 : w2);
+    if (o == 1 && dz_mask) w *= dz_mask[b];
+    const float d = pred[i] - tgt[i];
+    acc = fmaf(w * d, d, acc);
+    if (dout) dout[i] = 2.f * w * d * grad_scale / static_cast<float>(B);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += s_part[k];
+    *loss = t / static_cast<float>(B);
+  }
+}
+int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, int B, int O, float w0, float w1,
+                    float w2, float grad_scale, float* dout, float* loss, cudaStream_t st) {
+  PNVO_REQUIRE(pred && tgt && loss, "mse_loss: null argument");
+  mse_loss_kernel<<<1, 256, 0, st>>>(pred, tgt, dz_mask, B, O, w0, w1, w2, grad_scale, dout, loss);
+  count_launch();
+  return check_launch("mse_loss");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Adam over a flat fp32 bucket (torch.optim.Adam semantics, weight_decay = 0, amsgrad = False)
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,

@@ -200,6 +200,10 @@ def op_head_bwd(dout, h, W, dW, db2, dz16, db1, B, K, O, accumulate=False):
     return _op(OP_HEAD_BWD, [B, K, O, int(accumulate)], (), [dout, h, W, dW, db2, dz16, db1])
 
 
+def op_mse_loss(pred, target, dz_mask, dout, loss, B, O, weights=(1.0, 1.0, 1.0), grad_scale=1.0):
+    return _op(OP_MSE_LOSS, [B, O], [weights[0], weights[1], weights[2], grad_scale], [pred, target, dz_mask, dout, loss])
+
+
 def op_adam(p, g, m, v, n, step, lr, beta1, beta2, eps):
     lo, hi = _lohi(n)
     return _op(OP_ADAM, [lo, hi, step], [lr, beta1, beta2, eps], [p, g, m, v])

@@ -39,12 +39,21 @@ def discretize_depth(raw_depth, n_channels=10, end_vals=None, check=True, out=No
         end_vals = discretize_end_vals(n_channels)
     assert len(end_vals) == n_channels + 1
     d = raw_depth.contiguous().float()
+    stride = n_channels
     if out is None:
         out = torch.empty((*d.shape, n_channels), dtype=torch.float32, device=d.device)
+    else:
+        # a channel slice of a wider NHWC tensor: rows of n_channels floats, `stride` floats apart
+        assert out.dtype == torch.float32 and out.shape == (*d.shape, n_channels) and out.stride(-1) == 1
+        stride = out.stride(-2)
+        exp = stride
+        for k in range(out.dim() - 2, -1, -1):
+            assert out.stride(k) == exp, "out must be a uniform-stride channel slice"
+            exp *= out.shape[k]
     err = torch.zeros(1, dtype=torch.int32, device=d.device) if check else None
     lib = _lib.load()
     _lib.check(lib.pnvo_discretize_depth(_lib.ptr(d), d.numel(), _lib.ptr(_edges(end_vals, d.device)), n_channels,
-                                         _lib.ptr(out), n_channels, None, _lib.ptr(err), _lib.stream_ptr(d.device)))
+                                         _lib.ptr(out), stride, None, _lib.ptr(err), _lib.stream_ptr(d.device)))
     if check:
         assert int(err.item()) == 0, "depth outside [0, 1]"  # :136-137
     return out

@@ -1,0 +1,87 @@
+"""One VO optimisation step entirely on the device, without autograd or torch.optim in the loop:
+
+    forward program -> loss + d(loss)/d(pred) -> backward program -> [NCCL all-reduce of the flat gradient
+    bucket] -> Adam over the flat parameter bucket
+
+Semantics follow the reference's engine: per-delta mean((gt - pred)^2 * w) summed over dx/dz/dyaw
+(vo/engine/vo_cnn_engine.py:135-198), optimiser Adam(lr=2.5e-4, eps=1e-8, weight_decay=0)
+(vo_cnn_regression_geo_invariance_engine.py:122-133, configs/vo/vo_pointnav.yaml:36-40).
+Data-parallel training (new capability; the reference trains VO on one GPU): every rank
+holds a replica, the flat gradient bucket is summed with ONE all-reduce and scaled by 1/world inside the
+loss-gradient kernel, which equals the single-GPU gradient of the mean loss over the concatenated batch
+when every rank has the same batch size.
+"""
+import torch
+
+from ... import lib as L
+
+
+class FusedVOTrainStep:
+    def __init__(self, model, lr=2.5e-4, betas=(0.9, 0.999), eps=1e-8, loss_weights=(1.0, 1.0, 1.0),
+                 process_group=None):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.loss_weights = tuple(float(w) for w in loss_weights)
+        self.group = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.step_count = 0
+        self._flat = None
+        self._plan = None
+
+    # parameters are re-pointed into one flat fp32 buffer ordered like the plan's gradient bucket, so the
+    # optimiser and the all-reduce each touch a single contiguous range
+    def _flatten(self, plan):
+        names = plan.param_names()
+        P = dict(self.model.named_parameters())
+        missing = set(P) - set(names)
+        assert not missing, f"parameters without a gradient slot: {sorted(missing)}"
+        n = sum(P[k].numel() for k in names)
+        dev = plan.dev
+        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        for k in names:
+            m = P[k].numel()
+            flat[off:off + m].copy_(P[k].data.reshape(-1))
+            P[k].data = flat[off:off + m].view(P[k].shape)
+            off += m
+        self._flat = flat
+        self._m = torch.zeros_like(flat)
+        self._v = torch.zeros_like(flat)
+        self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self.world > 1:  # replicas start from rank 0's weights (as DDP does, ddppo.py:55-58)
+            torch.distributed.broadcast(flat, 0, group=self.group)
+
+    def _get_plan(self, obs):
+        model = self.model
+        plan = model._plan_for(obs, True)
+        if self._flat is None:
+            self._flatten(plan)
+            model._plans.clear()
+            plan = model._plan_for(obs, True)  # rebuilt on the flat storage
+        if plan is not self._plan:
+            B, O = plan.B, plan.head["out_dim"]
+            self._target = torch.zeros(B, O, dtype=torch.float32, device=plan.dev)
+            self._loss_prog = L.Program([L.op_mse_loss(plan.out, self._target, None, plan.dout, self._loss, B, O,
+                                                       self.loss_weights, 1.0 / self.world)])
+            self._plan = plan
+        return plan
+
+    def step(self, obs, target):
+        """obs: dict of NHWC fp32 CUDA tensors (the model's forward input); target: [B, 3] fp32 CUDA.
+        Returns the (device) loss tensor of this rank's batch."""
+        model = self.model
+        plan = self._get_plan(obs)
+        self._target.copy_(target)
+        model._run_forward(plan, obs, model.training)
+        self._loss_prog.run(plan.dev)
+        plan.bwd_prog.run(plan.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(plan.grad_flat, group=self.group)
+        self.step_count += 1
+        L.run_ops([L.op_adam(self._flat, plan.grad_flat, self._m, self._v, self._flat.numel(), self.step_count, self.lr,
+                             self.betas[0], self.betas[1], self.eps)], plan.dev)
+        # the optimiser wrote through raw pointers: tell the module its packed fp16 weights are stale
+        model._packed_version = None
+        return self._loss

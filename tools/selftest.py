@@ -292,6 +292,31 @@ def vo_model():
         loss = sum(vo.vo_losses(y, target))
         loss.backward()
         torch.cuda.synchronize()
+        # gradient taps: oracle autograd (fp32, GPU) vs the plan's gradient buffers
+        sdg = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+        taps = {}
+        vo.QUANT[0] = os.environ.get("PNVO_QUANT_ORACLE", "1") == "1"  # emulate fp16 storage in the oracle
+        yo, _ = vo.vo_forward(obs, sdg, space, backbone, training=True, taps=taps)
+        vo.QUANT[0] = False
+        for t in taps.values():
+            if t.requires_grad:
+                t.retain_grad()
+        sum(vo.vo_losses(yo, target)).backward()
+        plan = [p for p in m._plans.values() if p.training][0]
+        report(f"{case} train out vs gpu oracle", y, yo.detach(), 1e-3)
+        report(f"{case} gtap compression", plan.g_feat[..., :cc].permute(0, 3, 1, 2), taps["compression"].grad, 1e-2)
+        li = 0
+        for bi, blk in enumerate(plan.blocks):
+            nxt = plan.blocks[bi + 1]["name"] if bi + 1 < len(plan.blocks) else None
+            if nxt is None or nxt.split(".")[-2] != blk["name"].split(".")[-2]:
+                li += 1
+                report(f"{case} gtap layer{li}", blk["g_y"].permute(0, 3, 1, 2), taps[f"layer{li}"].grad, 1e-2)
+        report(f"{case} gtap pool", plan.g_pool.permute(0, 3, 1, 2), taps["pool"].grad, 1e-2)
+        report(f"{case} gtap conv1_raw", plan.dx1.permute(0, 3, 1, 2), taps["conv1_raw"].grad, 1e-2)
+        Pm = dict(m.named_parameters())
+        for k in ("output_head.1.weight", "visual_fc.2.bias", "visual_fc.2.weight", "visual_encoder.compression.0.weight",
+                  "visual_encoder.compression.1.weight", "visual_encoder.backbone.conv1.0.weight"):
+            report(f"{case} grad {k[-40:]}", Pm[k].grad, sdg[k].grad, 1e-2)
         report(f"{case} train out", y, torch.from_numpy(g["train_out"]), 1e-3)
         sdn = m.state_dict()
         report(f"{case} rmv mean", sdn["visual_encoder.running_mean_and_var._mean"], torch.from_numpy(g["train_mean"]), 1e-4)
@@ -331,12 +356,82 @@ def main():
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--check", name], timeout=args.timeout,
                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            print(r.stdout[-12000:], flush=True)
+            print(r.stdout[-60000:], flush=True)
             print(f"[{name}] exit code {r.returncode}", flush=True)
         except subprocess.TimeoutExpired as e:
             out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
             print(out[-6000:])
             print(f"[{name}] TIMEOUT after {args.timeout}s", flush=True)
+
+
+
+@check
+def vo_blocks():
+    """Backward logic, block by block: the oracle block is fed with the plan's OWN activations and upstream
+    gradient, so only one block's rounding separates the two (no accumulated fp16 noise, few ReLU flips)."""
+    from oracle import vo_oracle as vo
+    from tests import helpers
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for case in ("r18_8ch", "r50_8ch"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"vo_{case}.npz"))
+        m, space, backbone = _load_vo(case)
+        obs = helpers.vo_inputs(2, 11, space, "cuda")
+        m.train()
+        target = torch.from_numpy(g["target"]).cuda()
+        y = m(obs)
+        sum(vo.vo_losses(y, target)).backward()
+        torch.cuda.synchronize()
+        plan = [p for p in m._plans.values() if p.training][0]
+        P = dict(m.named_parameters())
+        ng = m.visual_encoder.ngroups
+        kind = vo.RESNET_LAYERS[backbone][0]
+        fn = vo._basic_block if kind == "basic" else vo._bottleneck
+
+        def nchw(t, c=None):
+            t = t.float().permute(0, 3, 1, 2)
+            return t if c is None else t[:, :c]
+
+        # head + compression
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+        x4 = nchw(plan.blocks[-1]["y"]).clone().requires_grad_(True)
+        feat = vo.encoder_tail(x4, sd, "visual_encoder")
+        h = F.relu(F.linear(feat.flatten(1), sd["visual_fc.2.weight"], sd["visual_fc.2.bias"]))
+        out = F.linear(h, sd["output_head.1.weight"], sd["output_head.1.bias"])
+        sum(vo.vo_losses(out, target)).backward()
+        report(f"{case} head: out", y, out.detach(), 2e-3)
+        report(f"{case} head: g layer4", nchw(plan.blocks[-1]["g_y"]), x4.grad, 1e-2)
+        for k in ("output_head.1.weight", "output_head.1.bias", "visual_fc.2.weight", "visual_fc.2.bias",
+                  "visual_encoder.compression.0.weight", "visual_encoder.compression.1.weight",
+                  "visual_encoder.compression.1.bias"):
+            report(f"{case} head: {k[-36:]}", P[k].grad, sd[k].grad, 1e-2)
+        # residual blocks
+        for bi in range(len(plan.blocks) - 1, -1, -1):
+            blk = plan.blocks[bi]
+            p = blk["name"].replace("visual_encoder.backbone.", "")
+            sd = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if blk["name"] in k}
+            xin = nchw(blk["x_in"]).clone().requires_grad_(True)
+            stride = blk["convs"][0 if kind == "basic" else 1].stride
+            yb = fn(xin, sd, blk["name"], ng, stride, blk["down"] is not None)
+            report(f"{case} {p}: y", nchw(blk["y"]), yb.detach(), 5e-3)
+            yb.backward(nchw(blk["g_y"]))
+            gx = plan.blocks[bi - 1]["g_y"] if bi > 0 else plan.g_pool
+            report(f"{case} {p}: g_x", nchw(gx), xin.grad, 1e-2)
+            for k in sd:
+                report(f"{case} {p}: {k.split(p)[-1]}", P[k].grad, sd[k].grad, 1e-2)
+        # stem
+        C = m.visual_encoder.input_channels
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if ".conv1." in k}
+        x0 = nchw(plan.x0, C)
+        pfx = "visual_encoder.backbone"
+        a = F.conv2d(x0, sd[pfx + ".conv1.0.weight"], None, 2, 3)
+        a = F.relu(F.group_norm(a, ng, sd[pfx + ".conv1.1.weight"], sd[pfx + ".conv1.1.bias"], 1e-5))
+        pl = F.max_pool2d(a, 3, 2, 1)
+        report(f"{case} stem: pool", nchw(plan.pool), pl.detach(), 5e-3)
+        pl.backward(nchw(plan.g_pool))
+        for k in sd:
+            report(f"{case} stem: {k[-20:]}", P[k].grad, sd[k].grad, 1e-2)
 
 
 if __name__ == "__main__":
