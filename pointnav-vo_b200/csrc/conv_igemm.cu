@@ -15,13 +15,13 @@
 // (sample, group)) reduced with a warp butterfly and one atomicAdd per value, fp16 (or fp32) store.
 #include "common.cuh"
 #include "ops.cuh"
+#include "tmap.cuh"
 
 namespace pnvo {
 
 static constexpr int kTileM = 128;
 static constexpr int kTileK = 64;  // fp16 elements per K stage = one 128-byte swizzle row
 static constexpr int kProducerThreads = 128;
-static constexpr int kLookahead = 2;  // cp.async groups in flight per producer thread
 
 template <int V>
 __device__ __forceinline__ void warp_reduce_scatter(float* a, int lane) {
@@ -78,29 +78,36 @@ __device__ __forceinline__ void chunk_stats(const float* v, int sample, bool row
   }
 }
 
-__global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p) {
+__global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const __grid_constant__ ConvTmaps tm) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_full[8];
   __shared__ __align__(8) uint64_t s_empty[8];
   __shared__ __align__(8) uint64_t s_accum;
   __shared__ uint32_t s_tmem;
-  __shared__ short2 s_tap[128];  // tap -> (r, s)
+  __shared__ short2 s_tap[64];   // tap -> (r, s)
+  __shared__ int s_tapoff[64];   // tap -> element offset of the tap relative to the row pointer
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int stages = p.stages;
   const int m0 = blockIdx.x * kTileM;
   const int n0 = blockIdx.y * p.N;
-  const uint32_t a_bytes = kTileM * 128;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.N) * 128;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.chunk_k) * 2;  // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, Cin = 32)
+  const uint32_t a_bytes = kTileM * row_bytes;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.N) * row_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   // dynamic smem base rounded up to 1024 B (128B swizzle atoms repeat every 1024 B)
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
-  for (int i = tid; i < p.R * p.S; i += blockDim.x) s_tap[i] = make_short2(i / p.S, i % p.S);
+  for (int i = tid; i < p.R * p.S; i += blockDim.x) {
+    const int r = i / p.S, sx = i % p.S;
+    s_tap[i] = make_short2(r, sx);
+    // valid taps sit on the stride lattice, where (ohb + r) / div == floor(ohb / div) + ceil(r / div)
+    s_tapoff[i] = (((r + p.div - 1) / p.div) * p.IW + (sx + p.div - 1) / p.div) * p.Cin;
+  }
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kProducerThreads);
+      mbar_init(smem_u32(&s_full[s]), p.tma ? 1 : kProducerThreads);
       mbar_init(smem_u32(&s_empty[s]), 1);
     }
     mbar_init(smem_u32(&s_accum), 1);
@@ -115,87 +122,125 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  if (warp < 4) {
-    // ============================ im2col / weight producers ============================
-    const int row = tid;  // A-tile row == output pixel m0 + row
-    const int m = m0 + row;
-    const bool row_valid = m < p.M;
-    int b = 0, oh = 0, ow = 0;
-    if (row_valid) {
+  if (warp < 4 && p.tma) {
+    // ================================ TMA producer ================================
+    // One elected thread per CTA: per K chunk (one filter tap x chunk_k channels) one im2col TMA brings
+    // the 128-pixel x chunk_k activation tile (halo / batch tail zero-filled by the TMA unit) and one
+    // tiled TMA the N x chunk_k weight tile, both landing 64/128-byte swizzled exactly as tcgen05.mma
+    // reads them.  No per-element address arithmetic on the SM.
+    if (tid == 0) {
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
       const int ohw = p.OH * p.OW;
-      b = m / ohw;
-      const int rem = m - b * ohw;
-      oh = rem / p.OW;
-      ow = rem - oh * p.OW;
+      const int n_img = m0 / ohw;
+      const int rem = m0 - n_img * ohw;
+      const int p0 = rem / p.OW, q0 = rem - p0 * p.OW;
+      const int w0 = q0 * p.mul - p.pad_w, h0 = p0 * p.mul - p.pad;
+      const int nkb = p.nkb;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        if (kb >= stages) mbar_wait(smem_u32(&s_empty[s]), ((kb / stages) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&s_full[s]);
+        const uint32_t sA = smem_base + s * stage_bytes;
+        const int kf = kb * p.chunk_k;
+        const short2 rs = s_tap[kf >> p.cin_log2];
+        mbar_arrive_expect_tx(bar, stage_bytes);
+        tma_load_im2col_4d(sA, &tm.a, bar, kf & p.cmask, w0, h0, n_img, static_cast<uint16_t>(rs.y),
+                           static_cast<uint16_t>(rs.x));
+        tma_load_2d(sA + a_bytes, &tm.b, bar, kf, n0);
+      }
     }
-    const int ohb = oh * p.mul - p.pad, owb = ow * p.mul - p.pad_w;
-    const __half* __restrict__ xb = p.x + static_cast<int64_t>(b) * p.IH * p.IW * p.Cin;
-    const int dmask = p.div - 1, dshift = (p.div == 2) ? 1 : 0;
-    const int cmask = p.cmask;
-    const uint32_t a_row_off = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
-    const int rx = row & 7;
+  }
+  if (warp < 4) {
+    const int ohw = p.OH * p.OW;
+    if (!p.tma) {
+    // ============================ im2col / weight producers ============================
+    // Thread t owns 16-byte chunk j = t % 8 of rows (t / 8) + 16 i, i = 0..7: the 8 lanes of a row
+    // fetch one contiguous 128-byte line (or two 64-byte runs when Cin = 32), so a warp-level cp.async
+    // touches 4 lines instead of 32 (the SM -> L2 request rate, not bandwidth, bounded the first version).
+    const int j = tid & 7, rsub = tid >> 3;
+    const int dshift = (p.div == 2) ? 1 : 0, dmask = p.div - 1;
+    const int n_taps = p.R * p.S;
+    // Per row: pointer to x[b, floor(ohb/div), floor(owb/div), 0] and a bit mask of the taps that fall
+    // inside the input (and on the stride lattice for dgrad).  Per stage and chunk the address is then
+    // row pointer + tap offset (smem LUT) and the predicate one bit test -- the first version spent
+    // ~40 instructions per 16-byte chunk on this and was issue-bound.
+    const __half* rowptr[8];
+    unsigned long long tmask[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mi = m0 + rsub + 16 * i;
+      rowptr[i] = p.x;
+      tmask[i] = 0ull;
+      if (mi < p.M) {
+        const int bi = mi / ohw;
+        const int rem = mi - bi * ohw;
+        const int oh = rem / p.OW;
+        const int ohb = oh * p.mul - p.pad;
+        const int owb = (rem - oh * p.OW) * p.mul - p.pad_w;
+        rowptr[i] = p.x + (static_cast<int64_t>(bi) * p.IH * p.IW +
+                           static_cast<int64_t>(ohb >> dshift) * p.IW + (owb >> dshift)) * p.Cin;
+        unsigned long long mk = 0ull;
+        for (int t = 0; t < n_taps; ++t) {
+          const short2 rs = s_tap[t];
+          const int th = ohb + rs.x, tw = owb + rs.y;
+          const bool ok = (th >= 0) && (tw >= 0) && (((th | tw) & dmask) == 0) && ((th >> dshift) < p.IH) &&
+                          ((tw >> dshift) < p.IW);
+          mk |= static_cast<unsigned long long>(ok ? 1u : 0u) << t;
+        }
+        tmask[i] = mk;
+      }
+    }
+    const uint32_t t_off = static_cast<uint32_t>((rsub >> 3) * 1024 + (rsub & 7) * 128 + ((j ^ (rsub & 7)) << 4));
+    const int nb_rows = p.N >> 4;  // B rows handled by this thread: rsub + 16 i
+    const __half* wrow = p.w + static_cast<int64_t>(n0 + rsub) * p.w_ld + j * 8;
+    const int64_t w_step = static_cast<int64_t>(16) * p.w_ld;
 
     auto issue_stage = [&](int kb) {
       const int s = kb % stages;
-      const uint32_t sA = smem_base + s * stage_bytes;
+      const uint32_t sA = smem_base + s * stage_bytes + t_off;
       const uint32_t sB = sA + a_bytes;
-      // ---- A: 8 chunks of 8 channels for this row ----
-      const __half* src = nullptr;
-      bool ok = false;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kf = kb * kTileK + j * 8;
-        if (j == 0 || (kf & cmask) == 0) {
-          ok = false;
-          if (row_valid && kf < p.K) {
-            const int tap = kf >> p.cin_log2;
-            const short2 rs = s_tap[tap];
-            const int th = ohb + rs.x, tw = owb + rs.y;
-            if (th >= 0 && tw >= 0 && ((th | tw) & dmask) == 0) {
-              const int ih = th >> dshift, iw = tw >> dshift;
-              if (ih < p.IH && iw < p.IW) {
-                ok = true;
-                src = xb + (static_cast<int64_t>(ih) * p.IW + iw) * p.Cin + (kf & cmask);
-              }
-            }
-          }
-        } else {
-          src += 8;
-        }
-        cp_async_16(sA + a_row_off + ((j ^ rx) << 4), ok ? static_cast<const void*>(src) : static_cast<const void*>(p.x),
-                    ok ? 16u : 0u);
+      const int kf = kb * kTileK + j * 8;
+      int tap = 0, toff = 0;
+      unsigned long long kvalid = 0ull;
+      if (kf < p.K) {
+        tap = kf >> p.cin_log2;
+        toff = s_tapoff[tap] + (kf & p.cmask);
+        kvalid = 1ull;
       }
-      // ---- B: weight rows (always in range: packed weights are zero-padded to [n_total][w_ld]) ----
-      for (int r = row; r < p.N; r += kProducerThreads) {
-        const __half* wsrc = p.w + static_cast<int64_t>(n0 + r) * p.w_ld + kb * kTileK;
-        const uint32_t dst = sB + static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128);
-        const int rr = r & 7;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cp_async_16(dst + ((j ^ rr) << 4), wsrc + j * 8, 16u);
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = ((tmask[i] >> tap) & kvalid) != 0ull;
+        cp_async_16(sA + i * 2048, rowptr[i] + toff, ok ? 16u : 0u);
       }
+      const __half* wsrc = wrow + kb * kTileK;
+      for (int i = 0; i < nb_rows; ++i) cp_async_16(sB + i * 2048, wsrc + i * w_step, 16u);
     };
 
     const int nkb = p.nkb;
+    const int la = p.lookahead;  // committed cp.async groups kept in flight per thread
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % stages;
       if (kb >= stages) mbar_wait(smem_u32(&s_empty[s]), ((kb / stages) & 1) ^ 1);
       issue_stage(kb);
       cp_async_commit();
-      if (kb >= kLookahead) {
-        cp_async_wait<kLookahead>();
+      if (kb >= la) {
+        cp_async_wait_dyn(la);
         fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&s_full[(kb - kLookahead) % stages]));
+        mbar_arrive(smem_u32(&s_full[(kb - la) % stages]));
       }
     }
-    // drain
-    if (nkb >= 2) {
-      cp_async_wait<1>();
+    for (int rem = min(la, nkb) - 1; rem >= 0; --rem) {  // drain
+      cp_async_wait_dyn(rem);
       fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&s_full[(nkb - 2) % stages]));
+      mbar_arrive(smem_u32(&s_full[(nkb - 1 - rem) % stages]));
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    mbar_arrive(smem_u32(&s_full[(nkb - 1) % stages]));
+
+    }  // !tma
+    const int row = tid;  // epilogue: thread == accumulator row == output pixel m0 + tid
+    const int m = m0 + row;
+    const bool row_valid = m < p.M;
+    const int b = row_valid ? m / ohw : 0;
 
     // ==================================== epilogue ====================================
     mbar_wait(smem_u32(&s_accum), 0);
@@ -272,10 +317,10 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p) {
         mbar_wait(smem_u32(&s_full[s]), (kb / stages) & 1);
         tc_fence_after();
         const uint32_t sA = smem_base + s * stage_bytes;
-        const uint64_t adesc = umma_desc_sw128(sA, 16, 1024);
-        const uint64_t bdesc = umma_desc_sw128(sA + a_bytes, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < kTileK / 16; ++k) {
+        const uint64_t adesc = umma_desc(sA, 16, 8 * row_bytes, row_bytes);
+        const uint64_t bdesc = umma_desc(sA + a_bytes, 16, 8 * row_bytes, row_bytes);
+        const int ksteps = p.chunk_k >> 4;
+        for (int k = 0; k < ksteps; ++k) {
           // +32 bytes (16 fp16 of K) inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
           tc_mma_f16(tmem_base, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                      (kb | k) != 0 ? 1u : 0u);
@@ -303,7 +348,7 @@ static int pow2_cols(int n) {
 int conv_plan(ConvArgs& a) {
   PNVO_REQUIRE(a.Cin >= 8 && a.Cin % 8 == 0 && (a.R * a.S == 1 || (a.Cin & (a.Cin - 1)) == 0),
                "conv: Cin=%d must be a multiple of 8 (power of two unless 1x1)", a.Cin);
-  PNVO_REQUIRE(a.R * a.S <= 128, "conv: filter %dx%d too large", a.R, a.S);
+  PNVO_REQUIRE(a.R * a.S <= 64, "conv: filter %dx%d too large", a.R, a.S);
   PNVO_REQUIRE(a.div == 1 || a.div == 2, "conv: div=%d unsupported", a.div);
   PNVO_REQUIRE(a.n_total % 16 == 0, "conv: padded Cout=%d must be a multiple of 16", a.n_total);
   if (a.R * a.S == 1) {  // 1x1: tap is always 0, any channel count
@@ -316,8 +361,11 @@ int conv_plan(ConvArgs& a) {
   }
   a.M = a.B * a.OH * a.OW;
   a.K = a.R * a.S * a.Cin;
-  a.nkb = ceil_div(a.K, kTileK);
-  PNVO_REQUIRE(a.w_ld >= a.nkb * kTileK, "conv: packed weight row stride %d < padded K %d", a.w_ld, a.nkb * kTileK);
+  // TMA im2col path: unit "dilation" (div == 1), square filter / symmetric padding, channels in chunks of 32 or 64
+  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && !a.force_generic) ? 1 : 0;
+  a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : kTileK;
+  a.nkb = ceil_div(a.K, a.chunk_k);
+  PNVO_REQUIRE(a.w_ld >= a.nkb * a.chunk_k, "conv: packed weight row stride %d < padded K %d", a.w_ld, a.nkb * a.chunk_k);
   // N tile: whole Cout when <= 256, else the largest divisor <= 256 that is a multiple of 32
   int N = a.n_total;
   if (N > 256) {
@@ -331,10 +379,13 @@ int conv_plan(ConvArgs& a) {
     PNVO_REQUIRE(a.cpg <= 32 || N % 32 == 0, "conv: bad group tiling");
     PNVO_REQUIRE(N % 32 == 0, "conv: GroupNorm statistics need Cout %% 32 == 0 (got %d)", N);
   }
-  const int stage_bytes = kTileM * 128 + N * 128;
-  int stages = (N <= 64) ? 4 : 3;
-  if (a.nkb < stages) stages = a.nkb < 2 ? 2 : a.nkb;
+  const int stage_bytes = (kTileM + N) * a.chunk_k * 2;
+  // two CTAs per SM when a >= 4-stage ring fits in ~100 KB, else one CTA with a deep ring
+  int stages = std::min(8, (100 * 1024) / stage_bytes);
+  if (stages < 4) stages = std::min(6, (198 * 1024) / stage_bytes);
+  if (a.nkb < stages) stages = std::max(2, a.nkb);
   a.stages = stages;
+  a.lookahead = std::max(1, std::min(4, stages - 2));
   a.smem_bytes = stages * stage_bytes + 1024;
   a.grid_x = ceil_div(a.M, kTileM);
   a.grid_y = a.n_total / N;
@@ -350,7 +401,13 @@ int conv_launch(ConvArgs a, cudaStream_t st) {
     cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     max_smem_set = 200 * 1024;
   }
-  conv_igemm_kernel<<<dim3(a.grid_x, a.grid_y), 160, a.smem_bytes, st>>>(a);
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (a.tma) {
+    if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM)) return -1;
+    if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.N, a.chunk_k)) return -1;
+  }
+  conv_igemm_kernel<<<dim3(a.grid_x, a.grid_y), 160, a.smem_bytes, st>>>(a, tm);
   count_launch();
   return check_launch("conv_igemm");
 }

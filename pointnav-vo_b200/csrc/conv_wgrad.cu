@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
   __shared__ __align__(8) uint64_t s_empty[4];
   __shared__ __align__(8) uint64_t s_accum;
   __shared__ uint32_t s_tmem;
-  __shared__ short2 s_tap[128];
+  __shared__ short2 s_tap[64];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -61,85 +61,94 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
   if (n_chunks > 0) {
     if (warp < 4) {
       // =============================== producers ===============================
-      const int row = tid & 63;   // pixel row inside the stage
-      const int half = tid >> 6;  // which half of the column blocks this thread fills
-      const int rx = row & 7;
-      const uint32_t row_off = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
-      const int cmask = p.cmask;
+      // Thread t owns 16-byte chunk j = t % 8 of pixel rows (t / 8) + 16 i, i = 0..3, in every 64-wide
+      // column block: the 8 lanes of a row fetch one contiguous 128-byte line (coalesced L2 requests).
+      const int j = tid & 7, rsub = tid >> 3;
+      const uint32_t t_off = static_cast<uint32_t>((rsub >> 3) * 1024 + (rsub & 7) * 128 + ((j ^ (rsub & 7)) << 4));
       const int ohw = p.OH * p.OW;
       const int n_ablocks = mt * 2;
+      const int n_bblocks = (p.N + 63) >> 6;
+      // running (sample, oh, ow) of this thread's 4 pixel rows; advanced by 64 pixels per stage
+      int pb[4], poh[4], pow_[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = c_begin * kPix + rsub + 16 * i;
+        pb[i] = m / ohw;
+        const int rem = m - pb[i] * ohw;
+        poh[i] = rem / p.OW;
+        pow_[i] = rem - poh[i] * p.OW;
+      }
 
       auto issue_stage = [&](int it) {
         const int s = it % stages;
-        const uint32_t sA = smem_base + s * stage_bytes;
+        const uint32_t sA = smem_base + s * stage_bytes + t_off;
         const uint32_t sB = sA + a_bytes;
-        const int m = (c_begin + it) * kPix + row;
-        const bool row_valid = m < p.M;
-        int b = 0, oh = 0, ow = 0;
-        if (row_valid) {
-          b = m / ohw;
-          const int rem = m - b * ohw;
-          oh = rem / p.OW;
-          ow = rem - oh * p.OW;
-        }
-        const int ohb = oh * p.mul - p.pad, owb = ow * p.mul - p.pad_w;
-        const __half* __restrict__ xb = p.x + static_cast<int64_t>(b) * p.IH * p.IW * p.Cin;
-        // ---- A: im2col rows, blocks of 64 consecutive k ----
-        for (int blk = half; blk < n_ablocks; blk += 2) {
-          const int kf0 = (tile0 * 2 + blk) * 64;
-          const uint32_t dst = sA + static_cast<uint32_t>(blk) * 8192 + row_off;
-          const __half* src = nullptr;
-          bool ok = false;
+        const __half* rowptr[4];
+        const __half* dyptr[4];
+        int rlo[4], rspan[4], slo[4], sspan[4];
+        uint32_t dy_ok[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int kf = kf0 + j * 8;
-            if (j == 0 || (kf & cmask) == 0) {
-              ok = false;
-              if (row_valid && kf < p.K) {
-                const int tap = kf >> p.cin_log2;
-                const short2 rs = s_tap[tap];
-                const int ih = ohb + rs.x, iw = owb + rs.y;
-                if (ih >= 0 && iw >= 0 && ih < p.IH && iw < p.IW) {
-                  ok = true;
-                  src = xb + (static_cast<int64_t>(ih) * p.IW + iw) * p.Cin + (kf & cmask);
-                }
-              }
-            } else {
-              src += 8;
-            }
-            cp_async_16(dst + ((j ^ rx) << 4), ok ? static_cast<const void*>(src) : static_cast<const void*>(p.x),
-                        ok ? 16u : 0u);
+        for (int i = 0; i < 4; ++i) {
+          const int m = (c_begin + it) * kPix + rsub + 16 * i;
+          const bool valid = m < p.M;
+          const int ohb = poh[i] * p.mul - p.pad, owb = pow_[i] * p.mul - p.pad_w;
+          rowptr[i] = p.x + ((static_cast<int64_t>(pb[i]) * p.IH + ohb) * p.IW + owb) * p.Cin;
+          // tap (r, s) is inside the input iff rlo <= r < rlo + rspan and slo <= s < slo + sspan
+          rlo[i] = max(0, -ohb);
+          rspan[i] = valid ? max(0, min(p.R, p.IH - ohb) - rlo[i]) : 0;
+          slo[i] = max(0, -owb);
+          sspan[i] = max(0, min(p.S, p.IW - owb) - slo[i]);
+          dyptr[i] = p.dy + static_cast<int64_t>(valid ? m : 0) * p.ld_dy + n0 + j * 8;
+          dy_ok[i] = valid ? 16u : 0u;
+          // advance to the next stage
+          pow_[i] += kPix;
+          while (pow_[i] >= p.OW) { pow_[i] -= p.OW; ++poh[i]; }
+          while (poh[i] >= p.OH) { poh[i] -= p.OH; ++pb[i]; }
+        }
+        // ---- A: im2col rows, blocks of 64 consecutive k ----
+        for (int blk = 0; blk < n_ablocks; ++blk) {
+          const int kf = (tile0 * 2 + blk) * 64 + j * 8;
+          int r = -(1 << 20), sx = 0, toff = 0;
+          if (kf < p.K) {
+            const int tap = kf >> p.cin_log2;
+            const short2 rs = s_tap[tap];
+            r = rs.x;
+            sx = rs.y;
+            toff = (r * p.IW + sx) * p.Cin + (kf & p.cmask);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = (static_cast<unsigned>(r - rlo[i]) < static_cast<unsigned>(rspan[i])) &&
+                            (static_cast<unsigned>(sx - slo[i]) < static_cast<unsigned>(sspan[i]));
+            cp_async_16(sA + blk * 8192 + i * 2048, rowptr[i] + toff, ok ? 16u : 0u);
           }
         }
         // ---- B: dy rows ----
-        const __half* dyr = p.dy + static_cast<int64_t>(row_valid ? m : 0) * p.ld_dy + n0;
-        const int n_bchunks = p.N >> 3;  // 16-byte chunks per pixel row
-        for (int q = half; q < n_bchunks; q += 2) {
-          const int blk = q >> 3, j = q & 7;
-          cp_async_16(sB + static_cast<uint32_t>(blk) * 8192 + row_off + ((j ^ rx) << 4), dyr + q * 8,
-                      row_valid ? 16u : 0u);
+        for (int blk = 0; blk < n_bblocks; ++blk) {
+          if (blk * 64 + j * 8 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async_16(sB + blk * 8192 + i * 2048, dyptr[i] + blk * 64, dy_ok[i]);
+          }
         }
       };
 
+      const int la = p.lookahead;
       for (int it = 0; it < n_chunks; ++it) {
         const int s = it % stages;
         if (it >= stages) mbar_wait(smem_u32(&s_empty[s]), ((it / stages) & 1) ^ 1);
         issue_stage(it);
         cp_async_commit();
-        if (it >= 2) {
-          cp_async_wait<2>();
+        if (it >= la) {
+          cp_async_wait_dyn(la);
           fence_proxy_async_smem();
-          mbar_arrive(smem_u32(&s_full[(it - 2) % stages]));
+          mbar_arrive(smem_u32(&s_full[(it - la) % stages]));
         }
       }
-      if (n_chunks >= 2) {
-        cp_async_wait<1>();
+      for (int rem = min(la, n_chunks) - 1; rem >= 0; --rem) {
+        cp_async_wait_dyn(rem);
         fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&s_full[(n_chunks - 2) % stages]));
+        mbar_arrive(smem_u32(&s_full[(n_chunks - 1 - rem) % stages]));
       }
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&s_full[(n_chunks - 1) % stages]));
 
       // =============================== epilogue ===============================
       mbar_wait(smem_u32(&s_accum), 0);
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
 int wgrad_plan(WgradArgs& a) {
   PNVO_REQUIRE(a.Cin >= 8 && a.Cin % 8 == 0 && (a.R * a.S == 1 || (a.Cin & (a.Cin - 1)) == 0),
                "wgrad: Cin=%d must be a multiple of 8 (power of two unless 1x1)", a.Cin);
-  PNVO_REQUIRE(a.R * a.S <= 128, "wgrad: filter too large");
+  PNVO_REQUIRE(a.R * a.S <= 64, "wgrad: filter too large");
   PNVO_REQUIRE(a.n_total % 16 == 0, "wgrad: padded Cout=%d must be a multiple of 16", a.n_total);
   if (a.R * a.S == 1) {
     a.cin_log2 = 30;
@@ -222,12 +231,13 @@ int wgrad_plan(WgradArgs& a) {
   a.n_ntiles = a.n_total / N;
   const int nb = (N + 63) / 64;
   int mt = std::min(a.n_mtiles, 512 / N);
-  while (mt > 1 && (mt * 16384 + nb * 8192) > 64 * 1024) --mt;
+  while (mt > 1 && (mt * 16384 + nb * 8192) > 48 * 1024) --mt;
   a.mt = mt;
   int cols = 32;
   while (cols < mt * N) cols <<= 1;
   a.tmem_cols = cols;
-  a.stages = 3;
+  a.stages = std::max(3, std::min(4, (200 * 1024) / (mt * 16384 + nb * 8192)));
+  a.lookahead = a.stages - 2;
   a.smem_bytes = a.stages * (mt * 16384 + nb * 8192) + 1024;
   a.grid_x = ceil_div(a.n_mtiles, mt);
   a.grid_y = a.n_ntiles;

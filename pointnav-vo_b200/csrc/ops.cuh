@@ -17,8 +17,10 @@ struct ConvArgs {
   int n_total, n_store, ldo;
   int cpg, G;
   int out_fp32;
+  int force_generic;   // 1: never use the TMA im2col producer (A/B testing)
+  int tma, chunk_k;    // derived: TMA producer on/off, K elements per pipeline stage (64 or 32)
   // derived by conv_plan
-  int cin_log2, cmask, M, K, nkb, N, tmem_cols, stages, smem_bytes, grid_x, grid_y;
+  int cin_log2, cmask, M, K, nkb, N, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y;
 };
 int conv_plan(ConvArgs& a);
 int conv_launch(ConvArgs a, cudaStream_t st);
@@ -31,8 +33,10 @@ struct WgradArgs {
   int OH, OW;
   int R, S, mul, pad, pad_w;
   int w_ld, n_total, ld_dy;
+  int force_generic;
+  int tma, chunk_k;
   // derived
-  int cin_log2, cmask, M, K, n_mtiles, mt, N, n_ntiles, tmem_cols, stages, smem_bytes, grid_x, grid_y, grid_z, chunks_per_split;
+  int cin_log2, cmask, M, K, n_mtiles, mt, N, n_ntiles, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y, grid_z, chunks_per_split;
 };
 int wgrad_plan(WgradArgs& a);
 int wgrad_launch(WgradArgs a, cudaStream_t st);
