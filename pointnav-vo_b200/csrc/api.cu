@@ -147,6 +147,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = z, p1 = bias, p2 = h32, p3 = h16; i0 = B, i1 = N, i2 = relu
       return bias_relu_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]), i[0], i[1], i[2],
                               static_cast<float*>(p[2]), static_cast<__half*>(p[3]), st);
+    case PNVO_OP_BIAS_RELU_BWD:
+      // p0 = dh, p1 = h, p2 = dz16, p3 = db; i0 = B, i1 = N, i2 = accumulate
+      return bias_relu_bwd_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]), i[0], i[1],
+                                  static_cast<__half*>(p[2]), static_cast<float*>(p[3]), i[2], st);
     case PNVO_OP_HEAD_FWD:
       // p0 = h, p1 = W, p2 = bias, p3 = out; i0 = B, i1 = K, i2 = O
       return head_fwd_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),

@@ -69,6 +69,8 @@ int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_
                      int accumulate, cudaStream_t st);
 int bias_relu_launch(const float* z, const float* bias, int B, int N, int relu, float* h32, __half* h16,
                      cudaStream_t st);
+int bias_relu_bwd_launch(const float* dh, const float* h, int B, int N, __half* dz16, float* db, int accumulate,
+                         cudaStream_t st);
 int head_fwd_launch(const float* h, const float* W, const float* bias, int B, int K, int O, float* out,
                     cudaStream_t st);
 int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,

@@ -720,6 +720,33 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
     db2[threadIdx.x] = accumulate ? db2[threadIdx.x] + v : v;
   }
 }
+// backward of h = relu(z + b): dz = dh * [h > 0] (fp16 for the tensor-core wgrad/dgrad), db = sum_b dz
+__global__ void __launch_bounds__(128) bias_relu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h,
+                                                            int B, int N, __half* __restrict__ dz16,
+                                                            float* __restrict__ db, int accumulate) {
+  const int k = blockIdx.x;
+  __shared__ float s_red[4];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float v = h[static_cast<int64_t>(b) * N + k] > 0.f ? dh[static_cast<int64_t>(b) * N + k] : 0.f;
+    dz16[static_cast<int64_t>(b) * N + k] = __float2half_rn(v);
+    acc += v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float v = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    db[k] = accumulate ? db[k] + v : v;
+  }
+}
+int bias_relu_bwd_launch(const float* dh, const float* h, int B, int N, __half* dz16, float* db, int accumulate,
+                         cudaStream_t st) {
+  if (B <= 0 || N <= 0) return 0;
+  bias_relu_bwd_kernel<<<N, 128, 0, st>>>(dh, h, B, N, dz16, db, accumulate);
+  count_launch();
+  return check_launch("bias_relu_bwd");
+}
 int bias_relu_launch(const float* z, const float* bias, int B, int N, int relu, float* h32, __half* h16,
                      cudaStream_t st) {
   if (B * N <= 0) return 0;

@@ -251,11 +251,13 @@ class EncoderPlan:
         self.raw_c = self._act(B, self.fH, self.fW, self.comp.cout_pad, raw_dt)
         self.feat = self._act(B, self.fH, self.fW, self.comp.cout_pad)
         if self.head is not None:
-            hid, od = self.head["hidden"], self.head["out_dim"]
+            hid, od = self.head["hidden"], self.head.get("out_dim")
+            assert hid == self.fc.cout_pad, "hidden size must be a multiple of 32"
             self.z = torch.empty(B, self.fc.cout_pad, dtype=torch.float32, device=dev)
             self.h32 = torch.empty(B, hid, dtype=torch.float32, device=dev)
             self.h16 = torch.empty(B, hid, dtype=torch.float16, device=dev)
-            self.out = torch.empty(B, od, dtype=torch.float32, device=dev)
+            # with an output layer the plan's result is [B, out_dim]; without, the hidden features [B, hidden]
+            self.out = torch.empty(B, od, dtype=torch.float32, device=dev) if od else self.h32
         if tr:
             # gradient buffers (w.r.t. post-activation tensors, fp16) and raw-gradient scratch
             self.g_feat = torch.empty_like(self.feat)
@@ -271,7 +273,8 @@ class EncoderPlan:
             self.dy1 = torch.empty(self.raw1.shape, dtype=torch.float16, device=dev)
             self.dx1 = torch.empty(self.raw1.shape, dtype=torch.float16, device=dev)
             if self.head is not None:
-                self.dout = torch.zeros(B, self.head["out_dim"], dtype=torch.float32, device=dev)
+                od = self.head.get("out_dim")
+                self.dout = torch.zeros(B, od if od else self.head["hidden"], dtype=torch.float32, device=dev)
                 self.dz16 = torch.zeros(B, self.fc.cout_pad, dtype=torch.float16, device=dev)
             else:
                 self.g_feat_in = self.g_feat
@@ -292,7 +295,9 @@ class EncoderPlan:
         for g in self.all_gns():
             names += [g.key + ".weight", g.key + ".bias"]
         if self.head is not None:
-            names += [self.head["fc_b"], self.head["out_w"], self.head["out_b"]]
+            names += [self.head["fc_b"]]
+            if self.head.get("out_dim"):
+                names += [self.head["out_w"], self.head["out_b"]]
         return names
 
     # ------------------------------------------------------------------------------------------
@@ -349,8 +354,9 @@ class EncoderPlan:
             feat_flat = self.feat  # [B, 1, 1, fH*fW*c_pad] as far as the 1x1 "conv" is concerned
             ops.append(self.fc.op_fwd(feat_flat, self.z, B, None, 0, 0, True))
             ops.append(L.op_bias_relu(self.z, self.P[hd["fc_b"]], self.h32, self.h16, B, hd["hidden"], True))
-            ops.append(L.op_head_fwd(self.h32, self.P[hd["out_w"]], self.P[hd["out_b"]], self.out, B, hd["hidden"],
-                                     hd["out_dim"]))
+            if hd.get("out_dim"):
+                ops.append(L.op_head_fwd(self.h32, self.P[hd["out_w"]], self.P[hd["out_b"]], self.out, B, hd["hidden"],
+                                         hd["out_dim"]))
         self.fwd_ops = ops
         self.fwd_prog = L.Program(ops)
         if not self.training:
@@ -361,9 +367,12 @@ class EncoderPlan:
             ops.append(L.op_zero(c.dwp))
         if self.head is not None:
             hd = self.head
-            ops.append(L.op_head_bwd(self.dout, self.h32, self.P[hd["out_w"]], self.grads[hd["out_w"]],
-                                     self.grads[hd["out_b"]], self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"],
-                                     hd["out_dim"]))
+            if hd.get("out_dim"):
+                ops.append(L.op_head_bwd(self.dout, self.h32, self.P[hd["out_w"]], self.grads[hd["out_w"]],
+                                         self.grads[hd["out_b"]], self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"],
+                                         hd["out_dim"]))
+            else:  # gradient arrives w.r.t. the hidden features
+                ops.append(L.op_bias_relu_bwd(self.dout, self.h32, self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"]))
             ops.append(self.fc.op_wgrad(self.feat, self.dz16, B))
             ops.append(self.fc.op_dgrad(self.dz16, self.g_feat, B))
         HWf = self.fH * self.fW
@@ -407,9 +416,23 @@ class EncoderPlan:
         self.bwd_prog = L.Program(ops)
 
     # ------------------------------------------------------------------------------------------
+    def input_ops(self, obs):
+        """avg-pool input path of the RL encoder (resnet_policy.py:146-168): sources are pooled 2x2 and written
+        into the channel slots of x0 (pad channels stay zero)."""
+        ops, coff = [], 0
+        for k, n, scale in self.sources:
+            t = obs[k]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            assert t.shape[-1] == n
+            ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale))
+            coff += n
+            self._keepalive = t
+        return ops
+
     def conv_flops(self, backward=False):
         f = sum(c.flops(self.B) for c in self.all_convs())
-        if self.head is not None:
+        if self.head is not None and self.head.get("out_dim"):
             f += 2.0 * self.B * self.head["hidden"] * self.head["out_dim"]
         if backward:
             f = 3 * f - self.conv1.flops(self.B)

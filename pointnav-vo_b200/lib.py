@@ -192,6 +192,10 @@ def op_bias_relu(z, bias, h32, h16, B, N, relu=True):
     return _op(OP_BIAS_RELU, [B, N, int(relu)], (), [z, bias, h32, h16])
 
 
+def op_bias_relu_bwd(dh, h, dz16, db, B, N, accumulate=False):
+    return _op(OP_BIAS_RELU_BWD, [B, N, int(accumulate)], (), [dh, h, dz16, db])
+
+
 def op_head_fwd(h, W, bias, out, B, K, O):
     return _op(OP_HEAD_FWD, [B, K, O], (), [h, W, bias, out])
 

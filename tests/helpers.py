@@ -81,3 +81,35 @@ def vo_state_shapes(case):
     from pointnav_vo_b200.vo.models.shapes import vo_state_dict_shapes
     name, space, backbone, kw = VO_CASES[case]
     return vo_state_dict_shapes(space, backbone, act_embed="act_embed" in case, **kw)
+
+
+class _Box:
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
+class _Dict:
+    def __init__(self, spaces):
+        self.spaces = spaces
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n = n
+
+
+def policy_spaces():
+    """gym-like observation / action spaces of the shipped depth-only policy (ddppo_pointnav.yaml)."""
+    return _Dict({"depth": _Box((192, 341, 1)), "pointgoal_with_gps_compass": _Box((2,))}), _Discrete(4)
+
+
+def policy_state_dict(seed=9, device="cpu"):
+    from pointnav_vo_b200.rl.policies.resnet_policy import PointNavResNetPolicy
+
+    obs_space, act_space = policy_spaces()
+    pol = PointNavResNetPolicy(observation_space=obs_space, action_space=act_space, backbone="resnet18",
+                               vis_types=["depth"])
+    proto = {k: np.empty(tuple(v.shape), dtype=np.float32) for k, v in pol.state_dict().items()}
+    sd = synth.fill_state_dict(proto, seed=seed)
+    pol.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return pol.to(device)

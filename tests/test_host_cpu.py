@@ -1,0 +1,173 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/pnvo.h declares,
+the host mirror has the reference's module surface (registry names, state_dict keys and shapes), the
+kernel launch planner accepts every layer of the supported networks, and the data-parallel host logic
+works over gloo with world_size 2."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from pointnav_vo_b200 import lib as L
+
+    return L
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "pnvo.h")).read()
+    declared = set(re.findall(r"\b(pnvo_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pnvo_op", "pnvo_topdown_consts", "pnvo_opcode"}
+    handle = lib.load()
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in include/pnvo.h but not exported"
+    assert set(lib.EXPORTS) <= declared
+    assert handle.pnvo_abi_version() == 1
+
+
+def test_product_path_fails_loudly_without_gpu(lib):
+    from pointnav_vo_b200.utils import geometry_utils as gu
+
+    with pytest.raises(lib.PnvoError):
+        gu.discretize_depth(torch.zeros(4, 4))  # CPU tensor: no fallback
+
+
+def test_registry_names():
+    from pointnav_vo_b200.vo.models import vo_cnn, vo_cnn_act_embed  # noqa: F401
+    from pointnav_vo_b200.rl.policies import resnet_policy  # noqa: F401
+    from pointnav_vo_b200.utils.baseline_registry import baseline_registry as reg
+
+    for n in ["vo_cnn", "vo_cnn_rgb", "vo_cnn_wider", "vo_cnn_deeper", "vo_cnn_rgb_d_dd", "vo_cnn_rgb_d_top_down",
+              "vo_cnn_rgb_dd_top_down", "vo_cnn_d_dd_top_down", "vo_cnn_rgb_d_dd_top_down",
+              "vo_cnn_discretize_depth_top_down", "vo_cnn_act_embed", "vo_cnn_wider_act_embed"]:
+        assert reg.get_vo_model(n) is not None, n
+    assert reg.get_policy("resnet_rnn_policy") is not None
+
+
+@pytest.mark.parametrize("case", ["r18_30ch", "r18_8ch", "r50_8ch", "r18_8ch_act_embed"])
+def test_state_dict_keys_and_shapes_match_reference(case, golden_dir):
+    from tests import helpers
+
+    g = np.load(os.path.join(golden_dir, f"vo_{case}.npz"))
+    shapes = helpers.vo_state_shapes(case)
+    assert [str(k) for k in g["keys"]] == list(shapes.keys())
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert tuple(g[k].shape) == shapes[k[5:]], k
+
+
+def test_policy_state_dict_keys(golden_dir):
+    from pointnav_vo_b200.rl.policies.resnet_policy import PointNavResNetPolicy
+    from tests.helpers import policy_spaces
+
+    obs_space, act_space = policy_spaces()
+    pol = PointNavResNetPolicy(observation_space=obs_space, action_space=act_space, backbone="resnet18",
+                               vis_types=["depth"])
+    g = np.load(os.path.join(golden_dir, "policy_r18_depth.npz"))
+    assert [str(k) for k in g["keys"]] == list(pol.state_dict().keys())
+    assert tuple(g["output_shape"]) == tuple(pol.net.visual_encoder.output_shape)
+
+
+def test_topdown_host_constants_match_oracle():
+    from oracle import preproc_oracle as po
+    from pointnav_vo_b200.utils.geometry_utils import NormalizedDepth2TopDownViewHabitatTorch as TD
+
+    orc, mine = po.TopDownOracle(), TD(0.1, 10.0, 192, 341, 70)
+    assert np.array_equal(orc.ray, mine._ray)
+    c = mine._consts
+    for a, b in [(orc.min_x, c.min_x), (orc.x_den, c.x_den), (orc.z_den, c.z_den), (orc.depth_scale, c.depth_scale),
+                 (orc.depth_off, c.depth_off)]:
+        assert np.float32(a) == np.float32(b)
+
+
+def test_launch_planner_covers_every_layer(lib):
+    """conv_plan (no GPU needed) accepts fprop / dgrad / wgrad of every layer of R18-30ch, R50-8ch and the policy."""
+    from pointnav_vo_b200.engine import ConvLayer, LinearLayer, RESNET_LAYERS
+
+    def layers(backbone, cin, H, W, comp, fc_hidden=512):
+        kind, nb = RESNET_LAYERS[backbone]
+        out = [ConvLayer("c1", cin, 32, 7, 7, 2, 3, H, W, need_dgrad=False, cin_pad=max(8, 1 << (cin - 1).bit_length()))]
+        h, w = (out[0].OH + 1) // 2, (out[0].OW + 1) // 2
+        inpl, exp = 32, (1 if kind == "basic" else 4)
+        for li, n in enumerate(nb):
+            planes = 32 * 2 ** li
+            for b in range(n):
+                s = 2 if (b == 0 and li > 0) else 1
+                if kind == "basic":
+                    cs = [ConvLayer("a", inpl, planes, 3, 3, s, 1, h, w)]
+                    cs.append(ConvLayer("b", planes, planes, 3, 3, 1, 1, cs[0].OH, cs[0].OW))
+                else:
+                    cs = [ConvLayer("a", inpl, planes, 1, 1, 1, 0, h, w), ConvLayer("b", planes, planes, 3, 3, s, 1, h, w)]
+                    cs.append(ConvLayer("c", planes, planes * 4, 1, 1, 1, 0, cs[1].OH, cs[1].OW))
+                if b == 0 and (s != 1 or inpl != planes * exp):
+                    cs.append(ConvLayer("d", inpl, planes * exp, 1, 1, s, 0, h, w))
+                out += cs
+                h, w, inpl = cs[-2 if len(cs) > 2 and cs[-1].key == "d" else -1].OH, cs[0 if kind == "basic" else 1].OW, planes * exp
+                h = cs[0 if kind == "basic" else 1].OH
+        out.append(ConvLayer("comp", inpl, comp, 3, 3, 1, 1, h, w))
+        out.append(LinearLayer("fc", comp, h, w, out[-1].cout_pad, fc_hidden))
+        return out
+
+    n = 0
+    for args in [("resnet18", 30, 192, 341, 31), ("resnet50", 8, 192, 341, 31), ("resnet18", 1, 96, 170, 114)]:
+        for c in layers(*args):
+            for B in (1, 256):
+                info = lib.conv_launch_info(c.op_fwd(None, None, B, None, 2, 16))
+                assert info["smem_bytes"] <= 200 * 1024 and info["tmem_cols"] <= 512
+                if c.need_dgrad:
+                    assert lib.conv_launch_info(c.op_dgrad(None, None, B))["smem_bytes"] <= 200 * 1024
+                assert lib.conv_launch_info(c.op_wgrad(None, None, B))["tmem_cols"] <= 512
+                n += 1
+    assert n > 100
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pointnav_vo_b200.parallel_utils import allreduce_flat_bucket, merge_input_stats
+
+        # flat gradient bucket: SUM all-reduce; the 1/world factor lives in the loss-gradient kernel
+        g = torch.full((1000,), float(rank + 1))
+        allreduce_flat_bucket(g)
+        ok = bool(torch.all(g == sum(range(1, world + 1))))
+        # RunningMeanAndVar: packed (sum, sumsq) all-reduce == statistics of the concatenated batch
+        torch.manual_seed(rank)
+        x = torch.rand(4, 3, 8, 8, dtype=torch.float64) + rank
+        packed = torch.stack((x.sum((0, 2, 3)), (x * x).sum((0, 2, 3))), 1).reshape(-1)
+        mean, var = merge_input_stats(packed, n_local=4, pix=64)
+        xs = [None] * world
+        dist.all_gather_object(xs, x)
+        full = torch.cat(xs)
+        ok &= torch.allclose(mean, full.mean((0, 2, 3))) and torch.allclose(var, full.var((0, 2, 3), unbiased=False))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
