@@ -331,6 +331,7 @@ using namespace pnvo;
 extern "C" int pnvo_discretize_depth(const float* depth, int64_t n_pix, const float* edges, int n_channels,
                                      float* onehot, int64_t onehot_stride, uint8_t* index, int32_t* err_count,
                                      void* stream) {
+  if (n_pix <= 0) return 0;
   PNVO_REQUIRE(depth && edges, "discretize_depth: null input");
   PNVO_REQUIRE(n_channels >= 1 && n_channels <= 64, "discretize_depth: n_channels %d not in [1,64]", n_channels);
   PNVO_REQUIRE(!onehot || onehot_stride >= n_channels, "discretize_depth: onehot_stride < n_channels");
