@@ -10,13 +10,14 @@
 // coalesced fp32 atomics into the packed dW buffer.
 #include "common.cuh"
 #include "ops.cuh"
+#include "tmap.cuh"
 
 namespace pnvo {
 
 static constexpr int kPix = 64;  // pixels (GEMM-K) per stage
 static constexpr int kWProducerThreads = 128;
 
-__global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
+__global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p, const __grid_constant__ ConvTmaps tm) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_full[4];
   __shared__ __align__(8) uint64_t s_empty[4];
@@ -36,14 +37,19 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
   const int n_chunks = max(0, c_end - c_begin);
   const int nb = (p.N + 63) >> 6;                           // 64-channel blocks of the dy tile
   const uint32_t a_bytes = static_cast<uint32_t>(p.mt) * 2 * 8192;
-  const uint32_t b_bytes = static_cast<uint32_t>(nb) * 8192;
+  // TMA path: A blocks are chunk_k (32 or 64) k-columns wide, dy blocks min(64, N) channels wide; a pixel row of a
+  // block is 64 or 128 bytes (SWIZZLE_64B / SWIZZLE_128B).  The cp.async path always uses 128-byte rows.
+  const uint32_t a_row = p.tma ? static_cast<uint32_t>(p.chunk_k) * 2 : 128u;
+  const int b_cols = p.tma ? min(64, p.N) : 64;
+  const uint32_t b_row = static_cast<uint32_t>(b_cols) * 2;
+  const uint32_t b_bytes = p.tma ? static_cast<uint32_t>(p.N / b_cols) * kPix * b_row : static_cast<uint32_t>(nb) * 8192;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
   for (int i = tid; i < p.R * p.S; i += blockDim.x) s_tap[i] = make_short2(i / p.S, i % p.S);
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kWProducerThreads);
+      mbar_init(smem_u32(&s_full[s]), p.tma ? 1 : kWProducerThreads);
       mbar_init(smem_u32(&s_empty[s]), 1);
     }
     mbar_init(smem_u32(&s_accum), 1);
@@ -58,8 +64,52 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
+  if (n_chunks > 0 && p.tma) {
+    // k tiles past the end of K (zero-padded rows of dW) are never loaded: clear them once so the MMA reads zeros
+    if ((tile0 + p.mt) * 128 > p.K) {
+      for (uint32_t off = tid * 16; off < static_cast<uint32_t>(stages) * stage_bytes; off += blockDim.x * 16)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + off), "r"(0u) : "memory");
+      fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // ================================ TMA producer ================================
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      const int ohw = p.OH * p.OW;
+      const int blocks_per_tile = 128 / p.chunk_k;
+      const uint32_t a_blk_bytes = kPix * a_row, b_blk_bytes = kPix * b_row;
+      const int n_bblk = p.N / b_cols;
+      int n_ablk = 0;  // blocks with k < K
+      for (int blk = 0; blk < mt * blocks_per_tile; ++blk) n_ablk += ((tile0 * 128 + blk * p.chunk_k) < p.K) ? 1 : 0;
+      const uint32_t tx = static_cast<uint32_t>(n_ablk) * a_blk_bytes + static_cast<uint32_t>(n_bblk) * b_blk_bytes;
+      for (int it = 0; it < n_chunks; ++it) {
+        const int s = it % stages;
+        if (it >= stages) mbar_wait(smem_u32(&s_empty[s]), ((it / stages) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&s_full[s]);
+        const uint32_t sA = smem_base + s * stage_bytes;
+        const int mc = (c_begin + it) * kPix;
+        const int n_img = mc / ohw;
+        const int rem = mc - n_img * ohw;
+        const int p0 = rem / p.OW, q0 = rem - p0 * p.OW;
+        const int w0 = q0 * p.mul - p.pad_w, h0 = p0 * p.mul - p.pad;
+        mbar_arrive_expect_tx(bar, tx);
+        for (int blk = 0; blk < mt * blocks_per_tile; ++blk) {
+          const int kf = tile0 * 128 + blk * p.chunk_k;
+          if (kf < p.K) {
+            const short2 rs = s_tap[kf >> p.cin_log2];
+            tma_load_im2col_4d(sA + blk * a_blk_bytes, &tm.a, bar, kf & p.cmask, w0, h0, n_img,
+                               static_cast<uint16_t>(rs.y), static_cast<uint16_t>(rs.x));
+          }
+        }
+        for (int blk = 0; blk < n_bblk; ++blk)
+          tma_load_2d(sA + a_bytes + blk * b_blk_bytes, &tm.b, bar, n0 + blk * b_cols, mc);
+      }
+    }
+  }
   if (n_chunks > 0) {
     if (warp < 4) {
+      if (!p.tma) {
       // =============================== producers ===============================
       // Thread t owns 16-byte chunk j = t % 8 of pixel rows (t / 8) + 16 i, i = 0..3, in every 64-wide
       // column block: the 8 lanes of a row fetch one contiguous 128-byte line (coalesced L2 requests).
@@ -150,6 +200,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
         mbar_arrive(smem_u32(&s_full[(n_chunks - 1 - rem) % stages]));
       }
 
+      }  // !tma
       // =============================== epilogue ===============================
       mbar_wait(smem_u32(&s_accum), 0);
       tc_fence_after();
@@ -179,14 +230,16 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p) {
           mbar_wait(smem_u32(&s_full[s]), (it / stages) & 1);
           tc_fence_after();
           const uint32_t sA = smem_base + s * stage_bytes;
-          const uint64_t bdesc = umma_desc_sw128(sA + a_bytes, 8192, 1024);
+          // MN-major operands: LBO = distance between successive M/N blocks (64 pixel rows), SBO = 8 pixel rows
+          const uint64_t bdesc = umma_desc(sA + a_bytes, kPix * b_row, 8 * b_row, b_row);
 #pragma unroll
           for (int k = 0; k < kPix / 16; ++k) {
-            // 16 pixels of K = two 8-row groups = 2048 bytes
-            const uint64_t koff = static_cast<uint64_t>((k * 2048) >> 4);
+            // 16 pixels of GEMM-K = 16 rows of each block
+            const uint64_t koff_a = static_cast<uint64_t>((k * 16 * a_row) >> 4);
+            const uint64_t koff_b = static_cast<uint64_t>((k * 16 * b_row) >> 4);
             for (int i = 0; i < mt; ++i) {
-              const uint64_t adesc = umma_desc_sw128(sA + static_cast<uint32_t>(i) * 16384, 8192, 1024);
-              tc_mma_f16(tmem_base + static_cast<uint32_t>(i * p.N), adesc + koff, bdesc + koff, idesc,
+              const uint64_t adesc = umma_desc(sA + static_cast<uint32_t>(i) * 16384, kPix * a_row, 8 * a_row, a_row);
+              tc_mma_f16(tmem_base + static_cast<uint32_t>(i * p.N), adesc + koff_a, bdesc + koff_b, idesc,
                          (it | k) != 0 ? 1u : 0u);
             }
           }
@@ -220,6 +273,8 @@ int wgrad_plan(WgradArgs& a) {
   }
   a.M = a.B * a.OH * a.OW;
   a.K = a.R * a.S * a.Cin;
+  a.tma = (a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && !a.force_generic) ? 1 : 0;
+  a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : 64;
   PNVO_REQUIRE(a.w_ld >= a.K, "wgrad: w_ld %d < K %d", a.w_ld, a.K);
   a.n_mtiles = ceil_div(a.K, 128);
   int N = a.n_total;
@@ -259,7 +314,13 @@ int wgrad_launch(WgradArgs a, cudaStream_t st) {
     cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  conv_wgrad_kernel<<<dim3(a.grid_x, a.grid_y, a.grid_z), 160, a.smem_bytes, st>>>(a);
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (a.tma) {
+    if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kPix)) return -1;
+    if (tmap_tiled2d(&tm.b, a.dy, a.M, a.n_total, a.ld_dy, kPix, std::min(64, a.N))) return -1;
+  }
+  conv_wgrad_kernel<<<dim3(a.grid_x, a.grid_y, a.grid_z), 160, a.smem_bytes, st>>>(a, tm);
   count_launch();
   return check_launch("conv_wgrad");
 }

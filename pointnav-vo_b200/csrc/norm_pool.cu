@@ -103,50 +103,63 @@ __global__ void __launch_bounds__(kAsmPix) assemble_kernel(const AssembleArgs a)
   }
 }
 
-// per-channel sum / sum of squares of the assembled (un-normalised) input: fp32 per-thread partials over
-// kStatsTiles pixels, fp64 from the warp reduction upwards
-static constexpr int kStatsTiles = 8;
-__global__ void __launch_bounds__(kAsmPix) input_stats_kernel(const AssembleArgs a, double* __restrict__ stats) {
-  extern __shared__ __align__(16) float s_src[];
-  __shared__ double s_acc[2 * kMaxInC];
-  __shared__ int s_base[4];
-  if (threadIdx.x < 2 * kMaxInC) s_acc[threadIdx.x] = 0.0;
-  float s[kMaxInC], q[kMaxInC];
+// per-channel sum / sum of squares of the assembled (un-normalised) input.  Each source tensor is streamed as a
+// flat float4 array: with nch channels per pixel the channel of a float4 lane repeats every lcm(nch,4)/4
+// vectors, so a thread whose vector index advances in multiples of that period keeps a FIXED channel per lane
+// and accumulates in 8 registers (no gathers, fully coalesced 16-byte loads).  Block partials are combined in
+// shared memory in a fixed order and added to the fp64 global accumulator with one atomic per channel.
+static constexpr int kStatsThreads = 240;   // multiple of every period (1, 3, 5 for nch = 2, 6, 20)
+static constexpr int kStatsVecPerThread = 64;
+__global__ void __launch_bounds__(kStatsThreads) input_stats_kernel(const AssembleArgs a, double* __restrict__ stats,
+                                                                    int t, int period, int64_t n_vec) {
+  __shared__ float s_part[kStatsThreads][8];
+  const int nch = a.nch[t];
+  const float pre = a.pre_scale[t];
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(a.src[t]);
+  float acc[8];
 #pragma unroll
-  for (int c = 0; c < kMaxInC; ++c) s[c] = q[c] = 0.f;
-  for (int it = 0; it < kStatsTiles; ++it) {
-    const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kStatsTiles + it) * kAsmPix;
-    if (pix0 >= a.n_pix) break;
-    const int npix = static_cast<int>(min(static_cast<int64_t>(kAsmPix), a.n_pix - pix0));
-    __syncthreads();
-    stage_sources(a, pix0, npix, s_src, s_base);
-    __syncthreads();
-    if (static_cast<int>(threadIdx.x) < npix) {
-      float v[kMaxInC];
-      pick_pixel(a, s_src, s_base, threadIdx.x, v);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kStatsThreads * kStatsVecPerThread + threadIdx.x;
+#pragma unroll 8
+  for (int k = 0; k < kStatsVecPerThread; ++k) {
+    const int64_t i = base + static_cast<int64_t>(k) * kStatsThreads;
+    if (i < n_vec) {
+      float4 v = __ldg(src + i);
+      v.x *= pre; v.y *= pre; v.z *= pre; v.w *= pre;
+      acc[0] += v.x; acc[1] = fmaf(v.x, v.x, acc[1]);
+      acc[2] += v.y; acc[3] = fmaf(v.y, v.y, acc[3]);
+      acc[4] += v.z; acc[5] = fmaf(v.z, v.z, acc[5]);
+      acc[6] += v.w; acc[7] = fmaf(v.w, v.w, acc[7]);
+    }
+  }
 #pragma unroll
-      for (int c = 0; c < kMaxInC; ++c) {
-        s[c] += v[c];
-        q[c] = fmaf(v[c], v[c], q[c]);
+  for (int i = 0; i < 8; ++i) s_part[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  // thread c < nch sums lane e of every thread whose (vector index * 4 + e) % nch == c
+  const int c = threadIdx.x;
+  if (c < nch) {
+    double ds = 0.0, dq = 0.0;
+    for (int r = 0; r < period; ++r) {        // residue class of the vector index modulo the period
+      for (int e = 0; e < 4; ++e) {
+        if ((r * 4 + e) % nch != c) continue;
+        float fs = 0.f, fq = 0.f;
+        for (int th = r; th < kStatsThreads; th += period) {
+          fs += s_part[th][2 * e];
+          fq += s_part[th][2 * e + 1];
+        }
+        ds += fs;
+        dq += fq;
       }
     }
-  }
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int c = 0; c < kMaxInC; ++c) {
-    double ds = s[c], dq = q[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ds += __shfl_xor_sync(0xffffffffu, ds, o);
-      dq += __shfl_xor_sync(0xffffffffu, dq, o);
-    }
-    if (lane == 0 && c < a.C) {
-      atomicAdd(&s_acc[2 * c], ds);
-      atomicAdd(&s_acc[2 * c + 1], dq);
+    // output channel of (source t, channel c): prev half -> first block, cur half -> second block
+    int oc = -1;
+    for (int o = 0; o < a.C; ++o)
+      if (a.src_idx[o] == t && a.src_ch[o] == c) oc = o;
+    if (oc >= 0) {
+      atomicAdd(stats + 2 * oc, ds);
+      atomicAdd(stats + 2 * oc + 1, dq);
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 2 * a.C) atomicAdd(stats + threadIdx.x, s_acc[threadIdx.x]);
 }
 
 // RunningMeanAndVar (running_mean_and_var.py:22-63): optional Chan merge of the batch statistics into
@@ -203,11 +216,19 @@ int assemble_launch(const AssembleArgs& a, cudaStream_t st) {
 int input_stats_launch(const AssembleArgs& a, double* stats, cudaStream_t st) {
   PNVO_REQUIRE(a.C <= kMaxInC, "input_stats: too many channels");
   if (a.n_pix <= 0) return 0;
-  int tot = 0;
-  for (int t = 0; t < a.n_src; ++t) tot += a.nch[t];
-  input_stats_kernel<<<static_cast<int>(ceil_div64(a.n_pix, kAsmPix * kStatsTiles)), kAsmPix,
-                       tot * kAsmPix * sizeof(float), st>>>(a, stats);
-  count_launch();
+  for (int t = 0; t < a.n_src; ++t) {
+    const int nch = a.nch[t];
+    int period = 1;
+    while ((period * 4) % nch != 0) ++period;  // lcm(nch, 4) / 4
+    PNVO_REQUIRE(kStatsThreads % period == 0, "input_stats: %d channels per pixel not supported", nch);
+    const int64_t n_float = a.n_pix * nch;
+    PNVO_REQUIRE(n_float % 4 == 0, "input_stats: source %d size not a multiple of 4 floats", t);
+    const int64_t n_vec = n_float / 4;
+    // block size 240 and 64 vectors per thread keep (block start) a multiple of every period
+    const int blocks = static_cast<int>(ceil_div64(n_vec, static_cast<int64_t>(kStatsThreads) * kStatsVecPerThread));
+    input_stats_kernel<<<blocks, kStatsThreads, 0, st>>>(a, stats, t, period, n_vec);
+    count_launch();
+  }
   return check_launch("input_stats");
 }
 int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample, float* mean, float* var,
@@ -455,7 +476,16 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
         sx[e] = fmaf(g[e], xh, sx[e]);
       }
     }
-    if (start < per_sample) {
+    // lanes l and l + c8 (+ 2 c8 ...) of a warp own the same 8 channels: combine them with shuffles first
+    // (for C = 32 this turns 512 shared-memory atomics per warp on 64 addresses into 64)
+    for (int off = 16; off >= c8 && off >= 1; off >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], off);
+        sx[e] += __shfl_xor_sync(0xffffffffu, sx[e], off);
+      }
+    }
+    if ((threadIdx.x & 31) < c8 || c8 >= 32) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         atomicAdd(&s_acc[2 * (cc + e)], sd[e]);
@@ -520,18 +550,24 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
   }
 }
 
-// dgamma[c] = sum_b sums[b][c][1], dbeta[c] = sum_b sums[b][c][0]
-__global__ void gn_param_grad_kernel(const float* __restrict__ sums, int B, int C, int C_real,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// dgamma[c] = sum_b sums[b][c][1], dbeta[c] = sum_b sums[b][c][0]; one warp per channel, lanes over the batch
+__global__ void __launch_bounds__(128) gn_param_grad_kernel(const float* __restrict__ sums, int B, int C, int C_real,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int accumulate) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C_real) return;
   float dg = 0.f, db = 0.f;
-  for (int b = 0; b < B; ++b) {
-    db += sums[(static_cast<int64_t>(b) * C + c) * 2];
-    dg += sums[(static_cast<int64_t>(b) * C + c) * 2 + 1];
+  for (int b = lane; b < B; b += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(sums + (static_cast<int64_t>(b) * C + c) * 2);
+    db += v.x;
+    dg += v.y;
   }
-  if (accumulate) { dgamma[c] += dg; dbeta[c] += db; }
-  else { dgamma[c] = dg; dbeta[c] = db; }
+  dg = warp_sum(dg);
+  db = warp_sum(db);
+  if (lane == 0) {
+    if (accumulate) { dgamma[c] += dg; dbeta[c] += db; }
+    else { dgamma[c] = dg; dbeta[c] = db; }
+  }
 }
 
 static int gn_grid_x(int64_t per_sample_items, int B, int c8) {
@@ -587,7 +623,7 @@ int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
 }
 int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st) {
-  gn_param_grad_kernel<<<ceil_div(C_real, 128), 128, 0, st>>>(sums, B, C, C_real, dgamma, dbeta, accumulate);
+  gn_param_grad_kernel<<<ceil_div(C_real * 32, 128), 128, 0, st>>>(sums, B, C, C_real, dgamma, dbeta, accumulate);
   count_launch();
   return check_launch("gn_param_grad");
 }
