@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-A step = one training step (forward + backward + Adam) of the shipped default VO model
+A step = one training step (forward + backward + Adam, dropout 0.2 as the reference trains) of the shipped default VO model
 (vo_cnn_rgb_d_dd_top_down, GroupNorm-ResNet-18, 30 input channels) on a batch of 256 synthetic frame
 pairs per GPU (BASELINE configs[1]).  `value` times the step with the model inputs already resident in
 HBM; `e2e` times the same step from pinned HOST buffers (uint8 rgb + fp32 depth), including the H2D
@@ -98,7 +98,7 @@ def synth_batch(B, seed):
     return rgb, dep, tgt
 
 
-def build_model(device, dropout_p=0.0):
+def build_model(device, dropout_p=0.2):
     from pointnav_vo_b200.vo.models import vo_cnn
 
     torch.manual_seed(0)

@@ -106,7 +106,8 @@ enum pnvo_opcode {
   PNVO_OP_AVGPOOL2 = 20,      /* F.avg_pool2d(x, 2) -> fp16 NHWC (resnet_policy.py:168) */
   PNVO_OP_GN_PARAM_GRAD = 21, /* dgamma/dbeta from the per-(sample,channel) sums */
   PNVO_OP_CAST = 22,          /* fp32 <-> fp16 copies with channel padding */
-  PNVO_OP_MAX = 23
+  PNVO_OP_DROPOUT = 23,       /* in-place inverted dropout, counter-based generator (vo_cnn.py:218,224) */
+  PNVO_OP_MAX = 24
 };
 
 typedef struct {

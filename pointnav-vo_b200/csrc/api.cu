@@ -126,7 +126,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.stats = static_cast<const float*>(p[3]); a.gamma = static_cast<const float*>(p[4]);
       a.sums = static_cast<float*>(p[5]); a.dx = static_cast<__half*>(p[6]); a.dy_out = static_cast<__half*>(p[7]);
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.x_fp32 = i[6]; a.C_real = i[11];
-      a.cnt = f[0]; a.eps = f[1];
+      a.cnt = f[0]; a.eps = f[1]; a.g_scale = (f[2] == 0.f) ? 1.f : f[2];
       if (op.code == PNVO_OP_GN_BWD_REDUCE) return gn_bwd_reduce_launch(a, i[0], st);
       return gn_bwd_apply_launch(a, i[0], st);
     }
@@ -159,13 +159,18 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = dout, p1 = h, p2 = W, p3 = dW, p4 = db2, p5 = dz16, p6 = db1; i0 = B, i1 = K, i2 = O, i3 = accumulate
       return head_bwd_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
                              static_cast<const float*>(p[2]), i[0], i[1], i[2], static_cast<float*>(p[3]),
-                             static_cast<float*>(p[4]), static_cast<__half*>(p[5]), static_cast<float*>(p[6]), i[3], st);
+                             static_cast<float*>(p[4]), static_cast<__half*>(p[5]), static_cast<float*>(p[6]), i[3],
+                             (f[0] == 0.f) ? 1.f : f[0], st);
     case PNVO_OP_MSE_LOSS:
       // p0 = pred, p1 = target, p2 = dz mask (nullable), p3 = dout (nullable), p4 = loss; i0 = B, i1 = O;
       // f0..f2 = loss weights, f3 = gradient scale
       return mse_loss_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
                              static_cast<const float*>(p[2]), i[0], i[1], f[0], f[1], f[2], f[3],
                              static_cast<float*>(p[3]), static_cast<float*>(p[4]), st);
+    case PNVO_OP_DROPOUT:
+      // p0 = buffer (in place), p1 = uint64 seed on device; i0|i1 = n, i2 = is_fp16, i3 = site, i4 = advance seed; f0 = p
+      return dropout_launch(p[0], (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), i[2],
+                            static_cast<uint64_t*>(p[1]), i[3], f[0], i[4], st);
     case PNVO_OP_ADAM:
       // p0 = param, p1 = grad, p2 = m, p3 = v; i0|i1 = n, i2 = step; f0 = lr, f1 = beta1, f2 = beta2, f3 = eps
       return adam_launch(static_cast<float*>(p[0]), static_cast<const float*>(p[1]), static_cast<float*>(p[2]),

@@ -57,6 +57,7 @@ struct GnBwdArgs {
   __half* dy_out;          // apply pass, optional: masked g (identity-branch gradient)
   int C, C_real, G, cpg, HW;
   float cnt, eps;
+  float g_scale;           // multiplies the incoming gradient where the ReLU mask is set (inverted dropout)
 };
 int gn_bwd_reduce_launch(const GnBwdArgs& a, int B, cudaStream_t st);
 int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st);
@@ -74,7 +75,8 @@ int bias_relu_bwd_launch(const float* dh, const float* h, int B, int N, __half* 
 int head_fwd_launch(const float* h, const float* W, const float* bias, int B, int K, int O, float* out,
                     cudaStream_t st);
 int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,
-                    __half* dz16, float* db1, int accumulate, cudaStream_t st);
+                    __half* dz16, float* db1, int accumulate, float dh_scale, cudaStream_t st);
+int dropout_launch(void* buf, int64_t n, int is_fp16, uint64_t* seed, int site, float p, int advance, cudaStream_t st);
 int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, int B, int O, float w0, float w1,
                     float w2, float grad_scale, float* dout, float* loss, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,

@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
         float y[8];
         load8(a.relu_ref, base + i, 0, y);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] : 0.f;
+        for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] * a.g_scale : 0.f;
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
       float y[8];
       load8(a.relu_ref, base + i, 0, y);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] : 0.f;
+      for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] * a.g_scale : 0.f;
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ W, int B, int K, int O,
                                                        float* __restrict__ dW, float* __restrict__ db2,
                                                        __half* __restrict__ dz16, float* __restrict__ db1,
-                                                       int accumulate) {
+                                                       int accumulate, float dh_scale) {
   const int k = blockIdx.x;
   __shared__ float s_red[4][9];
   float accW[8];
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
       accW[o] = fmaf(d, hv, accW[o]);
       dh = fmaf(d, W[static_cast<int64_t>(o) * K + k], dh);
     }
-    const float dzv = hv > 0.f ? dh : 0.f;
+    const float dzv = hv > 0.f ? dh * dh_scale : 0.f;  // h is post-dropout: zeros carry the mask
     dz16[static_cast<int64_t>(b) * K + k] = __float2half_rn(dzv);
     accb1 += dzv;
   }
@@ -798,12 +798,53 @@ int head_fwd_launch(const float* h, const float* W, const float* bias, int B, in
   return check_launch("head_fwd");
 }
 int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,
-                    __half* dz16, float* db1, int accumulate, cudaStream_t st) {
+                    __half* dz16, float* db1, int accumulate, float dh_scale, cudaStream_t st) {
   PNVO_REQUIRE(O <= 8, "head_bwd: output_dim %d > 8", O);
   if (B <= 0) return 0;
-  head_bwd_kernel<<<K, 128, 0, st>>>(dout, h, W, B, K, O, dW, db2, dz16, db1, accumulate);
+  head_bwd_kernel<<<K, 128, 0, st>>>(dout, h, W, B, K, O, dW, db2, dz16, db1, accumulate, dh_scale);
   count_launch();
   return check_launch("head_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverted dropout, in place (vo_cnn.py:218,224: nn.Dropout(p) before both Linear layers).  The keep mask
+// is a counter-based hash of (seed, site, element index); the seed lives in device memory and is advanced
+// by a one-thread kernel after the last dropout site of a forward pass, so replayed op programs draw fresh
+// masks.  The mask is not stored: the backward pass recovers it from the zeros of the post-ReLU tensor.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_u32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return static_cast<uint32_t>(x >> 16);
+}
+__global__ void dropout_kernel(void* __restrict__ buf, int64_t n, int is_fp16, const uint64_t* __restrict__ seed,
+                               uint64_t site, uint32_t thresh, float scale) {
+  const uint64_t s0 = *seed + site * 0x9E3779B97F4A7C15ULL;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool keep = hash_u32(s0 + static_cast<uint64_t>(i) * 0xD6E8FEB86659FD93ULL) >= thresh;
+    if (is_fp16) {
+      __half* p = static_cast<__half*>(buf);
+      p[i] = keep ? __float2half_rn(__half2float(p[i]) * scale) : __float2half_rn(0.f);
+    } else {
+      float* p = static_cast<float*>(buf);
+      p[i] = keep ? p[i] * scale : 0.f;
+    }
+  }
+}
+__global__ void seed_advance_kernel(uint64_t* seed) { *seed = *seed * 6364136223846793005ULL + 1442695040888963407ULL; }
+int dropout_launch(void* buf, int64_t n, int is_fp16, uint64_t* seed, int site, float p, int advance, cudaStream_t st) {
+  PNVO_REQUIRE(buf && seed && p >= 0.f && p < 1.f, "dropout: bad arguments");
+  if (n > 0 && p > 0.f) {
+    const uint32_t thresh = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+    dropout_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 148 * 8)), 256, 0, st>>>(
+        buf, n, is_fp16, seed, static_cast<uint64_t>(site), thresh, 1.f / (1.f - p));
+    count_launch();
+  }
+  if (advance) {
+    seed_advance_kernel<<<1, 1, 0, st>>>(seed);
+    count_launch();
+  }
+  return check_launch("dropout");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -118,7 +118,7 @@ class EncoderPlan:
 
     def __init__(self, *, params, buffers, B, H, W, in_channels, sources, backbone, baseplanes, ngroups,
                  compression_channels, prefix, head=None, training=True, avgpool_input=False, device="cuda",
-                 world_size=1, raw_fp32=False):
+                 world_size=1, raw_fp32=False, dropout_p=0.0):
         """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
         head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim)."""
@@ -133,6 +133,7 @@ class EncoderPlan:
         self.world_size = world_size
         self.raw_fp32 = raw_fp32
         self.head = head
+        self.dropout_p = float(dropout_p) if head is not None and head.get("out_dim") else 0.0
         self.grads = {}
         self._build_layers(backbone, baseplanes, ngroups, compression_channels)
         self._alloc()
@@ -234,6 +235,7 @@ class EncoderPlan:
         if self.avgpool_input:
             self.x0.zero_()  # pad channels stay zero (avgpool writes only the real ones)
         self.in_stats = torch.zeros(2 * 32 + 2, dtype=torch.float64, device=dev)
+        self.drop_seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
         self.in_scale = torch.ones(32, dtype=torch.float32, device=dev)
         self.in_shift = torch.zeros(32, dtype=torch.float32, device=dev)
         c1 = self.conv1
@@ -306,15 +308,15 @@ class EncoderPlan:
         return L.op_gn_apply(x, g.stats, self.P[g.key + ".weight"], self.P[g.key + ".bias"], y, B, g.C, g.G, g.cpg, HW,
                              float(g.cpg_real * HW), relu, res, self.raw_fp32, 1e-5, g.C_real)
 
-    def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW):
+    def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
         return L.op_gn_bwd(reduce, gin, relu_ref, x, g.stats, self.P[g.key + ".weight"], g.sums, dx, dy_out, self.B,
-                           g.C, g.G, g.cpg, HW, float(g.cpg_real * HW), self.raw_fp32, 1e-5, g.C_real)
+                           g.C, g.G, g.cpg, HW, float(g.cpg_real * HW), self.raw_fp32, 1e-5, g.C_real, g_scale)
 
-    def _gn_bwd_all(self, ops, g, gin, relu_ref, x, dx, dy_out, HW):
-        ops.append(self._gn_bwd(True, g, gin, relu_ref, x, dx, dy_out, HW))
+    def _gn_bwd_all(self, ops, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
+        ops.append(self._gn_bwd(True, g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
         ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B, g.C,
                                       g.C_real))
-        ops.append(self._gn_bwd(False, g, gin, relu_ref, x, dx, dy_out, HW))
+        ops.append(self._gn_bwd(False, g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
 
     def _build_programs(self):
         B = self.B
@@ -349,11 +351,16 @@ class EncoderPlan:
         cc, gc = self.comp, self.gnc
         ops.append(cc.op_fwd(x, self.raw_c, B, gc.stats, gc.cpg, gc.G, self.raw_fp32))
         ops.append(self._gn_apply(gc, self.raw_c, self.feat, self.fH * self.fW, relu=True))
+        p_drop = self.dropout_p
+        if p_drop > 0:  # nn.Dropout in front of visual_fc (vo_cnn.py:218)
+            ops.append(L.op_dropout(self.feat, self.drop_seed, 0, p_drop))
         if self.head is not None:
             hd = self.head
             feat_flat = self.feat  # [B, 1, 1, fH*fW*c_pad] as far as the 1x1 "conv" is concerned
             ops.append(self.fc.op_fwd(feat_flat, self.z, B, None, 0, 0, True))
             ops.append(L.op_bias_relu(self.z, self.P[hd["fc_b"]], self.h32, self.h16, B, hd["hidden"], True))
+            if p_drop > 0:  # nn.Dropout in front of output_head (vo_cnn.py:224)
+                ops.append(L.op_dropout(self.h32, self.drop_seed, 1, p_drop, advance=True))
             if hd.get("out_dim"):
                 ops.append(L.op_head_fwd(self.h32, self.P[hd["out_w"]], self.P[hd["out_b"]], self.out, B, hd["hidden"],
                                          hd["out_dim"]))
@@ -370,13 +377,14 @@ class EncoderPlan:
             if hd.get("out_dim"):
                 ops.append(L.op_head_bwd(self.dout, self.h32, self.P[hd["out_w"]], self.grads[hd["out_w"]],
                                          self.grads[hd["out_b"]], self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"],
-                                         hd["out_dim"]))
+                                         hd["out_dim"], False, 1.0 / (1.0 - self.dropout_p)))
             else:  # gradient arrives w.r.t. the hidden features
                 ops.append(L.op_bias_relu_bwd(self.dout, self.h32, self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"]))
             ops.append(self.fc.op_wgrad(self.feat, self.dz16, B))
             ops.append(self.fc.op_dgrad(self.dz16, self.g_feat, B))
         HWf = self.fH * self.fW
-        self._gn_bwd_all(ops, gc, self.g_feat, self.feat, self.raw_c, self.dx_c, None, HWf)
+        self._gn_bwd_all(ops, gc, self.g_feat, self.feat, self.raw_c, self.dx_c, None, HWf,
+                         g_scale=1.0 / (1.0 - self.dropout_p))
         ops.append(cc.op_wgrad(x, self.dx_c, B))
         ops.append(cc.op_dgrad(self.dx_c, self.blocks[-1]["g_y"], B))
         for bi in range(len(self.blocks) - 1, -1, -1):

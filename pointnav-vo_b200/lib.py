@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST = range(16, 23)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT = range(16, 24)
 
 
 class PnvoOp(ctypes.Structure):
@@ -170,9 +170,9 @@ def op_pool_bwd(g, pooled, argmax, dy, B, C, H, W, PH, PW):
 
 
 def op_gn_bwd(reduce, g, relu_ref, x, stats, gamma, sums, dx, dy_out, B, C, G, cpg, HW, cnt, x_fp32=False, eps=1e-5,
-              C_real=None):
+              C_real=None, g_scale=1.0):
     return _op(OP_GN_BWD_REDUCE if reduce else OP_GN_BWD_APPLY,
-               [B, C, G, cpg, HW, 0, int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real], [cnt, eps],
+               [B, C, G, cpg, HW, 0, int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real], [cnt, eps, g_scale],
                [g, relu_ref, x, stats, gamma, sums, dx, dy_out])
 
 
@@ -200,8 +200,13 @@ def op_head_fwd(h, W, bias, out, B, K, O):
     return _op(OP_HEAD_FWD, [B, K, O], (), [h, W, bias, out])
 
 
-def op_head_bwd(dout, h, W, dW, db2, dz16, db1, B, K, O, accumulate=False):
-    return _op(OP_HEAD_BWD, [B, K, O, int(accumulate)], (), [dout, h, W, dW, db2, dz16, db1])
+def op_head_bwd(dout, h, W, dW, db2, dz16, db1, B, K, O, accumulate=False, dh_scale=1.0):
+    return _op(OP_HEAD_BWD, [B, K, O, int(accumulate)], [dh_scale], [dout, h, W, dW, db2, dz16, db1])
+
+
+def op_dropout(buf, seed, site, p, advance=False):
+    lo, hi = _lohi(buf.numel())
+    return _op(OP_DROPOUT, [lo, hi, int(buf.dtype == torch.float16), site, int(advance)], [p], [buf, seed])
 
 
 def op_mse_loss(pred, target, dz_mask, dout, loss, B, O, weights=(1.0, 1.0, 1.0), grad_scale=1.0):

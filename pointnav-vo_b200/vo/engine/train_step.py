@@ -55,11 +55,11 @@ class FusedVOTrainStep:
 
     def _get_plan(self, obs):
         model = self.model
-        plan = model._plan_for(obs, True)
+        plan = model._plan_for(obs, True, model.training)
         if self._flat is None:
             self._flatten(plan)
             model._plans.clear()
-            plan = model._plan_for(obs, True)  # rebuilt on the flat storage
+            plan = model._plan_for(obs, True, model.training)  # rebuilt on the flat storage
         if plan is not self._plan:
             B, O = plan.B, plan.head["out_dim"]
             self._target = torch.zeros(B, O, dtype=torch.float32, device=plan.dev)

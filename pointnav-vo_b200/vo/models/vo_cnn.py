@@ -81,7 +81,7 @@ class _VOFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, obs, training, need_grad, *params):
-        plan = model._plan_for(obs, need_grad)
+        plan = model._plan_for(obs, need_grad, training)
         model._run_forward(plan, obs, training)
         ctx.model, ctx.plan = model, plan
         return plan.out.clone()
@@ -146,7 +146,7 @@ class VisualOdometryCNNBase(nn.Module):
     def _signature(self):
         return tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers())
 
-    def _plan_for(self, obs, need_grad):
+    def _plan_for(self, obs, need_grad, training=False):
         enc = self.visual_encoder
         first = obs[enc._sources[0][0]]
         if not first.is_cuda:
@@ -158,7 +158,8 @@ class VisualOdometryCNNBase(nn.Module):
             self._ptr_sig = sig
             self._packed_version = None
         B, H, W = first.shape[0], first.shape[1], first.shape[2]
-        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32)
+        drop = self._dropout_p if training else 0.0  # nn.Dropout is the identity in eval mode
+        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32, drop)
         plan = self._plans.get(key)
         if plan is None:
             P, Bf = self._tensors()
@@ -174,7 +175,7 @@ class VisualOdometryCNNBase(nn.Module):
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0],
                                prefix="visual_encoder", head=head, training=bool(need_grad), device=first.device,
-                               world_size=world, raw_fp32=self.raw_fp32)
+                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop)
             self._plans[key] = plan
         return plan
 
@@ -223,9 +224,6 @@ class VisualOdometryCNNBase(nn.Module):
         plan.fwd_prog.run(dev)
 
     def forward(self, observation_pairs):
-        if self.training and self._dropout_p > 0:
-            raise NotImplementedError("training-mode dropout is not implemented on the B200 path yet; "
-                                      "construct the model with dropout_p=0.0")
         params = [p for _, p in self.named_parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         return _VOFunction.apply(self, observation_pairs, self.training, need_grad, *params)

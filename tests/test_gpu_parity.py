@@ -397,3 +397,40 @@ def test_policy_against_reference_golden(golden_dir):
     (v.mean() + lp.mean() + ent).backward()
     gw = pol.net.visual_encoder.backbone.conv1[0].weight.grad
     assert gw is not None and torch.isfinite(gw).all() and gw.abs().sum() > 0
+
+
+def test_dropout_training_mode():
+    """nn.Dropout(p) in front of both Linear layers (vo_cnn.py:218,224): identity in eval mode; in training mode a
+    fresh mask per forward, kept fraction ~ 1-p, survivors scaled by 1/(1-p), and the backward pass sees the same mask."""
+    from pointnav_vo_b200.vo.models import vo_cnn
+
+    name, space, backbone, kw = helpers.VO_CASES["r18_8ch"]
+    m = vo_cnn.baseline_registry.get_vo_model(name)(observation_space=space, observation_size=(341, 192),
+                                                    hidden_size=512, backbone=backbone, normalize_visual_inputs=True,
+                                                    output_dim=3, dropout_p=0.2, **kw)
+    m.load_state_dict(helpers.vo_state_dict("r18_8ch"))
+    m = m.cuda()
+    obs = helpers.vo_inputs(4, 11, space, "cuda")
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(obs)
+        y_eval2 = m(obs)
+    assert rel(y_eval, y_eval2) <= 6e-3
+    m.train()
+    y1 = m(obs)
+    plan = [p for p in m._plans.values() if p.training and p.dropout_p > 0][0]
+    h1 = plan.h32.clone()
+    kept_h = (h1 != 0).float().mean().item()
+    y1.square().sum().backward()
+    dz = plan.dz16.float()
+    assert bool(((h1 == 0) <= (dz == 0)).all())  # no gradient flows through dropped / inactive hidden units
+    y2 = m(obs)
+    assert not torch.equal(plan.h32 == 0, h1 == 0)  # fresh mask
+    assert rel(y1, y2) > 1e-2
+    with torch.no_grad():
+        m.eval()
+        h_eval_nonzero = None
+        m(obs)
+        plan_e = [p for p in m._plans.values() if not p.training][0]
+        h_eval_nonzero = (plan_e.h32 != 0).float().mean().item()
+    assert abs(kept_h - 0.8 * h_eval_nonzero) <= 0.04
