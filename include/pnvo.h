@@ -107,7 +107,9 @@ enum pnvo_opcode {
   PNVO_OP_GN_PARAM_GRAD = 21, /* dgamma/dbeta from the per-(sample,channel) sums */
   PNVO_OP_CAST = 22,          /* fp32 <-> fp16 copies with channel padding */
   PNVO_OP_DROPOUT = 23,       /* in-place inverted dropout, counter-based generator (vo_cnn.py:218,224) */
-  PNVO_OP_MAX = 24
+  PNVO_OP_CONV_STEM = 24,     /* 7x7/s2 stem conv, row-raster operands (no im2col expansion), tcgen05 */
+  PNVO_OP_PACK_W_STEM = 25,   /* OIHW fp32 -> [r][tap pair][cout][64] fp16 for the stem kernel */
+  PNVO_OP_MAX = 26
 };
 
 typedef struct {
@@ -123,6 +125,10 @@ int pnvo_run_ops(const pnvo_op* ops, int n_ops, void* stream);
 /* Dynamic shared memory / TMEM columns / grid the conv op would use (for tests and DESIGN.md tables). */
 int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, int32_t* smem_bytes,
                           int32_t* tmem_cols, int32_t* stages);
+
+/* Width (pixels) of the zero-padded input rows the stem kernel (PNVO_OP_CONV_STEM) expects: 3 zero pixels left of the
+ * image, zeros on the right; the image starts at pixel 3 of every row. */
+int pnvo_stem_padded_width(int IW);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t pnvo_launch_count(void);

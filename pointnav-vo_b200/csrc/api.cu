@@ -52,6 +52,8 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       }
       a.C = i[5];
       a.Cpad = i[6];
+      a.row_w = i[25];
+      a.out_pitch = i[26];
       a.n_pix = (static_cast<int64_t>(static_cast<uint32_t>(i[8])) << 32) | static_cast<uint32_t>(i[7]);
       PNVO_REQUIRE(a.C >= 1 && a.C <= kMaxInC, "assemble: C=%d", a.C);
       for (int c = 0; c < kMaxInC; ++c) {
@@ -97,7 +99,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.dy = static_cast<const __half*>(p[1]);
       a.dw = static_cast<float*>(p[2]);
       a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
-      a.mul = i[8]; a.pad = i[9]; a.w_ld = i[11]; a.n_total = i[12]; a.ld_dy = i[14]; a.pad_w = i[18]; a.force_generic = i[19];
+      a.mul = i[8]; a.pad = i[9]; a.w_ld = i[11]; a.n_total = i[12]; a.ld_dy = i[14]; a.pad_w = i[18]; a.force_generic = i[19]; a.x_row_pitch = i[20];
       return wgrad_launch(a, st);
     }
     case PNVO_OP_GN_APPLY:
@@ -167,6 +169,13 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       return mse_loss_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
                              static_cast<const float*>(p[2]), i[0], i[1], f[0], f[1], f[2], f[3],
                              static_cast<float*>(p[3]), static_cast<float*>(p[4]), st);
+    case PNVO_OP_CONV_STEM:
+      // p0 = x [B,IH,IW,32] fp16, p1 = stem-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = stages
+      return conv_stem_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
+                                  static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
+    case PNVO_OP_PACK_W_STEM:
+      // p0 = w OIHW fp32 [32][Cin][7][7], p1 = packed; i0 = Cin
+      return pack_w_stem_launch(static_cast<const float*>(p[0]), i[0], static_cast<__half*>(p[1]), st);
     case PNVO_OP_DROPOUT:
       // p0 = buffer (in place), p1 = uint64 seed on device; i0|i1 = n, i2 = is_fp16, i3 = site, i4 = advance seed; f0 = p
       return dropout_launch(p[0], (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), i[2],
@@ -194,6 +203,7 @@ using namespace pnvo;
 extern "C" const char* pnvo_last_error(void) { return g_err; }
 extern "C" int pnvo_abi_version(void) { return PNVO_ABI_VERSION; }
 extern "C" int64_t pnvo_launch_count(void) { return g_launches.load(); }
+extern "C" int pnvo_stem_padded_width(int IW) { return stem_padded_width(IW); }
 
 extern "C" int pnvo_check_device(void) {
   int dev = 0;

@@ -1,0 +1,288 @@
+// Stem convolution (7x7 / stride 2 / pad 3, Cin_pad = 32, Cout = 32: resnet.py:156-164) without im2col
+// expansion.
+//
+// With NHWC fp16 and 32 channels a pixel is 64 bytes, so a stride-2 step along W is 128 bytes -- exactly the
+// row pitch of a SWIZZLE_128B UMMA operand.  An input row staged ONCE in shared memory (as TMA wrote it) is
+// therefore already the A operand of every filter column pair: for output pixels ow0..ow0+127 and taps
+// (s, s+1), s even, the operand rows are the 128-byte pixel pairs starting at raster pixel 2*ow + s, i.e. the
+// SAME bytes viewed through a descriptor whose start address is shifted by s/2 rows.  One CTA computes one
+// output row (b, oh): 7 pipeline stages (filter rows r), each = one input row (TMA tiled, zero-filled halo)
+// + the [4 pairs][32][64] weight slice of that filter row; 2 tiles x 4 pairs x 4 k-steps tcgen05.mma per stage.
+// L2 -> smem traffic drops from 12.25x (im2col) to 3.5x the input.
+#include "common.cuh"
+#include "ops.cuh"
+#include "tmap.cuh"
+
+namespace pnvo {
+
+struct StemArgs {
+  void* y;        // [B, OH, OW, 32] fp16
+  float* stats;   // [B][G][2]
+  int B, IH, IW, OH, OW;
+  int G, cpg;
+  int stages;
+  int xrow_bytes;   // smem bytes reserved per staged input row (multiple of 1024)
+  int box_px;       // pixels per TMA box (two boxes per row)
+  int ow1;          // first output pixel of the second tile (OW - 128), or -1 when OW <= 128
+};
+
+static constexpr int kStemW = 16384;  // weight slice of one filter row: 4 pairs x 32 cout x 128 B
+
+template <int CPG>
+__device__ __forceinline__ void group_sums(const float* v, float* out) {
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+      const float x = v[g * CPG + c];
+      a += x;
+      q = fmaf(x, x, q);
+    }
+    out[2 * g] = a;
+    out[2 * g + 1] = q;
+  }
+}
+
+__global__ void __launch_bounds__(192) conv_stem_fwd_kernel(const StemArgs p, const __grid_constant__ ConvTmaps tm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_full[8];
+  __shared__ __align__(8) uint64_t s_empty[8];
+  __shared__ __align__(8) uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages;
+  const int b = blockIdx.x / p.OH, oh = blockIdx.x - b * p.OH;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.xrow_bytes) + kStemW;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const int n_tiles = p.ow1 >= 0 ? 2 : 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&s_accum), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&s_tmem), 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 5) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      const uint32_t box_bytes = static_cast<uint32_t>(p.box_px) * 128;  // box_px = pixel PAIRS per row
+      for (int r = 0; r < 7; ++r) {
+        const int s = r % stages;
+        if (r >= stages) mbar_wait(smem_u32(&s_empty[s]), ((r / stages) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&s_full[s]);
+        const uint32_t sX = smem_base + s * stage_bytes;
+        const int ih = 2 * oh - 3 + r;
+        mbar_arrive_expect_tx(bar, box_bytes + kStemW);
+        tma_load_4d(sX, &tm.a, bar, 0, 0, ih, b);  // whole W-padded input row as 128-byte pixel pairs (rows ih < 0 / >= IH: zeros)
+        tma_load_2d(sX + p.xrow_bytes, &tm.b, bar, 0, r * 128);       // [4 pairs x 32 cout][64] of filter row r
+      }
+    }
+  } else if (warp == 4) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, 32, 0, 0);
+      for (int r = 0; r < 7; ++r) {
+        const int s = r % stages;
+        mbar_wait(smem_u32(&s_full[s]), (r / stages) & 1);
+        tc_fence_after();
+        const uint32_t sX = smem_base + s * stage_bytes;
+        const uint32_t sW = sX + p.xrow_bytes;
+        for (int t = 0; t < n_tiles; ++t) {
+          const int ow0 = t == 0 ? 0 : p.ow1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // taps (2j, 2j+1): operand row m = raster pixels 2*(ow0+m)+2j, +1 -> start shifted by (ow0 + j) rows
+            const uint64_t adesc = umma_desc(sX + static_cast<uint32_t>(ow0 + j) * 128, 16, 1024, 128);
+            const uint64_t bdesc = umma_desc(sW + j * 4096, 16, 1024, 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tc_mma_f16(tmem_base + t * 32, adesc + static_cast<uint64_t>(q * 2), bdesc + static_cast<uint64_t>(q * 2),
+                         idesc, (r | j | q) != 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(smem_u32(&s_empty[s]));
+      }
+      tc_commit(smem_u32(&s_accum));
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================================ epilogue (warps 0-3) ================================
+    mbar_wait(smem_u32(&s_accum), 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int t = 0; t < n_tiles; ++t) {
+      float v[32];
+      tmem_ld32(t_row + t * 32, v);
+      tmem_ld_wait();
+      const int ow = (t == 0 ? 0 : p.ow1) + tid;
+      // tile 1 re-computes pixels [ow1, 128): only its rows >= 128 are new
+      const bool valid = (t == 0) ? (ow < p.OW) : (ow >= 128 && ow < p.OW);
+      if (p.stats) {
+        // all rows of this CTA belong to sample b: plain butterfly over the warp, zeros for masked rows
+        float sgrp[32];
+        const int ng = 32 / p.cpg;  // cpg in {2,4,8,16,32}
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sgrp[i] = 0.f;
+        if (valid) {
+          switch (p.cpg) {
+            case 2: group_sums<2>(v, sgrp); break;
+            case 4: group_sums<4>(v, sgrp); break;
+            case 8: group_sums<8>(v, sgrp); break;
+            case 16: group_sums<16>(v, sgrp); break;
+            default: group_sums<32>(v, sgrp); break;
+          }
+        }
+        // reduce-scatter over the 32 lanes: lane i ends with the total of value i
+        int off = 16;
+#pragma unroll
+        for (int cnt = 16; cnt >= 1; cnt >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < cnt; ++i) {
+            const float send = up ? sgrp[i] : sgrp[i + cnt];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+            sgrp[i] = (up ? sgrp[i + cnt] : sgrp[i]) + recv;
+          }
+          off >>= 1;
+        }
+        if (lane < 2 * ng) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, sgrp[0]);
+      }
+      if (valid) {
+        __half* yp = reinterpret_cast<__half*>(p.y) + (static_cast<int64_t>(b) * p.OH * p.OW + static_cast<int64_t>(oh) * p.OW + ow) * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(yp + q * 8) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// OIHW fp32 [32][Cin][7][7] -> [r][pair j][cout][64] fp16, column = (s & 1) * 32 + c, tap s = 2j + (s & 1); the
+// 8th tap (j = 3, odd half) and channels >= Cin stay zero (buffer zero-initialised once).
+__global__ void pack_w_stem_kernel(const float* __restrict__ w, int Cin, __half* __restrict__ wr) {
+  const int total = 32 * Cin * 49;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int s = i % 7, r = (i / 7) % 7, c = (i / 49) % Cin, n = i / (49 * Cin);
+    wr[((r * 4 + (s >> 1)) * 32 + n) * 64 + (s & 1) * 32 + c] = __float2half_rn(w[i]);
+  }
+}
+
+int pack_w_stem_launch(const float* w, int Cin, __half* wr, cudaStream_t st) {
+  PNVO_REQUIRE(w && wr && Cin <= 32, "pack_w_stem: bad arguments");
+  pack_w_stem_kernel<<<ceil_div(32 * Cin * 49, 256), 256, 0, st>>>(w, Cin, wr);
+  count_launch();
+  return check_launch("pack_w_stem");
+}
+
+// x: W-padded input [B, IH, Wp, 32] fp16 with Wp = stem_padded_width(IW): 3 zero pixels on the left (so that raster
+// pixel p' = iw + 3 and tap pairs start on even p'), zeros on the right up to an even pixel count.
+int stem_padded_width(int IW) {
+  const int OW = (IW + 6 - 7) / 2 + 1;
+  const int npx = 2 * (std::max(OW, 128) - 1) + 8;
+  return std::max((IW + 3 + 1) & ~1, (npx + 1) & ~1);
+}
+
+int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+                         int stages, cudaStream_t st) {
+  PNVO_REQUIRE(x && wr && y, "conv_stem: null pointer");
+  StemArgs a{};
+  a.y = y; a.stats = stats; a.B = B; a.IH = IH; a.IW = IW;
+  a.OH = (IH + 6 - 7) / 2 + 1;
+  a.OW = (IW + 6 - 7) / 2 + 1;
+  PNVO_REQUIRE(a.OW <= 256, "conv_stem: output width %d > 256", a.OW);
+  PNVO_REQUIRE(!stats || (cpg >= 2 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && G * cpg == 32), "conv_stem: bad group config");
+  a.G = G; a.cpg = cpg;
+  a.ow1 = a.OW > 128 ? a.OW - 128 : -1;
+  const int Wp = stem_padded_width(IW);
+  a.box_px = Wp / 2;                             // pixel pairs per staged row (one TMA box)
+  PNVO_REQUIRE(a.box_px <= 256, "conv_stem: row too wide for one TMA box");
+  a.xrow_bytes = (a.box_px * 128 + 1023) & ~1023;
+  a.stages = std::max(2, std::min(stages, 7));
+  const int smem_bytes = a.stages * (a.xrow_bytes + kStemW) + 1024;
+  PNVO_REQUIRE(smem_bytes <= 220 * 1024, "conv_stem: %d bytes of shared memory", smem_bytes);
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  // pixel pairs as the innermost 128-byte dimension: [B, IH, Wp/2, 64]
+  if (tmap_tiled4d(&tm.a, x, B, IH, Wp / 2, 64, a.box_px)) return -1;
+  if (tmap_tiled2d(&tm.b, wr, 7 * 4 * 32, 64, 64, 128, 64)) return -1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr = true;
+  }
+  conv_stem_fwd_kernel<<<B * a.OH, 192, smem_bytes, st>>>(a, tm);
+  count_launch();
+  return check_launch("conv_stem_fwd");
+}
+
+}  // namespace pnvo
+
+// ---------------------------------------------------------------------------------------------------------
+// debug: TMA-load two boxes of one input row and dump the raw shared-memory bytes (layout inspection)
+// ---------------------------------------------------------------------------------------------------------
+namespace pnvo {
+__global__ void tma_dump_kernel(const __grid_constant__ ConvTmaps tm, int box_px, int ih, int b, int w0, uint4* out,
+                                int n16) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "r"(0xFFFFFFFFu) : "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(smem_u32(&bar), 2 * box_px * 64);
+    tma_load_4d(base, &tm.a, smem_u32(&bar), 0, w0, ih, b);
+    tma_load_4d(base + box_px * 64, &tm.a, smem_u32(&bar), 0, w0 + box_px, ih, b);
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + i * 16));
+    out[i] = v;
+  }
+}
+}  // namespace pnvo
+
+extern "C" int pnvo_debug_tma_dump(const void* x, int B, int IH, int IW, int box_px, int ih, int b, int w0, void* out,
+                                   int n16, void* stream) {
+  using namespace pnvo;
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (tmap_tiled4d(&tm.a, x, B, IH, IW, 32, box_px)) return -1;
+  cudaFuncSetAttribute(tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  tma_dump_kernel<<<1, 256, n16 * 16 + 1024, static_cast<cudaStream_t>(stream)>>>(tm, box_px, ih, b, w0,
+                                                                                static_cast<uint4*>(out), n16);
+  return check_launch("tma_dump");
+}

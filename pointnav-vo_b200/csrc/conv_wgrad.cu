@@ -308,6 +308,7 @@ int wgrad_plan(WgradArgs& a) {
 int wgrad_launch(WgradArgs a, cudaStream_t st) {
   if (wgrad_plan(a)) return -1;
   PNVO_REQUIRE(a.x && a.dy && a.dw, "wgrad: null pointer");
+  PNVO_REQUIRE(a.tma || a.x_row_pitch == 0 || a.x_row_pitch == a.IW, "wgrad: padded input rows need the TMA path");
   if (a.M == 0) return 0;
   static bool attr = false;
   if (!attr) {
@@ -317,7 +318,7 @@ int wgrad_launch(WgradArgs a, cudaStream_t st) {
   alignas(64) ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
   if (a.tma) {
-    if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kPix)) return -1;
+    if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kPix, a.x_row_pitch)) return -1;
     if (tmap_tiled2d(&tm.b, a.dy, a.M, a.n_total, a.ld_dy, kPix, std::min(64, a.N))) return -1;
   }
   conv_wgrad_kernel<<<dim3(a.grid_x, a.grid_y, a.grid_z), 160, a.smem_bytes, st>>>(a, tm);

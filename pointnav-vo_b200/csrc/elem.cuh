@@ -16,8 +16,9 @@ struct AssembleArgs {
   signed char src_ch[kMaxInC];   // output channel -> channel inside that source
   const float* scale;      // per output channel (nullable = 1)
   const float* shift;      // per output channel (nullable = 0)
-  __half* out;             // [n_pix][Cpad]
+  __half* out;             // [n_pix][Cpad], or W-padded rows when out_pitch > 0
   int64_t n_pix;
+  int row_w, out_pitch;    // pixels per image row / pixels per padded output row (image starts at pixel 3)
 };
 int assemble_launch(const AssembleArgs& a, cudaStream_t st);
 int input_stats_launch(const AssembleArgs& a, double* stats, cudaStream_t st);

@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(kAsmPix) assemble_kernel(const AssembleArgs a)
   if (lp >= npix) return;
   float v[kMaxInC];
   pick_pixel(a, s_src, s_base, lp, v);
-  __half* __restrict__ out = a.out + (pix0 + lp) * a.Cpad;
+  int64_t opix = pix0 + lp;
+  if (a.out_pitch > 0) opix = (opix / a.row_w) * a.out_pitch + (opix % a.row_w) + 3;  // zero halo left of the image
+  __half* __restrict__ out = a.out + opix * a.Cpad;
 #pragma unroll
   for (int q = 0; q < kMaxInC / 8; ++q) {
     if (q * 8 < a.Cpad) {

@@ -33,11 +33,16 @@ struct WgradArgs {
   int OH, OW;
   int R, S, mul, pad, pad_w;
   int w_ld, n_total, ld_dy;
+  int x_row_pitch;     // pixels between input rows (0 = IW); TMA path only
   int force_generic;
   int tma, chunk_k;
   // derived
   int cin_log2, cmask, M, K, n_mtiles, mt, N, n_ntiles, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y, grid_z, chunks_per_split;
 };
+int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+                         int stages, cudaStream_t st);
+int stem_padded_width(int IW);
+int pack_w_stem_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
 int wgrad_plan(WgradArgs& a);
 int wgrad_launch(WgradArgs a, cudaStream_t st);
 

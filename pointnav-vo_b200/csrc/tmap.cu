@@ -41,10 +41,11 @@ static int resolve() {
 }
 
 int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad,
-                int channels, int pixels) {
+                int channels, int pixels, int row_pitch_px) {
+  if (row_pitch_px <= 0) row_pitch_px = W;
   std::lock_guard<std::mutex> lk(g_mu);
   if (resolve()) return -1;
-  std::vector<int64_t> key = {1, reinterpret_cast<int64_t>(x), N, H, W, C, R, S, stride, pad, channels, pixels};
+  std::vector<int64_t> key = {1, reinterpret_cast<int64_t>(x), N, H, W, C, R, S, stride, pad, channels, pixels, row_pitch_px};
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     *out = it->second;
@@ -53,8 +54,8 @@ int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int
   alignas(64) CUtensorMap m;
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                               static_cast<cuuint64_t>(N)};
-  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
-                                 static_cast<cuuint64_t>(H) * W * C * 2};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(row_pitch_px) * C * 2,
+                                 static_cast<cuuint64_t>(H) * row_pitch_px * C * 2};
   // bounding box of the filter origin: [-pad, dim + pad - (filter - 1)) in both W and H
   const int lower[2] = {-pad, -pad};
   const int upper[2] = {pad - (S - 1), pad - (R - 1)};
@@ -73,6 +74,34 @@ int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int
   // cute/atom/copy_traits_sm90_im2col.hpp)
   if (g_driver <= 13010 && static_cast<int64_t>(N) * H * W * C * 2 < 131072)
     reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  g_cache[key] = m;
+  *out = m;
+  return 0;
+}
+
+int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (resolve()) return -1;
+  std::vector<int64_t> key = {3, reinterpret_cast<int64_t>(x), N, H, W, C, box_w};
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  alignas(64) CUtensorMap m;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                                 static_cast<cuuint64_t>(H) * W * C * 2};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(C), static_cast<cuuint32_t>(box_w), 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = g_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d) for [%d,%d,%d,%d] box %d", static_cast<int>(r), N, H, W, C, box_w);
+    return -1;
+  }
   g_cache[key] = m;
   *out = m;
   return 0;

@@ -17,7 +17,10 @@ struct ConvTmaps {
 // NHWC fp16 activations [N, H, W, C]; a load fetches `pixels` consecutive output positions (w fastest,
 // wrapping over h and n inside the padded bounding box) x `channels` channels of one filter tap.
 int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad,
-                int channels, int pixels);
+                int channels, int pixels, int row_pitch_px = 0);
+// NHWC fp16 activations [N, H, W, C]: plain tiled boxes of box_w pixels x C channels of one image row,
+// SWIZZLE_128B (C*2 <= 128 bytes), out-of-range pixels / rows zero-filled
+int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w);
 // row-major fp16 matrix [rows, ld] (cols valid columns); box = box_rows x box_cols
 int tmap_tiled2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                  int box_cols);
@@ -32,6 +35,12 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y) {

@@ -80,9 +80,9 @@ class ConvLayer:
                          self.R - 1 - self.pad, self.stride, self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, add,
                          None, 0, 0, False, pad_w=self.S - 1 - self.pad)
 
-    def op_wgrad(self, x, dy, B):
+    def op_wgrad(self, x, dy, B, x_row_pitch=0):
         return L.op_wgrad(x, dy, self.dwp, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
-                          self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad)
+                          self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad, x_row_pitch=x_row_pitch)
 
     def op_unpack(self, grad):
         return L.op_unpack_dw(self.dwp, grad, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld)
@@ -231,7 +231,18 @@ class EncoderPlan:
                 g.sums = self.sums_all[off:off + B * g.C * 2]
                 off += B * g.C * 2
         raw_dt = torch.float32 if self.raw_fp32 else torch.float16
-        self.x0 = self._act(B, self.inH, self.inW, self.cin_pad)
+        # stem kernel (conv_stem.cu): needs 64-byte pixels, 32 output channels and W-padded rows with a zero halo
+        self.use_stem = (not self.avgpool_input and not self.raw_fp32 and self.cin_pad == 32 and self.conv1.cout_pad == 32
+                         and self.conv1.Cout == 32 and self.conv1.OW <= 256 and self.conv1.OW >= 128)
+        if self.use_stem:
+            self.x0_pitch = L.load().pnvo_stem_padded_width(self.inW)
+            self.x0 = torch.zeros(B, self.inH, self.x0_pitch, self.cin_pad, dtype=torch.float16, device=dev)
+            self.x0_img = self.x0[:, :, 3:, :]  # view whose data_ptr is the first image pixel
+            self.w_stem = torch.zeros(7 * 4 * 32, 64, dtype=torch.float16, device=dev)
+        else:
+            self.x0_pitch = 0
+            self.x0 = self._act(B, self.inH, self.inW, self.cin_pad)
+            self.x0_img = self.x0
         if self.avgpool_input:
             self.x0.zero_()  # pad channels stay zero (avgpool writes only the real ones)
         self.in_stats = torch.zeros(2 * 32 + 2, dtype=torch.float64, device=dev)
@@ -321,11 +332,18 @@ class EncoderPlan:
     def _build_programs(self):
         B = self.B
         # ---- pack ----
-        self.pack_prog = L.Program([c.op_pack(self.P[c.key]) for c in self.all_convs()])
+        pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
+        if self.use_stem:
+            pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
+        self.pack_prog = L.Program(pack)
         # ---- forward (after the input tensor x0 has been produced) ----
         ops = [L.op_zero(self.stats_all)]
         c1, g1 = self.conv1, self.gn1
-        ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32))
+        if self.use_stem and not self.raw_fp32:
+            ops.append(L.op_conv_stem(self.x0, self.w_stem, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg, 2))
+        else:
+            assert not self.use_stem, "raw_fp32 is not supported together with the stem kernel"
+            ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32))
         ops.append(L.op_gn_pool(self.raw1, g1.stats, self.P[g1.key + ".weight"], self.P[g1.key + ".bias"], self.pool,
                                 self.argmax, B, g1.C, g1.G, g1.cpg, c1.OH, c1.OW, self.PH, self.PW,
                                 float(g1.cpg_real * c1.OH * c1.OW), self.raw_fp32, 1e-5, g1.C_real))
@@ -417,7 +435,7 @@ class EncoderPlan:
         # stem: max-pool + ReLU routing, GN, conv1 weight gradient (no data gradient: the input is data)
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
         self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
-        ops.append(c1.op_wgrad(self.x0, self.dx1, B))
+        ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
         for c in self.all_convs():
             ops.append(c.op_unpack(self.grads[c.key]))
         self.bwd_ops = ops

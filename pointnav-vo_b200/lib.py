@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT = range(16, 24)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM = range(16, 26)
 
 
 class PnvoOp(ctypes.Structure):
@@ -36,7 +36,7 @@ _lib = None
 
 EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_discretize_depth",
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
-           "pnvo_launch_count"]
+           "pnvo_launch_count", "pnvo_stem_padded_width"]
 
 
 def load():
@@ -53,6 +53,8 @@ def load():
     lib.pnvo_abi_version.restype = i32
     lib.pnvo_check_device.restype = i32
     lib.pnvo_launch_count.restype = i64
+    lib.pnvo_stem_padded_width.argtypes = [i32]
+    lib.pnvo_stem_padded_width.restype = i32
     lib.pnvo_discretize_depth.argtypes = [vp, i64, vp, i32, vp, i64, vp, vp, vp]
     lib.pnvo_topdown_project.argtypes = [vp, i64, i32, i32, i32, vp, ctypes.POINTER(TopdownConsts), vp, i64, i64, vp, vp]
     lib.pnvo_gae_scan.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
@@ -126,8 +128,9 @@ def _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix):
     return ints + words, list(pre_scale) + [1.0] * (4 - len(pre_scale))
 
 
-def op_assemble(srcs, nch, pre_scale, lut, C, Cpad, n_pix, scale, shift, out):
+def op_assemble(srcs, nch, pre_scale, lut, C, Cpad, n_pix, scale, shift, out, row_w=0, out_pitch=0):
     ints, fl = _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix)
+    ints = ints + [0] * (25 - len(ints)) + [row_w, out_pitch]
     return _op(OP_ASSEMBLE, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [scale, shift, out])
 
 
@@ -147,9 +150,9 @@ def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total,
                          int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats])
 
 
-def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None):
+def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None, x_row_pitch=0):
     return _op(OP_WGRAD, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, 1, w_ld, n_total, 0, ld_dy, 0, 0, 0,
-                          pad if pad_w is None else pad_w], (), [x, dy, dw])
+                          pad if pad_w is None else pad_w, 0, x_row_pitch], (), [x, dy, dw])
 
 
 def op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, cnt, relu=True, res=None, x_fp32=False, eps=1e-5,
@@ -211,6 +214,14 @@ def op_dropout(buf, seed, site, p, advance=False):
 
 def op_mse_loss(pred, target, dz_mask, dout, loss, B, O, weights=(1.0, 1.0, 1.0), grad_scale=1.0):
     return _op(OP_MSE_LOSS, [B, O], [weights[0], weights[1], weights[2], grad_scale], [pred, target, dz_mask, dout, loss])
+
+
+def op_conv_stem(x, wr, y, stats, B, IH, IW, G, cpg, stages=4):
+    return _op(OP_CONV_STEM, [B, IH, IW, G, cpg, stages], (), [x, wr, y, stats])
+
+
+def op_pack_w_stem(w, wr, Cin):
+    return _op(OP_PACK_W_STEM, [Cin], (), [w, wr])
 
 
 def op_adam(p, g, m, v, n, step, lr, beta1, beta2, eps):

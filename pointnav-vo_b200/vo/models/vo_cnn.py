@@ -215,7 +215,8 @@ class VisualOdometryCNNBase(nn.Module):
             scale, shift = plan.in_scale, plan.in_shift
         else:
             scale = shift = None
-        ops.append(L.op_assemble(srcs, nch, pre, lut, C, plan.cin_pad, n_pix, scale, shift, plan.x0))
+        ops.append(L.op_assemble(srcs, nch, pre, lut, C, plan.cin_pad, n_pix, scale, shift, plan.x0,
+                                 row_w=plan.W if plan.x0_pitch else 0, out_pitch=plan.x0_pitch))
         L.run_ops(ops, dev)
         ver = self._weights_version()
         if ver != self._packed_version or plan is not getattr(self, "_packed_plan", None):

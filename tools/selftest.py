@@ -274,7 +274,7 @@ def vo_model():
             vo.vo_forward(obs, sd, space, backbone, training=False, taps=taps)
         plan = list(m._plans.values())[0]
         C = m.visual_encoder.input_channels
-        report(f"{case} tap input", plan.x0[..., :C].permute(0, 3, 1, 2), taps["input"], 2e-3)
+        report(f"{case} tap input", plan.x0_img[:, :, :plan.W, :C].permute(0, 3, 1, 2), taps["input"], 2e-3)
         report(f"{case} tap conv1_raw", plan.raw1.permute(0, 3, 1, 2), taps["conv1_raw"], 3e-3)
         report(f"{case} tap pool", plan.pool.permute(0, 3, 1, 2), taps["pool"], 3e-3)
         li = 0
@@ -423,7 +423,7 @@ def vo_blocks():
         # stem
         C = m.visual_encoder.input_channels
         sd = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if ".conv1." in k}
-        x0 = nchw(plan.x0, C)
+        x0 = nchw(plan.x0_img[:, :, :plan.W], C)
         pfx = "visual_encoder.backbone"
         a = F.conv2d(x0, sd[pfx + ".conv1.0.weight"], None, 2, 3)
         a = F.relu(F.group_norm(a, ng, sd[pfx + ".conv1.1.weight"], sd[pfx + ".conv1.1.bias"], 1e-5))
