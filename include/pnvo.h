@@ -109,7 +109,8 @@ enum pnvo_opcode {
   PNVO_OP_DROPOUT = 23,       /* in-place inverted dropout, counter-based generator (vo_cnn.py:218,224) */
   PNVO_OP_CONV_STEM = 24,     /* 7x7/s2 stem conv, row-raster operands (no im2col expansion), tcgen05 */
   PNVO_OP_PACK_W_STEM = 25,   /* OIHW fp32 -> [r][tap pair][cout][64] fp16 for the stem kernel */
-  PNVO_OP_MAX = 26
+  PNVO_OP_WGRAD_STEM = 26,    /* stem weight gradient on the row raster */
+  PNVO_OP_MAX = 27
 };
 
 typedef struct {

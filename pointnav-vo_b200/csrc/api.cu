@@ -173,6 +173,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = x [B,IH,IW,32] fp16, p1 = stem-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = stages
       return conv_stem_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
                                   static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
+    case PNVO_OP_WGRAD_STEM:
+      // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld, i4 = rows per CTA
+      return conv_stem_wgrad_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),
+                                    static_cast<float*>(p[2]), i[3], i[0], i[1], i[2], i[4], st);
     case PNVO_OP_PACK_W_STEM:
       // p0 = w OIHW fp32 [32][Cin][7][7], p1 = packed; i0 = Cin
       return pack_w_stem_launch(static_cast<const float*>(p[0]), i[0], static_cast<__half*>(p[1]), st);

@@ -241,6 +241,162 @@ int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, float* stat
   return check_launch("conv_stem_fwd");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Stem weight gradient on the same raster: dW[n, (r, s, c)] = sum_{b,oh,ow} dy[b,oh,ow,n] * x[b, 2oh-3+r, 2ow-3+s, c].
+// GEMM-K = output pixels along a row.  A (MN-major, M = 128 = two adjacent tap pairs x 64) is again a shifted
+// view of the staged input row: block 0 starts at pixel pair (ow + 2h), block 1 one 128-byte row later
+// (LBO = 128 B).  B = the dy row segment (MN-major, SWIZZLE_64B, N = 32).  A CTA owns (sample, half row, range of
+// output rows): input rows live in a 9-slot ring (each is used by 3-4 consecutive output rows, two new rows per
+// step), all 14 = 7 r x 2 accumulators stay in TMEM (448 columns) for the whole range, one atomic flush at the end.
+// ---------------------------------------------------------------------------------------------------------
+struct StemWgradArgs {
+  float* dw;  // packed fp32 [32][w_ld], kflat = (r*7 + s)*32 + c
+  int w_ld;
+  int B, IH, OH, OW;
+  int rows_per_cta, n_chunks;
+};
+static constexpr int kSwRow = 13312;   // 104 pixel pairs x 128 B
+static constexpr int kSwDy = 6144;     // 96 pixels x 64 B
+static constexpr int kSwHalf0 = 96;    // output pixels [0, 96) and [96, 176)
+
+__global__ void __launch_bounds__(192) conv_stem_wgrad_kernel(const StemWgradArgs p,
+                                                              const __grid_constant__ ConvTmaps tm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ __align__(8) uint64_t s_empty[2];
+  __shared__ __align__(8) uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t s_dy = smem_base + 9 * kSwRow;
+  int bid = blockIdx.x;
+  const int chunk = bid % p.n_chunks; bid /= p.n_chunks;
+  const int half = bid & 1;
+  const int b = bid >> 1;
+  const int oh_begin = chunk * p.rows_per_cta;
+  const int oh_end = min(p.OH, oh_begin + p.rows_per_cta);
+  const int n_rows = oh_end - oh_begin;
+  const int ow_base = half ? kSwHalf0 : 0;
+  const int ksteps = half ? (ceil_div(p.OW - kSwHalf0, 16)) : (kSwHalf0 / 16);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&s_accum), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&s_tmem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      // ================================ TMA producer ================================
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      for (int t = 0; t < n_rows; ++t) {
+        const int oh = oh_begin + t, pslot = t & 1;
+        if (t >= 2) mbar_wait(smem_u32(&s_empty[pslot]), ((t >> 1) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&s_full[pslot]);
+        const int r_first = (t == 0) ? 0 : 5;  // first step: all 7 rows of the window; later: the two new ones
+        mbar_arrive_expect_tx(bar, static_cast<uint32_t>(7 - r_first) * kSwRow + kSwDy);
+        for (int r = r_first; r < 7; ++r) {
+          const int ih = 2 * oh - 3 + r;
+          const int slot = (2 * oh + r) % 9;  // == (ih + 3) mod 9
+          tma_load_4d(smem_base + slot * kSwRow, &tm.a, bar, 0, ow_base, ih, b);
+        }
+        tma_load_4d(s_dy + pslot * kSwDy, &tm.b, bar, 0, ow_base, oh, b);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // ================================ MMA issuer ================================
+      const uint32_t idesc = umma_idesc_f16(128, 32, 1, 1);
+      for (int t = 0; t < n_rows; ++t) {
+        const int oh = oh_begin + t, pslot = t & 1;
+        mbar_wait(smem_u32(&s_full[pslot]), (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sB = s_dy + pslot * kSwDy;
+        for (int r = 0; r < 7; ++r) {
+          const uint32_t sX = smem_base + static_cast<uint32_t>((2 * oh + r) % 9) * kSwRow;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            for (int q = 0; q < ksteps; ++q) {
+              // K step q = output pixels ow_base + 16q .. +15 -> staged pair rows (16q + 2h) .. ; block 1 one row later
+              const uint64_t adesc = umma_desc(sX + static_cast<uint32_t>(16 * q + 2 * h) * 128, 128, 1024, 128);
+              const uint64_t bdesc = umma_desc(sB + static_cast<uint32_t>(q) * 1024, 64, 512, 64);
+              tc_mma_f16(tmem_base + static_cast<uint32_t>((r * 2 + h) * 32), adesc, bdesc, idesc, (t | q) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        tc_commit(smem_u32(&s_empty[pslot]));
+      }
+      tc_commit(smem_u32(&s_accum));
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================================ epilogue ================================
+    mbar_wait(smem_u32(&s_accum), 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int jj = tid >> 6, within = tid & 63;
+    for (int r = 0; r < 7; ++r) {
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_ld32(t_row + (r * 2 + h) * 32, v);
+        tmem_ld_wait();
+        const int s = 2 * (2 * h + jj) + (within >> 5);
+        if (s < 7) {
+          const int kf = (r * 7 + s) * 32 + (within & 31);
+#pragma unroll
+          for (int n = 0; n < 32; ++n) atomicAdd(p.dw + static_cast<int64_t>(n) * p.w_ld + kf, v[n]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW,
+                           int rows_per_cta, cudaStream_t st) {
+  PNVO_REQUIRE(x && dy && dw, "conv_stem_wgrad: null pointer");
+  StemWgradArgs a{};
+  a.dw = dw; a.w_ld = w_ld; a.B = B; a.IH = IH;
+  a.OH = (IH + 6 - 7) / 2 + 1;
+  a.OW = (IW + 6 - 7) / 2 + 1;
+  PNVO_REQUIRE(a.OW > kSwHalf0 && a.OW <= 176, "conv_stem_wgrad: output width %d not in (96, 176]", a.OW);
+  PNVO_REQUIRE(w_ld >= 49 * 32, "conv_stem_wgrad: w_ld too small");
+  a.rows_per_cta = std::max(4, rows_per_cta);
+  a.n_chunks = ceil_div(a.OH, a.rows_per_cta);
+  const int Wp = stem_padded_width(IW);
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (tmap_tiled4d(&tm.a, x, B, IH, Wp / 2, 64, kSwRow / 128)) return -1;   // 104 pixel pairs per box
+  if (tmap_tiled4d(&tm.b, dy, B, a.OH, a.OW, 32, kSwHalf0, 64)) return -1;   // 96 pixels x 32 channels, SWIZZLE_64B
+  const int smem_bytes = 9 * kSwRow + 2 * kSwDy + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    attr = true;
+  }
+  conv_stem_wgrad_kernel<<<B * 2 * a.n_chunks, 192, smem_bytes, st>>>(a, tm);
+  count_launch();
+  return check_launch("conv_stem_wgrad");
+}
+
 }  // namespace pnvo
 
 // ---------------------------------------------------------------------------------------------------------

@@ -42,6 +42,8 @@ struct WgradArgs {
 int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
                          int stages, cudaStream_t st);
 int stem_padded_width(int IW);
+int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW,
+                           int rows_per_cta, cudaStream_t st);
 int pack_w_stem_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
 int wgrad_plan(WgradArgs& a);
 int wgrad_launch(WgradArgs a, cudaStream_t st);

@@ -79,10 +79,10 @@ int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int
   return 0;
 }
 
-int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w) {
+int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w, int swizzle_bytes) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (resolve()) return -1;
-  std::vector<int64_t> key = {3, reinterpret_cast<int64_t>(x), N, H, W, C, box_w};
+  std::vector<int64_t> key = {3, reinterpret_cast<int64_t>(x), N, H, W, C, box_w, swizzle_bytes};
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     *out = it->second;
@@ -96,8 +96,9 @@ int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, in
   const cuuint32_t box[4] = {static_cast<cuuint32_t>(C), static_cast<cuuint32_t>(box_w), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = g_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(4d) failed (%d) for [%d,%d,%d,%d] box %d", static_cast<int>(r), N, H, W, C, box_w);
     return -1;

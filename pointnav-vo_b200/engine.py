@@ -435,7 +435,10 @@ class EncoderPlan:
         # stem: max-pool + ReLU routing, GN, conv1 weight gradient (no data gradient: the input is data)
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
         self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
-        ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
+        if self.use_stem and 96 < c1.OW <= 176:
+            ops.append(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48))
+        else:
+            ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
         for c in self.all_convs():
             ops.append(c.op_unpack(self.grads[c.key]))
         self.bwd_ops = ops

@@ -60,3 +60,45 @@ if __name__ == "__main__":
     run(2, 192, 341, 30, 2)
     for st in (2, 3, 4, 5):
         run(256, 192, 341, 30, st, time_it=True)
+
+
+def run_wgrad(B, IH, IW, Cin, rows, time_it=False):
+    dev = "cuda"
+    torch.manual_seed(1)
+    OH, OW = (IH - 1) // 2 + 1, (IW - 1) // 2 + 1
+    Wp = L.load().pnvo_stem_padded_width(IW)
+    xp = torch.zeros(B, IH, Wp, 32, device=dev, dtype=torch.float16)
+    x = torch.randn(B, IH, IW, 32, device=dev).half()
+    x[..., Cin:] = 0
+    xp[:, :, 3:3 + IW] = x
+    dy = torch.randn(B, OH, OW, 32, device=dev).half()
+    w_ld = 1600
+    dw = torch.zeros(32, w_ld, device=dev)
+    op = L.op_wgrad_stem(xp, dy, dw, B, IH, IW, w_ld, rows)
+    L.run_ops([op])
+    torch.cuda.synchronize()
+    w = torch.zeros(32, Cin, 7, 7, device=dev, requires_grad=True)
+    F.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), w, None, 2, 3).backward(dy.float().permute(0, 3, 1, 2))
+    got = dw[:, :49 * 32].reshape(32, 7, 7, 32)[..., :Cin].permute(0, 3, 1, 2)
+    r, bad = rel(got, w.grad)
+    print(f"stem wgrad B={B} {IH}x{IW} rows/cta={rows}: rel={r:.3e} nonfinite={bad}", flush=True)
+    if time_it:
+        prog = L.Program([op])
+        for _ in range(3):
+            prog.run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            prog.run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"   {ms:.3f} ms  {2.0 * B * OH * OW * 32 * 30 * 49 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    run_wgrad(1, 16, 341, 30, 8)
+    run_wgrad(2, 192, 341, 30, 32)
+    for rows in (16, 32, 48, 96):
+        run_wgrad(256, 192, 341, 30, rows, time_it=True)
