@@ -58,6 +58,12 @@ int pnvo_topdown_project(const float* depth, int64_t in_stride, int n_frames, in
                          const float* ray, const pnvo_topdown_consts* consts, float* out,
                          int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
 
+/* Same, reading frame f, pixel i at depth[f*in_frame_stride + i*in_pix_stride]: projects both frames of a
+ * [B, H, W, 2] depth-pair tensor in place (n_frames = 2B, in_frame_stride = ... see the host mirror). */
+int pnvo_topdown_project_strided(const float* depth, int64_t in_frame_stride, int64_t in_pix_stride, int n_frames,
+                                 int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
+                                 int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a13 GAE / discounted returns -- RolloutStorage.compute_returns
  *     (pointnav_vo/rl/common/rollout_storage.py:102-120).
@@ -110,7 +116,10 @@ enum pnvo_opcode {
   PNVO_OP_CONV_STEM = 24,     /* 7x7/s2 stem conv, row-raster operands (no im2col expansion), tcgen05 */
   PNVO_OP_PACK_W_STEM = 25,   /* OIHW fp32 -> [r][tap pair][cout][64] fp16 for the stem kernel */
   PNVO_OP_WGRAD_STEM = 26,    /* stem weight gradient on the row raster */
-  PNVO_OP_MAX = 27
+  PNVO_OP_GN_BWD_FUSED = 27, /* GroupNorm(+ReLU) backward in one pass: a thread-block cluster per sample, DSMEM reduce */
+  PNVO_OP_RAW_STATS = 28,    /* RunningMeanAndVar batch statistics straight from uint8 rgb / fp32 depth / top-down pairs */
+  PNVO_OP_RAW_ASSEMBLE = 29, /* raw pairs -> [rgb/255, depth, one-hot depth bins, top-down] x {prev, cur} -> normalised fp16 NHWC */
+  PNVO_OP_MAX = 30
 };
 
 typedef struct {
@@ -130,6 +139,9 @@ int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, i
 /* Width (pixels) of the zero-padded input rows the stem kernel (PNVO_OP_CONV_STEM) expects: 3 zero pixels left of the
  * image, zeros on the right; the image starts at pixel 3 of every row. */
 int pnvo_stem_padded_width(int IW);
+
+/* 1 when PNVO_OP_GN_BWD_FUSED can take a [HW, C] fp16 sample (else use GN_BWD_REDUCE + GN_BWD_APPLY). */
+int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t pnvo_launch_count(void);

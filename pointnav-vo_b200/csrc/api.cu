@@ -73,6 +73,9 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       }
       return input_stats_launch(a, static_cast<double*>(p[6]), st);
     }
+    case PNVO_OP_RAW_STATS:
+    case PNVO_OP_RAW_ASSEMBLE:
+      return raw_op(op.code, i, f, p, st);
     case PNVO_OP_RMV_UPDATE:
       // p0 = fp64 stats, p1 = _mean, p2 = _var, p3 = _count, p4 = scale, p5 = shift
       // i0 = C, i1 = update, i2 = have_rmv; f0 = batch samples (all ranks), f1 = pixels per sample
@@ -121,6 +124,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                              static_cast<const uint8_t*>(p[2]), static_cast<__half*>(p[3]), i[0], i[7], i[8], i[9],
                              i[10], i[1], st);
     case PNVO_OP_GN_BWD_REDUCE:
+    case PNVO_OP_GN_BWD_FUSED:
     case PNVO_OP_GN_BWD_APPLY: {
       // p0 = g, p1 = relu_ref, p2 = x, p3 = stats, p4 = gamma, p5 = sums, p6 = dx, p7 = dy_out
       GnBwdArgs a{};
@@ -130,6 +134,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1]; a.g_scale = (f[2] == 0.f) ? 1.f : f[2];
       if (op.code == PNVO_OP_GN_BWD_REDUCE) return gn_bwd_reduce_launch(a, i[0], st);
+      if (op.code == PNVO_OP_GN_BWD_FUSED) return gn_bwd_fused_launch(a, i[0], st);
       return gn_bwd_apply_launch(a, i[0], st);
     }
     case PNVO_OP_GN_PARAM_GRAD:
@@ -208,6 +213,11 @@ extern "C" const char* pnvo_last_error(void) { return g_err; }
 extern "C" int pnvo_abi_version(void) { return PNVO_ABI_VERSION; }
 extern "C" int64_t pnvo_launch_count(void) { return g_launches.load(); }
 extern "C" int pnvo_stem_padded_width(int IW) { return stem_padded_width(IW); }
+extern "C" int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32) {
+  GnBwdArgs a{};
+  a.C = C; a.HW = HW; a.x_fp32 = x_fp32;
+  return gn_bwd_fused_supported(a);
+}
 
 extern "C" int pnvo_check_device(void) {
   int dev = 0;

@@ -27,6 +27,8 @@ int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample
 int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
                     cudaStream_t st);
 int zero_launch(void* p, int64_t bytes, cudaStream_t st);
+// raw_input.cu: PNVO_OP_RAW_STATS / PNVO_OP_RAW_ASSEMBLE (field layout documented there)
+int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st);
 
 struct GnArgs {
   const void* x;       // raw conv output [B*HW][C] fp16 (or fp32 when x_fp32)
@@ -62,6 +64,8 @@ struct GnBwdArgs {
 };
 int gn_bwd_reduce_launch(const GnBwdArgs& a, int B, cudaStream_t st);
 int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st);
+int gn_bwd_fused_supported(const GnBwdArgs& a);
+int gn_bwd_fused_launch(const GnBwdArgs& a, int B, cudaStream_t st);
 int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st);
 

@@ -1,0 +1,274 @@
+// GroupNorm(+ReLU) backward in ONE pass over HBM (resnet.py:39-55 backward; replaces the reduce + apply pair
+// of norm_pool.cu whenever one sample fits in the shared memory of a thread-block cluster).
+//
+//   dy   = g * [relu_ref > 0] * g_scale
+//   S1_c = sum_hw dy,  S2_c = sum_hw dy * xhat          (per sample, per channel; xhat = (x - mean_g) * rstd_g)
+//   dx   = rstd_g * (gamma_c * dy - (sum_{c in g} gamma_c S1_c + xhat * sum_{c in g} gamma_c S2_c) / cnt)
+//
+// A cluster of `cs` CTAs (1, 2, 4 or 8) owns one sample; CTA r owns a contiguous slice of its [HW][C] fp16 data.
+// One thread brings the slices of g, x (and the ReLU reference) into shared memory with bulk async copies
+// (cp.async.bulk, mbarrier completion): each byte crosses HBM ONCE.  The per-channel sums are reduced in a fixed
+// order inside the CTA (shared memory) and across the cluster (distributed shared memory), so the result is
+// bit-reproducible and needs neither atomics nor a pre-zeroed buffer; dx (and the masked gradient of the identity
+// branch) are then produced from the staged slices.  HBM traffic: 3 reads + 1-2 writes per element instead of
+// 6 + 1-2; registers stay small, so several CTAs per SM overlap their load / reduce / store phases.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "elem.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pnvo {
+
+static constexpr int kGbfThreads = 256;
+static constexpr int kGbfScratch = kGbfThreads * 17 * 4;  // bytes of the CTA reduction scratch
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h2[e]);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// slice: vectors (16 B) per CTA, multiple of C/8; slice_bytes = slice * 16 rounded up to 128
+__global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdArgs a, const int n8, const int cs,
+                                                                   const int slice, const int slice_bytes,
+                                                                   const int y_region) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int C = a.C, G = a.G;
+  uint4* s_g = reinterpret_cast<uint4*>(s_raw);
+  uint4* s_x = reinterpret_cast<uint4*>(s_raw + slice_bytes);
+  uint4* s_y = reinterpret_cast<uint4*>(s_raw + 2 * slice_bytes);
+  float* s_part = reinterpret_cast<float*>(s_raw + 2 * slice_bytes);  // aliases the y slice (dead after masking)
+  float* s_loc = reinterpret_cast<float*>(s_raw + 2 * slice_bytes + y_region);  // [2C] CTA sums (read by peers)
+  float* s_tot = s_loc + 2 * C;                                                 // [2C] sample totals
+  float* s_coef = s_tot + 2 * C;                                                // [3C] A_c, B_c, C_c
+  float* s_mr = s_coef + 3 * C;                                                 // [2C] mean_c, rstd_c
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int rank = blockIdx.x;  // gridDim.x == cluster size
+  const int b = blockIdx.y;
+  const int c8 = C >> 3;
+  const int cc = (tid % c8) * 8;  // fixed 8-channel chunk of this thread (slice and 256 are multiples of c8)
+  const int first = rank * slice;
+  const int len = max(0, min(slice, n8 - first));
+  const int64_t base = static_cast<int64_t>(b) * n8 + first;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    fence_mbar_init();
+    const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
+    const uint32_t bar = smem_u32(&s_bar);
+    mbar_arrive_expect_tx(bar, bytes * (a.relu_ref ? 3u : 2u));
+    if (len > 0) {
+      bulk_g2s(smem_u32(s_g), reinterpret_cast<const uint4*>(a.g) + base, bytes, bar);
+      bulk_g2s(smem_u32(s_x), reinterpret_cast<const uint4*>(a.x) + base, bytes, bar);
+      if (a.relu_ref) bulk_g2s(smem_u32(s_y), reinterpret_cast<const uint4*>(a.relu_ref) + base, bytes, bar);
+    }
+  }
+  // per-channel mean / rstd of this sample (forward statistics) while the copies fly
+  for (int c = tid; c < C; c += kGbfThreads) {
+    const int g = c / a.cpg;
+    const float s = a.stats[(static_cast<int64_t>(b) * G + g) * 2], q = a.stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
+    const float mean = s / a.cnt;
+    const float var = fmaxf(q / a.cnt - mean * mean, 0.f);
+    s_mr[2 * c] = mean;
+    s_mr[2 * c + 1] = 1.0f / sqrtf(var + a.eps);
+  }
+  __syncthreads();  // barrier initialised before anybody waits on it
+  mbar_wait(smem_u32(&s_bar), 0);
+
+  // thread partials: sum g, sum g*x over this thread's vectors; masked g goes back to shared memory
+  float sd[8], sgx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sd[e] = sgx[e] = 0.f;
+  const bool has_y = a.relu_ref != nullptr;
+  for (int i = tid; i < len; i += kGbfThreads) {
+    uint4 gq = s_g[i];
+    const uint4 xq = s_x[i];
+    if (has_y) {
+      // mask: keep g where the saved post-ReLU output is > 0 (sign / zero test on the fp16 bits)
+      const uint4 yq = s_y[i];
+      uint32_t* gw = reinterpret_cast<uint32_t*>(&gq);
+      const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yq);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t y = yw[e];
+        const uint32_t lo = ((y & 0x7fffu) != 0u && (y & 0x8000u) == 0u) ? 0x0000ffffu : 0u;
+        const uint32_t hi = ((y & 0x7fff0000u) != 0u && (y & 0x80000000u) == 0u) ? 0xffff0000u : 0u;
+        gw[e] &= (lo | hi);
+      }
+      s_g[i] = gq;
+    }
+    float g[8], x[8];
+    unpack8(gq, g);
+    unpack8(xq, x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sd[e] += g[e];
+      sgx[e] = fmaf(g[e], x[e], sgx[e]);
+    }
+  }
+  __syncthreads();  // everybody is done with the y slice before the scratch overwrites it
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s_part[tid * 17 + 2 * e] = sd[e];
+    s_part[tid * 17 + 2 * e + 1] = sgx[e];
+  }
+  __syncthreads();
+  // CTA totals in a fixed order: output o = chunk * 16 + v  <->  (channel = chunk*8 + v/2, which = v & 1)
+  const int per_chunk = kGbfThreads / c8;
+  for (int o = tid; o < 2 * C; o += kGbfThreads) {
+    const int q = o >> 4, v = o & 15;
+    float t = 0.f;
+    for (int j = 0; j < per_chunk; ++j) t += s_part[(q + j * c8) * 17 + v];
+    s_loc[o] = t;
+  }
+  cluster.sync();
+  for (int o = tid; o < 2 * C; o += kGbfThreads) {
+    float t = 0.f;
+    for (int r = 0; r < cs; ++r) t += *(cluster.map_shared_rank(s_loc + o, r));
+    s_tot[o] = t;
+  }
+  cluster.sync();  // every CTA has finished reading its peers' s_loc
+  for (int c = tid; c < C; c += kGbfThreads) {
+    // (sum g, sum g*x) -> (S1, S2 = rstd * (sum g*x - mean * sum g)), scaled by g_scale
+    const float mean = s_mr[2 * c], rstd = s_mr[2 * c + 1];
+    const float S1 = s_tot[2 * c] * a.g_scale;
+    const float S2 = rstd * (s_tot[2 * c + 1] - mean * s_tot[2 * c]) * a.g_scale;
+    s_loc[2 * c] = S1;  // s_loc is free again: per-channel (S1, S2)
+    s_loc[2 * c + 1] = S2;
+    if (rank == 0) {
+      a.sums[(static_cast<int64_t>(b) * C + c) * 2] = S1;
+      a.sums[(static_cast<int64_t>(b) * C + c) * 2 + 1] = S2;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kGbfThreads) {
+    const int g = c / a.cpg;
+    float T1 = 0.f, T2 = 0.f;
+    for (int k = g * a.cpg; k < (g + 1) * a.cpg && k < a.C_real; ++k) {
+      const float gm = a.gamma[k];
+      T1 = fmaf(gm, s_loc[2 * k], T1);
+      T2 = fmaf(gm, s_loc[2 * k + 1], T2);
+    }
+    const float mean = s_mr[2 * c], rstd = s_mr[2 * c + 1];
+    const float k1 = rstd * T1 / a.cnt, k2 = rstd * T2 / a.cnt;
+    const float gm = (c < a.C_real) ? a.gamma[c] : 0.f;
+    // dx = rstd*gamma*dy - k1 - xhat*k2 = A*g + Bc + Cc*x
+    s_coef[3 * c] = rstd * gm * a.g_scale;
+    s_coef[3 * c + 1] = -k1 + mean * rstd * k2;
+    s_coef[3 * c + 2] = -rstd * k2;
+  }
+  __syncthreads();
+  float cA[8], cB[8], cC[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    cA[e] = s_coef[3 * (cc + e)];
+    cB[e] = s_coef[3 * (cc + e) + 1];
+    cC[e] = s_coef[3 * (cc + e) + 2];
+  }
+  uint4* __restrict__ dxp = reinterpret_cast<uint4*>(a.dx) + base;
+  uint4* __restrict__ dyp = a.dy_out ? reinterpret_cast<uint4*>(a.dy_out) + base : nullptr;
+  const bool scale_dy = a.g_scale != 1.f;
+  for (int i = tid; i < len; i += kGbfThreads) {
+    const uint4 gq = s_g[i];
+    float g[8], x[8];
+    unpack8(gq, g);
+    unpack8(s_x[i], x);
+    uint4 u;
+    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = fmaf(cA[2 * e], g[2 * e], fmaf(cC[2 * e], x[2 * e], cB[2 * e]));
+      const float d1 = fmaf(cA[2 * e + 1], g[2 * e + 1], fmaf(cC[2 * e + 1], x[2 * e + 1], cB[2 * e + 1]));
+      h2[e] = __floats2half2_rn(d0, d1);
+    }
+    dxp[i] = u;
+    if (dyp) {
+      if (scale_dy) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(g[2 * e] * a.g_scale, g[2 * e + 1] * a.g_scale);
+        dyp[i] = u;
+      } else {
+        dyp[i] = gq;
+      }
+    }
+  }
+}
+
+struct GbfPlan {
+  int cs, slice, slice_bytes, y_region, smem;
+};
+static bool gbf_plan(const GnBwdArgs& a, GbfPlan& p) {
+  if (a.x_fp32 || a.C % 8 != 0) return false;
+  const int c8 = a.C / 8;
+  if (c8 > kGbfThreads || (kGbfThreads % c8) != 0) return false;
+  const int64_t n8 = static_cast<int64_t>(a.HW) * c8;
+  if (n8 <= 0 || n8 > (1 << 24)) return false;
+  // smallest cluster whose CTAs stage <= ~48 KB (4 CTAs per SM), at most 8 CTAs (<= ~100 KB: 2 CTAs per SM)
+  for (int cs = 1; cs <= 8; cs <<= 1) {
+    int slice = static_cast<int>(ceil_div64(n8, cs));
+    slice = ceil_div(slice, c8) * c8;
+    const int slice_bytes = (slice * 16 + 127) & ~127;
+    const int y_region = std::max(kGbfScratch, a.relu_ref ? slice_bytes : 0);
+    const int smem = 2 * slice_bytes + y_region + 9 * a.C * 4;
+    if (smem <= 50 * 1024 || (cs == 8 && smem <= 110 * 1024)) {
+      p = GbfPlan{cs, slice, slice_bytes, y_region, smem};
+      return true;
+    }
+  }
+  return false;
+}
+
+// 1 when the fused kernel can take this shape (the caller falls back to reduce + apply otherwise)
+int gn_bwd_fused_supported(const GnBwdArgs& a) {
+  GnBwdArgs t = a;
+  t.relu_ref = reinterpret_cast<const __half*>(1);  // worst case: with a ReLU reference slice
+  GbfPlan p;
+  return gbf_plan(t, p) ? 1 : 0;
+}
+
+int gn_bwd_fused_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
+  GbfPlan p;
+  PNVO_REQUIRE(gbf_plan(a, p), "gn_bwd_fused: unsupported shape C=%d HW=%d", a.C, a.HW);
+  if (B <= 0 || a.HW <= 0) return 0;
+  const int n8 = a.HW * (a.C / 8);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.cs, B, 1);
+  cfg.blockDim = dim3(kGbfThreads, 1, 1);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p.cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel, a, n8, p.cs, p.slice, p.slice_bytes, p.y_region);
+  if (e != cudaSuccess) {
+    set_error("gn_bwd_fused: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  count_launch();
+  return check_launch("gn_bwd_fused");
+}
+
+}  // namespace pnvo

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(256) discretize_kernel(const float* __restrict
 struct TopDownArgs {
   const float* depth;
   int64_t in_stride;
+  int64_t in_pix;  // floats between consecutive pixels of one frame (1, or 2 for a [.., 2] depth-pair tensor)
+  int in_group, out_group;  // frames interleaved per group: frame n starts at (n / g) * stride + n % g
   int H, W;
   const float* ray;
   pnvo_topdown_consts k;
@@ -80,10 +82,10 @@ struct TopDownArgs {
   int32_t* count;
 };
 
-__device__ __forceinline__ float blur_h(const float* row, int c, int W) {
-  const float a = (c > 0) ? row[c - 1] : 0.0f;
-  const float b = row[c];
-  const float d = (c + 1 < W) ? row[c + 1] : 0.0f;
+__device__ __forceinline__ float blur_h(const float* row, int c, int W, int64_t ps) {
+  const float a = (c > 0) ? row[(c - 1) * ps] : 0.0f;
+  const float b = row[c * ps];
+  const float d = (c + 1 < W) ? row[(c + 1) * ps] : 0.0f;
   return __fadd_rn(__fmul_rn(__fadd_rn(a, d), 0.25f), __fmul_rn(b, 0.5f));
 }
 
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   __shared__ int s_bbox[4];
   __shared__ int s_max;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const float* __restrict__ D = a.depth + static_cast<int64_t>(blockIdx.x) * a.in_stride;
+  const float* __restrict__ D = a.depth + static_cast<int64_t>(blockIdx.x / a.in_group) * a.in_stride + blockIdx.x % a.in_group;
+  const int64_t ps = a.in_pix;
 
   for (int i = tid; i < hist_words; i += nt) hist[i] = 0u;
   for (int i = tid; i < H + W; i += nt) s_row_any[i] = 0;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   __syncthreads();
   // phase 1: any(depth > 0) per row / column (depth >= 0, so fp32 sum > 0 <=> any element > 0)
   for (int i = tid; i < n_cells; i += nt) {
-    const float d = __ldg(D + i);
+    const float d = __ldg(D + static_cast<int64_t>(i) * ps);
     if (d > 0.0f) {
       const int r = i / W;
       const int c = i - r * W;
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     if (s_col_any[i]) { atomicMin(&s_bbox[2], i); atomicMax(&s_bbox[3], i); }
   __syncthreads();
   const int r0 = s_bbox[0], r1 = s_bbox[1], c0 = s_bbox[2], c1 = s_bbox[3];
-  float* __restrict__ out = a.out + static_cast<int64_t>(blockIdx.x) * a.out_frame_stride;
+  float* __restrict__ out = a.out + static_cast<int64_t>(blockIdx.x / a.out_group) * a.out_frame_stride + blockIdx.x % a.out_group;
   int32_t* cnt_out = a.count ? a.count + static_cast<int64_t>(blockIdx.x) * n_cells : nullptr;
   if (r1 < 0) {  // geometry_utils.py:519-525: empty frame -> all-zero map
     for (int i = tid; i < n_cells; i += nt) {
@@ -152,9 +155,9 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     const int r = r0 + ra + rr;  // frame row
     const int c = c0 + cc;       // frame column
     // horizontal pass on rows r-1, r, r+1 (zero outside the crop == zero outside the frame / bbox)
-    const float hm = (r > r0) ? blur_h(D + static_cast<int64_t>(r - 1) * W, c, W) : 0.0f;
-    const float h0 = blur_h(D + static_cast<int64_t>(r) * W, c, W);
-    const float hp = (r < r1) ? blur_h(D + static_cast<int64_t>(r + 1) * W, c, W) : 0.0f;
+    const float hm = (r > r0) ? blur_h(D + static_cast<int64_t>(r - 1) * W * ps, c, W, ps) : 0.0f;
+    const float h0 = blur_h(D + static_cast<int64_t>(r) * W * ps, c, W, ps);
+    const float hp = (r < r1) ? blur_h(D + static_cast<int64_t>(r + 1) * W * ps, c, W, ps) : 0.0f;
     const float v = __fadd_rn(__fmul_rn(__fadd_rn(hm, hp), 0.25f), __fmul_rn(h0, 0.5f));
     const float z = __fadd_rn(__fmul_rn(v, a.k.depth_scale), a.k.depth_off);  // :558-560
     const float x = __fmul_rn(__ldg(a.ray + c), z);                            // :656
@@ -326,6 +329,11 @@ __global__ void goal_update_kernel(double* __restrict__ goal, const float* __res
 
 }  // namespace pnvo
 
+namespace pnvo {
+int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride, int in_group, int out_group,
+                   int n_frames, int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
+                   int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
+}
 using namespace pnvo;
 
 extern "C" int pnvo_discretize_depth(const float* depth, int64_t n_pix, const float* edges, int n_channels,
@@ -348,12 +356,30 @@ extern "C" int pnvo_discretize_depth(const float* depth, int64_t n_pix, const fl
 extern "C" int pnvo_topdown_project(const float* depth, int64_t in_stride, int n_frames, int H, int W,
                                     const float* ray, const pnvo_topdown_consts* consts, float* out,
                                     int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream) {
+  return pnvo::topdown_launch(depth, in_stride, 1, 1, 1, n_frames, H, W, ray, consts, out, out_frame_stride,
+                              out_pix_stride, count, stream);
+}
+
+extern "C" int pnvo_topdown_project_strided(const float* depth, int64_t in_stride, int64_t in_pix_stride, int n_frames,
+                                            int H, int W, const float* ray, const pnvo_topdown_consts* consts,
+                                            float* out, int64_t out_frame_stride, int64_t out_pix_stride,
+                                            int32_t* count, void* stream) {
+  return pnvo::topdown_launch(depth, in_stride, in_pix_stride, static_cast<int>(in_pix_stride),
+                              static_cast<int>(out_pix_stride), n_frames, H, W, ray, consts, out, out_frame_stride,
+                              out_pix_stride, count, stream);
+}
+
+namespace pnvo {
+int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride, int in_group, int out_group,
+                   int n_frames, int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
+                   int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream) {
   PNVO_REQUIRE(depth && ray && consts && out, "topdown_project: null argument");
   PNVO_REQUIRE(H > 0 && W > 0 && static_cast<int64_t>(H) * W <= 110000, "topdown_project: frame %dx%d too large", H, W);
   PNVO_REQUIRE(consts->rows_around_center * 2 * W < 65535, "topdown_project: too many points for uint16 counts");
   if (n_frames <= 0) return 0;
   TopDownArgs a;
-  a.depth = depth; a.in_stride = in_stride; a.H = H; a.W = W; a.ray = ray; a.k = *consts;
+  PNVO_REQUIRE(in_pix_stride >= 1, "topdown_project: in_pix_stride");
+  a.depth = depth; a.in_stride = in_stride; a.in_pix = in_pix_stride; a.in_group = in_group; a.out_group = out_group; a.H = H; a.W = W; a.ray = ray; a.k = *consts;
   a.out = out; a.out_frame_stride = out_frame_stride; a.out_pix_stride = out_pix_stride; a.count = count;
   const size_t smem = static_cast<size_t>((H * W + 1) / 2) * 4 + static_cast<size_t>(H + W) * 4;
   static bool attr_set = false;
@@ -365,6 +391,7 @@ extern "C" int pnvo_topdown_project(const float* depth, int64_t in_stride, int n
   count_launch();
   return check_launch("topdown_project");
 }
+}  // namespace pnvo
 
 extern "C" int pnvo_gae_scan(const float* rewards, float* value_preds, const float* masks, const float* next_value,
                              float* returns, int T, int N, int use_gae, float gamma, float gamma_tau, int mode,

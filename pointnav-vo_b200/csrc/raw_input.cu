@@ -1,0 +1,302 @@
+// VO input pipeline on the device: the reference derives the discretised-depth and
+// top-down channels on the host (vo/dataset/regression_geo_invariance_iter_dataset.py:237-267), ships 30 fp32
+// channels per pixel (120 B) and re-reads them for the running statistics and the concat / normalise
+// (vo_cnn.py:110-176, running_mean_and_var.py:22-63).  Here the step's inputs stay in their raw form -- uint8 rgb
+// pairs [B,H,W,6], fp32 depth pairs [B,H,W,2] and the top-down maps [B,H,W,2] produced by pnvo_topdown_project --
+// (22 B per pixel) and two streaming kernels read exactly those bytes:
+//   raw_stats    per-channel sum / sum of squares of the assembled (un-normalised) input: rgb exactly in integers,
+//                the one-hot depth bins as counts, depth / top-down in fp32 -> fp64 atomics per block
+//   raw_assemble [prev: rgb/255, depth, one-hot bins, top-down | cur: ...] -> (v*scale + shift) -> NHWC fp16,
+//                channels padded to Cpad, optional W-padded rows for the stem kernel
+// The one-hot bin follows base_trainer_with_vo.py:135-167 exactly (fp32 edges, >= / <, closed last bin).
+#include "common.cuh"
+#include "elem.cuh"
+
+namespace pnvo {
+
+static constexpr int kRawMaxBins = 16;
+
+struct RawArgs {
+  const uint8_t* rgb;   // [n_pix][6] (prev rgb, cur rgb) or null
+  const float* depth;   // [n_pix][2] or null (needed for the depth and the one-hot channels)
+  const float* td;      // [n_pix][2] or null
+  const float* edges;   // n_dd + 1 fp32 bin edges (device)
+  int use_rgb, use_depth, n_dd, use_td;
+  int C, Cpad;          // 2 * per-frame channels, padded channel count (multiple of 8, <= 32)
+  int64_t n_pix;
+  const float* scale;
+  const float* shift;
+  __half* out;
+  int row_w, out_pitch;
+  double* stats;        // [2C] (sum, sumsq) interleaved, accumulated
+};
+
+__device__ __forceinline__ int depth_bin(float d, const float* s_edges, int n) {
+  if (!(d >= s_edges[0] && d <= s_edges[n])) return -1;  // the reference asserts against this
+  int idx = 0;
+  for (int i = 1; i < n; ++i) idx += (d >= s_edges[i]) ? 1 : 0;
+  return idx;
+}
+
+// RGB / DEP / TD: 0 or 1; NDD: number of one-hot bins (compile-time layout), or -1 = every flag read at run time
+template <int RGB, int DEP, int NDD, int TD>
+__global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
+  __shared__ float s_scale[kMaxInC], s_shift[kMaxInC], s_edges[kRawMaxBins + 1];
+  if (threadIdx.x < kMaxInC) {
+    const int c = threadIdx.x;
+    s_scale[c] = (c < a.C) ? (a.scale ? a.scale[c] : 1.f) : 0.f;
+    s_shift[c] = (c < a.C && a.shift) ? a.shift[c] : 0.f;
+  }
+  if (threadIdx.x <= a.n_dd && a.n_dd > 0) s_edges[threadIdx.x] = a.edges[threadIdx.x];
+  __syncthreads();
+  constexpr bool kGeneric = NDD < 0;
+  const int use_rgb = kGeneric ? a.use_rgb : RGB, use_depth = kGeneric ? a.use_depth : DEP;
+  const int n_dd = kGeneric ? a.n_dd : NDD, use_td = kGeneric ? a.use_td : TD;
+  const int cf = 3 * use_rgb + use_depth + n_dd + use_td;  // channels per frame
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < a.n_pix;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v[kMaxInC];
+#pragma unroll
+    for (int c = 0; c < kMaxInC; ++c) v[c] = 0.f;
+    float rgbv[6] = {0, 0, 0, 0, 0, 0};
+    float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
+    if (use_rgb) {
+      const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
+      const uint32_t w0 = r16[0], w1 = r16[1], w2 = r16[2];
+      // rgb / 255 as the reference divides (vo_cnn.py:117-118): fp32 division
+      rgbv[0] = __fdiv_rn(static_cast<float>(w0 & 0xff), 255.f);
+      rgbv[1] = __fdiv_rn(static_cast<float>(w0 >> 8), 255.f);
+      rgbv[2] = __fdiv_rn(static_cast<float>(w1 & 0xff), 255.f);
+      rgbv[3] = __fdiv_rn(static_cast<float>(w1 >> 8), 255.f);
+      rgbv[4] = __fdiv_rn(static_cast<float>(w2 & 0xff), 255.f);
+      rgbv[5] = __fdiv_rn(static_cast<float>(w2 >> 8), 255.f);
+    }
+    if (use_depth || n_dd > 0) d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
+    if (use_td) t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
+    // channel placement, fully unrolled so that v[] stays in registers; with a compile-time layout every
+    // comparison below folds away
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      int cur = f * cf;
+      const float dd = f ? d.y : d.x;
+      if (use_rgb) {
+#pragma unroll
+        for (int c = 0; c < kMaxInC; ++c) {
+          if (c == cur) v[c] = rgbv[3 * f];
+          if (c == cur + 1) v[c] = rgbv[3 * f + 1];
+          if (c == cur + 2) v[c] = rgbv[3 * f + 2];
+        }
+        cur += 3;
+      }
+      if (use_depth) {
+#pragma unroll
+        for (int c = 0; c < kMaxInC; ++c)
+          if (c == cur) v[c] = dd;
+        cur += 1;
+      }
+      if (n_dd > 0) {
+        const int bin = depth_bin(dd, s_edges, n_dd);
+#pragma unroll
+        for (int c = 0; c < kMaxInC; ++c)
+          if (c >= cur && c < cur + n_dd && c - cur == bin) v[c] = 1.f;
+        cur += n_dd;
+      }
+      if (use_td) {
+        const float tv = f ? t.y : t.x;
+#pragma unroll
+        for (int c = 0; c < kMaxInC; ++c)
+          if (c == cur) v[c] = tv;
+      }
+    }
+    int64_t opix = p;
+    if (a.out_pitch > 0) opix = (p / a.row_w) * a.out_pitch + (p % a.row_w) + 3;  // zero halo left of the image
+    __half* __restrict__ out = a.out + opix * a.Cpad;
+#pragma unroll
+    for (int q = 0; q < kMaxInC / 8; ++q) {
+      if (q * 8 < a.Cpad) {
+        uint4 u;
+        __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = q * 8 + 2 * e;
+          h2[e] = __floats2half2_rn(fmaf(v[c], s_scale[c], s_shift[c]), fmaf(v[c + 1], s_scale[c + 1], s_shift[c + 1]));
+        }
+        *reinterpret_cast<uint4*>(out + q * 8) = u;
+      }
+    }
+  }
+}
+
+// values per thread: rgb 6 x (sum, sumsq) as uint32, depth / td 2 x (sum, sumsq) fp32, bins 2 x kRawMaxBins counts
+static constexpr int kRawVals = 12 + 4 + 4 + 2 * kRawMaxBins;
+
+__global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
+  __shared__ float s_edges[kRawMaxBins + 1];
+  __shared__ double s_red[8][kRawVals];
+  if (threadIdx.x <= a.n_dd && a.n_dd > 0) s_edges[threadIdx.x] = a.edges[threadIdx.x];
+  __syncthreads();
+  uint32_t ri[12];
+  float fs[8];
+  uint32_t cnt[2 * kRawMaxBins];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) ri[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fs[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * kRawMaxBins; ++i) cnt[i] = 0u;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < a.n_pix;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (a.use_rgb) {
+      const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
+      const uint32_t w[3] = {r16[0], r16[1], r16[2]};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t lo = w[k] & 0xff, hi = w[k] >> 8;
+        ri[4 * k] += lo; ri[4 * k + 1] += lo * lo;
+        ri[4 * k + 2] += hi; ri[4 * k + 3] += hi * hi;
+      }
+    }
+    if (a.depth) {
+      const float2 d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
+      fs[0] += d.x; fs[1] = fmaf(d.x, d.x, fs[1]);
+      fs[2] += d.y; fs[3] = fmaf(d.y, d.y, fs[3]);
+      if (a.n_dd > 0) {
+        const int b0 = depth_bin(d.x, s_edges, a.n_dd), b1 = depth_bin(d.y, s_edges, a.n_dd);
+#pragma unroll
+        for (int i = 0; i < kRawMaxBins; ++i) {
+          cnt[i] += (b0 == i) ? 1u : 0u;
+          cnt[kRawMaxBins + i] += (b1 == i) ? 1u : 0u;
+        }
+      }
+    }
+    if (a.use_td) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
+      fs[4] += t.x; fs[5] = fmaf(t.x, t.x, fs[5]);
+      fs[6] += t.y; fs[7] = fmaf(t.y, t.y, fs[7]);
+    }
+  }
+  // warp reduction (integers exactly, floats in fp64), then across the 8 warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double vals[kRawVals];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    uint32_t x = ri[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    vals[i] = static_cast<double>(x);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double x = static_cast<double>(fs[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    vals[12 + i] = x;
+  }
+#pragma unroll
+  for (int i = 0; i < 2 * kRawMaxBins; ++i) {
+    uint32_t x = cnt[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    vals[20 + i] = static_cast<double>(x);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kRawVals; ++i) s_red[warp][i] = vals[i];
+  }
+  __syncthreads();
+  // thread c < C: gather the (sum, sumsq) of output channel c and add it to the global accumulator
+  const int c = threadIdx.x;
+  if (c < a.C) {
+    const int cf = a.C >> 1;
+    const int f = c / cf;
+    int k = c - f * cf;
+    auto tot = [&](int i) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += s_red[w][i];
+      return t;
+    };
+    double s = 0.0, q = 0.0;
+    bool done = false;
+    if (a.use_rgb) {
+      if (k < 3) {
+        // rgb channel j = 3f + k lives in word j / 2, half j & 1: ri index 4*(j/2) + 2*(j&1)
+        const int j = 3 * f + k;
+        const int base = 4 * (j >> 1) + 2 * (j & 1);
+        s = tot(base) / 255.0;
+        q = tot(base + 1) / (255.0 * 255.0);
+        done = true;
+      }
+      k -= 3;
+    }
+    if (!done && a.use_depth) {
+      if (k == 0) { s = tot(12 + 2 * f); q = tot(12 + 2 * f + 1); done = true; }
+      k -= 1;
+    }
+    if (!done && a.n_dd > 0) {
+      if (k < a.n_dd) { s = q = tot(20 + f * kRawMaxBins + k); done = true; }
+      k -= a.n_dd;
+    }
+    if (!done && a.use_td && k == 0) { s = tot(16 + 2 * f); q = tot(16 + 2 * f + 1); }
+    atomicAdd(a.stats + 2 * c, s);
+    atomicAdd(a.stats + 2 * c + 1, q);
+  }
+}
+
+static int raw_check(const RawArgs& a) {
+  const int cf = 3 * a.use_rgb + a.use_depth + a.n_dd + a.use_td;
+  PNVO_REQUIRE(cf >= 1 && 2 * cf == a.C && a.C <= kMaxInC, "raw input: %d channels per frame do not match C=%d", cf, a.C);
+  PNVO_REQUIRE(a.n_dd >= 0 && a.n_dd <= kRawMaxBins, "raw input: %d depth bins (max %d)", a.n_dd, kRawMaxBins);
+  PNVO_REQUIRE(!a.use_rgb || a.rgb, "raw input: rgb missing");
+  PNVO_REQUIRE(!(a.use_depth || a.n_dd) || a.depth, "raw input: depth missing");
+  PNVO_REQUIRE(!a.n_dd || a.edges, "raw input: bin edges missing");
+  PNVO_REQUIRE(!a.use_td || a.td, "raw input: top-down maps missing");
+  return 0;
+}
+
+int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
+  if (raw_check(a)) return -1;
+  PNVO_REQUIRE(a.out && a.Cpad % 8 == 0 && a.Cpad <= kMaxInC && a.C <= a.Cpad, "raw_assemble: bad output layout");
+  if (a.n_pix <= 0) return 0;
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
+  if (a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
+  else if (a.use_rgb && a.use_depth && a.n_dd == 0 && !a.use_td) raw_assemble_kernel<1, 1, 0, 0><<<blocks, 256, 0, st>>>(a);
+  else raw_assemble_kernel<0, 0, -1, 0><<<blocks, 256, 0, st>>>(a);
+  count_launch();
+  return check_launch("raw_assemble");
+}
+
+int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
+  if (raw_check(a)) return -1;
+  PNVO_REQUIRE(a.stats, "raw_stats: null accumulator");
+  if (a.n_pix <= 0) return 0;
+  // each thread sums <= 2^24 / 65025 = 258 pixels exactly in 32-bit integers; keep it at <= 128
+  int64_t blocks = std::max<int64_t>(148 * 8, ceil_div64(a.n_pix, 256 * 128));
+  blocks = std::min<int64_t>(blocks, ceil_div64(a.n_pix, 256));
+  raw_stats_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(a);
+  count_launch();
+  return check_launch("raw_stats");
+}
+
+int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st) {
+  // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats
+  // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch
+  (void)f;
+  RawArgs a{};
+  a.rgb = static_cast<const uint8_t*>(p[0]);
+  a.depth = static_cast<const float*>(p[1]);
+  a.td = static_cast<const float*>(p[2]);
+  a.edges = static_cast<const float*>(p[3]);
+  a.scale = static_cast<const float*>(p[4]);
+  a.shift = static_cast<const float*>(p[5]);
+  a.use_rgb = i[0]; a.use_depth = i[1]; a.n_dd = i[2]; a.use_td = i[3]; a.C = i[4]; a.Cpad = i[5];
+  a.n_pix = (static_cast<int64_t>(static_cast<uint32_t>(i[7])) << 32) | static_cast<uint32_t>(i[6]);
+  a.row_w = i[8]; a.out_pitch = i[9];
+  if (code == PNVO_OP_RAW_ASSEMBLE) {
+    a.out = static_cast<__half*>(p[6]);
+    return raw_assemble_launch(a, st);
+  }
+  a.stats = static_cast<double*>(p[6]);
+  return raw_stats_launch(a, st);
+}
+
+}  // namespace pnvo

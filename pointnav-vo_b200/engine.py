@@ -134,6 +134,7 @@ class EncoderPlan:
         self.raw_fp32 = raw_fp32
         self.head = head
         self.dropout_p = float(dropout_p) if head is not None and head.get("out_dim") else 0.0
+        self.fuse_gn_bwd = True
         self.grads = {}
         self._build_layers(backbone, baseplanes, ngroups, compression_channels)
         self._alloc()
@@ -324,6 +325,12 @@ class EncoderPlan:
                            g.C, g.G, g.cpg, HW, float(g.cpg_real * HW), self.raw_fp32, 1e-5, g.C_real, g_scale)
 
     def _gn_bwd_all(self, ops, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
+        if self.fuse_gn_bwd and L.load().pnvo_gn_bwd_fused_supported(g.C, HW, int(self.raw_fp32)):
+            # one pass: a cluster per sample keeps g / x in registers between the reduction and the apply
+            ops.append(self._gn_bwd("fused", g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
+            ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B,
+                                          g.C, g.C_real))
+            return
         ops.append(self._gn_bwd(True, g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
         ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B, g.C,
                                       g.C_real))

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM = range(16, 27)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE = range(16, 30)
 
 
 class PnvoOp(ctypes.Structure):
@@ -36,7 +36,7 @@ _lib = None
 
 EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_discretize_depth",
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
-           "pnvo_launch_count", "pnvo_stem_padded_width"]
+           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided"]
 
 
 def load():
@@ -55,8 +55,13 @@ def load():
     lib.pnvo_launch_count.restype = i64
     lib.pnvo_stem_padded_width.argtypes = [i32]
     lib.pnvo_stem_padded_width.restype = i32
+    lib.pnvo_gn_bwd_fused_supported.argtypes = [i32, i32, i32]
+    lib.pnvo_gn_bwd_fused_supported.restype = i32
     lib.pnvo_discretize_depth.argtypes = [vp, i64, vp, i32, vp, i64, vp, vp, vp]
     lib.pnvo_topdown_project.argtypes = [vp, i64, i32, i32, i32, vp, ctypes.POINTER(TopdownConsts), vp, i64, i64, vp, vp]
+    lib.pnvo_topdown_project_strided.argtypes = [vp, i64, i64, i32, i32, i32, vp, ctypes.POINTER(TopdownConsts), vp, i64,
+                                                 i64, vp, vp]
+    lib.pnvo_topdown_project_strided.restype = i32
     lib.pnvo_gae_scan.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
     lib.pnvo_goal_update.argtypes = [vp, vp, vp, i32, vp]
     lib.pnvo_run_ops.argtypes = [ctypes.POINTER(PnvoOp), i32, vp]
@@ -139,6 +144,22 @@ def op_input_stats(srcs, nch, pre_scale, lut, C, Cpad, n_pix, stats_f64):
     return _op(OP_INPUT_STATS, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [None, None, stats_f64])
 
 
+def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0):
+    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch]
+
+
+def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, stats_f64):
+    """Batch statistics of the assembled input straight from the raw pairs (csrc/raw_input.cu)."""
+    return _op(OP_RAW_STATS, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix), (),
+               [rgb_u8, depth, td, edges, None, None, stats_f64])
+
+
+def op_raw_assemble(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, scale, shift, out,
+                    row_w=0, out_pitch=0):
+    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch), (),
+               [rgb_u8, depth, td, edges, scale, shift, out])
+
+
 def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv, n_batch, pix_per_sample):
     return _op(OP_RMV_UPDATE, [C, int(update), int(have_rmv)], [n_batch, pix_per_sample],
                [stats_f64, mean, var, count, scale, shift])
@@ -174,7 +195,8 @@ def op_pool_bwd(g, pooled, argmax, dy, B, C, H, W, PH, PW):
 
 def op_gn_bwd(reduce, g, relu_ref, x, stats, gamma, sums, dx, dy_out, B, C, G, cpg, HW, cnt, x_fp32=False, eps=1e-5,
               C_real=None, g_scale=1.0):
-    return _op(OP_GN_BWD_REDUCE if reduce else OP_GN_BWD_APPLY,
+    code = OP_GN_BWD_FUSED if reduce == "fused" else (OP_GN_BWD_REDUCE if reduce else OP_GN_BWD_APPLY)
+    return _op(code,
                [B, C, G, cpg, HW, 0, int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real], [cnt, eps, g_scale],
                [g, relu_ref, x, stats, gamma, sums, dx, dy_out])
 

@@ -139,6 +139,24 @@ class NormalizedDepth2TopDownViewHabitatTorch:
         return (res, cnt) if return_counts else res
 
 
+def gen_top_down_view_pairs(generator, depth_pairs, out=None):
+    """Top-down maps of both frames of every depth pair in ONE launch, reading the interleaved [B, H, W, 2]
+    tensor in place (no per-frame copies) and writing [B, H, W, 2] (channel 0 = prev, 1 = cur): what
+    base_trainer_with_vo.py:232-269 / regression_geo_invariance_iter_dataset.py:251-267 compute frame by frame."""
+    H, W = generator._vis_size_h, generator._vis_size_w
+    d = depth_pairs
+    assert d.is_cuda and d.dtype == torch.float32 and d.is_contiguous() and d.shape[1:] == (H, W, 2)
+    B = d.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, 2), dtype=torch.float32, device=d.device)
+    assert out.is_contiguous() and out.shape == (B, H, W, 2) and out.dtype == torch.float32
+    lib = _lib.load()
+    _lib.check(lib.pnvo_topdown_project_strided(_lib.ptr(d), 2 * H * W, 2, 2 * B, H, W,
+                                                _lib.ptr(generator._ray_on(d.device)), ctypes.byref(generator._consts),
+                                                _lib.ptr(out), 2 * H * W, 2, None, _lib.stream_ptr(d.device)))
+    return out
+
+
 def compute_goal_pos_batched(prev_goal_xyz, local_delta_states):
     """geometry_utils.py:115-144 for n agents at once.  prev_goal_xyz: CUDA fp64 [n,3] (updated in place),
     local_delta_states: CUDA fp32 [n,3] = (dx, dz, dyaw).  Returns {"cartesian": [n,3] f64, "polar": [n,2] f32}."""

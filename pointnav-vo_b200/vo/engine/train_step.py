@@ -16,6 +16,52 @@ import torch
 from ... import lib as L
 
 
+class PrefetchedBatches:
+    """Double-buffered host -> device staging of training batches (the device-side replacement of the reference's
+    `_transfer_batch`, vo_cnn_regression_geo_invariance_engine.py:283-353, which copies a list of unpinned CPU
+    tensors synchronously in front of every forward).  `submit()` enqueues the copy of the NEXT batch from pinned
+    host memory on a side stream; `acquire()` makes the compute stream wait for the oldest submitted batch and
+    returns its device tensors; `release()` lets the copy stream reuse the slot.  With two slots the PCIe copy of
+    batch i+1 overlaps the kernels of step i."""
+
+    def __init__(self, example, device, slots=2):
+        self.dev = torch.device(device)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in example.items()}
+                     for _ in range(slots)]
+        self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self.free = [torch.cuda.Event() for _ in range(slots)]
+        self.head = self.tail = 0  # next slot to fill / next slot to hand out
+        self.pending = 0
+        self.bytes_per_batch = sum(v.numel() * v.element_size() for v in example.values())
+
+    def submit(self, host_batch):
+        assert self.pending < len(self.bufs), "all staging slots are in flight: acquire()/release() one first"
+        s = self.head
+        self.stream.wait_event(self.free[s])
+        with torch.cuda.stream(self.stream):
+            for k, v in host_batch.items():
+                if not v.is_pinned():
+                    raise L.PnvoError(f"host batch tensor {k!r} must live in pinned memory")
+                self.bufs[s][k].copy_(v, non_blocking=True)
+            self.ready[s].record(self.stream)
+        self.head = (s + 1) % len(self.bufs)
+        self.pending += 1
+
+    def acquire(self):
+        assert self.pending > 0, "acquire() without a submitted batch"
+        s = self.tail
+        torch.cuda.current_stream(self.dev).wait_event(self.ready[s])
+        self._held = s
+        return self.bufs[s]
+
+    def release(self):
+        s = self._held
+        self.free[s].record(torch.cuda.current_stream(self.dev))
+        self.tail = (s + 1) % len(self.bufs)
+        self.pending -= 1
+
+
 class FusedVOTrainStep:
     def __init__(self, model, lr=2.5e-4, betas=(0.9, 0.999), eps=1e-8, loss_weights=(1.0, 1.0, 1.0),
                  process_group=None):
@@ -69,8 +115,9 @@ class FusedVOTrainStep:
         return plan
 
     def step(self, obs, target):
-        """obs: dict of NHWC fp32 CUDA tensors (the model's forward input); target: [B, 3] fp32 CUDA.
-        Returns the (device) loss tensor of this rank's batch."""
+        """obs: dict of NHWC fp32 CUDA tensors (the model's forward input), or the raw pairs
+        {"rgb": uint8 [B,H,W,6], "depth": fp32 [B,H,W,2]} (derived channels computed on the device);
+        target: [B, 3] fp32 CUDA.  Returns the (device) loss tensor of this rank's batch."""
         model = self.model
         plan = self._get_plan(obs)
         self._target.copy_(target)

@@ -146,9 +146,33 @@ class VisualOdometryCNNBase(nn.Module):
     def _signature(self):
         return tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers())
 
+    # ---------------------------------------------------------------- raw observation pairs
+    # forward() also accepts the step's inputs in the form the simulator / dataset stores them:
+    #   {"rgb": uint8 [B,H,W,6], "depth": fp32 [B,H,W,2]}   (prev | cur on the channel axis)
+    # The discretised-depth and top-down channels are then derived on the device (csrc/raw_input.cu,
+    # pnvo_topdown_project_strided) instead of being shipped as 22 extra fp32 channels per pixel
+    # (vo/dataset/regression_geo_invariance_iter_dataset.py:237-267, base_trainer_with_vo.py:212-269).
+    def set_raw_input_config(self, top_down_generator=None, discretized_depth_end_vals=None):
+        """Geometry of the derived channels; defaults = configs/vo/vo_pointnav.yaml (VO.GEOMETRY, 10 bins)."""
+        self._raw_td_gen = top_down_generator
+        self._raw_dd_end_vals = discretized_depth_end_vals
+
+    def _is_raw(self, obs):
+        enc = self.visual_encoder
+        rgb = obs.get("rgb")
+        if rgb is not None and rgb.dtype == torch.uint8:
+            return True
+        return any(k not in obs for k, _, _ in enc._sources)
+
+    def _first_tensor(self, obs):
+        for k in ("rgb", "depth"):
+            if k in obs:
+                return obs[k]
+        return obs[self.visual_encoder._sources[0][0]]
+
     def _plan_for(self, obs, need_grad, training=False):
         enc = self.visual_encoder
-        first = obs[enc._sources[0][0]]
+        first = self._first_tensor(obs) if self._is_raw(obs) else obs[enc._sources[0][0]]
         if not first.is_cuda:
             raise L.PnvoError("VO model inputs must be CUDA tensors: the B200 path has no CPU fallback")
         L.load()
@@ -182,7 +206,72 @@ class VisualOdometryCNNBase(nn.Module):
     def _weights_version(self):
         return sum(p._version for p in self.parameters())
 
+    def _run_forward_raw(self, plan, obs, training):
+        from ...utils import geometry_utils as gu
+
+        enc = self.visual_encoder
+        dev = plan.dev
+        keys = [k for k, _, _ in enc._sources]
+        use_rgb, use_depth = "rgb" in keys, "depth" in keys
+        n_dd = enc._n_input_discretized_depth // 2
+        use_td = "top_down_view" in keys
+        H, W, B = plan.H, plan.W, plan.B
+        rgb = depth = td = edges = None
+        if use_rgb:
+            rgb = obs["rgb"]
+            if rgb.dtype != torch.uint8 or not rgb.is_contiguous() or tuple(rgb.shape) != (B, H, W, 6):
+                raise L.PnvoError("raw rgb pairs must be contiguous uint8 [B, H, W, 6]")
+        if use_depth or n_dd or use_td:
+            depth = obs["depth"]
+            if depth.dtype != torch.float32 or not depth.is_contiguous() or tuple(depth.shape) != (B, H, W, 2):
+                raise L.PnvoError("raw depth pairs must be contiguous fp32 [B, H, W, 2]")
+        if n_dd:
+            end_vals = getattr(self, "_raw_dd_end_vals", None) or gu.discretize_end_vals(n_dd)
+            edges = gu._edges(end_vals, dev)
+        if use_td:
+            td = obs.get("top_down_view")
+            if td is None:
+                gen = getattr(self, "_raw_td_gen", None)
+                if gen is None:  # configs/vo/vo_pointnav.yaml: VO.GEOMETRY (hfov passed verbatim)
+                    gen = self._raw_td_gen = gu.NormalizedDepth2TopDownViewHabitatTorch(0.1, 10.0, H, W, 70)
+                if getattr(plan, "td_pair", None) is None:
+                    plan.td_pair = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev)
+                td = gu.gen_top_down_view_pairs(gen, depth, out=plan.td_pair)
+        C = enc.input_channels
+        n_pix = B * H * W
+        rmv = enc.running_mean_and_var
+        have_rmv = isinstance(rmv, RunningMeanAndVar)
+        ops = []
+        if have_rmv:
+            if training:
+                ops.append(L.op_zero(plan.in_stats))
+                ops.append(L.op_raw_stats(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
+                                          plan.in_stats))
+                if plan.world_size > 1:
+                    L.run_ops(ops, dev)
+                    ops = []
+                    torch.distributed.all_reduce(plan.in_stats)
+            ops.append(L.op_rmv_update(plan.in_stats, rmv._mean, rmv._var, rmv._count, plan.in_scale, plan.in_shift, C,
+                                       training, True, plan.B * plan.world_size, plan.H * plan.W))
+            scale, shift = plan.in_scale, plan.in_shift
+        else:
+            scale = shift = None
+        ops.append(L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
+                                     scale, shift, plan.x0, row_w=plan.W if plan.x0_pitch else 0,
+                                     out_pitch=plan.x0_pitch))
+        L.run_ops(ops, dev)
+        self._run_backbone(plan)
+
+    def _run_backbone(self, plan):
+        ver = self._weights_version()
+        if ver != self._packed_version or plan is not getattr(self, "_packed_plan", None):
+            plan.pack_prog.run(plan.dev)
+            self._packed_version, self._packed_plan = ver, plan
+        plan.fwd_prog.run(plan.dev)
+
     def _run_forward(self, plan, obs, training):
+        if self._is_raw(obs):
+            return self._run_forward_raw(plan, obs, training)
         enc = self.visual_encoder
         dev = plan.dev
         srcs, nch, pre, lut_prev, lut_cur = [], [], [], [], []
@@ -218,11 +307,7 @@ class VisualOdometryCNNBase(nn.Module):
         ops.append(L.op_assemble(srcs, nch, pre, lut, C, plan.cin_pad, n_pix, scale, shift, plan.x0,
                                  row_w=plan.W if plan.x0_pitch else 0, out_pitch=plan.x0_pitch))
         L.run_ops(ops, dev)
-        ver = self._weights_version()
-        if ver != self._packed_version or plan is not getattr(self, "_packed_plan", None):
-            plan.pack_prog.run(dev)
-            self._packed_version, self._packed_plan = ver, plan
-        plan.fwd_prog.run(dev)
+        self._run_backbone(plan)
 
     def forward(self, observation_pairs):
         params = [p for _, p in self.named_parameters()]

@@ -184,7 +184,7 @@ def test_conv_fprop_dgrad_wgrad(case, force_generic):
 
 
 @pytest.mark.parametrize("B,H,W,C,G,Cr", [(3, 24, 43, 64, 16, 64), (2, 6, 11, 32, 1, 31), (2, 12, 22, 128, 16, 128),
-                                         (2, 3, 6, 128, 1, 114)])
+                                         (2, 3, 6, 128, 1, 114), (3, 48, 86, 32, 16, 32), (2, 6, 11, 256, 16, 256)])
 def test_groupnorm_forward_backward(B, H, W, C, G, Cr):
     from pointnav_vo_b200 import lib as L
 
@@ -219,6 +219,36 @@ def test_groupnorm_forward_backward(B, H, W, C, G, Cr):
     assert rel(dg, gr.grad) <= 1e-3 and rel(db, br.grad) <= 1e-3
     mask = (ref.detach() > 0).float()
     assert rel(dyo[..., :Cr].permute(0, 3, 1, 2), g[..., :Cr].float().permute(0, 3, 1, 2) * mask) <= 1e-6
+    # one-pass variant (cluster per sample, DSMEM reduction): same results, bit-identical from run to run
+    assert L.load().pnvo_gn_bwd_fused_supported(C, HW, 0) == 1
+    outs = []
+    for _ in range(2):
+        sums2 = torch.full((B, C, 2), float("nan"), device=dev)  # the fused kernel needs no pre-zeroed buffer
+        dx2, dyo2 = torch.empty_like(x), torch.empty_like(x)
+        dg2, db2 = torch.zeros(Cr, device=dev), torch.zeros(Cr, device=dev)
+        args2 = (g, yfull, x, stats, gamma, sums2, dx2, dyo2, B, C, G, cpg, HW, float(cpg_r * HW), False, 1e-5, Cr)
+        L.run_ops([L.op_gn_bwd("fused", *args2), L.op_gn_param_grad(sums2, dg2, db2, B, C, Cr)])
+        outs.append((dx2, dyo2, dg2, db2))
+    assert rel(dx2[..., :Cr].permute(0, 3, 1, 2), xr.grad) <= 4e-3
+    assert rel(dg2, gr.grad) <= 1e-3 and rel(db2, br.grad) <= 1e-3
+    assert torch.equal(dyo2, dyo)
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+    # gradient scale (the compression GroupNorm behind inverted dropout), no identity-branch output
+    args3 = (g, yfull, x, stats, gamma, sums, dx, None, B, C, G, cpg, HW, float(cpg_r * HW), False, 1e-5, Cr, 1.25)
+    sums.zero_()
+    L.run_ops([L.op_gn_bwd(True, *args3), L.op_gn_bwd(False, *args3)])
+    dx3 = torch.empty_like(x)
+    args4 = (g, yfull, x, stats, gamma, sums2, dx3, None, B, C, G, cpg, HW, float(cpg_r * HW), False, 1e-5, Cr, 1.25)
+    L.run_ops([L.op_gn_bwd("fused", *args4)])
+    assert rel(dx3, dx) <= 4e-3  # two fp16-rounded evaluations of the same expression: one ulp of the largest values
+    # no ReLU (downsample branch GroupNorm)
+    args5 = (g, None, x, stats, gamma, sums, dx, None, B, C, G, cpg, HW, float(cpg_r * HW), False, 1e-5, Cr)
+    sums.zero_()
+    L.run_ops([L.op_gn_bwd(True, *args5), L.op_gn_bwd(False, *args5)])
+    args6 = (g, None, x, stats, gamma, sums2, dx3, None, B, C, G, cpg, HW, float(cpg_r * HW), False, 1e-5, Cr)
+    L.run_ops([L.op_gn_bwd("fused", *args6)])
+    assert rel(dx3, dx) <= 4e-3
 
 
 def test_groupnorm_maxpool_forward_backward():
@@ -293,6 +323,37 @@ def test_vo_model_against_reference_golden(case, golden_dir):
     for k in g.files:
         if k.startswith("grad/") and g[k].size > 64:
             assert rel_l2(P[k[5:]].grad, torch.from_numpy(g[k])) <= GRAD_TOL[case], k
+
+
+@pytest.mark.parametrize("case", ["r18_30ch", "r18_8ch"])
+def test_raw_input_pipeline_matches_reference_inputs(case):
+    """uint8 rgb + fp32 depth pairs (dd / top-down derived on the device) against the same model fed with the
+    reference's four fp32 tensors (dd / top-down from the pinned numpy oracle): the assembled fp16 input must
+    be identical up to the rgb/255 division-vs-multiplication ulp, the running statistics equal to 1e-6."""
+    model, space, backbone = _load_vo(case)
+    import copy
+
+    B = 3
+    obs = helpers.vo_inputs(B, 21, space, "cuda")
+    raw = {"rgb": obs["rgb"].to(torch.uint8).contiguous(), "depth": obs["depth"].contiguous()}
+    assert torch.equal(raw["rgb"].float(), obs["rgb"])
+    m2 = copy.deepcopy(model)
+    for train in (False, True):
+        model.train(train)
+        m2.train(train)
+        with torch.no_grad():
+            y1 = model(obs)
+            x1 = model._plan_for(obs, False, train).x0.clone()
+            y2 = m2(raw)
+            x2 = m2._plan_for(raw, False, train).x0.clone()
+        d = (x1.float() - x2.float()).abs()
+        assert d.max().item() <= 2e-3 and (d > 0).float().mean().item() < 0.05  # isolated fp16 ulps only
+        if train:
+            r1, r2 = model.visual_encoder.running_mean_and_var, m2.visual_encoder.running_mean_and_var
+            assert rel(r2._mean, r1._mean) <= 1e-5 and rel(r2._var, r1._var) <= 1e-5
+            assert float(r1._count) == float(r2._count)
+        else:
+            assert rel(y2, y1) <= 2e-3
 
 
 def test_vo_backward_block_by_block():
