@@ -212,7 +212,7 @@ def run_b200(args):
     ms = timed(lambda: trainer.step(obs, d_tgt), args.steps)
     launches = L.launch_count() - n0
     clocks = sampler.stop() if sampler else None
-    loss_val = float(trainer._loss.item())
+    loss_val = float(trainer._loss[0].item())
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 

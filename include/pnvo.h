@@ -119,7 +119,11 @@ enum pnvo_opcode {
   PNVO_OP_GN_BWD_FUSED = 27, /* GroupNorm(+ReLU) backward in one pass: a thread-block cluster per sample, DSMEM reduce */
   PNVO_OP_RAW_STATS = 28,    /* RunningMeanAndVar batch statistics straight from uint8 rgb / fp32 depth / top-down pairs */
   PNVO_OP_RAW_ASSEMBLE = 29, /* raw pairs -> [rgb/255, depth, one-hot depth bins, top-down] x {prev, cur} -> normalised fp16 NHWC */
-  PNVO_OP_MAX = 30
+  PNVO_OP_ACT_EMBED_FWD = 30, /* z += W[:, col0:col0+dim] . (Embedding(action) * dropout mask)  (vo_cnn_act_embed.py:65-75) */
+  PNVO_OP_ACT_EMBED_BWD = 31, /* gradients of the embedding columns of the hidden Linear and of the embedding table */
+  PNVO_OP_UPSAMPLE2 = 32,     /* zero-insertion x2 upsampling (stride-2 data gradients as stride-1 convolutions) */
+  PNVO_OP_GEO_INV_LOSS = 33,  /* geometric-inversion loss + gradient (vo_cnn_regression_geo_invariance_engine.py:367-449) */
+  PNVO_OP_MAX = 34
 };
 
 typedef struct {

@@ -73,6 +73,18 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       }
       return input_stats_launch(a, static_cast<double*>(p[6]), st);
     }
+    case PNVO_OP_GEO_INV_LOSS:
+      // p0 = pred [B][O], p1 = actions int64 [B], p2 = dout (nullable, accumulated), p3 = loss[3] (total+=, rot, pos)
+      // i0 = B, i1 = O, i2 = MOVE_FORWARD id; f0 = loss_inv_weight, f1 = gradient scale
+      return geo_inv_loss_launch(static_cast<const float*>(p[0]), static_cast<const int64_t*>(p[1]), i[0], i[1], i[2], f[0],
+                                 f[1], static_cast<float*>(p[2]), static_cast<float*>(p[3]), st);
+    case PNVO_OP_UPSAMPLE2:
+      // p0 = src [B,OH,OW,C] fp16, p1 = dst [B,IH,IW,C] fp16; i0 = B, i1 = OH, i2 = OW, i3 = IH, i4 = IW, i5 = C
+      return upsample2_launch(static_cast<const __half*>(p[0]), static_cast<__half*>(p[1]), i[0], i[1], i[2], i[3], i[4],
+                              i[5], st);
+    case PNVO_OP_ACT_EMBED_FWD:
+    case PNVO_OP_ACT_EMBED_BWD:
+      return act_embed_op(op.code, i, f, p, st);
     case PNVO_OP_RAW_STATS:
     case PNVO_OP_RAW_ASSEMBLE:
       return raw_op(op.code, i, f, p, st);
@@ -145,11 +157,11 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = w (OIHW fp32), p1 = wp, p2 = wt; i0..i3 = Cout, Cin, R, S; i4 = cin_pad, i5 = ld_p, i6 = cout_pad, i7 = ld_t,
       // i8 = t_mode (0: conv dgrad layout, 1: plain transpose of wp)
       return pack_w_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], static_cast<__half*>(p[1]), i[4],
-                           i[5], static_cast<__half*>(p[2]), i[6], i[7], i[8], st);
+                           i[5], static_cast<__half*>(p[2]), i[6], i[7], i[8], st, i[9]);
     case PNVO_OP_UNPACK_DW:
       // p0 = dwp, p1 = grad; i0..i3 = Cout, Cin, R, S; i4 = cin_pad, i5 = ld_p, i6 = accumulate
       return unpack_dw_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], i[4], i[5],
-                              static_cast<float*>(p[1]), i[6], st);
+                              static_cast<float*>(p[1]), i[6], st, i[7]);
     case PNVO_OP_BIAS_RELU:
       // p0 = z, p1 = bias, p2 = h32, p3 = h16; i0 = B, i1 = N, i2 = relu
       return bias_relu_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]), i[0], i[1], i[2],

@@ -99,6 +99,18 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n is warp-uniform
   }
 }
 
+// one lane of the (converged) warp: unlike `lane == 0`, ptxas knows the guarded region runs on a single thread and
+// issues tcgen05.mma / TMA from uniform registers without wrapping each one in an ELECT/branch loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------------

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
     // the 128-pixel x chunk_k activation tile (halo / batch tail zero-filled by the TMA unit) and one
     // tiled TMA the N x chunk_k weight tile, both landing 64/128-byte swizzled exactly as tcgen05.mma
     // reads them.  No per-element address arithmetic on the SM.
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
       const int ohw = p.OH * p.OW;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
     tc_fence_before();
   } else {
     // ================================ MMA issuer (warp 4) ================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(kTileM, p.N, 0, 0);
       const int nkb = p.nkb;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -362,7 +362,7 @@ int conv_plan(ConvArgs& a) {
   a.M = a.B * a.OH * a.OW;
   a.K = a.R * a.S * a.Cin;
   // TMA im2col path: unit "dilation" (div == 1), square filter / symmetric padding, channels in chunks of 32 or 64
-  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && !a.force_generic) ? 1 : 0;
+  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1) ? 1 : 0;
   a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : kTileK;
   a.nkb = ceil_div(a.K, a.chunk_k);
   PNVO_REQUIRE(a.w_ld >= a.nkb * a.chunk_k, "conv: packed weight row stride %d < padded K %d", a.w_ld, a.nkb * a.chunk_k);
@@ -393,6 +393,7 @@ int conv_plan(ConvArgs& a) {
 }
 
 int conv_launch(ConvArgs a, cudaStream_t st) {
+  if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster_supported(a)) return conv_raster_launch(a, st);
   if (conv_plan(a)) return -1;
   PNVO_REQUIRE(a.x && a.w && a.y, "conv: null pointer");
   if (a.M == 0) return 0;

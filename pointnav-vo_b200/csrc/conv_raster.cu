@@ -1,0 +1,330 @@
+// 3x3 / stride 1 / pad 1 convolution (resnet.py:11-26 BasicBlock convs of layer1 / layer2, forward and data
+// gradient) WITHOUT im2col expansion, as a persistent tcgen05 kernel.
+//
+// With NHWC fp16 and C = 32 (64) channels a pixel is 64 (128) bytes = one row of a SWIZZLE_64B (128B) UMMA operand.
+// A block of T+2 input rows, W+2 pixels wide (zero halo supplied by the TMA unit's out-of-range fill), staged ONCE
+// in shared memory as a linear raster with pitch P = W+2 pixels is therefore already the A operand of all nine
+// filter taps: for the 128 consecutive raster positions m0..m0+127 of the OUTPUT (same pitch; the two halo columns
+// per row are junk and masked in the epilogue) tap (r, s) reads raster positions m + r*P + s, i.e. the same bytes
+// through a descriptor whose start address is shifted by (r*P + s) pixels.  L2 -> smem traffic drops from 9x the
+// input (im2col) to (T+2)/T x.
+//
+// Persistent CTA (one per SM): the 9 weight taps stay resident in shared memory; units (sample, T output rows)
+// are strided over the grid; the input raster is double-buffered (TMA of unit i+1 overlaps the MMAs of unit i) and
+// so is the TMEM accumulator (the epilogue of tile j overlaps the MMAs of tile j+1).
+//   warp 9: TMA producer    warp 8: TMEM owner + single-thread MMA issuer
+//   warps 0-3 / 4-7: two epilogue groups, one per accumulator buffer (even / odd tiles)
+// Epilogue: optional accumulate input (dgrad into the identity-branch gradient), GroupNorm partial sums kept in
+// registers across the tiles of a unit (one sample) and flushed with a warp reduce-scatter + one atomic per value,
+// fp16 store (64 / 128 contiguous bytes per thread).
+#include "common.cuh"
+#include "ops.cuh"
+#include "tmap.cuh"
+
+namespace pnvo {
+
+struct RasterArgs {
+  __half* y;
+  const __half* add;
+  float* stats;
+  int B, H, W;
+  int cpg, G;
+  int P, T, n_tiles, rows_in;
+  int units_per_img, n_units;
+  int in_bytes;  // shared-memory bytes of one input raster buffer (multiple of 1024)
+};
+
+template <int CPG, int OFF>
+__device__ __forceinline__ void raster_group_sums(const float* v, float* acc) {
+  // 32 accumulator columns -> 32/CPG groups, (sum, sumsq) added at acc[OFF + 2g], acc[OFF + 2g + 1]
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+      const float x = v[g * CPG + c];
+      a += x;
+      q = fmaf(x, x, q);
+    }
+    acc[OFF + 2 * g] += a;
+    acc[OFF + 2 * g + 1] += q;
+  }
+}
+
+template <int C, int N>
+__global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, const __grid_constant__ ConvTmaps tm) {
+  constexpr int kPix = C * 2;             // bytes per pixel = operand row bytes
+  constexpr int kWTap = N * kPix;         // bytes of one weight tap [N][C]
+  constexpr int kWBytes = 9 * kWTap;
+  constexpr int kKSteps = C / 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_wfull;
+  __shared__ __align__(8) uint64_t s_infull[2];
+  __shared__ __align__(8) uint64_t s_inempty[2];
+  __shared__ __align__(8) uint64_t s_accfull[2];
+  __shared__ __align__(8) uint64_t s_accempty[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t sW = smem_base;
+  const uint32_t sIn0 = smem_base + ((kWBytes + 1023) & ~1023);
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_wfull), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_infull[s]), 1);
+      mbar_init(smem_u32(&s_inempty[s]), 1);
+      mbar_init(smem_u32(&s_accfull[s]), 1);
+      mbar_init(smem_u32(&s_accempty[s]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(smem_u32(&s_tmem), 2 * N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const int n_tiles = p.n_tiles;
+
+  if (warp == 9) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      const uint32_t wbar = smem_u32(&s_wfull);
+      mbar_arrive_expect_tx(wbar, kWBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * kWTap, &tm.b, wbar, tap * C, 0);
+      const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * kPix;
+      int i = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        const int slot = i & 1;
+        if (i >= 2) mbar_wait(smem_u32(&s_inempty[slot]), ((i >> 1) & 1) ^ 1);
+        const int b = u / p.units_per_img;
+        const int h0 = (u - b * p.units_per_img) * p.T;
+        const uint32_t bar = smem_u32(&s_infull[slot]);
+        mbar_arrive_expect_tx(bar, in_tx);
+        // rows h0-1 .. h0+T, pixels -1 .. W: out-of-range rows / pixels arrive as zeros (the conv's padding)
+        tma_load_4d(sIn0 + slot * p.in_bytes, &tm.a, bar, 0, -1, h0 - 1, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, N, 0, 0);
+      mbar_wait(smem_u32(&s_wfull), 0);
+      int i = 0, tc = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        const int slot = i & 1;
+        mbar_wait(smem_u32(&s_infull[slot]), (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sIn = sIn0 + slot * p.in_bytes;
+        for (int j = 0; j < n_tiles; ++j, ++tc) {
+          const int ab = tc & 1;
+          if (tc >= 2) {
+            mbar_wait(smem_u32(&s_accempty[ab]), ((tc >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t d_tmem = tmem_base + ab * N;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint64_t adesc = umma_desc(sIn + static_cast<uint32_t>(128 * j + r * p.P + s) * kPix, 16, 8 * kPix, kPix);
+            const uint64_t bdesc = umma_desc(sW + tap * kWTap, 16, 8 * kPix, kPix);
+#pragma unroll
+            for (int k = 0; k < kKSteps; ++k)
+              tc_mma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                         (tap | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&s_accfull[ab]));
+        }
+        tc_commit(smem_u32(&s_inempty[slot]));  // raster buffer free once this unit's MMAs have read it
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================================ epilogue (warps 0-7) ================================
+    // group g = warp / 4 drains accumulator buffer g (tiles with tc % 2 == g); a warp reads TMEM lanes 32 * (warp % 4)
+    const int grp = warp >> 2;
+    const int row = tid & 127;
+    const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int valid_pos = p.T * p.P;
+    int tc = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int b = u / p.units_per_img;
+      const int h0 = (u - b * p.units_per_img) * p.T;
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++tc) {
+        const int ab = tc & 1;
+        if (ab != grp) continue;
+        const int m = 128 * j + row;
+        const int orow = m / p.P;
+        const int ocol = m - orow * p.P;
+        const int oh = h0 + orow;
+        const bool valid = (m < valid_pos) && (ocol < p.W) && (oh < p.H);
+        const int64_t gofs = ((static_cast<int64_t>(b) * p.H + oh) * p.W + ocol) * N;
+        // identity-branch gradient to accumulate: fetched before the accumulator is waited for
+        uint4 addq[N / 8];
+        if (p.add && valid) {
+#pragma unroll
+          for (int q = 0; q < N / 8; ++q) addq[q] = __ldg(reinterpret_cast<const uint4*>(p.add + gofs) + q);
+        }
+        mbar_wait(smem_u32(&s_accfull[ab]), (tc >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < N / 32; ++ch) {
+          float v[32];
+          tmem_ld32(tmem_base + t_lane + ab * N + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == N / 32 - 1) {
+            // accumulator buffer drained: hand it back to the MMA issuer before the (slow) global stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_accempty[ab]));
+          }
+          if (p.add && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&addq[ch * 4 + q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                v[q * 8 + 2 * e] += f.x;
+                v[q * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.stats && valid) {
+            // N = 32: chunk 0 carries all 32/cpg groups; N = 64: chunk ch carries groups ch*32/cpg ...
+            if (ch == 0) {
+              if (p.cpg == 2) raster_group_sums<2, 0>(v, acc);
+              else if (p.cpg == 4) raster_group_sums<4, 0>(v, acc);
+              else raster_group_sums<8, 0>(v, acc);
+            } else {
+              if (p.cpg == 4) raster_group_sums<4, 16>(v, acc);
+              else raster_group_sums<8, 8>(v, acc);
+            }
+          }
+          if (valid) {
+            __half* yp = p.y + gofs + ch * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 uu;
+              __half2* h2 = reinterpret_cast<__half2*>(&uu);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(yp + q * 8) = uu;
+            }
+          }
+        }
+      }
+      if (p.stats) {
+        // reduce-scatter over the 32 lanes: lane i ends with the warp total of value i
+        int off = 16;
+#pragma unroll
+        for (int cnt = 16; cnt >= 1; cnt >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < cnt; ++i) {
+            const float send = up ? acc[i] : acc[i + cnt];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+            acc[i] = (up ? acc[i + cnt] : acc[i]) + recv;
+          }
+          off >>= 1;
+        }
+        if (lane < 2 * p.G) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, acc[0]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * N);
+  }
+}
+
+// eligibility + geometry.  Returns false when the generic implicit-GEMM kernel must be used.
+static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
+  if (a.R != 3 || a.S != 3 || a.mul != 1 || a.div != 1 || a.pad != 1 || a.pad_w != 1) return false;
+  if (a.IH != a.OH || a.IW != a.OW) return false;
+  if (!(a.Cin == 32 || a.Cin == 64) || !(a.n_total == 32 || a.n_total == 64)) return false;
+  if (a.n_store != a.n_total || a.ldo != a.n_total || a.out_fp32) return false;
+  if (a.w_ld < 9 * a.Cin) return false;
+  if (a.stats) {
+    if (a.G * a.cpg != a.n_total || a.G > 16) return false;
+    if (!(a.cpg == 2 || a.cpg == 4 || a.cpg == 8)) return false;
+  }
+  const int P = a.IW + 2;
+  if (P > 256 || a.IW < 8 || a.IH < 4) return false;
+  const int pix = a.Cin * 2;
+  const int w_bytes = (9 * a.n_total * pix + 1023) & ~1023;
+  double best = -1.0;
+  for (int T = 2; T <= std::min(a.IH, 64); ++T) {
+    const int rows_in = T + 2;
+    if (rows_in > 256) break;
+    const int n_tiles = ceil_div(T * P, 128);
+    const int positions = std::max(rows_in * P, n_tiles * 128 + 2 * P + 2);
+    const int in_bytes = (positions * pix + 1023) & ~1023;
+    const int smem = w_bytes + 2 * in_bytes + 1024;
+    if (smem > 200 * 1024) break;
+    const int upi = ceil_div(a.IH, T);
+    // useful fraction of the MMA rows, discounted by the halo re-read (T+2)/T (weakly) and unit imbalance
+    const int n_units = a.B * upi;
+    const int waves = ceil_div(n_units, 148);
+    const double balance = n_units >= 148 ? static_cast<double>(n_units) / (waves * 148.0) : 1.0;
+    const double eff = (static_cast<double>(a.IH) * a.IW) / (static_cast<double>(upi) * n_tiles * 128) * balance *
+                       (1.0 - 0.15 * 2.0 / (T + 2));
+    if (eff > best + 1e-9) {
+      best = eff;
+      r.P = P; r.T = T; r.n_tiles = n_tiles; r.rows_in = rows_in; r.units_per_img = upi; r.n_units = n_units;
+      r.in_bytes = in_bytes;
+      smem_bytes = smem;
+    }
+  }
+  if (best < 0.5) return false;
+  r.y = static_cast<__half*>(a.y); r.add = a.add; r.stats = a.stats;
+  r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
+  return true;
+}
+
+int conv_raster_supported(const ConvArgs& a) {
+  RasterArgs r{};
+  int smem = 0;
+  return raster_plan(a, r, smem) ? 1 : 0;
+}
+
+template <int C, int N>
+static int raster_launch_t(const RasterArgs& r, const ConvTmaps& tm, int smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_raster_kernel<C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  const int grid = std::min(r.n_units, 148);
+  conv_raster_kernel<C, N><<<grid, 320, smem, st>>>(r, tm);
+  count_launch();
+  return check_launch("conv_raster");
+}
+
+int conv_raster_launch(const ConvArgs& a, cudaStream_t st) {
+  RasterArgs r{};
+  int smem = 0;
+  PNVO_REQUIRE(raster_plan(a, r, smem), "conv_raster: unsupported geometry");
+  if (a.B <= 0) return 0;
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (tmap_tiled4d(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, r.P, a.Cin * 2 == 128 ? 128 : 64, r.rows_in)) return -1;
+  if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.n_total, a.Cin)) return -1;
+  if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32>(r, tm, smem, st);
+  if (a.Cin == 32 && a.n_total == 64) return raster_launch_t<32, 64>(r, tm, smem, st);
+  if (a.Cin == 64 && a.n_total == 32) return raster_launch_t<64, 32>(r, tm, smem, st);
+  return raster_launch_t<64, 64>(r, tm, smem, st);
+}
+
+}  // namespace pnvo

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(192) conv_stem_fwd_kernel(const StemArgs p, co
 
   if (warp == 5) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
       const uint32_t box_bytes = static_cast<uint32_t>(p.box_px) * 128;  // box_px = pixel PAIRS per row
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(192) conv_stem_fwd_kernel(const StemArgs p, co
     }
   } else if (warp == 4) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(128, 32, 0, 0);
       for (int r = 0; r < 7; ++r) {
         const int s = r % stages;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(192) conv_stem_wgrad_kernel(const StemWgradArg
   const uint32_t tmem_base = s_tmem;
 
   if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ================================ TMA producer ================================
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(192) conv_stem_wgrad_kernel(const StemWgradArg
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ================================ MMA issuer ================================
       const uint32_t idesc = umma_idesc_f16(128, 32, 1, 1);
       for (int t = 0; t < n_rows; ++t) {
@@ -441,4 +441,69 @@ extern "C" int pnvo_debug_tma_dump(const void* x, int B, int IH, int IW, int box
   tma_dump_kernel<<<1, 256, n16 * 16 + 1024, static_cast<cudaStream_t>(stream)>>>(tm, box_px, ih, b, w0,
                                                                                 static_cast<uint4*>(out), n16);
   return check_launch("tma_dump");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// debug / measurement: issue rate of tcgen05.mma (M = 128, K = 16, fp16) as a function of N, the swizzle mode and the
+// byte shift of the A descriptor's start address relative to the swizzle atom (the raster kernels shift it by whole
+// pixels).  One CTA per SM issues `n_mma` MMAs back to back on fixed shared-memory operands and reports cycles / MMA.
+// ---------------------------------------------------------------------------------------------------------
+namespace pnvo {
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int row_bytes, int a_shift, int a_step, int mn_major,
+                                                       int n_mma, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  for (uint32_t off = tid * 16; off < 96 * 1024; off += blockDim.x * 16)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + off), "r"(0x3c003c00u) : "memory");
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&s_tmem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, N, mn_major, mn_major);
+      const uint32_t sA = base + a_shift, sB = base + 64 * 1024;
+      const uint32_t lbo = mn_major ? row_bytes : 16;
+      const long long t0 = clock64();
+      for (int i = 0; i < n_mma; ++i) {
+        const uint64_t adesc = umma_desc(sA + static_cast<uint32_t>(i & 7) * a_step, lbo, 8 * row_bytes, row_bytes);
+        const uint64_t bdesc = umma_desc(sB, lbo, 8 * row_bytes, row_bytes);
+        tc_mma_f16(tmem_base + ((i & 1) ? 256 : 0), adesc, bdesc, idesc, i > 1 ? 1u : 0u);
+      }
+      tc_commit(smem_u32(&s_bar));
+      mbar_wait(smem_u32(&s_bar), 0);
+      const long long t1 = clock64();
+      out[blockIdx.x] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace pnvo
+
+extern "C" int pnvo_debug_mma_rate(int N, int row_bytes, int a_shift, int a_step, int mn_major, int n_mma, int n_ctas,
+                                   void* out_cycles, void* stream) {
+  using namespace pnvo;
+  PNVO_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && (row_bytes == 64 || row_bytes == 128) && out_cycles, "mma_rate: bad args");
+  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  mma_rate_kernel<<<n_ctas, 128, 97 * 1024, static_cast<cudaStream_t>(stream)>>>(N, row_bytes, a_shift, a_step, mn_major,
+                                                                                  n_mma, static_cast<long long*>(out_cycles));
+  return check_launch("mma_rate");
 }

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p, cons
       fence_proxy_async_smem();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       // ================================ TMA producer ================================
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p, cons
       tc_fence_before();
     } else {
       // =============================== MMA issuer ===============================
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t idesc = umma_idesc_f16(128, p.N, 1, 1);
         for (int it = 0; it < n_chunks; ++it) {
           const int s = it % stages;
@@ -273,7 +273,7 @@ int wgrad_plan(WgradArgs& a) {
   }
   a.M = a.B * a.OH * a.OW;
   a.K = a.R * a.S * a.Cin;
-  a.tma = (a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && !a.force_generic) ? 1 : 0;
+  a.tma = (a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1) ? 1 : 0;
   a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : 64;
   PNVO_REQUIRE(a.w_ld >= a.K, "wgrad: w_ld %d < K %d", a.w_ld, a.K);
   a.n_mtiles = ceil_div(a.K, 128);
@@ -306,6 +306,7 @@ int wgrad_plan(WgradArgs& a) {
 }
 
 int wgrad_launch(WgradArgs a, cudaStream_t st) {
+  if (a.force_generic == 0 && a.x && a.dy && a.dw && wgrad_raster_supported(a)) return wgrad_raster_launch(a, st);
   if (wgrad_plan(a)) return -1;
   PNVO_REQUIRE(a.x && a.dy && a.dw, "wgrad: null pointer");
   PNVO_REQUIRE(a.tma || a.x_row_pitch == 0 || a.x_row_pitch == a.IW, "wgrad: padded input rows need the TMA path");

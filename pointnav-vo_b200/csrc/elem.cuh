@@ -27,7 +27,10 @@ int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample
 int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
                     cudaStream_t st);
 int zero_launch(void* p, int64_t bytes, cudaStream_t st);
+int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int IH, int IW, int C, cudaStream_t st);
 // raw_input.cu: PNVO_OP_RAW_STATS / PNVO_OP_RAW_ASSEMBLE (field layout documented there)
+// act_embed.cu: PNVO_OP_ACT_EMBED_FWD / PNVO_OP_ACT_EMBED_BWD
+int act_embed_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st);
 int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st);
 
 struct GnArgs {
@@ -70,9 +73,9 @@ int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dga
                          cudaStream_t st);
 
 int pack_w_launch(const float* w, int Cout, int Cin, int R, int S, __half* wp, int cin_pad, int ld_p, __half* wt,
-                  int cout_pad, int ld_t, int t_mode, cudaStream_t st);
+                  int cout_pad, int ld_t, int t_mode, cudaStream_t st, int src_ld = 0);
 int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p, float* grad,
-                     int accumulate, cudaStream_t st);
+                     int accumulate, cudaStream_t st, int dst_ld = 0);
 int bias_relu_launch(const float* z, const float* bias, int B, int N, int relu, float* h32, __half* h16,
                      cudaStream_t st);
 int bias_relu_bwd_launch(const float* dh, const float* h, int B, int N, __half* dz16, float* db, int accumulate,
@@ -84,6 +87,8 @@ int head_bwd_launch(const float* dout, const float* h, const float* W, int B, in
 int dropout_launch(void* buf, int64_t n, int is_fp16, uint64_t* seed, int site, float p, int advance, cudaStream_t st);
 int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, int B, int O, float w0, float w1,
                     float w2, float grad_scale, float* dout, float* loss, cudaStream_t st);
+int geo_inv_loss_launch(const float* pred, const int64_t* actions, int B, int O, int move_forward, float weight,
+                        float grad_scale, float* dout, float* loss, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 int step, float grad_scale, cudaStream_t st);
 

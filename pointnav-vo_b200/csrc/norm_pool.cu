@@ -20,7 +20,14 @@ __global__ void zero_kernel(uint4* __restrict__ p, int64_t n16, unsigned char* t
 }
 int zero_launch(void* p, int64_t bytes, cudaStream_t st) {
   if (bytes <= 0) return 0;
-  PNVO_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "zero: pointer not 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) {  // small unaligned slices of the flat gradient bucket
+    const cudaError_t e = cudaMemsetAsync(p, 0, static_cast<size_t>(bytes), st);
+    if (e != cudaSuccess) {
+      set_error("zero: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    return 0;
+  }
   const int64_t n16 = bytes / 16;
   const int ntail = static_cast<int>(bytes - n16 * 16);
   const int blocks = static_cast<int>(std::min<int64_t>(std::max<int64_t>(1, ceil_div64(n16, 256)), 148 * 8));
@@ -240,6 +247,39 @@ int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample
                                       shift);
   count_launch();
   return check_launch("rmv_update");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zero-insertion upsampling by 2: dst[b, 2i, 2j, :] = src[b, i, j, :], every other element of dst = 0.
+// The data gradient of a stride-2 convolution is the stride-1 convolution of this tensor with the flipped
+// weights, which runs on the TMA / raster kernels instead of the divisibility-testing generic producer; for the
+// 1x1 / stride-2 downsample branch it scatters the compact 1x1 result back to the input resolution.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B,
+                                                        int OH, int OW, int IH, int IW, int c8) {
+  const int64_t total = static_cast<int64_t>(B) * IH * IW * c8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % c8);
+    int64_t t = i / c8;
+    const int w = static_cast<int>(t % IW);
+    t /= IW;
+    const int h = static_cast<int>(t % IH);
+    const int b = static_cast<int>(t / IH);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (((h | w) & 1) == 0 && (h >> 1) < OH && (w >> 1) < OW)
+      v = __ldg(src + ((static_cast<int64_t>(b) * OH + (h >> 1)) * OW + (w >> 1)) * c8 + q);
+    dst[i] = v;
+  }
+}
+int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int IH, int IW, int C, cudaStream_t st) {
+  PNVO_REQUIRE(src && dst && C % 8 == 0, "upsample2: bad arguments");
+  const int64_t total = static_cast<int64_t>(B) * IH * IW * (C / 8);
+  if (total <= 0) return 0;
+  upsample2_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B, OH, OW, IH, IW, C / 8);
+  count_launch();
+  return check_launch("upsample2");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -636,7 +676,8 @@ int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dga
 // entries are never written.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, __half* __restrict__ wp,
-                              int cin_pad, int ld_p, __half* __restrict__ wt, int cout_pad, int ld_t, int t_mode) {
+                              int cin_pad, int ld_p, __half* __restrict__ wt, int cout_pad, int ld_t, int t_mode,
+                              int src_ld) {
   const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -644,7 +685,8 @@ __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, in
     const int r = static_cast<int>((i / S) % R);
     const int c = static_cast<int>((i / (static_cast<int64_t>(S) * R)) % Cin);
     const int n = static_cast<int>(i / (static_cast<int64_t>(S) * R * Cin));
-    const __half h = __float2half_rn(w[i]);
+    // src_ld: elements between source rows (a Linear whose rows carry extra, non-visual columns)
+    const __half h = __float2half_rn(w[static_cast<int64_t>(n) * src_ld + (i - static_cast<int64_t>(n) * Cin * R * S)]);
     if (wp) wp[static_cast<int64_t>(n) * ld_p + (r * S + s) * cin_pad + c] = h;
     if (wt) {
       if (t_mode == 0) wt[static_cast<int64_t>(c) * ld_t + ((R - 1 - r) * S + (S - 1 - s)) * cout_pad + n] = h;
@@ -653,7 +695,7 @@ __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, in
   }
 }
 __global__ void unpack_dw_kernel(const float* __restrict__ dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p,
-                                 float* __restrict__ grad, int accumulate) {
+                                 float* __restrict__ grad, int accumulate, int dst_ld) {
   const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -662,24 +704,27 @@ __global__ void unpack_dw_kernel(const float* __restrict__ dwp, int Cout, int Ci
     const int c = static_cast<int>((i / (static_cast<int64_t>(S) * R)) % Cin);
     const int n = static_cast<int>(i / (static_cast<int64_t>(S) * R * Cin));
     const float v = dwp[static_cast<int64_t>(n) * ld_p + (r * S + s) * cin_pad + c];
-    grad[i] = accumulate ? grad[i] + v : v;
+    const int64_t o = static_cast<int64_t>(n) * dst_ld + (i - static_cast<int64_t>(n) * Cin * R * S);
+    grad[o] = accumulate ? grad[o] + v : v;
   }
 }
 int pack_w_launch(const float* w, int Cout, int Cin, int R, int S, __half* wp, int cin_pad, int ld_p, __half* wt,
-                  int cout_pad, int ld_t, int t_mode, cudaStream_t st) {
+                  int cout_pad, int ld_t, int t_mode, cudaStream_t st, int src_ld) {
+  if (src_ld <= 0) src_ld = Cin * R * S;
   const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
   if (total <= 0) return 0;
   pack_w_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 4)), 256, 0, st>>>(
-      w, Cout, Cin, R, S, wp, cin_pad, ld_p, wt, cout_pad, ld_t, t_mode);
+      w, Cout, Cin, R, S, wp, cin_pad, ld_p, wt, cout_pad, ld_t, t_mode, src_ld);
   count_launch();
   return check_launch("pack_w");
 }
 int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p, float* grad,
-                     int accumulate, cudaStream_t st) {
+                     int accumulate, cudaStream_t st, int dst_ld) {
+  if (dst_ld <= 0) dst_ld = Cin * R * S;
   const int64_t total = static_cast<int64_t>(Cout) * Cin * R * S;
   if (total <= 0) return 0;
   unpack_dw_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 4)), 256, 0, st>>>(
-      dwp, Cout, Cin, R, S, cin_pad, ld_p, grad, accumulate);
+      dwp, Cout, Cin, R, S, cin_pad, ld_p, grad, accumulate, dst_ld);
   count_launch();
   return check_launch("unpack_dw");
 }
@@ -883,6 +928,70 @@ int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, i
   mse_loss_kernel<<<1, 256, 0, st>>>(pred, tgt, dz_mask, B, O, w0, w1, w2, grad_scale, dout, loss);
   count_launch();
   return check_launch("mse_loss");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geometric-inversion loss (vo_cnn_regression_geo_invariance_engine.py:367-449) on predictions interleaved
+// [a0, b0, a1, b1, ...] (a = cur relative to prev, b = prev relative to cur), n = B/2 pairs:
+//   rot = mean_i (a.yaw + b.yaw)^2
+//   pos = mean_{i,k} m_ik (b.xz + R(b.yaw) a.xz)_k^2,  R = [[c, s], [-s, c]] (left-handed), m_i1 = 0 for MOVE_FORWARD
+// loss[0] += weight * (rot + pos) (added to the regression loss already there), loss[1] = rot, loss[2] = pos;
+// dout += weight * grad_scale * d(rot + pos)/d(pred).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geo_inv_loss_kernel(const float* __restrict__ pred,
+                                                           const int64_t* __restrict__ actions, int B, int O,
+                                                           int move_forward, float weight, float grad_scale,
+                                                           float* __restrict__ dout, float* __restrict__ loss) {
+  __shared__ float s_rot[8], s_pos[8];
+  const int n = B / 2;
+  float acc_rot = 0.f, acc_pos = 0.f;
+  const float inv_n = 1.f / static_cast<float>(n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* a = pred + static_cast<int64_t>(2 * i) * O;
+    const float* b = a + O;
+    const float m = (actions[2 * i] == move_forward) ? 0.f : 1.f;
+    const float yaw = a[2] + b[2];
+    const float c = cosf(b[2]), s = sinf(b[2]);
+    const float p0 = c * a[0] + s * a[1], p1 = -s * a[0] + c * a[1];
+    const float e0 = b[0] + p0, e1 = b[1] + p1;
+    acc_rot += yaw * yaw;
+    acc_pos += e0 * e0 + m * e1 * e1;
+    if (dout) {
+      const float k = weight * grad_scale * inv_n;
+      float* da = dout + static_cast<int64_t>(2 * i) * O;
+      float* db = da + O;
+      da[0] += k * (e0 * c - m * e1 * s);
+      da[1] += k * (e0 * s + m * e1 * c);
+      da[2] += k * 2.f * yaw;
+      db[0] += k * e0;
+      db[1] += k * m * e1;
+      db[2] += k * (2.f * yaw + e0 * p1 - m * e1 * p0);
+    }
+  }
+  acc_rot = warp_sum(acc_rot);
+  acc_pos = warp_sum(acc_pos);
+  if ((threadIdx.x & 31) == 0) {
+    s_rot[threadIdx.x >> 5] = acc_rot;
+    s_pos[threadIdx.x >> 5] = acc_pos;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f, q = 0.f;
+    for (int k = 0; k < 8; ++k) { r += s_rot[k]; q += s_pos[k]; }
+    r *= inv_n;
+    q *= inv_n * 0.5f;
+    loss[0] += weight * (r + q);
+    loss[1] = r;
+    loss[2] = q;
+  }
+}
+int geo_inv_loss_launch(const float* pred, const int64_t* actions, int B, int O, int move_forward, float weight,
+                        float grad_scale, float* dout, float* loss, cudaStream_t st) {
+  PNVO_REQUIRE(pred && actions && loss && O >= 3 && B % 2 == 0, "geo_inv_loss: bad arguments (B must be even: interleaved pairs)");
+  if (B == 0) return 0;
+  geo_inv_loss_kernel<<<1, 256, 0, st>>>(pred, actions, B, O, move_forward, weight, grad_scale, dout, loss);
+  count_launch();
+  return check_launch("geo_inv_loss");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -17,12 +17,15 @@ struct ConvArgs {
   int n_total, n_store, ldo;
   int cpg, G;
   int out_fp32;
-  int force_generic;   // 1: never use the TMA im2col producer (A/B testing)
+  int force_generic;   // 0: best kernel; 1: cp.async im2col producer; 2: TMA im2col producer (A/B testing)
   int tma, chunk_k;    // derived: TMA producer on/off, K elements per pipeline stage (64 or 32)
   // derived by conv_plan
   int cin_log2, cmask, M, K, nkb, N, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y;
 };
 int conv_plan(ConvArgs& a);
+// conv_raster.cu: persistent no-im2col kernel for 3x3 / stride 1 / pad 1 with 32 or 64 channels
+int conv_raster_supported(const ConvArgs& a);
+int conv_raster_launch(const ConvArgs& a, cudaStream_t st);
 int conv_launch(ConvArgs a, cudaStream_t st);
 
 struct WgradArgs {
@@ -46,6 +49,9 @@ int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_l
                            int rows_per_cta, cudaStream_t st);
 int pack_w_stem_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
 int wgrad_plan(WgradArgs& a);
+// conv_wgrad_raster.cu: persistent no-im2col weight gradient for 3x3 / stride 1 / pad 1 with 32 or 64 channels
+int wgrad_raster_supported(const WgradArgs& a);
+int wgrad_raster_launch(const WgradArgs& a, cudaStream_t st);
 int wgrad_launch(WgradArgs a, cudaStream_t st);
 
 }  // namespace pnvo

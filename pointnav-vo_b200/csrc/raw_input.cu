@@ -31,11 +31,14 @@ struct RawArgs {
   double* stats;        // [2C] (sum, sumsq) interleaved, accumulated
 };
 
+// bin i <=> e_i <= d < e_{i+1}, last bin closed at e_n (base_trainer_with_vo.py:143-154).  floor(d * n) is at most
+// one bin off (edges are fl(i/n)); the comparisons against the actual fp32 edges make the result exact.
 __device__ __forceinline__ int depth_bin(float d, const float* s_edges, int n) {
   if (!(d >= s_edges[0] && d <= s_edges[n])) return -1;  // the reference asserts against this
-  int idx = 0;
-  for (int i = 1; i < n; ++i) idx += (d >= s_edges[i]) ? 1 : 0;
-  return idx;
+  int k = min(n - 1, max(0, static_cast<int>(d * static_cast<float>(n))));
+  if (d < s_edges[k]) --k;
+  else if (k + 1 < n && d >= s_edges[k + 1]) ++k;
+  return k;
 }
 
 // RGB / DEP / TD: 0 or 1; NDD: number of one-hot bins (compile-time layout), or -1 = every flag read at run time
@@ -127,9 +130,22 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
   }
 }
 
-// values per thread: rgb 6 x (sum, sumsq) as uint32, depth / td 2 x (sum, sumsq) fp32, bins 2 x kRawMaxBins counts
+// values per block: rgb 6 x (sum, sumsq) as uint32, depth / td 2 x (sum, sumsq) fp32, bins 2 x kRawMaxBins counts
 static constexpr int kRawVals = 12 + 4 + 4 + 2 * kRawMaxBins;
 
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ double warp_sum_f64(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// A thread sees <= 255 pixels (launcher), so its per-bin counts fit in 8 bits: bins 0-7 / 8-15 of a frame are
+// packed into two 64-bit words and bumped with one shift-add instead of a compare chain per bin.
 __global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
   __shared__ float s_edges[kRawMaxBins + 1];
   __shared__ double s_red[8][kRawVals];
@@ -137,71 +153,58 @@ __global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
   __syncthreads();
   uint32_t ri[12];
   float fs[8];
-  uint32_t cnt[2 * kRawMaxBins];
+  unsigned long long cb[4] = {0ull, 0ull, 0ull, 0ull};  // [frame][bins 0-7 | bins 8-15]
 #pragma unroll
   for (int i = 0; i < 12; ++i) ri[i] = 0u;
 #pragma unroll
   for (int i = 0; i < 8; ++i) fs[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 2 * kRawMaxBins; ++i) cnt[i] = 0u;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < a.n_pix;
-       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < a.n_pix; p += stride) {
+    uint32_t w[3] = {0u, 0u, 0u};
+    float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
     if (a.use_rgb) {
       const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
-      const uint32_t w[3] = {r16[0], r16[1], r16[2]};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const uint32_t lo = w[k] & 0xff, hi = w[k] >> 8;
-        ri[4 * k] += lo; ri[4 * k + 1] += lo * lo;
-        ri[4 * k + 2] += hi; ri[4 * k + 3] += hi * hi;
-      }
+      w[0] = r16[0]; w[1] = r16[1]; w[2] = r16[2];
     }
-    if (a.depth) {
-      const float2 d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
-      fs[0] += d.x; fs[1] = fmaf(d.x, d.x, fs[1]);
-      fs[2] += d.y; fs[3] = fmaf(d.y, d.y, fs[3]);
-      if (a.n_dd > 0) {
-        const int b0 = depth_bin(d.x, s_edges, a.n_dd), b1 = depth_bin(d.y, s_edges, a.n_dd);
+    if (a.depth) d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
+    if (a.use_td) t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
 #pragma unroll
-        for (int i = 0; i < kRawMaxBins; ++i) {
-          cnt[i] += (b0 == i) ? 1u : 0u;
-          cnt[kRawMaxBins + i] += (b1 == i) ? 1u : 0u;
-        }
-      }
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t lo = w[k] & 0xff, hi = w[k] >> 8;
+      ri[4 * k] += lo; ri[4 * k + 1] += lo * lo;
+      ri[4 * k + 2] += hi; ri[4 * k + 3] += hi * hi;
     }
-    if (a.use_td) {
-      const float2 t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
-      fs[4] += t.x; fs[5] = fmaf(t.x, t.x, fs[5]);
-      fs[6] += t.y; fs[7] = fmaf(t.y, t.y, fs[7]);
+    fs[0] += d.x; fs[1] = fmaf(d.x, d.x, fs[1]);
+    fs[2] += d.y; fs[3] = fmaf(d.y, d.y, fs[3]);
+    fs[4] += t.x; fs[5] = fmaf(t.x, t.x, fs[5]);
+    fs[6] += t.y; fs[7] = fmaf(t.y, t.y, fs[7]);
+    if (a.n_dd > 0) {
+      const int b0 = depth_bin(d.x, s_edges, a.n_dd), b1 = depth_bin(d.y, s_edges, a.n_dd);
+      const unsigned long long i0 = (b0 >= 0) ? (1ull << ((b0 & 7) * 8)) : 0ull;
+      const unsigned long long i1 = (b1 >= 0) ? (1ull << ((b1 & 7) * 8)) : 0ull;
+      cb[0] += (b0 < 8) ? i0 : 0ull;
+      cb[1] += (b0 < 8) ? 0ull : i0;
+      cb[2] += (b1 < 8) ? i1 : 0ull;
+      cb[3] += (b1 < 8) ? 0ull : i1;
     }
   }
   // warp reduction (integers exactly, floats in fp64), then across the 8 warps through shared memory
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double vals[kRawVals];
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
-    uint32_t x = ri[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    vals[i] = static_cast<double>(x);
+    const uint32_t x = warp_sum_u32(ri[i]);
+    if (lane == 0) s_red[warp][i] = static_cast<double>(x);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    double x = static_cast<double>(fs[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    vals[12 + i] = x;
+    const double x = warp_sum_f64(static_cast<double>(fs[i]));
+    if (lane == 0) s_red[warp][12 + i] = x;
   }
 #pragma unroll
   for (int i = 0; i < 2 * kRawMaxBins; ++i) {
-    uint32_t x = cnt[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    vals[20 + i] = static_cast<double>(x);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kRawVals; ++i) s_red[warp][i] = vals[i];
+    const int f = i / kRawMaxBins, bin = i % kRawMaxBins;
+    const uint32_t x = warp_sum_u32(static_cast<uint32_t>((cb[2 * f + (bin >> 3)] >> ((bin & 7) * 8)) & 0xffull));
+    if (lane == 0) s_red[warp][20 + i] = static_cast<double>(x);
   }
   __syncthreads();
   // thread c < C: gather the (sum, sumsq) of output channel c and add it to the global accumulator
@@ -269,7 +272,7 @@ int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
   if (raw_check(a)) return -1;
   PNVO_REQUIRE(a.stats, "raw_stats: null accumulator");
   if (a.n_pix <= 0) return 0;
-  // each thread sums <= 2^24 / 65025 = 258 pixels exactly in 32-bit integers; keep it at <= 128
+  // a thread must see <= 255 pixels (8-bit packed bin counts; 32-bit integer rgb sums are exact far beyond): <= 128
   int64_t blocks = std::max<int64_t>(148 * 8, ceil_div64(a.n_pix, 256 * 128));
   blocks = std::min<int64_t>(blocks, ceil_div64(a.n_pix, 256));
   raw_stats_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(a);

@@ -53,6 +53,8 @@ class ConvLayer:
         # how the OIHW source is viewed by the pack kernel (Linear layers: [Cout, C, H, W] of the flatten)
         self.src_shape = src_shape or (Cout, Cin, R, S)
         self.wp = self.wt = self.dwp = None
+        self.up = None          # zero-upsampled dy (stride-2 data gradient), allocated on first use
+        self.fast_s2 = True
 
     def alloc(self, dev, training):
         self.wp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
@@ -80,6 +82,28 @@ class ConvLayer:
                          self.R - 1 - self.pad, self.stride, self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, add,
                          None, 0, 0, False, pad_w=self.S - 1 - self.pad)
 
+    def ops_dgrad(self, dy, gx, B, add=None, dev=None):
+        """Data gradient as a list of ops.  Stride-2 convolutions go through a zero-upsampled copy of dy so that
+        the stride-1 kernels (TMA im2col / shared-memory raster) do the work instead of the generic
+        divisibility-testing producer: 3x3/s2 = 3x3/s1 conv of up2(dy) with the flipped weights; 1x1/s2 = compact
+        1x1 conv of dy scattered to the even input positions."""
+        if self.stride == 1 or not self.fast_s2:
+            return [self.op_dgrad(dy, gx, B, add=add)]
+        assert self.stride == 2
+        if self.R == 1:
+            assert add is None and self.pad == 0
+            if self.up is None:
+                self.up = torch.empty(B, self.OH, self.OW, self.cin_pad, dtype=torch.float16, device=dy.device)
+            compact = L.op_conv(dy, self.wt, self.up, B, self.OH, self.OW, self.cout_pad, self.OH, self.OW, 1, 1, 1, 0, 1,
+                                self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, None, None, 0, 0, False, pad_w=0)
+            return [compact, L.op_upsample2(self.up, gx, B, self.OH, self.OW, self.IH, self.IW, self.cin_pad)]
+        if self.up is None:
+            self.up = torch.empty(B, self.IH, self.IW, self.cout_pad, dtype=torch.float16, device=dy.device)
+        conv = L.op_conv(self.up, self.wt, gx, B, self.IH, self.IW, self.cout_pad, self.IH, self.IW, self.R, self.S, 1,
+                         self.R - 1 - self.pad, 1, self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, add, None, 0, 0,
+                         False, pad_w=self.S - 1 - self.pad)
+        return [L.op_upsample2(dy, self.up, B, self.OH, self.OW, self.IH, self.IW, self.cout_pad), conv]
+
     def op_wgrad(self, x, dy, B, x_row_pitch=0):
         return L.op_wgrad(x, dy, self.dwp, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
                           self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad, x_row_pitch=x_row_pitch)
@@ -92,17 +116,19 @@ class LinearLayer(ConvLayer):
     """nn.Linear over an NCHW-flattened [C, H, W] feature map == 1x1 conv over the NHWC-flattened map
     (weight columns permuted by the pack kernel; vo_cnn.py:216-221, misc_utils.py:45-47)."""
 
-    def __init__(self, key, C, H, W, c_pad, Cout):
+    def __init__(self, key, C, H, W, c_pad, Cout, src_ld=0):
         super().__init__(key, H * W * c_pad, Cout, 1, 1, 1, 0, 1, 1, True, cin_pad=H * W * c_pad)
         self.fC, self.fH, self.fW, self.c_pad = C, H, W, c_pad
+        self.src_ld = src_ld  # columns of the nn.Linear weight when it carries extra (action-embedding) inputs
 
     def op_pack(self, w):
         # source viewed as OIHW [Cout, C, H, W]; packed column (h*W + w)*c_pad + c; wt = plain transpose
         return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld,
-                           self.cout_pad, self.wt_ld, 1)
+                           self.cout_pad, self.wt_ld, 1, src_ld=self.src_ld)
 
     def op_unpack(self, grad):
-        return L.op_unpack_dw(self.dwp, grad, self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld)
+        return L.op_unpack_dw(self.dwp, grad, self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld,
+                              dst_ld=self.src_ld)
 
 
 class GNLayer:
@@ -186,7 +212,9 @@ class EncoderPlan:
         self.gnc = GNLayer(self.prefix + ".compression.1", comp_ch, 1)
         self.comp_ch = comp_ch
         if self.head is not None:
-            self.fc = LinearLayer(self.head["fc_w"], comp_ch, h, w, self.comp.cout_pad, self.head["hidden"])
+            emb = self.head.get("embed")
+            src_ld = comp_ch * h * w + emb["dim"] if emb else 0
+            self.fc = LinearLayer(self.head["fc_w"], comp_ch, h, w, self.comp.cout_pad, self.head["hidden"], src_ld=src_ld)
 
     def all_convs(self):
         out = [self.conv1]
@@ -272,6 +300,11 @@ class EncoderPlan:
             self.h16 = torch.empty(B, hid, dtype=torch.float16, device=dev)
             # with an output layer the plan's result is [B, out_dim]; without, the hidden features [B, hidden]
             self.out = torch.empty(B, od, dtype=torch.float32, device=dev) if od else self.h32
+            emb = self.head.get("embed")
+            if emb:  # action-embedding inputs of the hidden layer (vo_cnn_act_embed.py:65-75)
+                self.actions = torch.zeros(B, dtype=torch.int64, device=dev)
+                self.e_used = torch.zeros(B, emb["dim"], dtype=torch.float32, device=dev)
+                self.e_mask = torch.ones(B, emb["dim"], dtype=torch.float32, device=dev)
         if tr:
             # gradient buffers (w.r.t. post-activation tensors, fp16) and raw-gradient scratch
             self.g_feat = torch.empty_like(self.feat)
@@ -310,6 +343,8 @@ class EncoderPlan:
             names += [g.key + ".weight", g.key + ".bias"]
         if self.head is not None:
             names += [self.head["fc_b"]]
+            if self.head.get("embed"):
+                names += [self.head["embed"]["table"]]
             if self.head.get("out_dim"):
                 names += [self.head["out_w"], self.head["out_b"]]
         return names
@@ -383,6 +418,12 @@ class EncoderPlan:
             hd = self.head
             feat_flat = self.feat  # [B, 1, 1, fH*fW*c_pad] as far as the 1x1 "conv" is concerned
             ops.append(self.fc.op_fwd(feat_flat, self.z, B, None, 0, 0, True))
+            emb = hd.get("embed")
+            if emb:
+                E = self.P[emb["table"]]
+                ops.append(L.op_act_embed_fwd(self.z, self.P[hd["fc_w"]], E, self.actions, self.e_used, self.e_mask,
+                                              self.drop_seed, B, hd["hidden"], emb["dim"], E.shape[0], self.fc.src_ld,
+                                              self.fc.src_ld - emb["dim"], p_drop))
             ops.append(L.op_bias_relu(self.z, self.P[hd["fc_b"]], self.h32, self.h16, B, hd["hidden"], True))
             if p_drop > 0:  # nn.Dropout in front of output_head (vo_cnn.py:224)
                 ops.append(L.op_dropout(self.h32, self.drop_seed, 1, p_drop, advance=True))
@@ -405,6 +446,14 @@ class EncoderPlan:
                                          hd["out_dim"], False, 1.0 / (1.0 - self.dropout_p)))
             else:  # gradient arrives w.r.t. the hidden features
                 ops.append(L.op_bias_relu_bwd(self.dout, self.h32, self.dz16, self.grads[hd["fc_b"]], B, hd["hidden"]))
+            emb = hd.get("embed")
+            if emb:
+                E = self.P[emb["table"]]
+                ops.append(L.op_zero(self.grads[emb["table"]]))
+                ops.append(L.op_act_embed_bwd(self.dz16, self.P[hd["fc_w"]], E, self.actions, self.e_used, self.e_mask,
+                                              self.grads[hd["fc_w"]], self.grads[emb["table"]], B, hd["hidden"],
+                                              emb["dim"], E.shape[0], self.fc.src_ld, self.fc.src_ld - emb["dim"],
+                                              self.fc.cout_pad))
             ops.append(self.fc.op_wgrad(self.feat, self.dz16, B))
             ops.append(self.fc.op_dgrad(self.dz16, self.g_feat, B))
         HWf = self.fH * self.fW
@@ -426,19 +475,19 @@ class EncoderPlan:
                 d, gd = blk["down"]
                 self._gn_bwd_all(ops, gd, blk["dy_last"], None, blk["raw_d"], blk["dx_d"], None, d.OH * d.OW)
                 ops.append(d.op_wgrad(blk["x_in"], blk["dx_d"], B))
-                ops.append(d.op_dgrad(blk["dx_d"], g_x, B))
+                ops += d.ops_dgrad(blk["dx_d"], g_x, B)
                 add = g_x
             for k in range(n - 1, -1, -1):
                 c, g = convs[k], gns[k]
                 xin = blk["x_in"] if k == 0 else blk["mid"][k - 1]
                 ops.append(c.op_wgrad(xin, blk["dx"][k], B))
                 if k > 0:
-                    ops.append(c.op_dgrad(blk["dx"][k], blk["g_mid"][k - 1], B))
+                    ops += c.ops_dgrad(blk["dx"][k], blk["g_mid"][k - 1], B)
                     cp, gp = convs[k - 1], gns[k - 1]
                     self._gn_bwd_all(ops, gp, blk["g_mid"][k - 1], blk["mid"][k - 1], blk["raw"][k - 1],
                                      blk["dx"][k - 1], None, cp.OH * cp.OW)
                 else:
-                    ops.append(c.op_dgrad(blk["dx"][0], g_x, B, add=add))
+                    ops += c.ops_dgrad(blk["dx"][0], g_x, B, add=add)
         # stem: max-pool + ReLU routing, GN, conv1 weight gradient (no data gradient: the input is data)
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
         self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)

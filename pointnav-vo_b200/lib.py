@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE = range(16, 30)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS = range(16, 34)
 
 
 class PnvoOp(ctypes.Structure):
@@ -205,12 +205,31 @@ def op_gn_param_grad(sums, dgamma, dbeta, B, C, C_real, accumulate=False):
     return _op(OP_GN_PARAM_GRAD, [B, C, C_real, int(accumulate)], (), [sums, dgamma, dbeta])
 
 
-def op_pack_w(w, wp, wt, Cout, Cin, R, S, cin_pad, ld_p, cout_pad=0, ld_t=0, t_mode=0):
-    return _op(OP_PACK_W, [Cout, Cin, R, S, cin_pad, ld_p, cout_pad, ld_t, t_mode], (), [w, wp, wt])
+def op_pack_w(w, wp, wt, Cout, Cin, R, S, cin_pad, ld_p, cout_pad=0, ld_t=0, t_mode=0, src_ld=0):
+    return _op(OP_PACK_W, [Cout, Cin, R, S, cin_pad, ld_p, cout_pad, ld_t, t_mode, src_ld], (), [w, wp, wt])
 
 
-def op_unpack_dw(dwp, grad, Cout, Cin, R, S, cin_pad, ld_p, accumulate=False):
-    return _op(OP_UNPACK_DW, [Cout, Cin, R, S, cin_pad, ld_p, int(accumulate)], (), [dwp, grad])
+def op_unpack_dw(dwp, grad, Cout, Cin, R, S, cin_pad, ld_p, accumulate=False, dst_ld=0):
+    return _op(OP_UNPACK_DW, [Cout, Cin, R, S, cin_pad, ld_p, int(accumulate), dst_ld], (), [dwp, grad])
+
+
+def op_geo_inv_loss(pred, actions, dout, loss3, B, O, weight, grad_scale=1.0, move_forward=1):
+    """loss3[0] += weight * (rot + pos), loss3[1] = rot, loss3[2] = pos; dout += weight * grad_scale * gradient."""
+    return _op(OP_GEO_INV_LOSS, [B, O, move_forward], [weight, grad_scale], [pred, actions, dout, loss3])
+
+
+def op_upsample2(src, dst, B, OH, OW, IH, IW, C):
+    return _op(OP_UPSAMPLE2, [B, OH, OW, IH, IW, C], (), [src, dst])
+
+
+def op_act_embed_fwd(z, W, E, actions, e_used, mask, seed, B, hidden, dim, n_rows, w_ld, col0, p_drop=0.0):
+    return _op(OP_ACT_EMBED_FWD, [B, hidden, dim, n_rows, w_ld, col0, 0], [p_drop],
+               [z, W, E, actions, e_used, mask, seed])
+
+
+def op_act_embed_bwd(dz16, W, E, actions, e_used, mask, dW, dE, B, hidden, dim, n_rows, w_ld, col0, dz_ld):
+    return _op(OP_ACT_EMBED_BWD, [B, hidden, dim, n_rows, w_ld, col0, dz_ld], (),
+               [dz16, W, E, actions, e_used, mask, dW, dE])
 
 
 def op_bias_relu(z, bias, h32, h16, B, N, relu=True):

@@ -64,10 +64,14 @@ class PrefetchedBatches:
 
 class FusedVOTrainStep:
     def __init__(self, model, lr=2.5e-4, betas=(0.9, 0.999), eps=1e-8, loss_weights=(1.0, 1.0, 1.0),
-                 process_group=None):
+                 process_group=None, loss_inv_weight=0.0, move_forward_id=1):
+        """loss_inv_weight > 0 adds the geometric-inversion loss (VO.TRAIN.loss_inv_weight,
+        vo_cnn_regression_geo_invariance_engine.py:367-449,792): batches are then interleaved pairs
+        [cur->prev, prev->cur, ...] and step() needs the per-row action ids."""
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.loss_weights = tuple(float(w) for w in loss_weights)
+        self.loss_inv_weight, self.move_forward_id = float(loss_inv_weight), int(move_forward_id)
         self.group = process_group
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -95,7 +99,7 @@ class FusedVOTrainStep:
         self._flat = flat
         self._m = torch.zeros_like(flat)
         self._v = torch.zeros_like(flat)
-        self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._loss = torch.zeros(3, dtype=torch.float32, device=dev)  # [total, inversion rot, inversion pos]
         if self.world > 1:  # replicas start from rank 0's weights (as DDP does, ddppo.py:55-58)
             torch.distributed.broadcast(flat, 0, group=self.group)
 
@@ -109,18 +113,27 @@ class FusedVOTrainStep:
         if plan is not self._plan:
             B, O = plan.B, plan.head["out_dim"]
             self._target = torch.zeros(B, O, dtype=torch.float32, device=plan.dev)
-            self._loss_prog = L.Program([L.op_mse_loss(plan.out, self._target, None, plan.dout, self._loss, B, O,
-                                                       self.loss_weights, 1.0 / self.world)])
+            ops = [L.op_mse_loss(plan.out, self._target, None, plan.dout, self._loss, B, O, self.loss_weights,
+                                 1.0 / self.world)]
+            if self.loss_inv_weight > 0:
+                self._actions = torch.zeros(B, dtype=torch.int64, device=plan.dev)
+                ops.append(L.op_geo_inv_loss(plan.out, self._actions, plan.dout, self._loss, B, O, self.loss_inv_weight,
+                                             1.0 / self.world, self.move_forward_id))
+            self._loss_prog = L.Program(ops)
             self._plan = plan
         return plan
 
-    def step(self, obs, target):
+    def step(self, obs, target, actions=None):
         """obs: dict of NHWC fp32 CUDA tensors (the model's forward input), or the raw pairs
         {"rgb": uint8 [B,H,W,6], "depth": fp32 [B,H,W,2]} (derived channels computed on the device);
         target: [B, 3] fp32 CUDA.  Returns the (device) loss tensor of this rank's batch."""
         model = self.model
         plan = self._get_plan(obs)
         self._target.copy_(target)
+        if self.loss_inv_weight > 0:
+            if actions is None:
+                raise L.PnvoError("the geometric-inversion loss needs the per-row action ids")
+            self._actions.copy_(actions.reshape(-1))
         model._run_forward(plan, obs, model.training)
         self._loss_prog.run(plan.dev)
         plan.bwd_prog.run(plan.dev)
@@ -131,4 +144,4 @@ class FusedVOTrainStep:
                              self.betas[0], self.betas[1], self.eps)], plan.dev)
         # the optimiser wrote through raw pointers: tell the module its packed fp16 weights are stale
         model._packed_version = None
-        return self._loss
+        return self._loss[:1]

@@ -195,6 +195,8 @@ class VisualOdometryCNNBase(nn.Module):
             if isinstance(rmv, RunningMeanAndVar) and rmv._distributed:
                 world = torch.distributed.get_world_size()
             head = dict(self._fc_keys, hidden=self._hidden_size, out_dim=self._output_dim)
+            if getattr(self, "_embed", None):
+                head["embed"] = dict(self._embed)
             plan = EncoderPlan(params=P, buffers=Bf, B=B, H=H, W=W, in_channels=enc.input_channels,
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0],
@@ -263,6 +265,11 @@ class VisualOdometryCNNBase(nn.Module):
         self._run_backbone(plan)
 
     def _run_backbone(self, plan):
+        if getattr(self, "_embed", None):
+            acts = self._cur_actions
+            if not acts.is_cuda:
+                raise L.PnvoError("actions must be a CUDA tensor")
+            plan.actions.copy_(acts.reshape(-1))
         ver = self._weights_version()
         if ver != self._packed_version or plan is not getattr(self, "_packed_plan", None):
             plan.pack_prog.run(plan.dev)
