@@ -123,7 +123,9 @@ enum pnvo_opcode {
   PNVO_OP_ACT_EMBED_BWD = 31, /* gradients of the embedding columns of the hidden Linear and of the embedding table */
   PNVO_OP_UPSAMPLE2 = 32,     /* zero-insertion x2 upsampling (stride-2 data gradients as stride-1 convolutions) */
   PNVO_OP_GEO_INV_LOSS = 33,  /* geometric-inversion loss + gradient (vo_cnn_regression_geo_invariance_engine.py:367-449) */
-  PNVO_OP_MAX = 34
+  PNVO_OP_CONV_STEM2 = 34,    /* stem conv, pixels-as-N formulation: D[(4 rows x cout), ow], resident weights, persistent */
+  PNVO_OP_PACK_W_STEM2 = 35,  /* OIHW fp32 -> [tap pair][descending filter rows by parity][cout][64] fp16 */
+  PNVO_OP_MAX = 36
 };
 
 typedef struct {
@@ -143,6 +145,9 @@ int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, i
 /* Width (pixels) of the zero-padded input rows the stem kernel (PNVO_OP_CONV_STEM) expects: 3 zero pixels left of the
  * image, zeros on the right; the image starts at pixel 3 of every row. */
 int pnvo_stem_padded_width(int IW);
+
+/* 1 when PNVO_OP_CONV_STEM2 can take an [IH, IW] input (output width <= 240). */
+int pnvo_conv_stem2_supported(int IH, int IW);
 
 /* 1 when PNVO_OP_GN_BWD_FUSED can take a [HW, C] fp16 sample (else use GN_BWD_REDUCE + GN_BWD_APPLY). */
 int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32);

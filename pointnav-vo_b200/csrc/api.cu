@@ -190,6 +190,12 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = x [B,IH,IW,32] fp16, p1 = stem-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = stages
       return conv_stem_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
                                   static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
+    case PNVO_OP_CONV_STEM2:
+      // p0 = W-padded x, p1 = stem2-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg
+      return conv_stem2_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
+                                   static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], st);
+    case PNVO_OP_PACK_W_STEM2:
+      return pack_w_stem2_launch(static_cast<const float*>(p[0]), i[0], static_cast<__half*>(p[1]), st);
     case PNVO_OP_WGRAD_STEM:
       // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld, i4 = rows per CTA
       return conv_stem_wgrad_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),
@@ -225,6 +231,7 @@ extern "C" const char* pnvo_last_error(void) { return g_err; }
 extern "C" int pnvo_abi_version(void) { return PNVO_ABI_VERSION; }
 extern "C" int64_t pnvo_launch_count(void) { return g_launches.load(); }
 extern "C" int pnvo_stem_padded_width(int IW) { return stem_padded_width(IW); }
+extern "C" int pnvo_conv_stem2_supported(int IH, int IW) { return conv_stem2_supported(IH, IW); }
 extern "C" int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32) {
   GnBwdArgs a{};
   a.C = C; a.HW = HW; a.x_fp32 = x_fp32;

@@ -12,8 +12,9 @@
 // Persistent CTA (one per SM): the 9 weight taps stay resident in shared memory; units (sample, T output rows)
 // are strided over the grid; the input raster is double-buffered (TMA of unit i+1 overlaps the MMAs of unit i) and
 // so is the TMEM accumulator (the epilogue of tile j overlaps the MMAs of tile j+1).
-//   warp 9: TMA producer    warp 8: TMEM owner + single-thread MMA issuer
-//   warps 0-3 / 4-7: two epilogue groups, one per accumulator buffer (even / odd tiles)
+//   kNG epilogue warpgroups (warps 0 .. 4*kNG-1), one per TMEM accumulator buffer (tile tc -> buffer tc % kNG): a lone
+//   warp per scheduler issues at ~1 instruction / 4-6 clk, so the ~250-instruction tile epilogue needs several
+//   groups in flight to keep up with 18-36 MMAs per tile;  then the MMA issuer warp (TMEM owner) and the TMA warp
 // Epilogue: optional accumulate input (dgrad into the identity-branch gradient), GroupNorm partial sums kept in
 // registers across the tiles of a unit (one sample) and flushed with a warp reduce-scatter + one atomic per value,
 // fp16 store (64 / 128 contiguous bytes per thread).
@@ -51,18 +52,22 @@ __device__ __forceinline__ void raster_group_sums(const float* v, float* acc) {
   }
 }
 
+static constexpr int kNG = 3;  // epilogue groups == accumulator buffers (4 would cap the kernel at 96 registers -> spills)
+static constexpr int kRasterThreads = kNG * 128 + 64;
+
 template <int C, int N>
-__global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, const __grid_constant__ ConvTmaps tm) {
+__global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const RasterArgs p, const __grid_constant__ ConvTmaps tm) {
   constexpr int kPix = C * 2;             // bytes per pixel = operand row bytes
   constexpr int kWTap = N * kPix;         // bytes of one weight tap [N][C]
   constexpr int kWBytes = 9 * kWTap;
   constexpr int kKSteps = C / 16;
+  constexpr int kTmemCols = kNG * N <= 128 ? 128 : (kNG * N <= 256 ? 256 : 512);
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_wfull;
   __shared__ __align__(8) uint64_t s_infull[2];
   __shared__ __align__(8) uint64_t s_inempty[2];
-  __shared__ __align__(8) uint64_t s_accfull[2];
-  __shared__ __align__(8) uint64_t s_accempty[2];
+  __shared__ __align__(8) uint64_t s_accfull[kNG];
+  __shared__ __align__(8) uint64_t s_accempty[kNG];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
@@ -74,13 +79,15 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&s_infull[s]), 1);
       mbar_init(smem_u32(&s_inempty[s]), 1);
+    }
+    for (int s = 0; s < kNG; ++s) {
       mbar_init(smem_u32(&s_accfull[s]), 1);
       mbar_init(smem_u32(&s_accempty[s]), 4);
     }
     fence_mbar_init();
   }
-  if (warp == 8) {
-    tmem_alloc(smem_u32(&s_tmem), 2 * N);
+  if (warp == 4 * kNG) {
+    tmem_alloc(smem_u32(&s_tmem), kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -89,7 +96,7 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
   const uint32_t tmem_base = s_tmem;
   const int n_tiles = p.n_tiles;
 
-  if (warp == 9) {
+  if (warp == 4 * kNG + 1) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       tma_prefetch_desc(&tm.a);
@@ -110,33 +117,39 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
         tma_load_4d(sIn0 + slot * p.in_bytes, &tm.a, bar, 0, -1, h0 - 1, b);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 4 * kNG) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(128, N, 0, 0);
+      // descriptors as (lo, hi): hi (SBO = 8 rows, version, swizzle mode) is shared by A and B; lo = (addr >> 4) | LBO.
+      // Per-tap low-word deltas are loop invariant, so the inner loop is one add per operand + the MMA.
+      const uint64_t d0 = umma_desc(0, 16, 8 * kPix, kPix);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
+      uint32_t tap_a[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) tap_a[tap] = static_cast<uint32_t>(((tap / 3) * p.P + (tap % 3)) * kPix) >> 4;
+      const uint32_t b_lo0 = lo0 + (sW >> 4);
       mbar_wait(smem_u32(&s_wfull), 0);
       int i = 0, tc = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int slot = i & 1;
         mbar_wait(smem_u32(&s_infull[slot]), (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t sIn = sIn0 + slot * p.in_bytes;
+        const uint32_t in_lo = lo0 + ((sIn0 + slot * p.in_bytes) >> 4);
         for (int j = 0; j < n_tiles; ++j, ++tc) {
-          const int ab = tc & 1;
-          if (tc >= 2) {
-            mbar_wait(smem_u32(&s_accempty[ab]), ((tc >> 1) & 1) ^ 1);
+          const int ab = tc % kNG;
+          if (tc >= kNG) {
+            mbar_wait(smem_u32(&s_accempty[ab]), ((tc / kNG) & 1) ^ 1);
             tc_fence_after();
           }
           const uint32_t d_tmem = tmem_base + ab * N;
+          const uint32_t a_lo = in_lo + static_cast<uint32_t>((128 * j * kPix) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint64_t adesc = umma_desc(sIn + static_cast<uint32_t>(128 * j + r * p.P + s) * kPix, 16, 8 * kPix, kPix);
-            const uint64_t bdesc = umma_desc(sW + tap * kWTap, 16, 8 * kPix, kPix);
 #pragma unroll
             for (int k = 0; k < kKSteps; ++k)
-              tc_mma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                         (tap | k) != 0 ? 1u : 0u);
+              tc_mma_f16_lohi(d_tmem, a_lo + tap_a[tap] + 2 * k, b_lo0 + ((tap * kWTap) >> 4) + 2 * k, hi, idesc,
+                              (tap | k) != 0 ? 1u : 0u);
           }
           tc_commit(smem_u32(&s_accfull[ab]));
         }
@@ -146,8 +159,8 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
     __syncwarp();
     tc_fence_before();
   } else {
-    // ================================ epilogue (warps 0-7) ================================
-    // group g = warp / 4 drains accumulator buffer g (tiles with tc % 2 == g); a warp reads TMEM lanes 32 * (warp % 4)
+    // ================================ epilogue (warps 0 .. 4*kNG-1) ================================
+    // group g = warp / 4 drains accumulator buffer g (tiles with tc % kNG == g); a warp reads TMEM lanes 32 * (warp % 4)
     const int grp = warp >> 2;
     const int row = tid & 127;
     const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++tc) {
-        const int ab = tc & 1;
+        const int ab = tc % kNG;
         if (ab != grp) continue;
         const int m = 128 * j + row;
         const int orow = m / p.P;
@@ -174,7 +187,7 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
 #pragma unroll
           for (int q = 0; q < N / 8; ++q) addq[q] = __ldg(reinterpret_cast<const uint4*>(p.add + gofs) + q);
         }
-        mbar_wait(smem_u32(&s_accfull[ab]), (tc >> 1) & 1);
+        mbar_wait(smem_u32(&s_accfull[ab]), (tc / kNG) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < N / 32; ++ch) {
@@ -243,9 +256,9 @@ __global__ void __launch_bounds__(320) conv_raster_kernel(const RasterArgs p, co
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4 * kNG) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * N);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -307,7 +320,7 @@ static int raster_launch_t(const RasterArgs& r, const ConvTmaps& tm, int smem, c
     attr = true;
   }
   const int grid = std::min(r.n_units, 148);
-  conv_raster_kernel<C, N><<<grid, 320, smem, st>>>(r, tm);
+  conv_raster_kernel<C, N><<<grid, kRasterThreads, smem, st>>>(r, tm);
   count_launch();
   return check_launch("conv_raster");
 }

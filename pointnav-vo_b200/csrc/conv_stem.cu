@@ -95,23 +95,23 @@ __global__ void __launch_bounds__(192) conv_stem_fwd_kernel(const StemArgs p, co
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(128, 32, 0, 0);
+      const uint64_t d0 = umma_desc(0, 16, 1024, 128);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
       for (int r = 0; r < 7; ++r) {
         const int s = r % stages;
         mbar_wait(smem_u32(&s_full[s]), (r / stages) & 1);
         tc_fence_after();
         const uint32_t sX = smem_base + s * stage_bytes;
-        const uint32_t sW = sX + p.xrow_bytes;
+        const uint32_t x_lo = lo0 + (sX >> 4), w_lo = lo0 + ((sX + p.xrow_bytes) >> 4);
         for (int t = 0; t < n_tiles; ++t) {
           const int ow0 = t == 0 ? 0 : p.ow1;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             // taps (2j, 2j+1): operand row m = raster pixels 2*(ow0+m)+2j, +1 -> start shifted by (ow0 + j) rows
-            const uint64_t adesc = umma_desc(sX + static_cast<uint32_t>(ow0 + j) * 128, 16, 1024, 128);
-            const uint64_t bdesc = umma_desc(sW + j * 4096, 16, 1024, 128);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              tc_mma_f16(tmem_base + t * 32, adesc + static_cast<uint64_t>(q * 2), bdesc + static_cast<uint64_t>(q * 2),
-                         idesc, (r | j | q) != 0 ? 1u : 0u);
+              tc_mma_f16_lohi(tmem_base + t * 32, x_lo + static_cast<uint32_t>(ow0 + j) * 8 + q * 2, w_lo + j * 256 + q * 2, hi,
+                              idesc, (r | j | q) != 0 ? 1u : 0u);
           }
         }
         tc_commit(smem_u32(&s_empty[s]));
@@ -319,20 +319,22 @@ __global__ void __launch_bounds__(192) conv_stem_wgrad_kernel(const StemWgradArg
     if (elect_one()) {
       // ================================ MMA issuer ================================
       const uint32_t idesc = umma_idesc_f16(128, 32, 1, 1);
+      const uint64_t da0 = umma_desc(0, 128, 1024, 128), db0 = umma_desc(0, 64, 512, 64);
+      const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), a_lo0 = static_cast<uint32_t>(da0);
+      const uint32_t b_hi = static_cast<uint32_t>(db0 >> 32), b_lo0 = static_cast<uint32_t>(db0);
       for (int t = 0; t < n_rows; ++t) {
         const int oh = oh_begin + t, pslot = t & 1;
         mbar_wait(smem_u32(&s_full[pslot]), (t >> 1) & 1);
         tc_fence_after();
-        const uint32_t sB = s_dy + pslot * kSwDy;
+        const uint32_t b_lo = b_lo0 + ((s_dy + pslot * kSwDy) >> 4);
         for (int r = 0; r < 7; ++r) {
-          const uint32_t sX = smem_base + static_cast<uint32_t>((2 * oh + r) % 9) * kSwRow;
+          const uint32_t x_lo = a_lo0 + ((smem_base + static_cast<uint32_t>((2 * oh + r) % 9) * kSwRow) >> 4);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             for (int q = 0; q < ksteps; ++q) {
               // K step q = output pixels ow_base + 16q .. +15 -> staged pair rows (16q + 2h) .. ; block 1 one row later
-              const uint64_t adesc = umma_desc(sX + static_cast<uint32_t>(16 * q + 2 * h) * 128, 128, 1024, 128);
-              const uint64_t bdesc = umma_desc(sB + static_cast<uint32_t>(q) * 1024, 64, 512, 64);
-              tc_mma_f16(tmem_base + static_cast<uint32_t>((r * 2 + h) * 32), adesc, bdesc, idesc, (t | q) != 0 ? 1u : 0u);
+              tc_mma_f16_parts(tmem_base + static_cast<uint32_t>((r * 2 + h) * 32), x_lo + static_cast<uint32_t>(16 * q + 2 * h) * 8,
+                               a_hi, b_lo + static_cast<uint32_t>(q) * 64, b_hi, idesc, (t | q) != 0 ? 1u : 0u);
             }
           }
         }

@@ -1,0 +1,283 @@
+// Stem convolution (7x7 / stride 2 / pad 3, Cin_pad = 32, Cout = 32: resnet.py:156-164), second formulation:
+// output PIXELS are the UMMA N dimension and (4 output rows x 32 channels) the M dimension.
+//
+// conv_stem.cu computes D[pixel, cout] with N = 32: every tcgen05.mma re-reads a 4 KB pixel tile from shared memory
+// for 128 x 32 x 16 MACs and runs at 40 clk (measured, tools/mma_rate.py: 32 + N/4 clk for N <= 128, N/2 above), i.e.
+// 40 % of the tensor-pipe rate, and the 112 KB of stem weights are re-streamed from L2 for every output row.  Here
+//
+//   D[(q, cout), ow] += W_r(q)[cout, (s, c)] * x[h, 2 ow + s, c]        q = 0..3 <-> output row oh0 + q, r(q) = h + 3 - 2 (oh0 + q)
+//
+// for every input row h that touches the group of 4 output rows (13 rows): the B operand is the staged input row
+// seen as 128-byte pixel pairs (tap pairs = descriptor shifts by one pair, as before), N = 176 >= OW columns at the
+// full MMA rate (88 clk for 128 x 176 x 16); the A operand is a window of 4 consecutive entries of the filter rows
+// stored in descending order of the same parity ([6,4,2,0] / [5,3,1]), so the 4 blocks of M are contiguous; blocks
+// whose tap falls outside 0..6 are switched off with tcgen05.mma's disable_output_lane mask.  Persistent CTA: all
+// weights resident (112 KB), input rows streamed ONCE per group through a TMA ring, accumulator double-buffered in
+// TMEM (2 x 176 columns) so the epilogue of group g overlaps the MMAs of group g+1.
+// Epilogue: thread = (q, cout), 32 lanes of a warp = the 32 channels of one pixel -> 64-byte coalesced fp16 stores;
+// GroupNorm partial sums per thread over the row, folded across the group's lanes by shuffles, one atomic per value.
+#include "common.cuh"
+#include "ops.cuh"
+#include "tmap.cuh"
+
+namespace pnvo {
+
+struct Stem2Args {
+  __half* y;      // [B, OH, OW, 32] fp16
+  float* stats;   // [B][G][2]
+  int B, IH, OH, OW;
+  int G, cpg;
+  int n_cols;         // UMMA N: OW rounded up to 16
+  int xrow_bytes;     // shared-memory bytes of one staged input row (multiple of 1024)
+  int stages;         // ring depth
+  int groups_per_img, n_groups;
+};
+
+static constexpr int kS2Plane = 7 * 32 * 128;   // one tap-pair plane: 7 filter rows x 32 cout x 128 B
+static constexpr int kS2W = 4 * kS2Plane;       // 114688 B
+
+__device__ __forceinline__ void tc_mma_f16_masked(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                  uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, {%6, %7, %8, %9}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+
+// order in which the 13 input rows of a group are processed: d = 6 first (all four blocks valid -> it initialises
+// every accumulator lane with accumulate = 0), then the rest
+__device__ __forceinline__ int stem2_row(int k) { return k == 0 ? 6 : (k <= 6 ? k - 1 : k); }
+
+__global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, const __grid_constant__ ConvTmaps tm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_wfull;
+  __shared__ __align__(8) uint64_t s_xfull[4];
+  __shared__ __align__(8) uint64_t s_xempty[4];
+  __shared__ __align__(8) uint64_t s_accfull[2];
+  __shared__ __align__(8) uint64_t s_accempty[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  // [x stage 0][weights][x stages 1..]: weight windows that start before the first plane / run past the last one
+  // (their lanes are masked) still read inside the allocation
+  const uint32_t sW = smem_base + p.xrow_bytes;
+  const int stages = p.stages;
+  auto stage_addr = [&](int s) -> uint32_t {
+    return s == 0 ? smem_base : sW + kS2W + static_cast<uint32_t>(s - 1) * p.xrow_bytes;
+  };
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_wfull), 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(smem_u32(&s_xfull[s]), 1);
+      mbar_init(smem_u32(&s_xempty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_accfull[s]), 1);
+      mbar_init(smem_u32(&s_accempty[s]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&s_tmem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 5) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      const uint32_t wbar = smem_u32(&s_wfull);
+      mbar_arrive_expect_tx(wbar, kS2W);
+      for (int j = 0; j < 4; ++j) tma_load_2d(sW + j * kS2Plane, &tm.b, wbar, 0, j * 224);
+      const uint32_t x_tx = static_cast<uint32_t>(p.n_cols + 8) * 128;
+      int ctr = 0;
+      for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+        const int b = g / p.groups_per_img;
+        const int oh0 = (g - b * p.groups_per_img) * 4;
+        for (int k = 0; k < 13; ++k) {
+          const int d = stem2_row(k);
+          const int h = 2 * oh0 - 3 + d;
+          if (k != 0 && (h < 0 || h >= p.IH)) continue;  // all-zero row: nothing to add
+          const int s = ctr % stages;
+          if (ctr >= stages) mbar_wait(smem_u32(&s_xempty[s]), ((ctr / stages) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&s_xfull[s]);
+          mbar_arrive_expect_tx(bar, x_tx);
+          tma_load_4d(stage_addr(s), &tm.a, bar, 0, 0, h, b);  // whole W-padded row as pixel pairs; outside the image: zeros
+          ++ctr;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, p.n_cols, 0, 0);
+      const uint64_t d0 = umma_desc(0, 16, 1024, 128);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
+      mbar_wait(smem_u32(&s_wfull), 0);
+      int ctr = 0, i = 0;
+      for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++i) {
+        const int b = g / p.groups_per_img;
+        const int oh0 = (g - b * p.groups_per_img) * 4;
+        const int ab = i & 1;
+        if (i >= 2) {
+          mbar_wait(smem_u32(&s_accempty[ab]), ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + ab * 256;
+        for (int k = 0; k < 13; ++k) {
+          const int d = stem2_row(k);
+          const int h = 2 * oh0 - 3 + d;
+          if (k != 0 && (h < 0 || h >= p.IH)) continue;
+          const int s = ctr % stages;
+          mbar_wait(smem_u32(&s_xfull[s]), (ctr / stages) & 1);
+          tc_fence_after();
+          // window of 4 filter rows: even d -> [6,4,2,0] from position (6-d)/2, odd d -> [5,3,1] from (5-d)/2
+          const int odd = d & 1;
+          const int p0 = odd ? (5 - d) / 2 : (6 - d) / 2;   // exact divisions (numerators are even)
+          const int npos = odd ? 3 : 4;
+          uint32_t m[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[q] = (p0 + q >= 0 && p0 + q < npos) ? 0u : 0xFFFFFFFFu;
+          const int a_off = (odd ? 4 * 4096 : 0) + p0 * 4096;  // may be negative: masked lanes, valid addresses
+          const uint32_t a_lo = lo0 + (static_cast<uint32_t>(static_cast<int>(sW) + a_off) >> 4);
+          const uint32_t b_lo = lo0 + (stage_addr(s) >> 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_f16_masked(d_tmem, a_lo + j * (kS2Plane >> 4) + kk * 2, b_lo + j * 8 + kk * 2, hi, idesc, m[0], m[1],
+                                m[2], m[3], (k | j | kk) != 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&s_xempty[s]));
+          ++ctr;
+        }
+        tc_commit(smem_u32(&s_accfull[ab]));
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================================ epilogue (warps 0-3: warp = output row of the group, lane = channel) ================
+    const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+    int i = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++i) {
+      const int b = g / p.groups_per_img;
+      const int oh = (g - b * p.groups_per_img) * 4 + warp;
+      const int ab = i & 1;
+      const bool row_valid = oh < p.OH;
+      __half* yrow = p.y + (static_cast<int64_t>(b) * p.OH + oh) * p.OW * 32 + lane;
+      float sum = 0.f, ssq = 0.f;
+      mbar_wait(smem_u32(&s_accfull[ab]), (i >> 1) & 1);
+      tc_fence_after();
+      const int n_chunks = (p.n_cols + 31) >> 5;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        float v[32];
+        tmem_ld32(tmem_base + t_lane + ab * 256 + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == n_chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_accempty[ab]));
+        }
+        if (row_valid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int ow = ch * 32 + e;
+            if (ow < p.OW) {
+              yrow[static_cast<int64_t>(ow) * 32] = __float2half_rn(v[e]);
+              sum += v[e];
+              ssq = fmaf(v[e], v[e], ssq);
+            }
+          }
+        }
+      }
+      if (p.stats) {
+        for (int o = 1; o < p.cpg; o <<= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        }
+        if (row_valid && (lane % p.cpg) == 0) {
+          float* st = p.stats + (static_cast<int64_t>(b) * p.G + lane / p.cpg) * 2;
+          atomicAdd(st, sum);
+          atomicAdd(st + 1, ssq);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// OIHW fp32 [32][Cin][7][7] -> [pair j][position][cout][64] fp16: positions 0..3 = filter rows 6,4,2,0, positions 4..6 =
+// rows 5,3,1; column = (s & 1) * 32 + c with s = 2j + (s & 1); tap s = 7 and channels >= Cin stay zero.
+__global__ void pack_w_stem2_kernel(const float* __restrict__ w, int Cin, __half* __restrict__ wr) {
+  const int total = 32 * Cin * 49;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int s = i % 7, r = (i / 7) % 7, c = (i / 49) % Cin, n = i / (49 * Cin);
+    const int pos = (r & 1) ? 4 + (5 - r) / 2 : (6 - r) / 2;
+    wr[(((s >> 1) * 7 + pos) * 32 + n) * 64 + (s & 1) * 32 + c] = __float2half_rn(w[i]);
+  }
+}
+
+int pack_w_stem2_launch(const float* w, int Cin, __half* wr, cudaStream_t st) {
+  PNVO_REQUIRE(w && wr && Cin <= 32, "pack_w_stem2: bad arguments");
+  pack_w_stem2_kernel<<<ceil_div(32 * Cin * 49, 256), 256, 0, st>>>(w, Cin, wr);
+  count_launch();
+  return check_launch("pack_w_stem2");
+}
+
+int conv_stem2_supported(int IH, int IW) {
+  const int OW = (IW + 6 - 7) / 2 + 1;
+  const int n_cols = ceil_div(OW, 16) * 16;
+  return (n_cols <= 240 && IH >= 7) ? 1 : 0;
+}
+
+int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+                          cudaStream_t st) {
+  PNVO_REQUIRE(x && wr && y, "conv_stem2: null pointer");
+  PNVO_REQUIRE(conv_stem2_supported(IH, IW), "conv_stem2: unsupported geometry %dx%d", IH, IW);
+  PNVO_REQUIRE(!stats || (cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && G * cpg == 32), "conv_stem2: bad group config");
+  Stem2Args a{};
+  a.y = static_cast<__half*>(y); a.stats = stats; a.B = B; a.IH = IH;
+  a.OH = (IH + 6 - 7) / 2 + 1;
+  a.OW = (IW + 6 - 7) / 2 + 1;
+  a.G = G; a.cpg = cpg;
+  a.n_cols = ceil_div(a.OW, 16) * 16;
+  a.xrow_bytes = ((a.n_cols + 8) * 128 + 1023) & ~1023;
+  a.groups_per_img = ceil_div(a.OH, 4);
+  a.n_groups = B * a.groups_per_img;
+  a.stages = std::min(4, (210 * 1024 - kS2W) / a.xrow_bytes);
+  PNVO_REQUIRE(a.stages >= 2, "conv_stem2: input rows too wide for the shared-memory ring");
+  const int smem_bytes = a.stages * a.xrow_bytes + kS2W + 1024;
+  const int Wp = stem_padded_width(IW);
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  // pixel pairs as the innermost 128-byte dimension: [B, IH, Wp/2, 64]; the box may run past Wp/2 (zero fill)
+  if (tmap_tiled4d(&tm.a, x, B, IH, Wp / 2, 64, a.n_cols + 8)) return -1;
+  if (tmap_tiled2d(&tm.b, wr, 4 * 7 * 32, 64, 64, 224, 64)) return -1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_stem2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    attr = true;
+  }
+  if (B <= 0) return 0;
+  conv_stem2_fwd_kernel<<<std::min(a.n_groups, 148), 192, smem_bytes, st>>>(a, tm);
+  count_launch();
+  return check_launch("conv_stem2_fwd");
+}
+
+}  // namespace pnvo

@@ -90,24 +90,28 @@ __global__ void __launch_bounds__(192) conv_wgrad_raster_kernel(const WgRasterAr
     if (elect_one()) {
       // ================================ MMA issuer ================================
       const uint32_t idesc = umma_idesc_f16(128, N, 1, 1);
+      // (lo, hi) descriptors: hi (SBO, version, swizzle) and the LBO bits of lo are shared by A and B; per-row deltas
+      // are loop invariant -> one add per operand between two MMAs
+      const uint64_t d0 = umma_desc(0, kPix, 8 * kPix, kPix);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
+      uint32_t row_a[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) row_a[r] = static_cast<uint32_t>(r * p.P * kPix) >> 4;
       int i = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int slot = i & 1;
         mbar_wait(smem_u32(&s_full[slot]), (i >> 1) & 1);
         tc_fence_after();
         const uint32_t sX = smem_base + slot * stage_bytes;
-        const uint32_t sD = sX + p.x_bytes;
-        for (int q = 0; q < p.n_k; ++q) {
+        uint32_t x_lo = lo0 + (sX >> 4), d_lo = lo0 + ((sX + p.x_bytes) >> 4);
+        for (int q = 0; q < p.n_k; ++q, x_lo += kPix, d_lo += kPix) {  // 16 positions * kPix bytes >> 4 = kPix
           // K step q = output raster positions 16q .. 16q+15
-          const uint64_t bdesc = umma_desc(sD + static_cast<uint32_t>(16 * q) * kPix, kPix, 8 * kPix, kPix);
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int h = 0; h < kMPR; ++h) {
-              const uint64_t adesc =
-                  umma_desc(sX + static_cast<uint32_t>(16 * q + r * p.P + h * kNB) * kPix, kPix, 8 * kPix, kPix);
-              tc_mma_f16(tmem_base + static_cast<uint32_t>((r * kMPR + h) * N), adesc, bdesc, idesc, (i | q) != 0 ? 1u : 0u);
-            }
+            for (int h = 0; h < kMPR; ++h)
+              tc_mma_f16_lohi(tmem_base + static_cast<uint32_t>((r * kMPR + h) * N), x_lo + row_a[r] + ((h * kNB * kPix) >> 4),
+                              d_lo, hi, idesc, (i | q) != 0 ? 1u : 0u);
           }
         }
         tc_commit(smem_u32(&s_empty[slot]));

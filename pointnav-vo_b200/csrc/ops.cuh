@@ -48,6 +48,11 @@ int stem_padded_width(int IW);
 int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW,
                            int rows_per_cta, cudaStream_t st);
 int pack_w_stem_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
+// conv_stem2.cu: pixels-as-N formulation of the stem (full-rate MMAs, resident weights, persistent)
+int conv_stem2_supported(int IH, int IW);
+int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+                          cudaStream_t st);
+int pack_w_stem2_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
 int wgrad_plan(WgradArgs& a);
 // conv_wgrad_raster.cu: persistent no-im2col weight gradient for 3x3 / stride 1 / pad 1 with 32 or 64 channels
 int wgrad_raster_supported(const WgradArgs& a);

@@ -161,6 +161,8 @@ class EncoderPlan:
         self.head = head
         self.dropout_p = float(dropout_p) if head is not None and head.get("out_dim") else 0.0
         self.fuse_gn_bwd = True
+        self.stem_version = 2
+        self.use_stem2 = False
         self.grads = {}
         self._build_layers(backbone, baseplanes, ngroups, compression_channels)
         self._alloc()
@@ -268,6 +270,9 @@ class EncoderPlan:
             self.x0 = torch.zeros(B, self.inH, self.x0_pitch, self.cin_pad, dtype=torch.float16, device=dev)
             self.x0_img = self.x0[:, :, 3:, :]  # view whose data_ptr is the first image pixel
             self.w_stem = torch.zeros(7 * 4 * 32, 64, dtype=torch.float16, device=dev)
+            # pixels-as-N stem kernel (conv_stem2.cu): full-rate MMAs, resident weights
+            self.use_stem2 = bool(self.stem_version >= 2 and L.load().pnvo_conv_stem2_supported(self.inH, self.inW))
+            self.w_stem2 = torch.zeros(4 * 7 * 32, 64, dtype=torch.float16, device=dev) if self.use_stem2 else None
         else:
             self.x0_pitch = 0
             self.x0 = self._act(B, self.inH, self.inW, self.cin_pad)
@@ -377,11 +382,15 @@ class EncoderPlan:
         pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
         if self.use_stem:
             pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
+            if self.use_stem2:
+                pack.append(L.op_pack_w_stem2(self.P[self.conv1.key], self.w_stem2, self.conv1.Cin))
         self.pack_prog = L.Program(pack)
         # ---- forward (after the input tensor x0 has been produced) ----
         ops = [L.op_zero(self.stats_all)]
         c1, g1 = self.conv1, self.gn1
-        if self.use_stem and not self.raw_fp32:
+        if self.use_stem2 and not self.raw_fp32:
+            ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg))
+        elif self.use_stem and not self.raw_fp32:
             ops.append(L.op_conv_stem(self.x0, self.w_stem, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg, 2))
         else:
             assert not self.use_stem, "raw_fp32 is not supported together with the stem kernel"

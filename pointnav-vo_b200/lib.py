@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS = range(16, 34)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2 = range(16, 36)
 
 
 class PnvoOp(ctypes.Structure):
@@ -36,7 +36,7 @@ _lib = None
 
 EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_discretize_depth",
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
-           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided"]
+           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_conv_stem2_supported"]
 
 
 def load():
@@ -55,6 +55,8 @@ def load():
     lib.pnvo_launch_count.restype = i64
     lib.pnvo_stem_padded_width.argtypes = [i32]
     lib.pnvo_stem_padded_width.restype = i32
+    lib.pnvo_conv_stem2_supported.argtypes = [i32, i32]
+    lib.pnvo_conv_stem2_supported.restype = i32
     lib.pnvo_gn_bwd_fused_supported.argtypes = [i32, i32, i32]
     lib.pnvo_gn_bwd_fused_supported.restype = i32
     lib.pnvo_discretize_depth.argtypes = [vp, i64, vp, i32, vp, i64, vp, vp, vp]
@@ -259,6 +261,14 @@ def op_mse_loss(pred, target, dz_mask, dout, loss, B, O, weights=(1.0, 1.0, 1.0)
 
 def op_conv_stem(x, wr, y, stats, B, IH, IW, G, cpg, stages=4):
     return _op(OP_CONV_STEM, [B, IH, IW, G, cpg, stages], (), [x, wr, y, stats])
+
+
+def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg):
+    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg], (), [x, wr, y, stats])
+
+
+def op_pack_w_stem2(w, wr, Cin):
+    return _op(OP_PACK_W_STEM2, [Cin], (), [w, wr])
 
 
 def op_wgrad_stem(x, dy, dw, B, IH, IW, w_ld, rows_per_cta=32):

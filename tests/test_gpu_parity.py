@@ -194,6 +194,39 @@ def test_conv_fprop_dgrad_wgrad(case, force_generic):
             assert rel(gx2[..., :Cin].permute(0, 3, 1, 2), want) <= 3e-3
 
 
+@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("B,IH,IW,Cin", [(2, 192, 341, 30), (3, 16, 341, 30), (150, 10, 341, 8)])
+def test_stem_conv_kernels(version, B, IH, IW, Cin):
+    """The two stem kernels (row raster with N = 32; pixels-as-N with masked filter-row windows) against torch fp32
+    on fp16-rounded operands: outputs <= 3e-3 * rms (one fp16 rounding), GroupNorm partial sums <= 1e-4."""
+    from pointnav_vo_b200 import lib as L
+
+    dev = "cuda"
+    torch.manual_seed(0)
+    OH, OW = (IH - 1) // 2 + 1, (IW - 1) // 2 + 1
+    w = (torch.randn(32, Cin, 7, 7, device=dev) / (Cin * 49) ** 0.5).contiguous()
+    Wp = L.load().pnvo_stem_padded_width(IW)
+    xp = torch.zeros(B, IH, Wp, 32, device=dev, dtype=torch.float16)
+    x = torch.randn(B, IH, IW, 32, device=dev).half()
+    x[..., Cin:] = 0
+    xp[:, :, 3:3 + IW] = x
+    y = torch.full((B, OH, OW, 32), float("nan"), dtype=torch.float16, device=dev)
+    stats = torch.zeros(B, 16, 2, device=dev)
+    wr = torch.zeros(4 * 7 * 32, 64, dtype=torch.float16, device=dev)
+    if version == 1:
+        if not 128 <= OW <= 256:
+            pytest.skip("row-raster stem kernel needs 128 <= OW <= 256")
+        ops = [L.op_pack_w_stem(w, wr, Cin), L.op_conv_stem(xp, wr, y, stats, B, IH, IW, 16, 2, 2)]
+    else:
+        assert L.load().pnvo_conv_stem2_supported(IH, IW) == 1
+        ops = [L.op_pack_w_stem2(w, wr, Cin), L.op_conv_stem2(xp, wr, y, stats, B, IH, IW, 16, 2)]
+    L.run_ops(ops)
+    ref = F.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), w.half().float(), None, 2, 3)
+    assert rel(y.permute(0, 3, 1, 2), ref) <= 3e-3
+    rs = ref.reshape(B, 16, -1)
+    assert rel(stats, torch.stack((rs.sum(-1), rs.pow(2).sum(-1)), -1)) <= 1e-4
+
+
 @pytest.mark.parametrize("B,H,W,C,G,Cr", [(3, 24, 43, 64, 16, 64), (2, 6, 11, 32, 1, 31), (2, 12, 22, 128, 16, 128),
                                          (2, 3, 6, 128, 1, 114), (3, 48, 86, 32, 16, 32), (2, 6, 11, 256, 16, 256)])
 def test_groupnorm_forward_backward(B, H, W, C, G, Cr):
@@ -542,3 +575,46 @@ def test_dropout_training_mode():
         plan_e = [p for p in m._plans.values() if not p.training][0]
         h_eval_nonzero = (plan_e.h32 != 0).float().mean().item()
     assert abs(kept_h - 0.8 * h_eval_nonzero) <= 0.04
+
+
+def test_ppo_update_on_device():
+    """a13 + a14: rollout storage on the device (GAE through pnvo_gae_scan, bit-exact against the oracle) and one
+    PPO update through the B200 actor-critic: finite losses, parameters move, returns equal the oracle's."""
+    from pointnav_vo_b200.rl.common.rollout_storage import RolloutStorage
+    from pointnav_vo_b200.rl.ppo.ppo import PPO
+
+    pol = helpers.policy_state_dict(device="cuda")
+    obs_space, act_space = helpers.policy_spaces()
+    T, N = 4, 4
+    rs = RolloutStorage(T, N, obs_space, act_space, 512, num_recurrent_layers=pol.net.num_recurrent_layers)
+    rs.to("cuda")
+    torch.manual_seed(5)
+    obs = {"depth": torch.rand(N, 192, 341, 1, device="cuda"), "pointgoal_with_gps_compass": torch.rand(N, 2, device="cuda")}
+    rs.observations["depth"][0].copy_(obs["depth"])
+    rs.observations["pointgoal_with_gps_compass"][0].copy_(obs["pointgoal_with_gps_compass"])
+    rs.masks[0].fill_(1.0)
+    pol.eval()
+    for t in range(T):
+        with torch.no_grad():
+            step_obs = {k: v[t] for k, v in rs.observations.items()}
+            v, a, lp, h = pol.act(step_obs, rs.recurrent_hidden_states[t], rs.prev_actions[t], rs.masks[t])
+        nxt = {"depth": torch.rand(N, 192, 341, 1, device="cuda"),
+               "pointgoal_with_gps_compass": torch.rand(N, 2, device="cuda")}
+        rs.insert(nxt, h, a, lp, v, torch.randn(N, 1, device="cuda"), (torch.rand(N, 1, device="cuda") > 0.1).float())
+    with torch.no_grad():
+        nv = pol.get_value({k: v[T] for k, v in rs.observations.items()}, rs.recurrent_hidden_states[T],
+                           rs.prev_actions[T], rs.masks[T])
+    vp_before = rs.value_preds.clone()
+    rs.compute_returns(nv, True, 0.99, 0.95)
+    want, _ = po.gae_returns(rs.rewards.cpu().numpy(), vp_before.cpu().numpy(), rs.masks.cpu().numpy(),
+                             nv.cpu().numpy(), True, 0.99, 0.95)
+    assert np.array_equal(rs.returns.cpu().numpy(), want)
+    agent = PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
+    before = [p.detach().clone() for p in pol.parameters()]
+    pol.train()
+    vl, al, ent = agent.update(rs)
+    assert all(np.isfinite(x) for x in (vl, al, ent)) and ent > 0
+    moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, pol.parameters()))
+    assert moved >= len(before) - 2
+    rs.after_update()

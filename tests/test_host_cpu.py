@@ -171,3 +171,43 @@ def test_data_parallel_host_logic_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_rollout_storage_generator_matches_per_env_gather():
+    """a14 host side: the single-gather recurrent_generator yields exactly what the reference's per-environment
+    Python loop stacks (rollout_storage.py:122-211): same shapes, time-major flattening, same permutation use."""
+    import torch
+
+    from pointnav_vo_b200.rl.common.rollout_storage import RolloutStorage
+    from tests import helpers
+
+    obs_space, act_space = helpers.policy_spaces()
+    obs_space.spaces["depth"].shape = (6, 7, 1)  # small frames: this test is about indexing only
+    T, N, mb = 5, 6, 3
+    rs = RolloutStorage(T, N, obs_space, act_space, 8, num_recurrent_layers=4)
+    g = torch.Generator().manual_seed(3)
+    for t in range(T):
+        rs.insert({k: torch.randn(N, *sp.shape, generator=g) for k, sp in obs_space.spaces.items()},
+                  torch.randn(4, N, 8, generator=g), torch.randint(0, 4, (N, 1), generator=g),
+                  torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g),
+                  (torch.rand(N, 1, generator=g) > 0.2).float())
+    assert rs.step == T and rs.actions.dtype == torch.long
+    adv = torch.randn(T, N, 1, generator=g)
+    torch.manual_seed(11)
+    got = list(rs.recurrent_generator(adv, mb))
+    torch.manual_seed(11)
+    perm = torch.randperm(N)
+    per = N // mb
+    assert len(got) == mb
+    for bi, sample in enumerate(got):
+        ind = perm[bi * per:(bi + 1) * per]
+        obs, hid, act, prev, vp, ret, msk, olp, ad = sample
+        want = lambda x: torch.stack([x[:T, i] for i in ind], 1).reshape(T * per, *x.shape[2:])  # noqa: E731
+        for k in obs:
+            assert torch.equal(obs[k], want(rs.observations[k]))
+        assert torch.equal(hid, torch.stack([rs.recurrent_hidden_states[0, :, i] for i in ind], 1))
+        for a, b in ((act, rs.actions), (prev, rs.prev_actions), (vp, rs.value_preds), (ret, rs.returns),
+                     (msk, rs.masks), (olp, rs.action_log_probs), (ad, adv)):
+            assert torch.equal(a, want(b))
+    rs.after_update()
+    assert rs.step == 0 and torch.equal(rs.masks[0], rs.masks[T])
