@@ -29,6 +29,9 @@ import torch  # noqa: E402
 
 H, W = 192, 341
 GFLOP_FWD, GFLOP_FWDBWD = 2.6845, 6.509  # per pair, BASELINE.md section 2
+# dram__bytes_read.sum + dram__bytes_write.sum of the stem kernel at B=256 from the committed `ncu --set full` capture
+# (profiles/r01_ncu_stem2_fwd.txt); None until that capture exists
+STEM_DRAM_BYTES = None
 METRIC = "VO frame-pairs/sec (341x192 RGB-D, bs256 per GPU, ResNet-18 fwd+bwd+Adam)"
 SPACE = ["rgb", "depth", "discretized_depth", "top_down_view"]
 
@@ -241,9 +244,11 @@ def run_b200(args):
     k_ms = e0.elapsed_time(e1) / reps
     k_flop = plan.conv1.flops(B)
     achieved = k_flop / (k_ms * 1e-3) / 1e12
-    roofline = {"kernel": "conv_stem_fwd_kernel (conv1 7x7/s2 30->32, B=%d)" % B, "bound": "tensor",
+    kname = "conv_stem2_fwd_kernel" if getattr(plan, "use_stem2", False) else "conv_stem_fwd_kernel"
+    roofline = {"kernel": "%s (conv1 7x7/s2 30->32, B=%d): 57 %% of the forward FLOPs" % (kname, B), "bound": "tensor",
                 "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None, "peak_source": how + " (burst)",
+                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": STEM_DRAM_BYTES, "peak_source": how + " (burst)",
+                "algorithmic_flop": "2 * 49 taps * 30 ch * 32 cout per output pixel x B*96*171 pixels",
                 "launch_ms": round(k_ms, 4), "flop_per_launch": k_flop,
                 "step_tflops": round(world * B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12, 2),
                 "step_frac_of_sustained": round(B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12

@@ -125,7 +125,8 @@ enum pnvo_opcode {
   PNVO_OP_GEO_INV_LOSS = 33,  /* geometric-inversion loss + gradient (vo_cnn_regression_geo_invariance_engine.py:367-449) */
   PNVO_OP_CONV_STEM2 = 34,    /* stem conv, pixels-as-N formulation: D[(4 rows x cout), ow], resident weights, persistent */
   PNVO_OP_PACK_W_STEM2 = 35,  /* OIHW fp32 -> [tap pair][descending filter rows by parity][cout][64] fp16 */
-  PNVO_OP_MAX = 36
+  PNVO_OP_WGRAD_STEM2 = 36,   /* stem weight gradient with a window of four dy rows as the UMMA N dimension (N = 128) */
+  PNVO_OP_MAX = 37
 };
 
 typedef struct {
@@ -138,6 +139,12 @@ typedef struct {
 /* Executes ops[0..n_ops) in order on `stream`.  `ops` is HOST memory. */
 int pnvo_run_ops(const pnvo_op* ops, int n_ops, void* stream);
 
+/* CUDA-graph replay of a program whose device buffers do not change between runs: capture once (nothing executes),
+ * then every pnvo_graph_launch replays all of its kernels with a single cudaGraphLaunch on `stream`. */
+int pnvo_graph_capture(const pnvo_op* ops, int n_ops, void** handle_out);
+int pnvo_graph_launch(void* handle, void* stream);
+int pnvo_graph_destroy(void* handle);
+
 /* Dynamic shared memory / TMEM columns / grid the conv op would use (for tests and DESIGN.md tables). */
 int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, int32_t* smem_bytes,
                           int32_t* tmem_cols, int32_t* stages);
@@ -148,6 +155,8 @@ int pnvo_stem_padded_width(int IW);
 
 /* 1 when PNVO_OP_CONV_STEM2 can take an [IH, IW] input (output width <= 240). */
 int pnvo_conv_stem2_supported(int IH, int IW);
+/* 1 when PNVO_OP_WGRAD_STEM2 can take it (output width <= 176). */
+int pnvo_conv_stem_wgrad2_supported(int IH, int IW);
 
 /* 1 when PNVO_OP_GN_BWD_FUSED can take a [HW, C] fp16 sample (else use GN_BWD_REDUCE + GN_BWD_APPLY). */
 int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32);

@@ -194,6 +194,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = W-padded x, p1 = stem2-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg
       return conv_stem2_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
                                    static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], st);
+    case PNVO_OP_WGRAD_STEM2:
+      // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld
+      return conv_stem_wgrad2_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),
+                                     static_cast<float*>(p[2]), i[3], i[0], i[1], i[2], st);
     case PNVO_OP_PACK_W_STEM2:
       return pack_w_stem2_launch(static_cast<const float*>(p[0]), i[0], static_cast<__half*>(p[1]), st);
     case PNVO_OP_WGRAD_STEM:
@@ -232,6 +236,7 @@ extern "C" int pnvo_abi_version(void) { return PNVO_ABI_VERSION; }
 extern "C" int64_t pnvo_launch_count(void) { return g_launches.load(); }
 extern "C" int pnvo_stem_padded_width(int IW) { return stem_padded_width(IW); }
 extern "C" int pnvo_conv_stem2_supported(int IH, int IW) { return conv_stem2_supported(IH, IW); }
+extern "C" int pnvo_conv_stem_wgrad2_supported(int IH, int IW) { return conv_stem_wgrad2_supported(IH, IW); }
 extern "C" int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32) {
   GnBwdArgs a{};
   a.C = C; a.HW = HW; a.x_fp32 = x_fp32;
@@ -270,6 +275,66 @@ extern "C" int pnvo_run_ops(const pnvo_op* ops, int n_ops, void* stream) {
       return rc;
     }
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-graph replay of an op program: the ~215 launches of a training step are mostly 3-60 us kernels, so the
+// host-side launch cost (tensor-map lookup, argument marshalling, ~4 us per cudaLaunchKernel) leaves the GPU idle
+// between them.  A program whose buffers are fixed (the plan owns them) is captured once and replayed with one
+// cudaGraphLaunch.
+// ---------------------------------------------------------------------------------------------------------
+struct PnvoGraph {
+  cudaGraphExec_t exec;
+  int n_kernels;
+};
+
+extern "C" int pnvo_graph_capture(const pnvo_op* ops, int n_ops, void** handle_out) {
+  PNVO_REQUIRE(ops && n_ops > 0 && handle_out, "graph_capture: bad arguments");
+  cudaStream_t s;
+  cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  PNVO_REQUIRE(e == cudaSuccess, "graph_capture: cudaStreamCreate: %s", cudaGetErrorString(e));
+  e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(s);
+    set_error("graph_capture: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  const int64_t before = g_launches.load();
+  int rc = 0;
+  for (int k = 0; k < n_ops && rc == 0; ++k) rc = run_op(ops[k], s);
+  const int n_kernels = static_cast<int>(g_launches.load() - before);
+  g_launches.fetch_sub(n_kernels);  // nothing ran yet: launches are counted per replay
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(s, &graph);
+  cudaStreamDestroy(s);
+  if (rc != 0) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  PNVO_REQUIRE(e == cudaSuccess && graph, "graph_capture: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  PNVO_REQUIRE(e == cudaSuccess, "graph_capture: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  *handle_out = new PnvoGraph{exec, n_kernels};
+  return 0;
+}
+
+extern "C" int pnvo_graph_launch(void* handle, void* stream) {
+  PNVO_REQUIRE(handle, "graph_launch: null handle");
+  PnvoGraph* g = static_cast<PnvoGraph*>(handle);
+  const cudaError_t e = cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream));
+  PNVO_REQUIRE(e == cudaSuccess, "graph_launch: %s", cudaGetErrorString(e));
+  count_launch(g->n_kernels);
+  return 0;
+}
+
+extern "C" int pnvo_graph_destroy(void* handle) {
+  if (!handle) return 0;
+  PnvoGraph* g = static_cast<PnvoGraph*>(handle);
+  cudaGraphExecDestroy(g->exec);
+  delete g;
   return 0;
 }
 

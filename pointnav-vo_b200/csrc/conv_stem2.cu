@@ -281,3 +281,232 @@ int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, float* sta
 }
 
 }  // namespace pnvo
+
+// ---------------------------------------------------------------------------------------------------------
+// Stem weight gradient, second formulation (same idea as the forward above: make the UMMA N dimension wide).
+//
+//   dW[n, r, s, c] = sum_{b, oh, ow} dy[b, oh, ow, n] * x[b, 2 oh - 3 + r, 2 ow - 3 + s, c]
+//
+// GEMM-K = output column ow.  For one input row h the filter rows that use it have the parity of h + 3:
+// r = r0 + 2q (r0 = (h+3) & 1, q = 0..3) and belong to the output rows oh = t - q, t = (h + 3 - r0) / 2.  So
+//   D_{r0, jh}[(tap pair block, pixel parity, c), (q, n)] += x_row_h[ow + pairs 2jh, 2jh+1]^T  *  [dy_t | dy_{t-1} | dy_{t-2} | dy_{t-3}]
+// with A = the staged input row (MN-major, M = 128 = two adjacent tap pairs x 64, blocks one 128-byte pair row apart,
+// exactly as conv_stem_wgrad_kernel) and B = a WINDOW OF FOUR dy ROWS (MN-major, N = 128 = 4 blocks x 32 channels,
+// blocks one ring slot = LBO apart): N = 128 runs at the full MMA rate (64 clk) instead of 40 clk for N = 32, and
+// every staged input row is used for all four filter rows it feeds.  The block -> filter-row map is fixed per
+// parity class, so only 2 x 2 accumulators (128 columns each = all 512 TMEM columns) live for the whole kernel.
+// dy rows sit in a 6-slot ring stored in DESCENDING row order (slot = -oh mod 6) so a window is 4 ascending slots;
+// slots 0..2 are mirrored behind the ring (slots 6..8) so windows never wrap.  Persistent CTA; one flush at the end.
+// ---------------------------------------------------------------------------------------------------------
+namespace pnvo {
+
+struct StemWg2Args {
+  float* dw;
+  int w_ld;
+  int B, IH, OH, OW;
+  int t_per_unit, units_per_img, n_units;
+};
+static constexpr int kWg2XRow = 23552;          // 184 pixel pairs x 128 B
+static constexpr int kWg2DyRow = 11264;         // 176 pixels x 64 B
+static constexpr int kWg2XStages = 4;
+static constexpr int kWg2DySlots = 9;           // 6-slot ring + 3 mirrors
+static constexpr int kWg2KSteps = 11;           // 176 output columns / 16
+
+__global__ void __launch_bounds__(192) conv_stem_wgrad2_kernel(const StemWg2Args p, const __grid_constant__ ConvTmaps tm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_full[kWg2XStages];
+  __shared__ __align__(8) uint64_t s_empty[kWg2XStages];
+  __shared__ __align__(8) uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t sDy = smem_base + kWg2XStages * kWg2XRow;
+  const int t_last = (p.IH + 2) / 2;  // largest t with an input row inside the image: h = 2t - 3 <= IH - 1
+
+  if (tid == 0) {
+    for (int s = 0; s < kWg2XStages; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&s_accum), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&s_tmem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 5) {
+    if (elect_one()) {
+      // ================================ TMA producer ================================
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      auto load_dy = [&](int oh, int b, uint32_t bar) -> uint32_t {
+        const int slot = ((-oh) % 6 + 6) % 6;
+        tma_load_4d(sDy + slot * kWg2DyRow, &tm.b, bar, 0, 0, oh, b);   // rows outside [0, OH) / columns >= OW: zeros
+        if (slot < 3) {
+          tma_load_4d(sDy + (slot + 6) * kWg2DyRow, &tm.b, bar, 0, 0, oh, b);
+          return 2u * kWg2DyRow;
+        }
+        return static_cast<uint32_t>(kWg2DyRow);
+      };
+      int ctr = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int b = u / p.units_per_img;
+        const int t0 = 1 + (u - b * p.units_per_img) * p.t_per_unit;
+        const int t1 = min(t_last + 1, t0 + p.t_per_unit);
+        // the dy slots of the previous unit may still be read: wait until every stage it used has been released
+        if (ctr > 0) {
+          for (int k = max(0, ctr - kWg2XStages); k < ctr; ++k)
+            mbar_wait(smem_u32(&s_empty[k % kWg2XStages]), (k / kWg2XStages) & 1);
+        }
+        for (int t = t0; t < t1; ++t) {
+          for (int r0 = 0; r0 < 2; ++r0) {
+            const int h = 2 * t - 3 + r0;
+            if (h < 0 || h >= p.IH) continue;
+            const int s = ctr % kWg2XStages;
+            // (stages re-used inside a unit: wait for the MMAs of the row 4 stages back)
+            if (ctr >= kWg2XStages) mbar_wait(smem_u32(&s_empty[s]), ((ctr / kWg2XStages) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&s_full[s]);
+            uint32_t tx = kWg2XRow;
+            // dy rows travel with the first input row that needs them
+            const bool first_of_t = (r0 == 0) || (2 * t - 3 < 0);
+            uint32_t dy_tx = 0;
+            if (first_of_t) {
+              if (t == t0) {
+                // unit start: the whole window t0-3 .. t0 (issued below, after expect_tx)
+                for (int oh = t0 - 3; oh <= t0; ++oh) dy_tx += ((((-oh) % 6 + 6) % 6) < 3) ? 2u * kWg2DyRow : kWg2DyRow;
+              } else {
+                dy_tx = ((((-t) % 6 + 6) % 6) < 3) ? 2u * kWg2DyRow : kWg2DyRow;
+              }
+            }
+            mbar_arrive_expect_tx(bar, tx + dy_tx);
+            tma_load_4d(smem_base + s * kWg2XRow, &tm.a, bar, 0, 0, h, b);
+            if (first_of_t) {
+              if (t == t0) {
+                for (int oh = t0 - 3; oh <= t0; ++oh) load_dy(oh, b, bar);
+              } else {
+                load_dy(t, b, bar);
+              }
+            }
+            ++ctr;
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (elect_one()) {
+      // ================================ MMA issuer ================================
+      const uint32_t idesc = umma_idesc_f16(128, 128, 1, 1);
+      const uint64_t da0 = umma_desc(0, 128, 1024, 128);           // x: 128-byte pair rows, blocks one row apart
+      const uint64_t db0 = umma_desc(0, kWg2DyRow, 512, 64);       // dy: 64-byte pixel rows, blocks one ring slot apart
+      const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), a_lo0 = static_cast<uint32_t>(da0);
+      const uint32_t b_hi = static_cast<uint32_t>(db0 >> 32), b_lo0 = static_cast<uint32_t>(db0);
+      uint32_t started = 0;  // bit (r0 * 2 + jh): accumulator already initialised
+      int ctr = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int b = u / p.units_per_img;
+        const int t0 = 1 + (u - b * p.units_per_img) * p.t_per_unit;
+        const int t1 = min(t_last + 1, t0 + p.t_per_unit);
+        (void)b;
+        for (int t = t0; t < t1; ++t) {
+          const int slot = ((-t) % 6 + 6) % 6;  // window = slots slot .. slot+3 (rows t, t-1, t-2, t-3)
+          const uint32_t b_lo = b_lo0 + ((sDy + slot * kWg2DyRow) >> 4);
+          for (int r0 = 0; r0 < 2; ++r0) {
+            const int h = 2 * t - 3 + r0;
+            if (h < 0 || h >= p.IH) continue;
+            const int s = ctr % kWg2XStages;
+            mbar_wait(smem_u32(&s_full[s]), (ctr / kWg2XStages) & 1);
+            tc_fence_after();
+            const uint32_t x_lo = a_lo0 + ((smem_base + s * kWg2XRow) >> 4);
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+              const uint32_t acc_bit = 1u << (r0 * 2 + jh);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((r0 * 2 + jh) * 128);
+              for (int q = 0; q < kWg2KSteps; ++q) {
+                // K step q = output columns 16q .. 16q+15 -> staged pair rows (16q + 2jh) .., dy pixels 16q ..
+                tc_mma_f16_parts(d_tmem, x_lo + static_cast<uint32_t>(16 * q + 2 * jh) * 8, a_hi, b_lo + static_cast<uint32_t>(q) * 64,
+                                 b_hi, idesc, ((started & acc_bit) != 0u || q != 0) ? 1u : 0u);
+              }
+              started |= acc_bit;
+            }
+            tc_commit(smem_u32(&s_empty[s]));
+            ++ctr;
+          }
+        }
+      }
+      tc_commit(smem_u32(&s_accum));
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================================ epilogue ================================
+    mbar_wait(smem_u32(&s_accum), 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int blk = tid >> 6, par = (tid >> 5) & 1, c = tid & 31;  // M index = (tap pair block, pixel parity, channel)
+    for (int r0 = 0; r0 < 2; ++r0) {
+      for (int jh = 0; jh < 2; ++jh) {
+        const int s = 2 * (2 * jh + blk) + par;
+        for (int q = 0; q < 4; ++q) {
+          const int r = r0 + 2 * q;
+          float v[32];
+          tmem_ld32(t_row + (r0 * 2 + jh) * 128 + q * 32, v);
+          tmem_ld_wait();
+          if (s < 7 && r < 7) {
+            float* dst = p.dw + (r * 7 + s) * 32 + c;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) atomicAdd(dst + static_cast<int64_t>(n) * p.w_ld, v[n]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int conv_stem_wgrad2_supported(int IH, int IW) {
+  const int OW = (IW + 6 - 7) / 2 + 1;
+  return (OW <= 176 && OW >= 16 && IH >= 7) ? 1 : 0;
+}
+
+int conv_stem_wgrad2_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW, cudaStream_t st) {
+  PNVO_REQUIRE(x && dy && dw, "conv_stem_wgrad2: null pointer");
+  PNVO_REQUIRE(conv_stem_wgrad2_supported(IH, IW), "conv_stem_wgrad2: unsupported geometry %dx%d", IH, IW);
+  PNVO_REQUIRE(w_ld >= 49 * 32, "conv_stem_wgrad2: w_ld too small");
+  StemWg2Args a{};
+  a.dw = dw; a.w_ld = w_ld; a.B = B; a.IH = IH;
+  a.OH = (IH + 6 - 7) / 2 + 1;
+  a.OW = (IW + 6 - 7) / 2 + 1;
+  const int n_t = (IH + 2) / 2;          // t = 1 .. t_last
+  a.units_per_img = std::max(1, std::min(4, n_t / 8));
+  a.t_per_unit = ceil_div(n_t, a.units_per_img);
+  a.units_per_img = ceil_div(n_t, a.t_per_unit);
+  a.n_units = B * a.units_per_img;
+  if (B <= 0) return 0;
+  const int Wp = stem_padded_width(IW);
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (tmap_tiled4d(&tm.a, x, B, IH, Wp / 2, 64, kWg2XRow / 128)) return -1;        // 184 pixel pairs per box
+  if (tmap_tiled4d(&tm.b, dy, B, a.OH, a.OW, 32, kWg2DyRow / 64, 64)) return -1;   // 176 pixels x 32 channels, SWIZZLE_64B
+  const int smem_bytes = kWg2XStages * kWg2XRow + kWg2DySlots * kWg2DyRow + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_stem_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    attr = true;
+  }
+  conv_stem_wgrad2_kernel<<<std::min(a.n_units, 148), 192, smem_bytes, st>>>(a, tm);
+  count_launch();
+  return check_launch("conv_stem_wgrad2");
+}
+
+}  // namespace pnvo

@@ -53,6 +53,8 @@ int conv_stem2_supported(int IH, int IW);
 int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
                           cudaStream_t st);
 int pack_w_stem2_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
+int conv_stem_wgrad2_supported(int IH, int IW);
+int conv_stem_wgrad2_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW, cudaStream_t st);
 int wgrad_plan(WgradArgs& a);
 // conv_wgrad_raster.cu: persistent no-im2col weight gradient for 3x3 / stride 1 / pad 1 with 32 or 64 channels
 int wgrad_raster_supported(const WgradArgs& a);

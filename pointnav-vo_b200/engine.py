@@ -384,7 +384,7 @@ class EncoderPlan:
             pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
             if self.use_stem2:
                 pack.append(L.op_pack_w_stem2(self.P[self.conv1.key], self.w_stem2, self.conv1.Cin))
-        self.pack_prog = L.Program(pack)
+        self.pack_prog = L.Program(pack, graph=True)
         # ---- forward (after the input tensor x0 has been produced) ----
         ops = [L.op_zero(self.stats_all)]
         c1, g1 = self.conv1, self.gn1
@@ -440,7 +440,7 @@ class EncoderPlan:
                 ops.append(L.op_head_fwd(self.h32, self.P[hd["out_w"]], self.P[hd["out_b"]], self.out, B, hd["hidden"],
                                          hd["out_dim"]))
         self.fwd_ops = ops
-        self.fwd_prog = L.Program(ops)
+        self.fwd_prog = L.Program(ops, graph=True)
         if not self.training:
             return
         # ---- backward ----
@@ -500,14 +500,16 @@ class EncoderPlan:
         # stem: max-pool + ReLU routing, GN, conv1 weight gradient (no data gradient: the input is data)
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
         self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
-        if self.use_stem and 96 < c1.OW <= 176:
+        if self.use_stem and self.stem_version >= 2 and L.load().pnvo_conv_stem_wgrad2_supported(self.inH, self.inW):
+            ops.append(L.op_wgrad_stem2(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld))
+        elif self.use_stem and 96 < c1.OW <= 176:
             ops.append(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48))
         else:
             ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
         for c in self.all_convs():
             ops.append(c.op_unpack(self.grads[c.key]))
         self.bwd_ops = ops
-        self.bwd_prog = L.Program(ops)
+        self.bwd_prog = L.Program(ops, graph=True)
 
     # ------------------------------------------------------------------------------------------
     def input_ops(self, obs):

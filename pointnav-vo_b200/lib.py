@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2 = range(16, 36)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2, OP_WGRAD_STEM2 = range(16, 37)
 
 
 class PnvoOp(ctypes.Structure):
@@ -36,7 +36,8 @@ _lib = None
 
 EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_discretize_depth",
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
-           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_conv_stem2_supported"]
+           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_conv_stem2_supported", "pnvo_conv_stem_wgrad2_supported", "pnvo_graph_capture", "pnvo_graph_launch",
+           "pnvo_graph_destroy"]
 
 
 def load():
@@ -56,6 +57,8 @@ def load():
     lib.pnvo_stem_padded_width.argtypes = [i32]
     lib.pnvo_stem_padded_width.restype = i32
     lib.pnvo_conv_stem2_supported.argtypes = [i32, i32]
+    lib.pnvo_conv_stem_wgrad2_supported.argtypes = [i32, i32]
+    lib.pnvo_conv_stem_wgrad2_supported.restype = i32
     lib.pnvo_conv_stem2_supported.restype = i32
     lib.pnvo_gn_bwd_fused_supported.argtypes = [i32, i32, i32]
     lib.pnvo_gn_bwd_fused_supported.restype = i32
@@ -67,6 +70,11 @@ def load():
     lib.pnvo_gae_scan.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
     lib.pnvo_goal_update.argtypes = [vp, vp, vp, i32, vp]
     lib.pnvo_run_ops.argtypes = [ctypes.POINTER(PnvoOp), i32, vp]
+    lib.pnvo_graph_capture.argtypes = [ctypes.POINTER(PnvoOp), i32, ctypes.POINTER(ctypes.c_void_p)]
+    lib.pnvo_graph_launch.argtypes = [vp, vp]
+    lib.pnvo_graph_destroy.argtypes = [vp]
+    for n in ("pnvo_graph_capture", "pnvo_graph_launch", "pnvo_graph_destroy"):
+        getattr(lib, n).restype = i32
     lib.pnvo_conv_launch_info.argtypes = [ctypes.POINTER(PnvoOp)] + [ctypes.POINTER(ctypes.c_int32)] * 5
     for n in ("pnvo_discretize_depth", "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops",
               "pnvo_conv_launch_info"):
@@ -267,6 +275,10 @@ def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg):
     return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg], (), [x, wr, y, stats])
 
 
+def op_wgrad_stem2(x, dy, dw, B, IH, IW, w_ld):
+    return _op(OP_WGRAD_STEM2, [B, IH, IW, w_ld], (), [x, dy, dw])
+
+
 def op_pack_w_stem2(w, wr, Cin):
     return _op(OP_PACK_W_STEM2, [Cin], (), [w, wr])
 
@@ -288,16 +300,42 @@ def op_avgpool2(src, out, B, H, W, C, Cpad, coff, pre_scale=1.0):
     return _op(OP_AVGPOOL2, [B, H, W, C, Cpad, coff], [pre_scale], [src, out])
 
 
-class Program:
-    """A list of pnvo_op records packed into one ctypes array, replayed with a single C call."""
+USE_GRAPHS = os.environ.get("PNVO_GRAPHS", "1") != "0"
 
-    def __init__(self, ops):
+
+class Program:
+    """A list of pnvo_op records packed into one ctypes array, replayed with a single C call.
+    graph=True: after one eager run (which also sets kernel attributes and fills the tensor-map cache) the program
+    is captured into a CUDA graph and later runs are one cudaGraphLaunch -- for programs whose buffers are fixed."""
+
+    def __init__(self, ops, graph=False):
         self.n = len(ops)
         self.arr = (PnvoOp * max(1, self.n))(*ops)
+        self.graph = bool(graph) and USE_GRAPHS
+        self._runs = 0
+        self._handle = None
 
     def run(self, device=None):
-        if self.n:
-            check(load().pnvo_run_ops(self.arr, self.n, stream_ptr(device)))
+        if not self.n:
+            return
+        lib = load()
+        if self.graph and self._runs >= 1:
+            if self._handle is None:
+                h = ctypes.c_void_p()
+                check(lib.pnvo_graph_capture(self.arr, self.n, ctypes.byref(h)))
+                self._handle = h
+            check(lib.pnvo_graph_launch(self._handle, stream_ptr(device)))
+        else:
+            check(lib.pnvo_run_ops(self.arr, self.n, stream_ptr(device)))
+        self._runs += 1
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None and _lib is not None:
+            try:
+                _lib.pnvo_graph_destroy(h)
+            except Exception:
+                pass
 
 
 def run_ops(ops, device=None):

@@ -225,6 +225,21 @@ def test_stem_conv_kernels(version, B, IH, IW, Cin):
     assert rel(y.permute(0, 3, 1, 2), ref) <= 3e-3
     rs = ref.reshape(B, 16, -1)
     assert rel(stats, torch.stack((rs.sum(-1), rs.pow(2).sum(-1)), -1)) <= 1e-4
+    # weight gradient on the same staged rows
+    dy = torch.randn(B, OH, OW, 32, device=dev).half()
+    w_ld = 1600
+    dw = torch.zeros(32, w_ld, device=dev)
+    if version == 1:
+        if not 96 < OW <= 176:
+            return
+        L.run_ops([L.op_wgrad_stem(xp, dy, dw, B, IH, IW, w_ld, 8)])
+    else:
+        assert L.load().pnvo_conv_stem_wgrad2_supported(IH, IW) == 1
+        L.run_ops([L.op_wgrad_stem2(xp, dy, dw, B, IH, IW, w_ld)])
+    wz = torch.zeros(32, Cin, 7, 7, device=dev, requires_grad=True)
+    F.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), wz, None, 2, 3).backward(dy.float().permute(0, 3, 1, 2))
+    got = dw[:, :49 * 32].reshape(32, 7, 7, 32)[..., :Cin].permute(0, 3, 1, 2)
+    assert rel(got, wz.grad) <= 3e-3
 
 
 @pytest.mark.parametrize("B,H,W,C,G,Cr", [(3, 24, 43, 64, 16, 64), (2, 6, 11, 32, 1, 31), (2, 12, 22, 128, 16, 128),
@@ -332,7 +347,7 @@ def _load_vo(case):
     return m.cuda(), space, backbone
 
 
-FWD_TOL = {"r18_30ch": 6e-3, "r18_8ch": 6e-3, "r50_8ch": 2.5e-2, "r18_8ch_act_embed": 6e-3}
+FWD_TOL = {"r18_30ch": 8e-3, "r18_8ch": 8e-3, "r50_8ch": 2.5e-2, "r18_8ch_act_embed": 8e-3}  # measured 3e-3 .. 6e-3 run to run
 GRAD_TOL = {"r18_30ch": 0.15, "r18_8ch": 0.15, "r50_8ch": 0.35, "r18_8ch_act_embed": 0.15}  # relative L2 per tensor (ReLU-flip noise, 53 layers)
 
 

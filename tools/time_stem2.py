@@ -33,3 +33,20 @@ for name, pack, op in (("stem v1 (N=32 raster)", L.op_pack_w_stem(w, wr, Cin), L
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"{name}: {ms:.3f} ms  {2.0 * B * OH * OW * 32 * Cin * 49 / ms / 1e9:.1f} TFLOP/s")
+
+dy = torch.randn(B, OH, OW, 32, device=dev).half()
+dw = torch.zeros(32, 1600, device=dev)
+for name, op in (("stem wgrad v1", L.op_wgrad_stem(xp, dy, dw, B, IH, IW, 1600, 48)),
+                 ("stem wgrad v2 (4 dy rows as N)", L.op_wgrad_stem2(xp, dy, dw, B, IH, IW, 1600))):
+    prog = L.Program([op])
+    for _ in range(3):
+        prog.run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        prog.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{name}: {ms:.3f} ms  {2.0 * B * OH * OW * 32 * Cin * 49 / ms / 1e9:.1f} TFLOP/s")
