@@ -31,7 +31,7 @@ H, W = 192, 341
 GFLOP_FWD, GFLOP_FWDBWD = 2.6845, 6.509  # per pair, BASELINE.md section 2
 # dram__bytes_read.sum + dram__bytes_write.sum of the stem kernel at B=256 from the committed `ncu --set full` capture
 # (profiles/r01_ncu_stem2_fwd.txt); None until that capture exists
-STEM_DRAM_BYTES = None
+STEM_DRAM_BYTES = 1347959832  # 1.095 GB read (= the W-padded fp16 input, once) + 0.253 GB written
 METRIC = "VO frame-pairs/sec (341x192 RGB-D, bs256 per GPU, ResNet-18 fwd+bwd+Adam)"
 SPACE = ["rgb", "depth", "discretized_depth", "top_down_view"]
 
@@ -54,7 +54,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -165,8 +165,13 @@ def run_b200(args):
             return pre(devb["rgb"], devb["depth"])
         return {"rgb": devb["rgb"], "depth": devb["depth"]}
 
+    h_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_steps(n):
-        """n steps from pinned host memory: the copy of batch i+1 is in flight while step i computes."""
+        """n steps from pinned host memory: the copy of batch i+1 is in flight while step i computes, and the loss
+        of step i is copied back asynchronously and read on the host while step i+1 runs (every step's loss is read
+        inside the timed region; the last one after the loop)."""
         last = None
         pipe.submit(host)
         for i in range(n):
@@ -175,7 +180,13 @@ def run_b200(args):
             devb = pipe.acquire()
             loss = trainer.step(to_obs(devb), devb["target"])
             pipe.release()
-            last = float(loss.item())  # D2H read of the step's result
+            h_loss[i & 1].copy_(loss, non_blocking=True)  # D2H read of the step's result
+            loss_ready[i & 1].record()
+            if i > 0:
+                loss_ready[(i - 1) & 1].synchronize()
+                last = float(h_loss[(i - 1) & 1][0])
+        loss_ready[(n - 1) & 1].synchronize()
+        last = float(h_loss[(n - 1) & 1][0])
         return last
 
     # resident inputs for the device-only measurement
@@ -224,6 +235,8 @@ def run_b200(args):
     e2e_value = world * B / (t_e2e / args.steps * 1e-3)
     h2d = pipe.bytes_per_batch
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
 
     # dominant kernel: the stem convolution (57 % of the forward FLOPs), timed alone with CUDA events
@@ -268,11 +281,13 @@ def run_b200(args):
            "e2e": {"value": round(e2e_value, 1), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": 4, "ms_per_step": round(t_e2e / args.steps, 3),
                    "path": "pinned uint8 rgb + fp32 depth -> H2D (double-buffered side stream) -> top-down + "
-                           "discretise + normalise on device -> train step -> loss.item()"},
+                           "discretise + normalise on device -> train step -> loss D2H (async, read one step later)"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val}
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def cpu_baseline(seconds=15.0, batch=4, threads=None):
