@@ -219,6 +219,18 @@ def run_b200(args):
         sync_all()
         return ms
 
+    if args.forward_only:
+        model.eval()
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                model(obs)
+            ms_f = timed(lambda: model(obs), args.steps) / args.steps
+        if rank == 0:
+            print(json.dumps({"metric": "VO frame-pairs/sec, eval-mode forward only (same model, batch 256 per GPU)",
+                              "value": round(world * B / (ms_f * 1e-3), 1), "unit": "pairs/s", "n_gpus": world,
+                              "ms_per_step": round(ms_f, 3),
+                              "forward_tflops": round(world * B * GFLOP_FWD * 1e9 / (ms_f * 1e-3) / 1e12, 1)}), flush=True)
+        model.train()
     for _ in range(args.warmup):
         trainer.step(obs, d_tgt)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -364,6 +376,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inputs", default="raw", choices=["raw", "dict"])
+    ap.add_argument("--forward-only", action="store_true",
+                    help="extra line: eval-mode forward (inference) throughput of the same model / batch, device-resident inputs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

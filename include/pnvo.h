@@ -126,7 +126,10 @@ enum pnvo_opcode {
   PNVO_OP_CONV_STEM2 = 34,    /* stem conv, pixels-as-N formulation: D[(4 rows x cout), ow], resident weights, persistent */
   PNVO_OP_PACK_W_STEM2 = 35,  /* OIHW fp32 -> [tap pair][descending filter rows by parity][cout][64] fp16 */
   PNVO_OP_WGRAD_STEM2 = 36,   /* stem weight gradient with a window of four dy rows as the UMMA N dimension (N = 128) */
-  PNVO_OP_MAX = 37
+  PNVO_OP_PACK_W_MULTI = 37,  /* PACK_W over a device table of descriptors (one launch for every layer) */
+  PNVO_OP_UNPACK_DW_MULTI = 38,
+  PNVO_OP_GN_PARAM_GRAD_MULTI = 39,
+  PNVO_OP_MAX = 40
 };
 
 typedef struct {

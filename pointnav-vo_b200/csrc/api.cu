@@ -73,6 +73,11 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       }
       return input_stats_launch(a, static_cast<double*>(p[6]), st);
     }
+    case PNVO_OP_PACK_W_MULTI:
+    case PNVO_OP_UNPACK_DW_MULTI:
+    case PNVO_OP_GN_PARAM_GRAD_MULTI:
+      // p0 = device table of PackDesc / UnpackDesc / GnParamDesc (elem.cuh); i0 = entries, i1 = B (param grad)
+      return multi_launch(op.code, p[0], i[0], i[1], st);
     case PNVO_OP_GEO_INV_LOSS:
       // p0 = pred [B][O], p1 = actions int64 [B], p2 = dout (nullable, accumulated), p3 = loss[3] (total+=, rot, pos)
       // i0 = B, i1 = O, i2 = MOVE_FORWARD id; f0 = loss_inv_weight, f1 = gradient scale

@@ -72,6 +72,25 @@ int gn_bwd_fused_launch(const GnBwdArgs& a, int B, cudaStream_t st);
 int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st);
 
+// descriptor tables of the batched (multi) ops; mirrored field by field in pointnav_vo_b200/lib.py
+struct PackDesc {
+  const float* w;
+  __half* wp;
+  __half* wt;
+  int Cout, Cin, R, S, cin_pad, ld_p, cout_pad, ld_t, t_mode, src_ld;
+};
+struct UnpackDesc {
+  const float* dwp;
+  float* grad;
+  int Cout, Cin, R, S, cin_pad, ld_p, accumulate, dst_ld;
+};
+struct GnParamDesc {
+  const float* sums;
+  float* dgamma;
+  float* dbeta;
+  int C, C_real;
+};
+int multi_launch(int code, const void* table, int n, int B, cudaStream_t st);
 int pack_w_launch(const float* w, int Cout, int Cin, int R, int S, __half* wp, int cin_pad, int ld_p, __half* wt,
                   int cout_pad, int ld_t, int t_mode, cudaStream_t st, int src_ld = 0);
 int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_pad, int ld_p, float* grad,

@@ -6,8 +6,8 @@
 //   dx   = rstd_g * (gamma_c * dy - (sum_{c in g} gamma_c S1_c + xhat * sum_{c in g} gamma_c S2_c) / cnt)
 //
 // A cluster of `cs` CTAs (1, 2, 4 or 8) owns one sample; CTA r owns a contiguous slice of its [HW][C] fp16 data.
-// One thread brings the slices of g, x (and the ReLU reference) into shared memory with bulk async copies
-// (cp.async.bulk, mbarrier completion): each byte crosses HBM ONCE.  The per-channel sums are reduced in a fixed
+// One thread brings the slices of g and x into shared memory with bulk async copies (cp.async.bulk, mbarrier
+// completion); the ReLU reference, needed once for the mask, is prefetched into registers: each byte crosses HBM ONCE.  The per-channel sums are reduced in a fixed
 // order inside the CTA (shared memory) and across the cluster (distributed shared memory), so the result is
 // bit-reproducible and needs neither atomics nor a pre-zeroed buffer; dx (and the masked gradient of the identity
 // branch) are then produced from the staged slices.  HBM traffic: 3 reads + 1-2 writes per element instead of
@@ -22,7 +22,6 @@ namespace cg = cooperative_groups;
 namespace pnvo {
 
 static constexpr int kGbfThreads = 256;
-static constexpr int kGbfScratch = kGbfThreads * 17 * 4;  // bytes of the CTA reduction scratch
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&u);
@@ -39,24 +38,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-// slice: vectors (16 B) per CTA, multiple of C/8; slice_bytes = slice * 16 rounded up to 128
+// slice: vectors (16 B) per CTA, multiple of C/8; slice_bytes = slice * 16 rounded up to 128.
+// The ReLU reference is NOT staged: every thread prefetches its <= kGbfMaxIt vectors of it into registers while the
+// bulk copies of g / x fly (it is needed once, for the mask), which keeps the CTA at two slices of shared memory.
+static constexpr int kGbfMaxIt = 9;
+
 __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdArgs a, const int n8, const int cs,
                                                                    const int slice, const int slice_bytes,
-                                                                   const int y_region) {
+                                                                   const int n_slots) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   const int C = a.C, G = a.G;
   uint4* s_g = reinterpret_cast<uint4*>(s_raw);
   uint4* s_x = reinterpret_cast<uint4*>(s_raw + slice_bytes);
-  uint4* s_y = reinterpret_cast<uint4*>(s_raw + 2 * slice_bytes);
-  float* s_part = reinterpret_cast<float*>(s_raw + 2 * slice_bytes);  // aliases the y slice (dead after masking)
-  float* s_loc = reinterpret_cast<float*>(s_raw + 2 * slice_bytes + y_region);  // [2C] CTA sums (read by peers)
-  float* s_tot = s_loc + 2 * C;                                                 // [2C] sample totals
-  float* s_coef = s_tot + 2 * C;                                                // [3C] A_c, B_c, C_c
-  float* s_mr = s_coef + 3 * C;                                                 // [2C] mean_c, rstd_c
+  float* s_part = reinterpret_cast<float*>(s_raw + 2 * slice_bytes);  // [n_slots][17] reduction scratch
+  float* s_loc = s_part + n_slots * 17;                               // [2C] CTA sums (read by peers)
+  float* s_tot = s_loc + 2 * C;                                       // [2C] sample totals
+  float* s_coef = s_tot + 2 * C;                                      // [3C] A_c, B_c, C_c
+  float* s_mr = s_coef + 3 * C;                                       // [2C] mean_c, rstd_c
+  float* s_gamma = s_mr + 2 * C;                                      // [C]
 
   cg::cluster_group cluster = cg::this_cluster();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = blockIdx.x;  // gridDim.x == cluster size
   const int b = blockIdx.y;
   const int c8 = C >> 3;
@@ -70,14 +73,24 @@ __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdAr
     fence_mbar_init();
     const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
     const uint32_t bar = smem_u32(&s_bar);
-    mbar_arrive_expect_tx(bar, bytes * (a.relu_ref ? 3u : 2u));
+    mbar_arrive_expect_tx(bar, bytes * 2u);
     if (len > 0) {
       bulk_g2s(smem_u32(s_g), reinterpret_cast<const uint4*>(a.g) + base, bytes, bar);
       bulk_g2s(smem_u32(s_x), reinterpret_cast<const uint4*>(a.x) + base, bytes, bar);
-      if (a.relu_ref) bulk_g2s(smem_u32(s_y), reinterpret_cast<const uint4*>(a.relu_ref) + base, bytes, bar);
     }
   }
-  // per-channel mean / rstd of this sample (forward statistics) while the copies fly
+  // ReLU reference of this thread's vectors -> registers (in flight together with the bulk copies)
+  const bool has_y = a.relu_ref != nullptr;
+  uint4 yq[kGbfMaxIt];
+  if (has_y) {
+    const uint4* __restrict__ yp = reinterpret_cast<const uint4*>(a.relu_ref) + base;
+#pragma unroll
+    for (int k = 0; k < kGbfMaxIt; ++k) {
+      const int i = tid + k * kGbfThreads;
+      yq[k] = (i < len) ? __ldg(yp + i) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  // per-channel mean / rstd of this sample (forward statistics) and gamma while the copies fly
   for (int c = tid; c < C; c += kGbfThreads) {
     const int g = c / a.cpg;
     const float s = a.stats[(static_cast<int64_t>(b) * G + g) * 2], q = a.stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
@@ -85,6 +98,7 @@ __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdAr
     const float var = fmaxf(q / a.cnt - mean * mean, 0.f);
     s_mr[2 * c] = mean;
     s_mr[2 * c + 1] = 1.0f / sqrtf(var + a.eps);
+    s_gamma[c] = (c < a.C_real) ? a.gamma[c] : 0.f;
   }
   __syncthreads();  // barrier initialised before anybody waits on it
   mbar_wait(smem_u32(&s_bar), 0);
@@ -93,42 +107,57 @@ __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdAr
   float sd[8], sgx[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) sd[e] = sgx[e] = 0.f;
-  const bool has_y = a.relu_ref != nullptr;
-  for (int i = tid; i < len; i += kGbfThreads) {
-    uint4 gq = s_g[i];
-    const uint4 xq = s_x[i];
-    if (has_y) {
-      // mask: keep g where the saved post-ReLU output is > 0 (sign / zero test on the fp16 bits)
-      const uint4 yq = s_y[i];
-      uint32_t* gw = reinterpret_cast<uint32_t*>(&gq);
-      const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yq);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t y = yw[e];
-        const uint32_t lo = ((y & 0x7fffu) != 0u && (y & 0x8000u) == 0u) ? 0x0000ffffu : 0u;
-        const uint32_t hi = ((y & 0x7fff0000u) != 0u && (y & 0x80000000u) == 0u) ? 0xffff0000u : 0u;
-        gw[e] &= (lo | hi);
+  for (int k = 0; k < kGbfMaxIt; ++k) {
+    const int i = tid + k * kGbfThreads;
+    if (i < len) {
+      uint4 gq = s_g[i];
+      const uint4 xq = s_x[i];
+      if (has_y) {
+        // mask: keep g where the saved post-ReLU output is > 0 (sign / zero test on the fp16 bits)
+        uint32_t* gw = reinterpret_cast<uint32_t*>(&gq);
+        const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yq[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t y = yw[e];
+          const uint32_t lo = ((y & 0x7fffu) != 0u && (y & 0x8000u) == 0u) ? 0x0000ffffu : 0u;
+          const uint32_t hi = ((y & 0x7fff0000u) != 0u && (y & 0x80000000u) == 0u) ? 0xffff0000u : 0u;
+          gw[e] &= (lo | hi);
+        }
+        s_g[i] = gq;
       }
-      s_g[i] = gq;
+      float g[8], x[8];
+      unpack8(gq, g);
+      unpack8(xq, x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sd[e] += g[e];
+        sgx[e] = fmaf(g[e], x[e], sgx[e]);
+      }
     }
-    float g[8], x[8];
-    unpack8(gq, g);
-    unpack8(xq, x);
+  }
+  // lanes l, l + c8, l + 2 c8 ... of a warp own the same channels: fold them with shuffles first (fixed order)
+  if (c8 < 32) {
+    for (int off = 16; off >= c8; off >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], off);
+        sgx[e] += __shfl_xor_sync(0xffffffffu, sgx[e], off);
+      }
+    }
+  }
+  const int slot = (c8 < 32) ? ((lane < c8) ? warp * c8 + lane : -1) : tid;
+  if (slot >= 0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      sd[e] += g[e];
-      sgx[e] = fmaf(g[e], x[e], sgx[e]);
+      s_part[slot * 17 + 2 * e] = sd[e];
+      s_part[slot * 17 + 2 * e + 1] = sgx[e];
     }
   }
-  __syncthreads();  // everybody is done with the y slice before the scratch overwrites it
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    s_part[tid * 17 + 2 * e] = sd[e];
-    s_part[tid * 17 + 2 * e + 1] = sgx[e];
-  }
   __syncthreads();
-  // CTA totals in a fixed order: output o = chunk * 16 + v  <->  (channel = chunk*8 + v/2, which = v & 1)
-  const int per_chunk = kGbfThreads / c8;
+  // CTA totals in a fixed order: output o = chunk * 16 + v  <->  (channel = chunk*8 + v/2, which = v & 1);
+  // the slots holding chunk q are q, q + c8, q + 2 c8, ...
+  const int per_chunk = n_slots / c8;
   for (int o = tid; o < 2 * C; o += kGbfThreads) {
     const int q = o >> 4, v = o & 15;
     float t = 0.f;
@@ -159,15 +188,14 @@ __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdAr
     const int g = c / a.cpg;
     float T1 = 0.f, T2 = 0.f;
     for (int k = g * a.cpg; k < (g + 1) * a.cpg && k < a.C_real; ++k) {
-      const float gm = a.gamma[k];
+      const float gm = s_gamma[k];
       T1 = fmaf(gm, s_loc[2 * k], T1);
       T2 = fmaf(gm, s_loc[2 * k + 1], T2);
     }
     const float mean = s_mr[2 * c], rstd = s_mr[2 * c + 1];
     const float k1 = rstd * T1 / a.cnt, k2 = rstd * T2 / a.cnt;
-    const float gm = (c < a.C_real) ? a.gamma[c] : 0.f;
     // dx = rstd*gamma*dy - k1 - xhat*k2 = A*g + Bc + Cc*x
-    s_coef[3 * c] = rstd * gm * a.g_scale;
+    s_coef[3 * c] = rstd * s_gamma[c] * a.g_scale;
     s_coef[3 * c + 1] = -k1 + mean * rstd * k2;
     s_coef[3 * c + 2] = -rstd * k2;
   }
@@ -209,7 +237,7 @@ __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdAr
 }
 
 struct GbfPlan {
-  int cs, slice, slice_bytes, y_region, smem;
+  int cs, slice, slice_bytes, n_slots, smem;
 };
 static bool gbf_plan(const GnBwdArgs& a, GbfPlan& p) {
   if (a.x_fp32 || a.C % 8 != 0) return false;
@@ -217,15 +245,17 @@ static bool gbf_plan(const GnBwdArgs& a, GbfPlan& p) {
   if (c8 > kGbfThreads || (kGbfThreads % c8) != 0) return false;
   const int64_t n8 = static_cast<int64_t>(a.HW) * c8;
   if (n8 <= 0 || n8 > (1 << 24)) return false;
-  // smallest cluster whose CTAs stage <= ~48 KB (4 CTAs per SM), at most 8 CTAs (<= ~100 KB: 2 CTAs per SM)
+  const int n_slots = c8 < 32 ? 8 * c8 : kGbfThreads;
+  // smallest cluster whose CTAs stage <= ~48 KB (4 CTAs per SM), at most 8 CTAs (<= ~75 KB: 3 CTAs per SM); a thread
+  // holds at most kGbfMaxIt vectors of the ReLU reference in registers
   for (int cs = 1; cs <= 8; cs <<= 1) {
     int slice = static_cast<int>(ceil_div64(n8, cs));
     slice = ceil_div(slice, c8) * c8;
+    if (slice > kGbfMaxIt * kGbfThreads) continue;
     const int slice_bytes = (slice * 16 + 127) & ~127;
-    const int y_region = std::max(kGbfScratch, a.relu_ref ? slice_bytes : 0);
-    const int smem = 2 * slice_bytes + y_region + 9 * a.C * 4;
-    if (smem <= 50 * 1024 || (cs == 8 && smem <= 110 * 1024)) {
-      p = GbfPlan{cs, slice, slice_bytes, y_region, smem};
+    const int smem = 2 * slice_bytes + (n_slots * 17 + 10 * a.C) * 4;
+    if (smem <= 48 * 1024 || (cs == 8 && smem <= 100 * 1024)) {
+      p = GbfPlan{cs, slice, slice_bytes, n_slots, smem};
       return true;
     }
   }
@@ -234,10 +264,8 @@ static bool gbf_plan(const GnBwdArgs& a, GbfPlan& p) {
 
 // 1 when the fused kernel can take this shape (the caller falls back to reduce + apply otherwise)
 int gn_bwd_fused_supported(const GnBwdArgs& a) {
-  GnBwdArgs t = a;
-  t.relu_ref = reinterpret_cast<const __half*>(1);  // worst case: with a ReLU reference slice
   GbfPlan p;
-  return gbf_plan(t, p) ? 1 : 0;
+  return gbf_plan(a, p) ? 1 : 0;
 }
 
 int gn_bwd_fused_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
@@ -247,7 +275,7 @@ int gn_bwd_fused_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
   const int n8 = a.HW * (a.C / 8);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -262,7 +290,7 @@ int gn_bwd_fused_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel, a, n8, p.cs, p.slice, p.slice_bytes, p.y_region);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel, a, n8, p.cs, p.slice, p.slice_bytes, p.n_slots);
   if (e != cudaSuccess) {
     set_error("gn_bwd_fused: %s", cudaGetErrorString(e));
     return -2;

@@ -446,32 +446,47 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __half* __restrict_
                                                        int H, int W, int PH, int PW, int C) {
   const int b = blockIdx.y;
   const int c8 = C >> 3;
-  const int64_t per_sample = static_cast<int64_t>(H) * W * c8;
+  const int per_sample = H * W * c8;
   const int64_t out_base = static_cast<int64_t>(b) * per_sample;
   const int64_t p_base = static_cast<int64_t>(b) * PH * PW * c8;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int q = static_cast<int>(i % c8);
-    const int w = static_cast<int>((i / c8) % W);
-    const int h = static_cast<int>(i / (static_cast<int64_t>(c8) * W));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
+    const int q = i % c8;
+    const int pix = i / c8;
+    const int w = pix % W;
+    const int h = pix / W;
+    // the (<= 2 x 2) pooling windows that contain (h, w): ph in {h/2, (h+1)/2}, pw likewise; all loads issued up front
+    const int ph0 = h >> 1, ph1 = (h + 1) >> 1, pw0 = w >> 1, pw1 = (w + 1) >> 1;
+    uint2 am[4];
+    uint4 gv[4], pv[4];
+    bool ok[4];
+    int tap[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ph = (k & 2) ? ph1 : ph0, pw = (k & 1) ? pw1 : pw0;
+      ok[k] = ph < PH && pw < PW && !((k & 2) && ph1 == ph0) && !((k & 1) && pw1 == pw0);
+      tap[k] = (h - (2 * ph - 1)) * 3 + (w - (2 * pw - 1));
+      am[k] = make_uint2(0xffffffffu, 0xffffffffu);
+      gv[k] = pv[k] = make_uint4(0, 0, 0, 0);
+      if (ok[k]) {
+        const int64_t pi = p_base + (static_cast<int64_t>(ph) * PW + pw) * c8 + q;
+        am[k] = __ldg(reinterpret_cast<const uint2*>(argmax) + pi);
+        gv[k] = __ldg(reinterpret_cast<const uint4*>(g) + pi);
+        pv[k] = __ldg(reinterpret_cast<const uint4*>(pooled) + pi);
+      }
+    }
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int ph = max(0, h / 2); ph <= min(PH - 1, (h + 1) / 2); ++ph) {
-      const int r = h - (2 * ph - 1);
-      for (int pw = max(0, w / 2); pw <= min(PW - 1, (w + 1) / 2); ++pw) {
-        const int s = w - (2 * pw - 1);
-        const int tap = r * 3 + s;
-        const int64_t pi = p_base + (static_cast<int64_t>(ph) * PW + pw) * c8 + q;
-        const uint2 am = __ldg(reinterpret_cast<const uint2*>(argmax) + pi);
-        float gv[8], pv[8];
-        load8(g, pi, 0, gv);
-        load8(pooled, pi, 0, pv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int t = ((e < 4 ? am.x : am.y) >> (8 * (e & 3))) & 0xff;
-          if (t == tap && pv[e] > 0.f) acc[e] += gv[e];
-        }
+    for (int k = 0; k < 4; ++k) {
+      const __half2* g2 = reinterpret_cast<const __half2*>(&gv[k]);
+      const __half2* p2 = reinterpret_cast<const __half2*>(&pv[k]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int t = ((e < 4 ? am[k].x : am[k].y) >> (8 * (e & 3))) & 0xff;
+        const float gval = (e & 1) ? __high2float(g2[e >> 1]) : __low2float(g2[e >> 1]);
+        const float pval = (e & 1) ? __high2float(p2[e >> 1]) : __low2float(p2[e >> 1]);
+        if (ok[k] && t == tap[k] && pval > 0.f) acc[e] += gval;
       }
     }
     store8h(dy, out_base + i, acc);
@@ -500,6 +515,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
     float sd[8], sx[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) sd[e] = sx[e] = 0.f;
+#pragma unroll 4
     for (int64_t i = start; i < per_sample; i += stride) {
       float g[8], x[8];
       load8(a.g, base + i, 0, g);
@@ -569,9 +585,23 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
   const int c8 = C >> 3;
   const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
   const int64_t base = static_cast<int64_t>(b) * per_sample;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int cc = static_cast<int>(i % c8) * 8;
+  const int64_t start = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const bool fixed = (stride % c8) == 0;  // then a thread keeps ONE 8-channel chunk: coefficients live in registers
+  float kA[8], kB[8], kC[8];             // dx = kA * g + kB + kC * x
+  auto coeffs = [&](int cc) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int grp = (cc + e) / a.cpg;
+      kA[e] = s_rstd[grp] * s_ga[cc + e];
+      kC[e] = -s_rstd[grp] * s_k2[grp];
+      kB[e] = -s_k1[grp] - s_mean[grp] * kC[e];
+    }
+  };
+  if (fixed) coeffs(static_cast<int>(start % c8) * 8);
+#pragma unroll 2
+  for (int64_t i = start; i < per_sample; i += stride) {
+    if (!fixed) coeffs(static_cast<int>(i % c8) * 8);
     float g[8], x[8], dx[8];
     load8(a.g, base + i, 0, g);
     load8(a.x, base + i, a.x_fp32, x);
@@ -582,11 +612,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
       for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.f) ? g[e] * a.g_scale : 0.f;
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int grp = (cc + e) / a.cpg;
-      const float xh = (x[e] - s_mean[grp]) * s_rstd[grp];
-      dx[e] = s_rstd[grp] * s_ga[cc + e] * g[e] - s_k1[grp] - xh * s_k2[grp];
-    }
+    for (int e = 0; e < 8; ++e) dx[e] = fmaf(kA[e], g[e], fmaf(kC[e], x[e], kB[e]));
     store8h(a.dx, base + i, dx);
     if (a.dy_out) store8h(a.dy_out, base + i, g);
   }
@@ -727,6 +753,71 @@ int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_
       dwp, Cout, Cin, R, S, cin_pad, ld_p, grad, accumulate, dst_ld);
   count_launch();
   return check_launch("unpack_dw");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched variants: one launch walks a device-resident table of descriptors (blockIdx.y = entry) instead of one
+// 3-5 us launch per layer -- 22 weight packs, 22 gradient unpacks and 21 GroupNorm parameter-gradient reductions per
+// training step become three launches.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_w_multi_kernel(const PackDesc* __restrict__ tab) {
+  const PackDesc d = tab[blockIdx.y];
+  const int64_t per = static_cast<int64_t>(d.Cin) * d.R * d.S;
+  const int64_t total = static_cast<int64_t>(d.Cout) * per;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i % d.S);
+    const int r = static_cast<int>((i / d.S) % d.R);
+    const int c = static_cast<int>((i / (static_cast<int64_t>(d.S) * d.R)) % d.Cin);
+    const int n = static_cast<int>(i / per);
+    const __half h = __float2half_rn(d.w[static_cast<int64_t>(n) * d.src_ld + (i - static_cast<int64_t>(n) * per)]);
+    if (d.wp) d.wp[static_cast<int64_t>(n) * d.ld_p + (r * d.S + s) * d.cin_pad + c] = h;
+    if (d.wt) {
+      if (d.t_mode == 0) d.wt[static_cast<int64_t>(c) * d.ld_t + ((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.cout_pad + n] = h;
+      else d.wt[static_cast<int64_t>((r * d.S + s) * d.cin_pad + c) * d.ld_t + n] = h;
+    }
+  }
+}
+__global__ void unpack_dw_multi_kernel(const UnpackDesc* __restrict__ tab) {
+  const UnpackDesc d = tab[blockIdx.y];
+  const int64_t per = static_cast<int64_t>(d.Cin) * d.R * d.S;
+  const int64_t total = static_cast<int64_t>(d.Cout) * per;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i % d.S);
+    const int r = static_cast<int>((i / d.S) % d.R);
+    const int c = static_cast<int>((i / (static_cast<int64_t>(d.S) * d.R)) % d.Cin);
+    const int n = static_cast<int>(i / per);
+    const float v = d.dwp[static_cast<int64_t>(n) * d.ld_p + (r * d.S + s) * d.cin_pad + c];
+    const int64_t o = static_cast<int64_t>(n) * d.dst_ld + (i - static_cast<int64_t>(n) * per);
+    d.grad[o] = d.accumulate ? d.grad[o] + v : v;
+  }
+}
+__global__ void __launch_bounds__(128) gn_param_grad_multi_kernel(const GnParamDesc* __restrict__ tab, int B) {
+  const GnParamDesc d = tab[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < d.C_real; c += (gridDim.x * blockDim.x) >> 5) {
+    float dg = 0.f, db = 0.f;
+    for (int b = lane; b < B; b += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(d.sums + (static_cast<int64_t>(b) * d.C + c) * 2);
+      db += v.x;
+      dg += v.y;
+    }
+    dg = warp_sum(dg);
+    db = warp_sum(db);
+    if (lane == 0) {
+      d.dgamma[c] = dg;
+      d.dbeta[c] = db;
+    }
+  }
+}
+int multi_launch(int code, const void* table, int n, int B, cudaStream_t st) {
+  PNVO_REQUIRE(table && n > 0, "multi op: empty table");
+  if (code == PNVO_OP_PACK_W_MULTI) pack_w_multi_kernel<<<dim3(64, n), 256, 0, st>>>(static_cast<const PackDesc*>(table));
+  else if (code == PNVO_OP_UNPACK_DW_MULTI) unpack_dw_multi_kernel<<<dim3(64, n), 256, 0, st>>>(static_cast<const UnpackDesc*>(table));
+  else gn_param_grad_multi_kernel<<<dim3(8, n), 128, 0, st>>>(static_cast<const GnParamDesc*>(table), B);
+  count_launch();
+  return check_launch("multi op");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -111,13 +111,23 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   }
   __syncthreads();
   // phase 1: any(depth > 0) per row / column (depth >= 0, so fp32 sum > 0 <=> any element > 0)
-  for (int i = tid; i < n_cells; i += nt) {
-    const float d = __ldg(D + static_cast<int64_t>(i) * ps);
-    if (d > 0.0f) {
-      const int r = i / W;
-      const int c = i - r * W;
-      if (!s_row_any[r]) s_row_any[r] = 1;
-      if (!s_col_any[c]) s_col_any[c] = 1;
+  // 8 independent loads in flight per thread (the CTA is alone on its SM: latency, not bandwidth, bounds this scan)
+  for (int i0 = tid; i0 < n_cells; i0 += nt * 8) {
+    float dv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * nt;
+      dv[k] = (i < n_cells) ? __ldg(D + static_cast<int64_t>(i) * ps) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (dv[k] > 0.0f) {
+        const int i = i0 + k * nt;
+        const int r = i / W;
+        const int c = i - r * W;
+        if (!s_row_any[r]) s_row_any[r] = 1;
+        if (!s_col_any[c]) s_col_any[c] = 1;
+      }
     }
   }
   __syncthreads();
@@ -149,6 +159,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   }
   const int n_pts = (rb - ra) * w;
   const float fH = static_cast<float>(H), fW = static_cast<float>(W);
+#pragma unroll 4
   for (int i = tid; i < n_pts; i += nt) {
     const int rr = i / w;
     const int cc = i - rr * w;

@@ -56,11 +56,11 @@ class ConvLayer:
         self.up = None          # zero-upsampled dy (stride-2 data gradient), allocated on first use
         self.fast_s2 = True
 
-    def alloc(self, dev, training):
+    def alloc(self, dev, training, own_dwp=True):
         self.wp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
         if self.need_dgrad and training:
             self.wt = torch.zeros(self.nt_total, self.wt_ld, dtype=torch.float16, device=dev)
-        if training:
+        if training and own_dwp:  # inside a plan dwp is a view of the gradient arena (one zero-fill per step)
             self.dwp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float32, device=dev)
 
     def flops(self, B):
@@ -111,6 +111,16 @@ class ConvLayer:
     def op_unpack(self, grad):
         return L.op_unpack_dw(self.dwp, grad, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld)
 
+    # descriptor-table entries of the batched pack / unpack launches
+    def pack_desc(self, w):
+        return L.PackDesc(w.data_ptr(), self.wp.data_ptr(), self.wt.data_ptr() if self.wt is not None else None,
+                          self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld, self.cout_pad, self.wt_ld, 0,
+                          self.Cin * self.R * self.S)
+
+    def unpack_desc(self, grad):
+        return L.UnpackDesc(self.dwp.data_ptr(), grad.data_ptr(), self.Cout, self.Cin, self.R, self.S, self.cin_pad,
+                            self.w_ld, 0, self.Cin * self.R * self.S)
+
 
 class LinearLayer(ConvLayer):
     """nn.Linear over an NCHW-flattened [C, H, W] feature map == 1x1 conv over the NHWC-flattened map
@@ -129,6 +139,16 @@ class LinearLayer(ConvLayer):
     def op_unpack(self, grad):
         return L.op_unpack_dw(self.dwp, grad, self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld,
                               dst_ld=self.src_ld)
+
+    def pack_desc(self, w):
+        ld = self.src_ld or self.fC * self.fH * self.fW
+        return L.PackDesc(w.data_ptr(), self.wp.data_ptr(), self.wt.data_ptr() if self.wt is not None else None,
+                          self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld, self.cout_pad, self.wt_ld, 1, ld)
+
+    def unpack_desc(self, grad):
+        ld = self.src_ld or self.fC * self.fH * self.fW
+        return L.UnpackDesc(self.dwp.data_ptr(), grad.data_ptr(), self.Cout, self.fC, self.fH, self.fW, self.c_pad,
+                            self.w_ld, 0, ld)
 
 
 class GNLayer:
@@ -162,6 +182,7 @@ class EncoderPlan:
         self.dropout_p = float(dropout_p) if head is not None and head.get("out_dim") else 0.0
         self.fuse_gn_bwd = True
         self.stem_version = 2
+        self.batch_small_ops = True  # one launch for all weight packs / gradient unpacks / GN parameter gradients
         self.use_stem2 = False
         self.grads = {}
         self._build_layers(backbone, baseplanes, ngroups, compression_channels)
@@ -245,7 +266,7 @@ class EncoderPlan:
     def _alloc(self):
         B, dev, tr = self.B, self.dev, self.training
         for c in self.all_convs():
-            c.alloc(dev, tr)
+            c.alloc(dev, tr, own_dwp=False)
         gns = self.all_gns()
         # one contiguous fp32 region for all GroupNorm partial sums -> a single ZERO op per forward
         tot = sum(B * g.G * 2 for g in gns)
@@ -255,12 +276,21 @@ class EncoderPlan:
             g.stats = self.stats_all[off:off + B * g.G * 2]
             off += B * g.G * 2
         if tr:
+            # one fp32 arena for everything the backward pass accumulates into: packed dW of every conv + the
+            # GroupNorm per-(sample, channel) sums -> ONE zero-fill launch per step
             tot = sum(B * g.C * 2 for g in gns)
-            self.sums_all = torch.zeros(_ru(tot, 4), dtype=torch.float32, device=dev)
+            n_dw = sum(c.cout_pad * c.w_ld for c in self.all_convs())
+            self.bwd_arena = torch.zeros(_ru(tot, 4) + n_dw, dtype=torch.float32, device=dev)
+            self.sums_all = self.bwd_arena[:_ru(tot, 4)]
             off = 0
             for g in gns:
                 g.sums = self.sums_all[off:off + B * g.C * 2]
                 off += B * g.C * 2
+            off = _ru(tot, 4)
+            for c in self.all_convs():
+                n = c.cout_pad * c.w_ld
+                c.dwp = self.bwd_arena[off:off + n].view(c.cout_pad, c.w_ld)
+                off += n
         raw_dt = torch.float32 if self.raw_fp32 else torch.float16
         # stem kernel (conv_stem.cu): needs 64-byte pixels, 32 output channels and W-padded rows with a zero halo
         self.use_stem = (not self.avgpool_input and not self.raw_fp32 and self.cin_pad == 32 and self.conv1.cout_pad == 32
@@ -368,18 +398,24 @@ class EncoderPlan:
         if self.fuse_gn_bwd and L.load().pnvo_gn_bwd_fused_supported(g.C, HW, int(self.raw_fp32)):
             # one pass: a cluster per sample keeps g / x in registers between the reduction and the apply
             ops.append(self._gn_bwd("fused", g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
-            ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B,
-                                          g.C, g.C_real))
+            if not self.batch_small_ops:
+                ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B,
+                                              g.C, g.C_real))
             return
         ops.append(self._gn_bwd(True, g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
-        ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B, g.C,
-                                      g.C_real))
+        if not self.batch_small_ops:
+            ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B, g.C,
+                                          g.C_real))
         ops.append(self._gn_bwd(False, g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
 
     def _build_programs(self):
         B = self.B
         # ---- pack ----
-        pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
+        if self.batch_small_ops:
+            self._pack_tab = L.device_table([c.pack_desc(self.P[c.key]) for c in self.all_convs()], self.dev)
+            pack = [L.op_multi(L.OP_PACK_W_MULTI, self._pack_tab, len(self.all_convs()))]
+        else:
+            pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
         if self.use_stem:
             pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
             if self.use_stem2:
@@ -444,9 +480,7 @@ class EncoderPlan:
         if not self.training:
             return
         # ---- backward ----
-        ops = [L.op_zero(self.sums_all)]
-        for c in self.all_convs():
-            ops.append(L.op_zero(c.dwp))
+        ops = [L.op_zero(self.bwd_arena)]
         if self.head is not None:
             hd = self.head
             if hd.get("out_dim"):
@@ -498,6 +532,8 @@ class EncoderPlan:
                 else:
                     ops += c.ops_dgrad(blk["dx"][0], g_x, B, add=add)
         # stem: max-pool + ReLU routing, GN, conv1 weight gradient (no data gradient: the input is data)
+        # (gathering the max-pool backward inside the two GroupNorm passes was measured slower -- 0.85 vs 0.62 ms --
+        # than materialising dy1 once: the 4-window gather runs twice)
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
         self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
         if self.use_stem and self.stem_version >= 2 and L.load().pnvo_conv_stem_wgrad2_supported(self.inH, self.inW):
@@ -506,8 +542,17 @@ class EncoderPlan:
             ops.append(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48))
         else:
             ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
-        for c in self.all_convs():
-            ops.append(c.op_unpack(self.grads[c.key]))
+        if self.batch_small_ops:
+            self._unpack_tab = L.device_table([c.unpack_desc(self.grads[c.key]) for c in self.all_convs()], self.dev)
+            ops.append(L.op_multi(L.OP_UNPACK_DW_MULTI, self._unpack_tab, len(self.all_convs())))
+            gns = self.all_gns()
+            self._gnp_tab = L.device_table(
+                [L.GnParamDesc(g.sums.data_ptr(), self.grads[g.key + ".weight"].data_ptr(),
+                               self.grads[g.key + ".bias"].data_ptr(), g.C, g.C_real) for g in gns], self.dev)
+            ops.append(L.op_multi(L.OP_GN_PARAM_GRAD_MULTI, self._gnp_tab, len(gns), B))
+        else:
+            for c in self.all_convs():
+                ops.append(c.op_unpack(self.grads[c.key]))
         self.bwd_ops = ops
         self.bwd_prog = L.Program(ops, graph=True)
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 # opcodes (include/pnvo.h: enum pnvo_opcode)
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
-OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2, OP_WGRAD_STEM2 = range(16, 37)
+OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2, OP_WGRAD_STEM2, OP_PACK_W_MULTI, OP_UNPACK_DW_MULTI, OP_GN_PARAM_GRAD_MULTI = range(16, 40)
 
 
 class PnvoOp(ctypes.Structure):
@@ -26,6 +26,32 @@ class TopdownConsts(ctypes.Structure):
     _fields_ = [("min_x", ctypes.c_float), ("x_den", ctypes.c_float), ("z_den", ctypes.c_float),
                 ("depth_scale", ctypes.c_float), ("depth_off", ctypes.c_float),
                 ("rows_around_center", ctypes.c_int), ("center_crop", ctypes.c_int)]
+
+
+class PackDesc(ctypes.Structure):  # csrc/elem.cuh
+    _fields_ = [("w", ctypes.c_void_p), ("wp", ctypes.c_void_p), ("wt", ctypes.c_void_p)] + \
+               [(n, ctypes.c_int32) for n in ("Cout", "Cin", "R", "S", "cin_pad", "ld_p", "cout_pad", "ld_t", "t_mode", "src_ld")]
+
+
+class UnpackDesc(ctypes.Structure):
+    _fields_ = [("dwp", ctypes.c_void_p), ("grad", ctypes.c_void_p)] + \
+               [(n, ctypes.c_int32) for n in ("Cout", "Cin", "R", "S", "cin_pad", "ld_p", "accumulate", "dst_ld")]
+
+
+class GnParamDesc(ctypes.Structure):
+    _fields_ = [("sums", ctypes.c_void_p), ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
+                ("C", ctypes.c_int32), ("C_real", ctypes.c_int32)]
+
+
+def device_table(descs, device):
+    """Uploads a list of ctypes descriptor structs as one device byte tensor (kept alive by the caller)."""
+    arr = (type(descs[0]) * len(descs))(*descs)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
+def op_multi(code, table, n, B=0):
+    return _op(code, [n, B], (), [table])
 
 
 class PnvoError(RuntimeError):
