@@ -399,33 +399,60 @@ __global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int
   }
   __syncthreads();
   const int c8 = C >> 3;
-  const int64_t per_sample = static_cast<int64_t>(PH) * PW * c8;
+  const int per_sample = PH * PW * c8;
   const int64_t in_base = static_cast<int64_t>(b) * H * W * c8;
   const int64_t out_base = static_cast<int64_t>(b) * per_sample;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int q = static_cast<int>(i % c8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
+    const int q = i % c8;
     const int cc = q * 8;
-    const int pw = static_cast<int>((i / c8) % PW);
-    const int ph = static_cast<int>(i / (static_cast<int64_t>(c8) * PW));
+    const int pp = i / c8;
+    const int pw = pp % PW;
+    const int ph = pp / PW;
+    // all nine taps are fetched before any of them is used (fp16 inputs; the fp32 path keeps the simple loop)
     float best[8];
     int arg[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+    float ga[8], gb[8];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = 2 * ph - 1 + r;
-      if (h < 0 || h >= H) continue;
+    for (int e = 0; e < 8; ++e) { ga[e] = s_ab[cc + e]; gb[e] = s_ab[C + cc + e]; }
+    if (!a.x_fp32) {
+      uint4 tapv[9];
+      bool ok[9];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = 2 * pw - 1 + s;
-        if (w < 0 || w >= W) continue;
-        float v[8];
-        load8(a.x, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, a.x_fp32, v);
+      for (int t = 0; t < 9; ++t) {
+        const int h = 2 * ph - 1 + t / 3, w = 2 * pw - 1 + t % 3;
+        ok[t] = h >= 0 && h < H && w >= 0 && w < W;
+        tapv[t] = make_uint4(0, 0, 0, 0);
+        if (ok[t]) tapv[t] = __ldg(reinterpret_cast<const uint4*>(a.x) + in_base + (static_cast<int64_t>(h) * W + w) * c8 + q);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (!ok[t]) continue;
+        const __half2* h2 = reinterpret_cast<const __half2*>(&tapv[t]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float y = fmaxf(fmaf(v[e], s_ab[cc + e], s_ab[C + cc + e]), 0.f);
-          if (y > best[e]) { best[e] = y; arg[e] = r * 3 + s; }
+          const float v = (e & 1) ? __high2float(h2[e >> 1]) : __low2float(h2[e >> 1]);
+          const float y = fmaxf(fmaf(v, ga[e], gb[e]), 0.f);
+          if (y > best[e]) { best[e] = y; arg[e] = t; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int h = 2 * ph - 1 + r;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int w = 2 * pw - 1 + s;
+          if (w < 0 || w >= W) continue;
+          float v[8];
+          load8(a.x, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, a.x_fp32, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float y = fmaxf(fmaf(v[e], ga[e], gb[e]), 0.f);
+            if (y > best[e]) { best[e] = y; arg[e] = r * 3 + s; }
+          }
         }
       }
     }

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   }
   const int n_pts = (rb - ra) * w;
   const float fH = static_cast<float>(H), fW = static_cast<float>(W);
+  // (warp-aggregating the histogram atomics with match.any was measured slower: 0.36 vs 0.335 ms for 512 frames)
 #pragma unroll 4
   for (int i = tid; i < n_pts; i += nt) {
     const int rr = i / w;
