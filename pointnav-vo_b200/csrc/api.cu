@@ -106,7 +106,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.w = static_cast<const __half*>(p[1]);
       a.y = p[2];
       a.add = static_cast<const __half*>(p[3]);
-      a.stats = static_cast<float*>(p[4]);
+      a.stats = static_cast<double*>(p[4]);
       a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
       a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];
       a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18]; a.force_generic = i[19];
@@ -127,7 +127,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = x, p1 = stats, p2 = gamma, p3 = beta, p4 = res, p5 = y, p6 = argmax
       // i0 = B, i1 = C, i2 = G, i3 = cpg, i4 = HW, i5 = relu, i6 = x_fp32, i7..i10 = H, W, PH, PW; f0 = cnt, f1 = eps
       GnArgs a{};
-      a.x = p[0]; a.stats = static_cast<const float*>(p[1]); a.gamma = static_cast<const float*>(p[2]);
+      a.x = p[0]; a.stats = static_cast<const double*>(p[1]); a.gamma = static_cast<const float*>(p[2]);
       a.beta = static_cast<const float*>(p[3]); a.res = static_cast<const __half*>(p[4]);
       a.y = static_cast<__half*>(p[5]);
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.relu = i[5]; a.x_fp32 = i[6]; a.C_real = i[11];
@@ -146,7 +146,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = g, p1 = relu_ref, p2 = x, p3 = stats, p4 = gamma, p5 = sums, p6 = dx, p7 = dy_out
       GnBwdArgs a{};
       a.g = static_cast<const __half*>(p[0]); a.relu_ref = static_cast<const __half*>(p[1]); a.x = p[2];
-      a.stats = static_cast<const float*>(p[3]); a.gamma = static_cast<const float*>(p[4]);
+      a.stats = static_cast<const double*>(p[3]); a.gamma = static_cast<const float*>(p[4]);
       a.sums = static_cast<float*>(p[5]); a.dx = static_cast<__half*>(p[6]); a.dy_out = static_cast<__half*>(p[7]);
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1]; a.g_scale = (f[2] == 0.f) ? 1.f : f[2];
@@ -194,11 +194,11 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
     case PNVO_OP_CONV_STEM:
       // p0 = x [B,IH,IW,32] fp16, p1 = stem-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = stages
       return conv_stem_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
-                                  static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
+                                  static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
     case PNVO_OP_CONV_STEM2:
       // p0 = W-padded x, p1 = stem2-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg
       return conv_stem2_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
-                                   static_cast<float*>(p[3]), i[0], i[1], i[2], i[3], i[4], st);
+                                   static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], st);
     case PNVO_OP_WGRAD_STEM2:
       // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld
       return conv_stem_wgrad2_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),
@@ -352,7 +352,7 @@ extern "C" int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t
     a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
     a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];
     a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18];
-    a.stats = static_cast<float*>(op->p[4]);
+    a.stats = static_cast<double*>(op->p[4]);
     if (conv_plan(a)) return -1;
     *grid_x = a.grid_x; *grid_y = a.grid_y; *smem_bytes = a.smem_bytes; *tmem_cols = a.tmem_cols; *stages = a.stages;
   } else {

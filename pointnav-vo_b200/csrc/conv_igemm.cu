@@ -43,7 +43,7 @@ __device__ __forceinline__ void warp_reduce_scatter(float* a, int lane) {
 // per-thread (sum, sumsq) of CPG-wide channel groups inside a 32-column chunk, reduced over the rows of
 // the warp that belong to the same sample, then one atomicAdd per value.
 template <int CPG>
-__device__ __forceinline__ void chunk_stats(const float* v, int sample, bool row_valid, float* stats, int G,
+__device__ __forceinline__ void chunk_stats(const float* v, int sample, bool row_valid, double* stats, int G,
                                             int group0, int lane) {
   constexpr int NG = 32 / CPG;
   constexpr int V = 2 * NG;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void chunk_stats(const float* v, int sample, bool row
     constexpr int kLanesPerVal = 32 / V;
     if ((lane & (kLanesPerVal - 1)) == 0) {
       const int e = lane / kLanesPerVal;
-      atomicAdd(stats + (static_cast<int64_t>(cur) * G + group0) * 2 + e, a[0]);
+      atomicAdd(stats + (static_cast<int64_t>(cur) * G + group0) * 2 + e, static_cast<double>(a[0]));
     }
     if (mine) pending = 0x7fffffff;
   }

@@ -27,7 +27,7 @@ namespace pnvo {
 struct RasterArgs {
   __half* y;
   const __half* add;
-  float* stats;
+  double* stats;
   int B, H, W;
   int cpg, G;
   int P, T, n_tiles, rows_in;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
           }
           off >>= 1;
         }
-        if (lane < 2 * p.G) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, acc[0]);
+        if (lane < 2 * p.G) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, static_cast<double>(acc[0]));
       }
     }
     tc_fence_before();

@@ -17,7 +17,7 @@ namespace pnvo {
 
 struct StemArgs {
   void* y;        // [B, OH, OW, 32] fp16
-  float* stats;   // [B][G][2]
+  double* stats;  // [B][G][2]
   int B, IH, IW, OH, OW;
   int G, cpg;
   int stages;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(192) conv_stem_fwd_kernel(const StemArgs p, co
           }
           off >>= 1;
         }
-        if (lane < 2 * ng) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, sgrp[0]);
+        if (lane < 2 * ng) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, static_cast<double>(sgrp[0]));
       }
       if (valid) {
         __half* yp = reinterpret_cast<__half*>(p.y) + (static_cast<int64_t>(b) * p.OH * p.OW + static_cast<int64_t>(oh) * p.OW + ow) * 32;
@@ -208,7 +208,7 @@ int stem_padded_width(int IW) {
   return std::max((IW + 3 + 1) & ~1, (npx + 1) & ~1);
 }
 
-int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
                          int stages, cudaStream_t st) {
   PNVO_REQUIRE(x && wr && y, "conv_stem: null pointer");
   StemArgs a{};

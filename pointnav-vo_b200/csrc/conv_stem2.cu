@@ -24,7 +24,7 @@ namespace pnvo {
 
 struct Stem2Args {
   __half* y;      // [B, OH, OW, 32] fp16
-  float* stats;   // [B][G][2]
+  double* stats;  // [B][G][2]
   int B, IH, OH, OW;
   int G, cpg;
   int n_cols;         // UMMA N: OW rounded up to 16
@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
         }
         if (row_valid && (lane % p.cpg) == 0) {
-          float* st = p.stats + (static_cast<int64_t>(b) * p.G + lane / p.cpg) * 2;
-          atomicAdd(st, sum);
-          atomicAdd(st + 1, ssq);
+          double* st = p.stats + (static_cast<int64_t>(b) * p.G + lane / p.cpg) * 2;
+          atomicAdd(st, static_cast<double>(sum));
+          atomicAdd(st + 1, static_cast<double>(ssq));
         }
       }
     }
@@ -246,7 +246,7 @@ int conv_stem2_supported(int IH, int IW) {
   return (n_cols <= 240 && IH >= 7) ? 1 : 0;
 }
 
-int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
                           cudaStream_t st) {
   PNVO_REQUIRE(x && wr && y, "conv_stem2: null pointer");
   PNVO_REQUIRE(conv_stem2_supported(IH, IW), "conv_stem2: unsupported geometry %dx%d", IH, IW);

@@ -36,7 +36,7 @@ int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStrea
 struct GnArgs {
   const void* x;       // raw conv output [B*HW][C] fp16 (or fp32 when x_fp32)
   int x_fp32;
-  const float* stats;  // [B][G][2]
+  const double* stats; // [B][G][2] fp64 (sum, sum of squares)
   const float* gamma;  // [C] (padded channels: 0)
   const float* beta;   // [C]
   const __half* res;   // optional residual [B*HW][C]
@@ -56,7 +56,7 @@ struct GnBwdArgs {
   const __half* relu_ref;  // saved post-ReLU output (mask = relu_ref > 0); null = no ReLU
   const void* x;           // raw conv output (GN input)
   int x_fp32;
-  const float* stats;
+  const double* stats;
   const float* gamma;
   float* sums;             // [B][C][2] (sum dy, sum dy*xhat), pre-zeroed for the reduce pass
   __half* dx;              // apply pass: gradient w.r.t. the raw conv output

@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(kGbfThreads) gn_bwd_fused_kernel(const GnBwdAr
   // per-channel mean / rstd of this sample (forward statistics) and gamma while the copies fly
   for (int c = tid; c < C; c += kGbfThreads) {
     const int g = c / a.cpg;
-    const float s = a.stats[(static_cast<int64_t>(b) * G + g) * 2], q = a.stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
-    const float mean = s / a.cnt;
-    const float var = fmaxf(q / a.cnt - mean * mean, 0.f);
-    s_mr[2 * c] = mean;
-    s_mr[2 * c + 1] = 1.0f / sqrtf(var + a.eps);
+    const double s = a.stats[(static_cast<int64_t>(b) * G + g) * 2], q = a.stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
+    const double m = s / static_cast<double>(a.cnt);
+    const double var = fmax(q / static_cast<double>(a.cnt) - m * m, 0.0);
+    s_mr[2 * c] = static_cast<float>(m);
+    s_mr[2 * c + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
     s_gamma[c] = (c < a.C_real) ? a.gamma[c] : 0.f;
   }
   __syncthreads();  // barrier initialised before anybody waits on it

@@ -315,12 +315,14 @@ int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scal
 // accumulated by the conv epilogue).  Per block (one sample) the affine per channel is put in smem:
 //   y = x * a_c + b_c,  a_c = gamma_c * rstd_g,  b_c = beta_c - mean_g * a_c
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void group_mean_rstd(const float* stats, int b, int G, int g, float cnt, float eps,
+__device__ __forceinline__ void group_mean_rstd(const double* stats, int b, int G, int g, float cnt, float eps,
                                                 float& mean, float& rstd) {
-  const float s = stats[(static_cast<int64_t>(b) * G + g) * 2], q = stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
-  mean = s / cnt;
-  const float var = fmaxf(q / cnt - mean * mean, 0.f);
-  rstd = 1.0f / sqrtf(var + eps);
+  // fp64 sums: mean / variance are formed in fp64 (no cancellation in E[x^2] - E[x]^2) and rounded once
+  const double s = stats[(static_cast<int64_t>(b) * G + g) * 2], q = stats[(static_cast<int64_t>(b) * G + g) * 2 + 1];
+  const double m = s / static_cast<double>(cnt);
+  const double var = fmax(q / static_cast<double>(cnt) - m * m, 0.0);
+  mean = static_cast<float>(m);
+  rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 
 __device__ __forceinline__ void load8(const void* base, int64_t idx8, int is_fp32, float* v) {

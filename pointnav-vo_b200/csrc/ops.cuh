@@ -9,7 +9,8 @@ struct ConvArgs {
   const __half* w;    // packed weights [n_total][w_ld] fp16, K-major, zero padded
   void* y;            // output [M][ldo] fp16 (or fp32 when out_fp32)
   const __half* add;  // optional [M][ldo] fp16 added before the store (dgrad accumulation)
-  float* stats;       // optional GroupNorm partial sums [B][G][2] (sum, sum of squares), pre-zeroed
+  double* stats;      // optional GroupNorm partial sums [B][G][2] (sum, sum of squares), pre-zeroed; fp64 accumulators:
+                      // the ORDER of the atomics then no longer shows in the fp32 mean / rstd (reproducible forward)
   int B, IH, IW, Cin;
   int OH, OW;
   int R, S, mul, pad, pad_w, div;  // t = o*mul - pad + r; tap valid iff t >= 0, t % div == 0, t/div < I
@@ -42,7 +43,7 @@ struct WgradArgs {
   // derived
   int cin_log2, cmask, M, K, n_mtiles, mt, N, n_ntiles, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y, grid_z, chunks_per_split;
 };
-int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+int conv_stem_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
                          int stages, cudaStream_t st);
 int stem_padded_width(int IW);
 int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW,
@@ -50,7 +51,7 @@ int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_l
 int pack_w_stem_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
 // conv_stem2.cu: pixels-as-N formulation of the stem (full-rate MMAs, resident weights, persistent)
 int conv_stem2_supported(int IH, int IW);
-int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, float* stats, int B, int IH, int IW, int G, int cpg,
+int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
                           cudaStream_t st);
 int pack_w_stem2_launch(const float* w, int Cin, __half* wr, cudaStream_t st);
 int conv_stem_wgrad2_supported(int IH, int IW);

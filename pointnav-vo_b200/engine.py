@@ -270,7 +270,8 @@ class EncoderPlan:
         gns = self.all_gns()
         # one contiguous fp32 region for all GroupNorm partial sums -> a single ZERO op per forward
         tot = sum(B * g.G * 2 for g in gns)
-        self.stats_all = torch.zeros(_ru(tot, 4), dtype=torch.float32, device=dev)
+        # fp64 accumulators: the order of the epilogues' atomics then no longer shows in the fp32 mean / rstd
+        self.stats_all = torch.zeros(_ru(tot, 4), dtype=torch.float64, device=dev)
         off = 0
         for g in gns:
             g.stats = self.stats_all[off:off + B * g.G * 2]

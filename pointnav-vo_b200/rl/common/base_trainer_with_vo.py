@@ -114,13 +114,21 @@ class VOInferenceMixin:
         returns in 'det' mode."""
         dev = self.device
         n = len(acts)
-        rgb = torch.as_tensor(np.stack([np.concatenate([np.asarray(p["rgb"]), np.asarray(c["rgb"])], axis=2)
-                                        for p, c in zip(prev_obs_list, cur_obs_list)])).to(dev).float()
+        rgb_np = np.stack([np.concatenate([np.asarray(p["rgb"]), np.asarray(c["rgb"])], axis=2)
+                           for p, c in zip(prev_obs_list, cur_obs_list)])
         dep = torch.as_tensor(np.stack([np.concatenate([np.asarray(p["depth"]), np.asarray(c["depth"])], axis=2)
-                                        for p, c in zip(prev_obs_list, cur_obs_list)])).to(dev).float()
-        obs = self._vo_inputs(rgb.contiguous(), dep.contiguous())
+                                        for p, c in zip(prev_obs_list, cur_obs_list)])).to(dev).float().contiguous()
+        cfg = self.config.VO.REGRESS_MODEL
+        if rgb_np.dtype == np.uint8 and cfg.discretize_depth == "hard":
+            # raw pairs: the simulator's uint8 rgb goes to the device as is (6 B/pixel instead of 24) and the model
+            # derives the discretised-depth / top-down channels itself (csrc/raw_input.cu), with this trainer's geometry
+            obs = {"rgb": torch.as_tensor(rgb_np).to(dev).contiguous(), "depth": dep}
+            for m in self.vo_model.values():
+                m.set_raw_input_config(getattr(self, "_top_down_view_generator", None),
+                                       getattr(self, "_discretized_depth_end_vals", None))
+        else:
+            obs = self._vo_inputs(torch.as_tensor(rgb_np).to(dev).float().contiguous(), dep)
         out = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        acts_t = torch.as_tensor(np.asarray(acts))
         with torch.no_grad():
             for key in sorted({self._vo_key(int(a)) for a in acts}):
                 idx = torch.tensor([i for i, a in enumerate(acts) if self._vo_key(int(a)) == key], device=dev)
@@ -128,5 +136,4 @@ class VOInferenceMixin:
                 model.eval()
                 sub = {k: v.index_select(0, idx).contiguous() for k, v in obs.items()}
                 out.index_copy_(0, idx, model(sub)[:, :3])
-        del acts_t
         return out

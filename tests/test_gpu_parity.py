@@ -156,7 +156,7 @@ def test_conv_fprop_dgrad_wgrad(case, force_generic):
     w = (torch.randn(Cout, Cin, R, S, device=dev) / (Cin * R * S) ** 0.5).contiguous()
     x = torch.randn(B, IH, IW, c.cin_pad, device=dev).half()
     x[..., Cin:] = 0
-    stats = torch.zeros(B, G, 2, device=dev)
+    stats = torch.zeros(B, G, 2, device=dev, dtype=torch.float64)
     y = torch.empty(B, c.OH, c.OW, c.cout_pad, dtype=torch.float16, device=dev)
     fwd = c.op_fwd(x, y, B, stats, c.cout_pad // G, G)
     fwd.i[19] = force_generic
@@ -211,7 +211,7 @@ def test_stem_conv_kernels(version, B, IH, IW, Cin):
     x[..., Cin:] = 0
     xp[:, :, 3:3 + IW] = x
     y = torch.full((B, OH, OW, 32), float("nan"), dtype=torch.float16, device=dev)
-    stats = torch.zeros(B, 16, 2, device=dev)
+    stats = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
     wr = torch.zeros(4 * 7 * 32, 64, dtype=torch.float16, device=dev)
     if version == 1:
         if not 128 <= OW <= 256:
@@ -256,7 +256,7 @@ def test_groupnorm_forward_backward(B, H, W, C, G, Cr):
     gamma, beta = torch.rand(Cr, device=dev) + 0.5, torch.randn(Cr, device=dev) * 0.1
     xf = x[..., :Cr].float().permute(0, 3, 1, 2)
     xs = xf.reshape(B, G, -1)
-    stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).contiguous()
+    stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).double().contiguous()
     y = torch.empty_like(x)
     cpg, cpg_r, HW = C // G, Cr // G, H * W
     L.run_ops([L.op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, float(cpg_r * HW), True, res, False, 1e-5, Cr)])
@@ -320,7 +320,7 @@ def test_groupnorm_maxpool_forward_backward():
     gamma, beta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
     xf = x.float().permute(0, 3, 1, 2)
     xs = xf.reshape(B, G, -1)
-    stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).contiguous()
+    stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).double().contiguous()
     y = torch.empty(B, PH, PW, C, dtype=torch.float16, device=dev)
     am = torch.empty(B, PH, PW, C, dtype=torch.uint8, device=dev)
     L.run_ops([L.op_gn_pool(x, stats, gamma, beta, y, am, B, C, G, C // G, H, W, PH, PW, float(C // G * H * W))])
@@ -482,6 +482,18 @@ def test_vo_backward_block_by_block():
             assert rel_l2(P[k].grad, sd[k].grad) <= 0.08, k
 
 
+def test_vo_forward_is_reproducible_run_to_run():
+    """GroupNorm statistics are accumulated with fp64 atomics, so their order no longer reaches the fp32 mean / rstd:
+    two eval-mode forwards of the same batch are bit-identical (with fp32 atomics they differed at the 4e-3 level)."""
+    m, space, _ = _load_vo("r18_30ch")
+    obs = helpers.vo_inputs(4, 13, space, "cuda")
+    m.eval()
+    with torch.no_grad():
+        outs = [m(obs).clone() for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 def test_vo_eval_is_batch_independent_at_full_size():
     """Size-independent property at the benchmark batch: in eval mode sample i of a batch-256 forward equals the
     same sample run in a batch of 8.  GroupNorm is per-sample, so the only coupling is the ORDER of the fp32
@@ -638,3 +650,50 @@ def test_ppo_update_on_device():
     moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, pol.parameters()))
     assert moved >= len(before) - 2
     rs.after_update()
+
+
+def test_vo_inference_in_the_rl_loop():
+    """a9: `_compute_local_delta_states_from_vo` (reference signature, numpy observations in, python lists out) against the
+    oracle chain discretise -> top-down -> VO net, and the batched variant (raw uint8 path) against the per-env calls."""
+    import types
+
+    from pointnav_vo_b200.rl.common.base_trainer_with_vo import VOInferenceMixin
+
+    case = "r18_30ch"
+    name, space, backbone, kw = helpers.VO_CASES[case]
+    sd = helpers.vo_state_dict(case)
+    models = {}
+    for act in ("forward", "left", "right"):
+        m, _, _ = _load_vo(case)
+        models[act] = m.eval()
+    ns = types.SimpleNamespace
+    trainer = VOInferenceMixin()
+    trainer.device = torch.device("cuda")
+    trainer.vo_model = models
+    trainer.config = ns(VO=ns(VO_TYPE="REGRESS", VIS_SIZE_H=192, VIS_SIZE_W=341,
+                              REGRESS_MODEL=ns(name=name, discretize_depth="hard", discretized_depth_channels=10,
+                                               regress_type="sep_act", mode="det", rnd_mode_n=2)),
+                        TASK_CONFIG=ns(SIMULATOR=ns(DEPTH_SENSOR=ns(MIN_DEPTH=0.1, MAX_DEPTH=10.0, HFOV=70))))
+    trainer._setup_vo_preproc()
+    rgb = synth.rgb_frames(6, seed=31)
+    dep = synth.depth_frames(6, seed=32)[..., None]
+    prev = [{"rgb": rgb[2 * i], "depth": dep[2 * i]} for i in range(3)]
+    cur = [{"rgb": rgb[2 * i + 1], "depth": dep[2 * i + 1]} for i in range(3)]
+    acts = [1, 2, 3]
+    orc = po.TopDownOracle()
+    singles = []
+    for p, c, a in zip(prev, cur, acts):
+        deltas, std, extra = trainer._compute_local_delta_states_from_vo(p, c, a)
+        assert isinstance(deltas, list) and len(deltas) == 3 and std == [0, 0, 0] and extra == {}
+        d2 = np.stack([p["depth"][..., 0], c["depth"][..., 0]])
+        oh = po.discretize_depth_onehot(d2)
+        obs = {"rgb": torch.from_numpy(np.concatenate([p["rgb"], c["rgb"]], -1)[None].astype(np.float32)),
+               "depth": torch.from_numpy(np.stack([d2[0], d2[1]], -1)[None]),
+               "discretized_depth": torch.from_numpy(np.concatenate([oh[0], oh[1]], -1)[None]),
+               "top_down_view": torch.from_numpy(np.stack([orc.gen_top_down_view(d2[j])[..., 0] for j in range(2)], -1)[None])}
+        ref, _ = vo.vo_forward(obs, sd, space, backbone, training=False)
+        assert rel(torch.tensor(deltas)[None], ref) <= 8e-3
+        singles.append(deltas)
+    batched = trainer.compute_local_delta_states_batched(prev, cur, acts)
+    assert batched.shape == (3, 3)
+    assert rel(batched, torch.tensor(np.array(singles))) <= 8e-3

@@ -58,7 +58,7 @@ def main():
         y = torch.empty(B, c.OH, c.OW, c.cout_pad, dtype=torch.float16, device=dev)
         dy = torch.randn(B, c.OH, c.OW, c.cout_pad, device=dev).half()
         gx = torch.empty_like(x)
-        stats = torch.zeros(B, 16, 2, device=dev)
+        stats = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
         L.run_ops([c.op_pack(w)])
         gf = c.flops(B) / 1e9
         for flag in [int(f) for f in a.flags.split(",")]:

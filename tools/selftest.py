@@ -90,7 +90,7 @@ def _conv_case(name, B, Cin, Cout, R, S, stride, pad, IH, IW, seed=0, stats_grou
     x[..., Cin:] = 0
     G = stats_groups
     cpg = c.cout_pad // G
-    stats = torch.zeros(B, G, 2, device=dev)
+    stats = torch.zeros(B, G, 2, device=dev, dtype=torch.float64)
     y = torch.empty(B, c.OH, c.OW, c.cout_pad, dtype=torch.float16, device=dev)
     ops = [c.op_pack(w), c.op_fwd(x, y, B, stats, cpg, G)]
     info = L.conv_launch_info(ops[1])
@@ -184,7 +184,7 @@ def gn_ops():
         beta = torch.randn(Cr, device=dev) * 0.1
         xf = x[..., :Cr].float().permute(0, 3, 1, 2)
         xs = xf.reshape(B, G, -1)
-        stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).contiguous()
+        stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).double().contiguous()
         y = torch.empty_like(x)
         cpg, cpg_r = C // G, Cr // G
         HW = H * W
@@ -219,7 +219,7 @@ def gn_ops():
     beta = torch.randn(C, device=dev) * 0.1
     xf = x.float().permute(0, 3, 1, 2)
     xs = xf.reshape(B, G, -1)
-    stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).contiguous()
+    stats = torch.stack((xs.sum(-1), xs.pow(2).sum(-1)), -1).double().contiguous()
     PH, PW = 48, 86
     y = torch.empty(B, PH, PW, C, dtype=torch.float16, device=dev)
     am = torch.empty(B, PH, PW, C, dtype=torch.uint8, device=dev)

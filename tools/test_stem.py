@@ -28,7 +28,7 @@ def run(B, IH, IW, Cin, stages, time_it=False):
     xp[:, :, 3:3 + IW] = x
     wr = torch.zeros(7 * 4 * 32, 64, dtype=torch.float16, device=dev)
     y = torch.zeros(B, OH, OW, 32, dtype=torch.float16, device=dev)
-    stats = torch.zeros(B, 16, 2, device=dev)
+    stats = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
     ops = [L.op_pack_w_stem(w, wr, Cin), L.op_conv_stem(xp, wr, y, stats, B, IH, IW, 16, 2, stages)]
     L.run_ops(ops)
     torch.cuda.synchronize()

@@ -16,7 +16,7 @@ Wp = L.load().pnvo_stem_padded_width(IW)
 xp = torch.zeros(B, IH, Wp, 32, device=dev, dtype=torch.float16)
 xp[:, :, 3:3 + IW, :Cin] = torch.randn(B, IH, IW, Cin, device=dev).half()
 y = torch.zeros(B, OH, OW, 32, dtype=torch.float16, device=dev)
-stats = torch.zeros(B, 16, 2, device=dev)
+stats = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
 wr = torch.zeros(4 * 7 * 32, 64, dtype=torch.float16, device=dev)
 for name, pack, op in (("stem v1 (N=32 raster)", L.op_pack_w_stem(w, wr, Cin), L.op_conv_stem(xp, wr, y, stats, B, IH, IW, 16, 2, 2)),
                        ("stem v2 (pixels as N)", L.op_pack_w_stem2(w, wr, Cin), L.op_conv_stem2(xp, wr, y, stats, B, IH, IW, 16, 2))):
