@@ -103,13 +103,18 @@ def synth_batch(B, seed):
     return rgb, dep, tgt
 
 
-def build_model(device, dropout_p=0.2):
+def build_model(device, dropout_p=0.2, model="r18_30ch"):
     from pointnav_vo_b200.vo.models import vo_cnn
 
     torch.manual_seed(0)
-    m = vo_cnn.baseline_registry.get_vo_model("vo_cnn_rgb_d_dd_top_down")(
-        observation_space=SPACE, observation_size=(W, H), hidden_size=512, backbone="resnet18",
-        normalize_visual_inputs=True, output_dim=3, dropout_p=dropout_p, discretized_depth_channels=10)
+    if model == "r50_8ch":  # BASELINE configs[2]/[3]: ResNet-50 is only constructible through the un-asserting base class
+        m = vo_cnn.VisualOdometryCNNBase(observation_space=["rgb", "depth"], observation_size=(W, H), hidden_size=512,
+                                         backbone="resnet50", normalize_visual_inputs=True, output_dim=3,
+                                         dropout_p=dropout_p)
+    else:
+        m = vo_cnn.baseline_registry.get_vo_model("vo_cnn_rgb_d_dd_top_down")(
+            observation_space=SPACE, observation_size=(W, H), hidden_size=512, backbone="resnet18",
+            normalize_visual_inputs=True, output_dim=3, dropout_p=dropout_p, discretized_depth_channels=10)
     return m.to(device).train()
 
 
@@ -152,7 +157,7 @@ def run_b200(args):
     B = args.batch
     from pointnav_vo_b200.vo.engine.train_step import PrefetchedBatches
 
-    model = build_model(dev)
+    model = build_model(dev, model=args.model)
     trainer = FusedVOTrainStep(model)
     rgb, dep, tgt = synth_batch(B, seed=1 + rank)
     host = {"rgb": torch.from_numpy(rgb).pin_memory(), "depth": torch.from_numpy(dep).pin_memory(),
@@ -278,12 +283,14 @@ def run_b200(args):
                 "step_tflops": round(world * B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12, 2),
                 "step_frac_of_sustained": round(B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12
                                                 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), 4)}
-    cpu = cpu_baseline(seconds=args.cpu_seconds) if world == 1 and not args.no_cpu else None
+    cpu = cpu_baseline(seconds=args.cpu_seconds) if world == 1 and not args.no_cpu and args.model == "r18_30ch" else None
     out = {"metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-           "config": {"workload": "VO ResNet-18 (vo_cnn_rgb_d_dd_top_down, 30 ch) forward+backward+Adam, "
-                                  "batch 256 per GPU, 341x192 RGB-D pairs (BASELINE configs[1]); step input = "
+           "config": {"workload": ("VO ResNet-50 (rgb + depth, 8 ch; BASELINE configs[2]) forward+backward+Adam, "
+                                   if args.model == "r50_8ch" else
+                                   "VO ResNet-18 (vo_cnn_rgb_d_dd_top_down, 30 ch) forward+backward+Adam, ") +
+                                  "batch 256 per GPU, 341x192 RGB-D pairs" + ("" if args.model == "r50_8ch" else " (BASELINE configs[1])") + "; step input = "
                                   + ("uint8 rgb + fp32 depth pairs, discretised-depth / top-down channels derived "
                                      "on the device inside the step" if pre is None else
                                      "the reference's four fp32 NHWC tensors"),
@@ -376,6 +383,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inputs", default="raw", choices=["raw", "dict"])
+    ap.add_argument("--model", default="r18_30ch", choices=["r18_30ch", "r50_8ch"],
+                    help="r18_30ch = the shipped default VO model (the headline); r50_8ch = ResNet-50 rgb+depth (BASELINE "
+                         "configs[2]/[3]), reported for the record -- roofline / cpu_baseline fields describe r18_30ch only")
     ap.add_argument("--forward-only", action="store_true",
                     help="extra line: eval-mode forward (inference) throughput of the same model / batch, device-resident inputs")
     args = ap.parse_args()

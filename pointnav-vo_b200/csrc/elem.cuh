@@ -90,6 +90,8 @@ struct GnParamDesc {
   float* dbeta;
   int C, C_real;
 };
+static_assert(sizeof(PackDesc) == 64 && sizeof(UnpackDesc) == 48 && sizeof(GnParamDesc) == 32,
+              "descriptor layouts are mirrored by ctypes structs in lib.py");
 int multi_launch(int code, const void* table, int n, int B, cudaStream_t st);
 int pack_w_launch(const float* w, int Cout, int Cin, int R, int S, __half* wp, int cin_pad, int ld_p, __half* wt,
                   int cout_pad, int ld_t, int t_mode, cudaStream_t st, int src_ld = 0);

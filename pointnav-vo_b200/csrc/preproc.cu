@@ -110,24 +110,30 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     s_max = 0;
   }
   __syncthreads();
-  // phase 1: any(depth > 0) per row / column (depth >= 0, so fp32 sum > 0 <=> any element > 0)
-  // 8 independent loads in flight per thread (the CTA is alone on its SM: latency, not bandwidth, bounds this scan)
-  for (int i0 = tid; i0 < n_cells; i0 += nt * 8) {
-    float dv[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = i0 + k * nt;
-      dv[k] = (i < n_cells) ? __ldg(D + static_cast<int64_t>(i) * ps) : 0.0f;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (dv[k] > 0.0f) {
-        const int i = i0 + k * nt;
-        const int r = i / W;
-        const int c = i - r * W;
-        if (!s_row_any[r]) s_row_any[r] = 1;
-        if (!s_col_any[c]) s_col_any[c] = 1;
+  // phase 1: any(depth > 0) per row / column (depth >= 0, so fp32 sum > 0 <=> any element > 0).  A warp owns whole
+  // rows (lanes over columns): the row flag is one ballot per 32 columns, the column flags are OR-ed in registers over
+  // the warp's rows and written once -- no per-pixel index arithmetic or shared-memory traffic (ncu: the kernel was
+  // instruction-issue bound, 236 instructions per pixel).
+  {
+    const int lane = tid & 31, wid = tid >> 5, n_warps = nt >> 5;
+    constexpr int kColChunks = 16;  // up to 512 columns
+    unsigned col_any = 0u;          // bit k: column lane + 32k of some row of this warp is > 0
+    for (int r = wid; r < H; r += n_warps) {
+      const float* row = D + static_cast<int64_t>(r) * W * ps;
+      bool any = false;
+#pragma unroll 4
+      for (int k = 0; k < kColChunks; ++k) {
+        const int c = lane + 32 * k;
+        if (c < W && __ldg(row + static_cast<int64_t>(c) * ps) > 0.0f) {
+          any = true;
+          col_any |= 1u << k;
+        }
       }
+      if (__any_sync(0xffffffffu, any) && lane == 0) s_row_any[r] = 1;
+    }
+    for (int k = 0; k < kColChunks; ++k) {
+      const int c = lane + 32 * k;
+      if (c < W && ((col_any >> k) & 1u)) s_col_any[c] = 1;
     }
   }
   __syncthreads();
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     const uint32_t wv = hist[i >> 1];
     const int c = (i & 1) ? static_cast<int>(wv >> 16) : static_cast<int>(wv & 0xFFFFu);
     float o = 0.0f;
-    if (mx > 0) o = fminf(__fdiv_rn(static_cast<float>(c), fm), 1.0f);
+    if (c > 0) o = fminf(__fdiv_rn(static_cast<float>(c), fm), 1.0f);  // c > 0 implies mx > 0; most cells are empty
     out[static_cast<int64_t>(i) * a.out_pix_stride] = o;
     if (cnt_out) cnt_out[i] = c;
   }
@@ -386,7 +392,7 @@ int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride,
                    int n_frames, int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
                    int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream) {
   PNVO_REQUIRE(depth && ray && consts && out, "topdown_project: null argument");
-  PNVO_REQUIRE(H > 0 && W > 0 && static_cast<int64_t>(H) * W <= 110000, "topdown_project: frame %dx%d too large", H, W);
+  PNVO_REQUIRE(H > 0 && W > 0 && W <= 512 && static_cast<int64_t>(H) * W <= 110000, "topdown_project: frame %dx%d too large", H, W);
   PNVO_REQUIRE(consts->rows_around_center * 2 * W < 65535, "topdown_project: too many points for uint16 counts");
   if (n_frames <= 0) return 0;
   TopDownArgs a;

@@ -211,3 +211,16 @@ def test_rollout_storage_generator_matches_per_env_gather():
             assert torch.equal(a, want(b))
     rs.after_update()
     assert rs.step == 0 and torch.equal(rs.masks[0], rs.masks[T])
+
+
+def test_descriptor_table_layouts_match_the_c_structs():
+    """The batched pack / unpack / GN-parameter-gradient launches read device tables of C structs (csrc/elem.cuh,
+    static_assert'ed there): the ctypes mirrors must have the same size and field offsets."""
+    import ctypes
+
+    from pointnav_vo_b200 import lib as L
+
+    assert ctypes.sizeof(L.PackDesc) == 64 and L.PackDesc.Cout.offset == 24 and L.PackDesc.src_ld.offset == 60
+    assert ctypes.sizeof(L.UnpackDesc) == 48 and L.UnpackDesc.Cout.offset == 16 and L.UnpackDesc.dst_ld.offset == 44
+    assert ctypes.sizeof(L.GnParamDesc) == 32 and L.GnParamDesc.C.offset == 24
+    assert ctypes.sizeof(L.PnvoOp) == 4 + 27 * 4 + 4 * 4 + 10 * 8
