@@ -196,6 +196,12 @@ class EncoderPlan:
         H, W = (self.H // 2, self.W // 2) if self.avgpool_input else (self.H, self.W)
         self.inH, self.inW = H, W
         self.cin_pad = _pow2(self.in_channels)
+        ow1 = (W + 6 - 7) // 2 + 1
+        if (not self.avgpool_input and not self.raw_fp32 and self.in_channels <= 32 and baseplanes == 32
+                and 128 <= ow1 <= 256):
+            # the stem kernels (conv_stem2.cu) work on 64-byte pixels: an 8-channel input (rgb + depth) is padded to 32
+            # zero channels rather than sent through the generic cp.async producer (measured 2.5 ms vs 0.5 ms at B=256)
+            self.cin_pad = 32
         self.convs, self.gns = {}, {}
         c1 = ConvLayer(pfx + ".conv1.0.weight", self.in_channels, baseplanes, 7, 7, 2, 3, H, W, need_dgrad=False,
                        cin_pad=self.cin_pad)

@@ -153,6 +153,39 @@ def _ddp_worker(rank, world, port, q):
         dist.all_gather_object(xs, x)
         full = torch.cat(xs)
         ok &= torch.allclose(mean, full.mean((0, 2, 3))) and torch.allclose(var, full.var((0, 2, 3), unbiased=False))
+        # DD-PPO (ddppo.py:18-96): advantage statistics over every rank, rank-0 weights, averaged gradients.  The
+        # mixin is host logic; a small torch module stands in for the CUDA actor-critic.
+        import types
+
+        from pointnav_vo_b200.rl.ppo.ppo import DDPPO, distributed_mean_and_var
+
+        v = torch.arange(6, dtype=torch.float32) + 10 * rank
+        m_all, var_all = distributed_mean_and_var(v)
+        allv = torch.cat([torch.arange(6, dtype=torch.float32) + 10 * r for r in range(world)])
+        ok &= torch.allclose(m_all, allv.mean()) and torch.allclose(var_all, allv.var(unbiased=False))
+        torch.manual_seed(100 + rank)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 1))
+        unused = torch.nn.Parameter(torch.ones(2))  # a parameter the loss never reaches (find_unused_parameters)
+        net.register_parameter("unused", unused)
+        agent = DDPPO(net, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.01,
+                      lr=1e-3, eps=1e-5, max_grad_norm=0.5)
+        agent.init_distributed()
+        w0 = [None] * world
+        dist.all_gather_object(w0, net[0].weight.detach().clone())
+        ok &= all(torch.equal(w0[0], w) for w in w0)  # every replica starts from rank 0's weights
+        xin = torch.full((5, 4), float(rank + 1))
+        loss = net(xin).sum()
+        net.zero_grad()
+        loss.backward()
+        local = net[0].weight.grad.clone()
+        agent.after_backward(loss)
+        grads = [None] * world
+        dist.all_gather_object(grads, local)
+        ok &= torch.allclose(net[0].weight.grad, sum(grads) / world) and bool(torch.all(net.unused.grad == 0))
+        rollouts = types.SimpleNamespace(returns=torch.arange(5.).view(5, 1, 1) + rank,
+                                         value_preds=torch.zeros(5, 1, 1))
+        adv = agent.get_advantages(rollouts)
+        ok &= adv.shape == (4, 1, 1)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
