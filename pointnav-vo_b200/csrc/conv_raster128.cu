@@ -1,0 +1,308 @@
+// 3x3 / stride 1 / pad 1 convolution with 128 input channels (layer3 of the GroupNorm ResNet-18/50 and the zero-upsampled
+// data gradient of layer3.0's stride-2 conv; resnet.py:11-26), forward and data gradient, on the shared-memory raster
+// of conv_raster.cu -- the variant for layers whose weights (9 x N x 256 B = 147-295 KB) do not fit next to the input.
+//
+// A unit = (sample, T output rows).  Its T+2 input rows are staged ONCE as two rasters of 128-byte pixels (channels
+// 0-63 / 64-127: two TMA boxes with a channel offset), all nine taps of all M tiles read them through shifted
+// descriptors, and the weights stream through a ring of [N][64-channel] stages in (tap, channel half) order; every
+// stage is used by ALL M tiles of the unit (one TMEM accumulator per tile), so a weight byte crosses L2 -> smem once
+// per unit instead of once per 128 output pixels.  L2 -> smem traffic per 128 outputs: 576 KB (im2col TMA kernel,
+// measured at the L2 -> SM ingest limit) -> ~130 KB.
+//   warp 13: TMA producer    warp 12: TMEM owner + MMA issuer    warps 0-11: epilogue, warpgroup g <-> M tile g
+#include "common.cuh"
+#include "ops.cuh"
+#include "tmap.cuh"
+
+namespace pnvo {
+
+struct Raster128Args {
+  __half* y;
+  const __half* add;
+  double* stats;
+  int B, H, W;
+  int cpg, G;
+  int P, T, n_tiles, rows_in;
+  int units_per_img, n_units;
+  int in_bytes;   // shared-memory bytes of ONE channel-half raster (multiple of 1024)
+  int w_stages;
+};
+
+static constexpr int kR128Threads = 12 * 32 + 64;
+
+template <int CPG, int OFF>
+__device__ __forceinline__ void r128_group_sums(const float* v, float* acc) {
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+      const float x = v[g * CPG + c];
+      a += x;
+      q = fmaf(x, x, q);
+    }
+    acc[OFF + 2 * g] += a;
+    acc[OFF + 2 * g + 1] += q;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Raster128Args p,
+                                                                       const __grid_constant__ ConvTmaps tm) {
+  constexpr int kWStage = N * 128;                 // one weight stage: [N][64 channels] fp16
+  constexpr int kTmemCols = 3 * N <= 256 ? 256 : 512;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_infull, s_inempty, s_accfull, s_accempty;
+  __shared__ __align__(8) uint64_t s_wfull[8];
+  __shared__ __align__(8) uint64_t s_wempty[8];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t sIn = smem_base;                                   // two channel-half rasters
+  const uint32_t sW = smem_base + 2 * p.in_bytes;                   // weight ring
+  const int ws = p.w_stages;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_infull), 1);
+    mbar_init(smem_u32(&s_inempty), 1);
+    mbar_init(smem_u32(&s_accfull), 1);
+    mbar_init(smem_u32(&s_accempty), 12);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(smem_u32(&s_wfull[s]), 1);
+      mbar_init(smem_u32(&s_wempty[s]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 12) {
+    tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const int n_tiles = p.n_tiles;
+
+  if (warp == 13) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      tma_prefetch_desc(&tm.a);
+      tma_prefetch_desc(&tm.b);
+      const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * 128u * 2u;
+      int i = 0, wctr = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        if (i >= 1) mbar_wait(smem_u32(&s_inempty), (i - 1) & 1);
+        const int b = u / p.units_per_img;
+        const int h0 = (u - b * p.units_per_img) * p.T;
+        const uint32_t bar = smem_u32(&s_infull);
+        mbar_arrive_expect_tx(bar, in_tx);
+        tma_load_4d(sIn, &tm.a, bar, 0, -1, h0 - 1, b);                 // channels 0..63
+        tma_load_4d(sIn + p.in_bytes, &tm.a, bar, 64, -1, h0 - 1, b);   // channels 64..127
+        for (int st = 0; st < 18; ++st, ++wctr) {                       // (tap, channel half) stages
+          const int s = wctr % ws;
+          if (wctr >= ws) mbar_wait(smem_u32(&s_wempty[s]), ((wctr / ws) & 1) ^ 1);
+          const uint32_t wbar = smem_u32(&s_wfull[s]);
+          mbar_arrive_expect_tx(wbar, kWStage);
+          tma_load_2d(sW + s * kWStage, &tm.b, wbar, st * 64, 0);       // K offset (tap * 128 + half * 64) == st * 64
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, N, 0, 0);
+      const uint64_t d0 = umma_desc(0, 16, 1024, 128);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
+      int i = 0, wctr = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        mbar_wait(smem_u32(&s_infull), i & 1);
+        if (i >= 1) mbar_wait(smem_u32(&s_accempty), (i - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int st = 0; st < 18; ++st, ++wctr) {
+          const int s = wctr % ws;
+          mbar_wait(smem_u32(&s_wfull[s]), (wctr / ws) & 1);
+          tc_fence_after();
+          const int tap = st >> 1, half = st & 1;
+          const uint32_t a_lo = lo0 + ((sIn + half * p.in_bytes) >> 4) + static_cast<uint32_t>((tap / 3) * p.P + (tap % 3)) * 8u;
+          const uint32_t b_lo = lo0 + ((sW + s * kWStage) >> 4);
+          for (int t = 0; t < n_tiles; ++t) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16_lohi(tmem_base + t * N, a_lo + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc,
+                              (st | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&s_wempty[s]));
+        }
+        tc_commit(smem_u32(&s_accfull));
+        tc_commit(smem_u32(&s_inempty));
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================================ epilogue: warpgroup g drains M tile g ================================
+    const int grp = warp >> 2;
+    const int row = tid & 127;
+    const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int valid_pos = p.T * p.P;
+    int i = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+      const int b = u / p.units_per_img;
+      const int h0 = (u - b * p.units_per_img) * p.T;
+      float acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+      mbar_wait(smem_u32(&s_accfull), i & 1);
+      tc_fence_after();
+      if (grp < n_tiles) {
+        const int m = 128 * grp + row;
+        const int orow = m / p.P;
+        const int ocol = m - orow * p.P;
+        const int oh = h0 + orow;
+        const bool valid = (m < valid_pos) && (ocol < p.W) && (oh < p.H);
+        const int64_t gofs = ((static_cast<int64_t>(b) * p.H + oh) * p.W + ocol) * N;
+#pragma unroll
+        for (int ch = 0; ch < N / 32; ++ch) {
+          float v[32];
+          tmem_ld32(tmem_base + t_lane + grp * N + ch * 32, v);
+          tmem_ld_wait();
+          if (p.add && valid) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.add + gofs + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 uu = __ldg(ap + q);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&uu);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                v[q * 8 + 2 * e] += f.x;
+                v[q * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.stats && valid) {
+            // cpg = N / 16 (8 or 4): a 32-column chunk carries 32 / cpg groups starting at group ch * 32 / cpg
+            if (p.cpg == 8) {
+              if (ch == 0) r128_group_sums<8, 0>(v, acc);
+              else if (ch == 1) r128_group_sums<8, 8>(v, acc);
+              else if (ch == 2) r128_group_sums<8, 16>(v, acc);
+              else r128_group_sums<8, 24>(v, acc);
+            } else {
+              if (ch == 0) r128_group_sums<4, 0>(v, acc);
+              else r128_group_sums<4, 16>(v, acc);
+            }
+          }
+          if (valid) {
+            __half* yp = p.y + gofs + ch * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 uu;
+              __half2* h2 = reinterpret_cast<__half2*>(&uu);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(yp + q * 8) = uu;
+            }
+          }
+        }
+      }
+      // accumulators drained (or not used by this group): hand them back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_accempty));
+      if (p.stats && grp < n_tiles) {
+        int off = 16;
+#pragma unroll
+        for (int cnt = 16; cnt >= 1; cnt >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int k = 0; k < cnt; ++k) {
+            const float send = up ? acc[k] : acc[k + cnt];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+            acc[k] = (up ? acc[k + cnt] : acc[k]) + recv;
+          }
+          off >>= 1;
+        }
+        if (lane < 2 * p.G) atomicAdd(p.stats + static_cast<int64_t>(b) * p.G * 2 + lane, static_cast<double>(acc[0]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes) {
+  if (a.R != 3 || a.S != 3 || a.mul != 1 || a.div != 1 || a.pad != 1 || a.pad_w != 1) return false;
+  if (a.IH != a.OH || a.IW != a.OW) return false;
+  // N = 64 (the zero-upsampled data gradient of layer3.0 at 24x43) was measured slower here than on the im2col kernel
+  // (95 vs 86 us at B = 256: single-buffered accumulators + the accumulate-input reads in the epilogue): N = 128 only
+  if (a.Cin != 128 || a.n_total != 128) return false;
+  if (a.n_store != a.n_total || a.ldo != a.n_total || a.out_fp32) return false;
+  if (a.w_ld < 9 * a.Cin) return false;
+  if (a.stats && (a.G != 16 || a.G * a.cpg != a.n_total)) return false;
+  const int P = a.IW + 2;
+  if (P > 256 || a.IW < 8 || a.IH < 4) return false;
+  const int w_stage = a.n_total * 128;
+  double best = -1.0;
+  for (int T = 2; T <= std::min(a.IH, 64); ++T) {
+    const int rows_in = T + 2;
+    const int n_tiles = ceil_div(T * P, 128);
+    if (n_tiles > 3) break;
+    const int positions = std::max(rows_in * P, n_tiles * 128 + 2 * P + 2);
+    const int in_bytes = (positions * 128 + 1023) & ~1023;
+    const int stages = std::min(8, (200 * 1024 - 2 * in_bytes) / w_stage);
+    if (stages < 3) break;
+    const int upi = ceil_div(a.IH, T);
+    const int n_units = a.B * upi;
+    const int waves = ceil_div(n_units, 148);
+    const double balance = n_units >= 148 ? static_cast<double>(n_units) / (waves * 148.0) : 1.0;
+    const double eff = (static_cast<double>(a.IH) * a.IW) / (static_cast<double>(upi) * n_tiles * 128) * balance *
+                       (1.0 - 0.15 * 2.0 / (T + 2));
+    if (eff > best + 1e-9) {
+      best = eff;
+      r.P = P; r.T = T; r.n_tiles = n_tiles; r.rows_in = rows_in; r.units_per_img = upi; r.n_units = n_units;
+      r.in_bytes = in_bytes; r.w_stages = stages;
+      smem_bytes = 2 * in_bytes + stages * w_stage + 1024;
+    }
+  }
+  if (best < 0.5) return false;
+  r.y = static_cast<__half*>(a.y); r.add = a.add; r.stats = a.stats;
+  r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
+  return true;
+}
+
+int conv_raster128_supported(const ConvArgs& a) {
+  Raster128Args r{};
+  int smem = 0;
+  return raster128_plan(a, r, smem) ? 1 : 0;
+}
+
+template <int N>
+static int raster128_launch_t(const Raster128Args& r, const ConvTmaps& tm, int smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_raster128_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    attr = true;
+  }
+  conv_raster128_kernel<N><<<std::min(r.n_units, 148), kR128Threads, smem, st>>>(r, tm);
+  count_launch();
+  return check_launch("conv_raster128");
+}
+
+int conv_raster128_launch(const ConvArgs& a, cudaStream_t st) {
+  Raster128Args r{};
+  int smem = 0;
+  PNVO_REQUIRE(raster128_plan(a, r, smem), "conv_raster128: unsupported geometry");
+  if (a.B <= 0) return 0;
+  alignas(64) ConvTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (tmap_tiled4d(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, r.P, 128, r.rows_in, 64)) return -1;
+  if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.n_total, 64)) return -1;
+  if (a.n_total == 64) return raster128_launch_t<64>(r, tm, smem, st);
+  return raster128_launch_t<128>(r, tm, smem, st);
+}
+
+}  // namespace pnvo

@@ -27,6 +27,9 @@ int conv_plan(ConvArgs& a);
 // conv_raster.cu: persistent no-im2col kernel for 3x3 / stride 1 / pad 1 with 32 or 64 channels
 int conv_raster_supported(const ConvArgs& a);
 int conv_raster_launch(const ConvArgs& a, cudaStream_t st);
+// conv_raster128.cu: the same raster for 128 input channels, weights streamed through a ring shared by all M tiles
+int conv_raster128_supported(const ConvArgs& a);
+int conv_raster128_launch(const ConvArgs& a, cudaStream_t st);
 int conv_launch(ConvArgs a, cudaStream_t st);
 
 struct WgradArgs {

@@ -79,10 +79,12 @@ int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int
   return 0;
 }
 
-int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w, int swizzle_bytes, int box_h) {
+int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w, int swizzle_bytes, int box_h,
+                 int box_c) {
+  if (box_c <= 0) box_c = C;
   std::lock_guard<std::mutex> lk(g_mu);
   if (resolve()) return -1;
-  std::vector<int64_t> key = {3, reinterpret_cast<int64_t>(x), N, H, W, C, box_w, swizzle_bytes, box_h};
+  std::vector<int64_t> key = {3, reinterpret_cast<int64_t>(x), N, H, W, C, box_w, swizzle_bytes, box_h, box_c};
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     *out = it->second;
@@ -93,7 +95,7 @@ int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, in
                               static_cast<cuuint64_t>(N)};
   const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
                                  static_cast<cuuint64_t>(H) * W * C * 2};
-  const cuuint32_t box[4] = {static_cast<cuuint32_t>(C), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = g_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE,

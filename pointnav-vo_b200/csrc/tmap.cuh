@@ -21,7 +21,7 @@ int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int
 // NHWC fp16 activations [N, H, W, C]: plain tiled boxes of box_w pixels x C channels of one image row,
 // SWIZZLE_128B (C*2 <= 128 bytes), out-of-range pixels / rows zero-filled
 int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w, int swizzle_bytes = 128,
-                 int box_h = 1);
+                 int box_h = 1, int box_c = 0);  // box_c: channels per box (0 = all C)
 // row-major fp16 matrix [rows, ld] (cols valid columns); box = box_rows x box_cols
 int tmap_tiled2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                  int box_cols);

@@ -133,6 +133,7 @@ CONV_CASES = [
     ("layer3.0 3x3s2 64->128 (odd width)", 3, 64, 128, 3, 3, 2, 1, 24, 43, 16, True, None),
     ("layer3.0 down 1x1s2 64->128 (odd width)", 3, 64, 128, 1, 1, 2, 0, 24, 43, 16, True, None),
     ("layer3 3x3s1 128->128", 3, 128, 128, 3, 3, 1, 1, 12, 22, 16, True, None),
+    ("raster128 many units 128->128", 300, 128, 128, 3, 3, 1, 1, 12, 22, 16, True, None),
     ("layer4 3x3s1 256->256", 3, 256, 256, 3, 3, 1, 1, 6, 11, 16, True, None),
     ("compression 256->31", 3, 256, 31, 3, 3, 1, 1, 6, 11, 1, True, None),
     ("policy conv1 1->32", 2, 1, 32, 7, 7, 2, 3, 96, 170, 16, False, None),
