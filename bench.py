@@ -164,6 +164,8 @@ def run_b200(args):
             "target": torch.from_numpy(tgt).pin_memory()}
     pipe = PrefetchedBatches(host, dev)
     pre = DevicePreproc(B, dev) if args.inputs == "dict" else None
+    # input pipeline of batch i+1 (top-down, statistics, assembly) on a side stream, under the kernels of step i
+    prefetch = pre is None and not args.no_prefetch
 
     def to_obs(devb):
         if pre is not None:
@@ -183,7 +185,9 @@ def run_b200(args):
             if i + 1 < n:
                 pipe.submit(host)
             devb = pipe.acquire()
-            loss = trainer.step(to_obs(devb), devb["target"])
+            nxt = pipe.peek_next() if (prefetch and i + 1 < n) else None
+            loss = trainer.step(to_obs(devb), devb["target"], prefetch=to_obs(nxt[0]) if nxt else None,
+                                prefetch_ready=nxt[1] if nxt else None)
             pipe.release()
             h_loss[i & 1].copy_(loss, non_blocking=True)  # D2H read of the step's result
             loss_ready[i & 1].record()
@@ -236,11 +240,12 @@ def run_b200(args):
                               "ms_per_step": round(ms_f, 3),
                               "forward_tflops": round(world * B * GFLOP_FWD * 1e9 / (ms_f * 1e-3) / 1e12, 1)}), flush=True)
         model.train()
+    pf = obs if prefetch else None
     for _ in range(args.warmup):
-        trainer.step(obs, d_tgt)
+        trainer.step(obs, d_tgt, prefetch=pf)
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = L.launch_count()
-    ms = timed(lambda: trainer.step(obs, d_tgt), args.steps)
+    ms = timed(lambda: trainer.step(obs, d_tgt, prefetch=pf), args.steps)
     launches = L.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     loss_val = float(trainer._loss[0].item())
@@ -383,6 +388,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inputs", default="raw", choices=["raw", "dict"])
+    ap.add_argument("--no-prefetch", action="store_true", help="do not run the next batch's input pipeline on a side stream")
     ap.add_argument("--model", default="r18_30ch", choices=["r18_30ch", "r50_8ch"],
                     help="r18_30ch = the shipped default VO model (the headline); r50_8ch = ResNet-50 rgb+depth (BASELINE "
                          "configs[2]/[3]), reported for the record -- roofline / cpu_baseline fields describe r18_30ch only")

@@ -564,6 +564,29 @@ class EncoderPlan:
         self.bwd_prog = L.Program(ops, graph=True)
 
     # ------------------------------------------------------------------------------------------
+    # ------------------------------------------------------------------------------------------
+    # Double-buffered input staging: programs_for(1) replays the forward / backward programs over a SECOND assembled
+    # input tensor x0, so the preprocessing of batch i+1 (top-down, statistics, assembly: HBM-bound, 14 % of a step)
+    # can run on a side stream while the tensor-core kernels of step i read the first one.
+    def x0_for(self, parity):
+        if parity == 0:
+            return self.x0
+        if getattr(self, "x0_alt", None) is None:
+            self.x0_alt = torch.zeros_like(self.x0)
+        return self.x0_alt
+
+    def programs_for(self, parity):
+        if parity == 0:
+            return self.fwd_prog, (self.bwd_prog if self.training else None)
+        if getattr(self, "_alt_progs", None) is None:
+            alt = self.x0_for(1)
+            off = self.x0_img.data_ptr() - self.x0.data_ptr()
+            mapping = {self.x0.data_ptr(): alt.data_ptr(), self.x0.data_ptr() + off: alt.data_ptr() + off}
+            fwd = L.Program(L.patch_ops(self.fwd_ops, mapping), graph=True)
+            bwd = L.Program(L.patch_ops(self.bwd_ops, mapping), graph=True) if self.training else None
+            self._alt_progs = (fwd, bwd)
+        return self._alt_progs
+
     def input_ops(self, obs):
         """avg-pool input path of the RL encoder (resnet_policy.py:146-168): sources are pooled 2x2 and written
         into the channel slots of x0 (pad channels stay zero)."""

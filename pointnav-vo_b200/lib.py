@@ -364,6 +364,21 @@ class Program:
                 pass
 
 
+def patch_ops(ops, mapping):
+    """Copies of `ops` with every pointer slot that equals a key of `mapping` replaced by its value: the same program
+    over an alternate buffer (e.g. the second input staging buffer of a double-buffered pipeline)."""
+    out = []
+    for op in ops:
+        c = PnvoOp()
+        ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(PnvoOp))
+        for k in range(10):
+            v = c.p[k]
+            if v is not None and v in mapping:
+                c.p[k] = mapping[v]
+        out.append(c)
+    return out
+
+
 def run_ops(ops, device=None):
     Program(list(ops)).run(device)
 

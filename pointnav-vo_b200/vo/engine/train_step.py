@@ -55,6 +55,14 @@ class PrefetchedBatches:
         self._held = s
         return self.bufs[s]
 
+    def peek_next(self):
+        """(device tensors, ready event) of the batch AFTER the one currently held, if it has been submitted: lets the
+        trainer start that batch's input pipeline on a side stream as soon as its copy has landed."""
+        if self.pending < 2:
+            return None
+        s = (self._held + 1) % len(self.bufs)
+        return self.bufs[s], self.ready[s]
+
     def release(self):
         s = self._held
         self.free[s].record(torch.cuda.current_stream(self.dev))
@@ -79,6 +87,12 @@ class FusedVOTrainStep:
         self.step_count = 0
         self._flat = None
         self._plan = None
+        # double-buffered input staging (step(..., prefetch=next_obs)): side stream, per-buffer events
+        self._side = None
+        self._parity = 0
+        self._prefetched = None   # (obs identity, parity) prepared ahead on the side stream
+        self._staged = [None, None]   # event: input buffer `parity` holds a prepared batch
+        self._consumed = [None, None]  # event: the step that read input buffer `parity` has finished
 
     # parameters are re-pointed into one flat fp32 buffer ordered like the plan's gradient bucket, so the
     # optimiser and the all-reduce each touch a single contiguous range
@@ -123,25 +137,71 @@ class FusedVOTrainStep:
             self._plan = plan
         return plan
 
-    def step(self, obs, target, actions=None):
+    def _prefetch(self, plan, obs, parity, ready=None):
+        """Input pipeline (top-down, statistics, assembly) of a FUTURE batch into staging buffer `parity`, on the side
+        stream: it only depends on the data, not on the weights, so it overlaps the current step's kernels."""
+        dev = plan.dev
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        if self._consumed[parity] is not None:
+            self._side.wait_event(self._consumed[parity])  # the step that read this buffer last is done with it
+        else:
+            self._side.wait_stream(torch.cuda.current_stream(dev))
+        if ready is not None:
+            self._side.wait_event(ready)  # e.g. the host->device copy of that batch
+        with torch.cuda.stream(self._side):
+            self.model._run_forward_raw(plan, obs, self.model.training, parity=parity, prepare_only=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._staged[parity] = ev
+        self._prefetched = (tuple(id(v) for v in obs.values()), parity)
+
+    def step(self, obs, target, actions=None, prefetch=None, prefetch_ready=None):
         """obs: dict of NHWC fp32 CUDA tensors (the model's forward input), or the raw pairs
         {"rgb": uint8 [B,H,W,6], "depth": fp32 [B,H,W,2]} (derived channels computed on the device);
-        target: [B, 3] fp32 CUDA.  Returns the (device) loss tensor of this rank's batch."""
+        target: [B, 3] fp32 CUDA.  prefetch: the NEXT step's raw pairs -- their input pipeline is started on a side
+        stream into the alternate staging buffer and overlaps this step (the next call must pass the same tensors as
+        `obs`); prefetch_ready: optional event the side stream waits for first (the batch's host->device copy).
+        Returns the (device) loss tensor of this rank's batch."""
         model = self.model
         plan = self._get_plan(obs)
+        dev = plan.dev
+        main = torch.cuda.current_stream(dev)
         self._target.copy_(target)
         if self.loss_inv_weight > 0:
             if actions is None:
                 raise L.PnvoError("the geometric-inversion loss needs the per-row action ids")
             self._actions.copy_(actions.reshape(-1))
-        model._run_forward(plan, obs, model.training)
-        self._loss_prog.run(plan.dev)
-        plan.bwd_prog.run(plan.dev)
+        key = tuple(id(v) for v in obs.values())
+        if self._prefetched is not None and self._prefetched[0] == key and model._is_raw(obs):
+            parity = self._prefetched[1]
+            main.wait_event(self._staged[parity])   # inputs were assembled ahead of time
+            self._prefetched = None
+            if prefetch is not None:
+                self._prefetch(plan, prefetch, 1 - parity, prefetch_ready)
+            model._run_backbone(plan, parity)
+        else:
+            parity = self._parity
+            self._prefetched = None
+            if model._is_raw(obs):
+                model._run_forward_raw(plan, obs, model.training, parity=parity, prepare_only=True)
+                if prefetch is not None:
+                    self._prefetch(plan, prefetch, 1 - parity, prefetch_ready)
+                model._run_backbone(plan, parity)
+            else:
+                parity = 0
+                model._run_forward(plan, obs, model.training)
+        self._parity = 1 - parity if prefetch is not None else parity
+        self._loss_prog.run(dev)
+        plan.programs_for(parity)[1].run(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._consumed[parity] = ev
         if self.world > 1:
             torch.distributed.all_reduce(plan.grad_flat, group=self.group)
         self.step_count += 1
         L.run_ops([L.op_adam(self._flat, plan.grad_flat, self._m, self._v, self._flat.numel(), self.step_count, self.lr,
-                             self.betas[0], self.betas[1], self.eps)], plan.dev)
+                             self.betas[0], self.betas[1], self.eps)], dev)
         # the optimiser wrote through raw pointers: tell the module its packed fp16 weights are stale
         model._packed_version = None
         return self._loss[:1]

@@ -208,7 +208,9 @@ class VisualOdometryCNNBase(nn.Module):
     def _weights_version(self):
         return sum(p._version for p in self.parameters())
 
-    def _run_forward_raw(self, plan, obs, training):
+    def _run_forward_raw(self, plan, obs, training, parity=0, prepare_only=False):
+        """parity selects the input staging buffer (engine.EncoderPlan.x0_for); prepare_only stops after the input
+        pipeline (top-down, statistics, assembly) so that it can run ahead of the backbone on a side stream."""
         from ...utils import geometry_utils as gu
 
         enc = self.visual_encoder
@@ -259,12 +261,13 @@ class VisualOdometryCNNBase(nn.Module):
         else:
             scale = shift = None
         ops.append(L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
-                                     scale, shift, plan.x0, row_w=plan.W if plan.x0_pitch else 0,
+                                     scale, shift, plan.x0_for(parity), row_w=plan.W if plan.x0_pitch else 0,
                                      out_pitch=plan.x0_pitch))
         L.run_ops(ops, dev)
-        self._run_backbone(plan)
+        if not prepare_only:
+            self._run_backbone(plan, parity)
 
-    def _run_backbone(self, plan):
+    def _run_backbone(self, plan, parity=0):
         if getattr(self, "_embed", None):
             acts = self._cur_actions
             if not acts.is_cuda:
@@ -274,7 +277,7 @@ class VisualOdometryCNNBase(nn.Module):
         if ver != self._packed_version or plan is not getattr(self, "_packed_plan", None):
             plan.pack_prog.run(plan.dev)
             self._packed_version, self._packed_plan = ver, plan
-        plan.fwd_prog.run(plan.dev)
+        plan.programs_for(parity)[0].run(plan.dev)
 
     def _run_forward(self, plan, obs, training):
         if self._is_raw(obs):

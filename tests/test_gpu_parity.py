@@ -698,3 +698,35 @@ def test_vo_inference_in_the_rl_loop():
     batched = trainer.compute_local_delta_states_batched(prev, cur, acts)
     assert batched.shape == (3, 3)
     assert rel(batched, torch.tensor(np.array(singles))) <= 8e-3
+
+
+def test_train_step_with_prefetched_input_pipeline():
+    """Double-buffered input staging: running the NEXT batch's input pipeline on a side stream (alternate staging buffer,
+    pointer-patched forward / backward programs) must not change the training trajectory."""
+    import copy
+
+    from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+    m1, space, _ = _load_vo("r18_30ch")
+    m2 = copy.deepcopy(m1)
+    m1.train()
+    m2.train()
+    count0 = float(m1.visual_encoder.running_mean_and_var._count)
+    batches = []
+    for k in range(4):
+        o = helpers.vo_inputs(2, 40 + k, space, "cuda")
+        batches.append(({"rgb": o["rgb"].to(torch.uint8).contiguous(), "depth": o["depth"].contiguous()},
+                        torch.randn(2, 3, device="cuda") * 0.1))
+    s1, s2 = FusedVOTrainStep(m1), FusedVOTrainStep(m2)
+    l1, l2 = [], []
+    for k, (obs, tgt) in enumerate(batches):
+        l1.append(s1.step(obs, tgt).item())
+        nxt = batches[k + 1][0] if k + 1 < len(batches) else None
+        l2.append(s2.step(obs, tgt, prefetch=nxt).item())
+    torch.cuda.synchronize()
+    for a, b in zip(l1, l2):
+        assert abs(a - b) <= 2e-2 * abs(a) + 1e-6, (l1, l2)  # dW atomics differ in the last bit; Adam amplifies sign flips
+    assert abs(l1[0] - l2[0]) <= 1e-6 * abs(l1[0])            # the first step sees identical weights: bit-equal forward
+    r1, r2 = m1.visual_encoder.running_mean_and_var, m2.visual_encoder.running_mean_and_var
+    assert float(r1._count) == float(r2._count) == count0 + 8.0
+    assert rel(r2._mean, r1._mean) <= 1e-6 and rel(r2._var, r1._var) <= 1e-6
