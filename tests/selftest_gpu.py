@@ -2,8 +2,8 @@
 """GPU bring-up harness: runs every kernel check in its own subprocess (a hang in one kernel cannot
 take the others down), prints error metrics instead of stopping at the first failure.
 
-    python tools/selftest.py                 # all checks, each under a timeout
-    python tools/selftest.py --check conv_fwd
+    python tests/selftest_gpu.py                 # all checks, each under a timeout
+    python tests/selftest_gpu.py --check conv_fwd
 """
 import argparse
 import os
