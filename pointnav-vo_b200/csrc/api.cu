@@ -69,6 +69,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.shift = static_cast<const float*>(p[5]);
       if (op.code == PNVO_OP_ASSEMBLE) {
         a.out = static_cast<__half*>(p[6]);
+        a.out_lo = static_cast<__half*>(p[7]);  // split-fp16 residual plane (nullable)
         return assemble_launch(a, st);
       }
       return input_stats_launch(a, static_cast<double*>(p[6]), st);
@@ -100,8 +101,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                                static_cast<float*>(p[2]), static_cast<float*>(p[3]), i[0], i[1], i[2],
                                static_cast<float*>(p[4]), static_cast<float*>(p[5]), st);
     case PNVO_OP_CONV: {
-      // p0 = x, p1 = w, p2 = y, p3 = add, p4 = stats
+      // p0 = x, p1 = w, p2 = y, p3 = add, p4 = stats, p5 = x_lo, p6 = w_lo (split-fp16 mode)
       ConvArgs a{};
+      a.x_lo = static_cast<const __half*>(p[5]);
+      a.w_lo = static_cast<const __half*>(p[6]);
       a.x = static_cast<const __half*>(p[0]);
       a.w = static_cast<const __half*>(p[1]);
       a.y = p[2];
@@ -130,6 +133,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.x = p[0]; a.stats = static_cast<const double*>(p[1]); a.gamma = static_cast<const float*>(p[2]);
       a.beta = static_cast<const float*>(p[3]); a.res = static_cast<const __half*>(p[4]);
       a.y = static_cast<__half*>(p[5]);
+      a.y_lo = static_cast<__half*>(p[7]); a.res_lo = static_cast<const __half*>(p[8]);  // split-fp16 planes (nullable)
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.relu = i[5]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1];
       if (op.code == PNVO_OP_GN_APPLY) return gn_apply_launch(a, i[0], st);
@@ -223,9 +227,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                          (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), f[0],
                          f[1], f[2], f[3], i[2], 1.0f, st);
     case PNVO_OP_AVGPOOL2:
-      // p0 = src fp32 NHWC, p1 = out fp16; i0 = B, i1 = H, i2 = W, i3 = C, i4 = Cpad, i5 = coff; f0 = pre_scale
+      // p0 = src fp32 NHWC, p1 = out fp16, p2 = out_lo (split-fp16 residual plane, nullable);
+      // i0 = B, i1 = H, i2 = W, i3 = C, i4 = Cpad, i5 = coff; f0 = pre_scale
       return avgpool2_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], f[0], static_cast<__half*>(p[1]),
-                             i[4], i[5], st);
+                             i[4], i[5], st, static_cast<__half*>(p[2]));
     default:
       set_error("run_ops: unknown opcode %d", op.code);
       return -3;

@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
   const uint32_t row_bytes = static_cast<uint32_t>(p.chunk_k) * 2;  // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, Cin = 32)
   const uint32_t a_bytes = kTileM * row_bytes;
   const uint32_t b_bytes = static_cast<uint32_t>(p.N) * row_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const bool split = p.x_lo != nullptr;  // stage = {A, B} or {A, B, A_lo, B_lo}
+  const uint32_t pair_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = split ? 2 * pair_bytes : pair_bytes;
   // dynamic smem base rounded up to 1024 B (128B swizzle atoms repeat every 1024 B)
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
     const int nb_rows = p.N >> 4;  // B rows handled by this thread: rsub + 16 i
     const __half* wrow = p.w + static_cast<int64_t>(n0 + rsub) * p.w_ld + j * 8;
     const int64_t w_step = static_cast<int64_t>(16) * p.w_ld;
+    const int64_t lo_dx = split ? (p.x_lo - p.x) : 0, lo_dw = split ? (p.w_lo - p.w) : 0;
 
     auto issue_stage = [&](int kb) {
       const int s = kb % stages;
@@ -215,6 +218,14 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
       }
       const __half* wsrc = wrow + kb * kTileK;
       for (int i = 0; i < nb_rows; ++i) cp_async_16(sB + i * 2048, wsrc + i * w_step, 16u);
+      if (split) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = ((tmask[i] >> tap) & kvalid) != 0ull;
+          cp_async_16(sA + pair_bytes + i * 2048, rowptr[i] + toff + lo_dx, ok ? 16u : 0u);
+        }
+        for (int i = 0; i < nb_rows; ++i) cp_async_16(sB + pair_bytes + i * 2048, wsrc + i * w_step + lo_dw, 16u);
+      }
     };
 
     const int nkb = p.nkb;
@@ -325,6 +336,14 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
           tc_mma_f16(tmem_base, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                      (kb | k) != 0 ? 1u : 0u);
         }
+        if (split) {  // + x_lo * w + x * w_lo (the lo * lo term is below fp32 resolution)
+          const uint64_t alo = umma_desc(sA + pair_bytes, 16, 8 * row_bytes, row_bytes);
+          const uint64_t blo = umma_desc(sA + pair_bytes + a_bytes, 16, 8 * row_bytes, row_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            tc_mma_f16(tmem_base, alo + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc, 1u);
+            tc_mma_f16(tmem_base, adesc + static_cast<uint64_t>(k * 2), blo + static_cast<uint64_t>(k * 2), idesc, 1u);
+          }
+        }
         tc_commit(smem_u32(&s_empty[s]));  // frees the smem stage once these MMAs have read it
       }
       tc_commit(smem_u32(&s_accum));  // accumulator complete -> epilogue
@@ -362,14 +381,17 @@ int conv_plan(ConvArgs& a) {
   a.M = a.B * a.OH * a.OW;
   a.K = a.R * a.S * a.Cin;
   // TMA im2col path: unit "dilation" (div == 1), square filter / symmetric padding, channels in chunks of 32 or 64
-  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1) ? 1 : 0;
+  const bool split = a.x_lo != nullptr;
+  PNVO_REQUIRE((a.x_lo != nullptr) == (a.w_lo != nullptr), "conv: split mode needs both x_lo and w_lo");
+  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1 && !split) ? 1 : 0;
   a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : kTileK;
   a.nkb = ceil_div(a.K, a.chunk_k);
   PNVO_REQUIRE(a.w_ld >= a.nkb * a.chunk_k, "conv: packed weight row stride %d < padded K %d", a.w_ld, a.nkb * a.chunk_k);
   // N tile: whole Cout when <= 256, else the largest divisor <= 256 that is a multiple of 32
   int N = a.n_total;
-  if (N > 256) {
-    N = 256;
+  const int n_max = split ? 128 : 256;  // split stages hold four tiles: keep >= 2 stages in shared memory
+  if (N > n_max) {
+    N = n_max;
     while (a.n_total % N) N -= 32;
   }
   a.N = N;
@@ -379,11 +401,12 @@ int conv_plan(ConvArgs& a) {
     PNVO_REQUIRE(a.cpg <= 32 || N % 32 == 0, "conv: bad group tiling");
     PNVO_REQUIRE(N % 32 == 0, "conv: GroupNorm statistics need Cout %% 32 == 0 (got %d)", N);
   }
-  const int stage_bytes = (kTileM + N) * a.chunk_k * 2;
+  const int stage_bytes = (kTileM + N) * a.chunk_k * 2 * (split ? 2 : 1);
   // two CTAs per SM when a >= 4-stage ring fits in ~100 KB, else one CTA with a deep ring
   int stages = std::min(8, (100 * 1024) / stage_bytes);
   if (stages < 4) stages = std::min(6, (198 * 1024) / stage_bytes);
   if (a.nkb < stages) stages = std::max(2, a.nkb);
+  PNVO_REQUIRE(stages >= 2, "conv: stage of %d bytes does not fit twice in shared memory", stage_bytes);
   a.stages = stages;
   a.lookahead = std::max(1, std::min(4, stages - 2));
   a.smem_bytes = stages * stage_bytes + 1024;
@@ -393,6 +416,7 @@ int conv_plan(ConvArgs& a) {
 }
 
 int conv_launch(ConvArgs a, cudaStream_t st) {
+  if (a.x_lo || a.w_lo) a.force_generic = 1;  // split-fp16 operands: only the cp.async producer stages the lo planes
   if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster_supported(a)) return conv_raster_launch(a, st);
   if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster128_supported(a)) return conv_raster128_launch(a, st);
   if (conv_plan(a)) return -1;

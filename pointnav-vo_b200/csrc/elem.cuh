@@ -17,6 +17,7 @@ struct AssembleArgs {
   const float* scale;      // per output channel (nullable = 1)
   const float* shift;      // per output channel (nullable = 0)
   __half* out;             // [n_pix][Cpad], or W-padded rows when out_pitch > 0
+  __half* out_lo;          // split-fp16 mode (nullable): value - fp16(value), same layout as out
   int64_t n_pix;
   int row_w, out_pitch;    // pixels per image row / pixels per padded output row (image starts at pixel 3)
 };
@@ -25,7 +26,7 @@ int input_stats_launch(const AssembleArgs& a, double* stats, cudaStream_t st);
 int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample, float* mean, float* var,
                       float* count, int C, int update, int have_rmv, float* scale, float* shift, cudaStream_t st);
 int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
-                    cudaStream_t st);
+                    cudaStream_t st, __half* out_lo = nullptr);
 int zero_launch(void* p, int64_t bytes, cudaStream_t st);
 int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int IH, int IW, int C, cudaStream_t st);
 // raw_input.cu: PNVO_OP_RAW_STATS / PNVO_OP_RAW_ASSEMBLE (field layout documented there)
@@ -41,6 +42,8 @@ struct GnArgs {
   const float* beta;   // [C]
   const __half* res;   // optional residual [B*HW][C]
   __half* y;           // [B*HW][C] (or pooled)
+  __half* y_lo;        // split-fp16 mode (nullable): residual plane y_fp32 - fp16(y_fp32), same layout as y
+  const __half* res_lo; // residual plane of `res` (nullable)
   int C, C_real, G, cpg, HW;
   float cnt;           // elements per group = cpg_real * HW
   float eps;

@@ -108,6 +108,17 @@ __global__ void __launch_bounds__(kAsmPix) assemble_kernel(const AssembleArgs a)
         h2[e] = __floats2half2_rn(fmaf(v[c], s_scale[c], s_shift[c]), fmaf(v[c + 1], s_scale[c + 1], s_shift[c + 1]));
       }
       *reinterpret_cast<uint4*>(out + q * 8) = u;
+      if (a.out_lo) {  // split-fp16 residual plane
+        uint4 ul;
+        __half2* l2 = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = q * 8 + 2 * e;
+          const float x0 = fmaf(v[c], s_scale[c], s_shift[c]), x1 = fmaf(v[c + 1], s_scale[c + 1], s_shift[c + 1]);
+          l2[e] = __floats2half2_rn(x0 - __low2float(h2[e]), x1 - __high2float(h2[e]));
+        }
+        *reinterpret_cast<uint4*>(a.out_lo + opix * a.Cpad + q * 8) = ul;
+      }
     }
   }
 }
@@ -286,7 +297,8 @@ int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int 
 // 2x2 average pool of fp32 NHWC sources -> fp16 NHWC (policy encoder, resnet_policy.py:146-168)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ src, int B, int H, int W, int C,
-                                                       float pre_scale, __half* __restrict__ out, int Cpad, int coff) {
+                                                       float pre_scale, __half* __restrict__ out, int Cpad, int coff,
+                                                       __half* __restrict__ out_lo) {
   const int OH = H / 2, OW = W / 2;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(B) * OH * OW;
@@ -298,14 +310,18 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__
   for (int c = 0; c < C; ++c) {
     // F.avg_pool2d sums the window then multiplies by 1/4
     const float s = ((p[c] + p[C + c]) + p[static_cast<int64_t>(W) * C + c]) + p[static_cast<int64_t>(W) * C + C + c];
-    out[idx * Cpad + coff + c] = __float2half_rn(s * 0.25f * pre_scale);
+    const float v = s * 0.25f * pre_scale;
+    const __half h = __float2half_rn(v);
+    out[idx * Cpad + coff + c] = h;
+    if (out_lo) out_lo[idx * Cpad + coff + c] = __float2half_rn(v - __half2float(h));  // split-fp16 residual plane
   }
 }
 int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
-                    cudaStream_t st) {
+                    cudaStream_t st, __half* out_lo) {
   const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2);
   if (total <= 0) return 0;
-  avgpool2_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, st>>>(src, B, H, W, C, pre_scale, out, Cpad, coff);
+  avgpool2_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, st>>>(src, B, H, W, C, pre_scale, out, Cpad, coff,
+                                                                            out_lo);
   count_launch();
   return check_launch("avgpool2");
 }
@@ -348,6 +364,13 @@ __device__ __forceinline__ void store8h(__half* base, int64_t idx8, const float*
   for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
   reinterpret_cast<uint4*>(base)[idx8] = u;
 }
+// residual plane of the split-fp16 representation: v - fp16(v), itself rounded to fp16
+__device__ __forceinline__ void store8h_lo(__half* base, int64_t idx8, const float* v) {
+  float r[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) r[e] = v[e] - __half2float(__float2half_rn(v[e]));
+  store8h(base, idx8, r);
+}
 
 // y = [relu]( GN(x) [+ res] )
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
@@ -377,12 +400,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
       load8(a.res, base + i, 0, r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += r[e];
+      if (a.res_lo) {
+        load8(a.res_lo, base + i, 0, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += r[e];
+      }
     }
     if (a.relu) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
     }
     store8h(a.y, base + i, v);
+    if (a.y_lo) store8h_lo(a.y_lo, base + i, v);
   }
 }
 
@@ -459,6 +488,7 @@ __global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int
       }
     }
     store8h(a.y, out_base + i, best);
+    if (a.y_lo) store8h_lo(a.y_lo, out_base + i, best);
     if (argmax) {
       uint2 u;
       u.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
@@ -741,10 +771,12 @@ __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, in
     const int c = static_cast<int>((i / (static_cast<int64_t>(S) * R)) % Cin);
     const int n = static_cast<int>(i / (static_cast<int64_t>(S) * R * Cin));
     // src_ld: elements between source rows (a Linear whose rows carry extra, non-visual columns)
-    const __half h = __float2half_rn(w[static_cast<int64_t>(n) * src_ld + (i - static_cast<int64_t>(n) * Cin * R * S)]);
+    const float wv = w[static_cast<int64_t>(n) * src_ld + (i - static_cast<int64_t>(n) * Cin * R * S)];
+    __half h = __float2half_rn(wv);
+    if (t_mode & 2) h = __float2half_rn(wv - __half2float(h));  // residual plane of the split-fp16 representation
     if (wp) wp[static_cast<int64_t>(n) * ld_p + (r * S + s) * cin_pad + c] = h;
     if (wt) {
-      if (t_mode == 0) wt[static_cast<int64_t>(c) * ld_t + ((R - 1 - r) * S + (S - 1 - s)) * cout_pad + n] = h;
+      if ((t_mode & 1) == 0) wt[static_cast<int64_t>(c) * ld_t + ((R - 1 - r) * S + (S - 1 - s)) * cout_pad + n] = h;
       else wt[static_cast<int64_t>((r * S + s) * cin_pad + c) * ld_t + n] = h;
     }
   }
@@ -799,10 +831,12 @@ __global__ void pack_w_multi_kernel(const PackDesc* __restrict__ tab) {
     const int r = static_cast<int>((i / d.S) % d.R);
     const int c = static_cast<int>((i / (static_cast<int64_t>(d.S) * d.R)) % d.Cin);
     const int n = static_cast<int>(i / per);
-    const __half h = __float2half_rn(d.w[static_cast<int64_t>(n) * d.src_ld + (i - static_cast<int64_t>(n) * per)]);
+    const float wv = d.w[static_cast<int64_t>(n) * d.src_ld + (i - static_cast<int64_t>(n) * per)];
+    __half h = __float2half_rn(wv);
+    if (d.t_mode & 2) h = __float2half_rn(wv - __half2float(h));  // residual plane (split-fp16 mode)
     if (d.wp) d.wp[static_cast<int64_t>(n) * d.ld_p + (r * d.S + s) * d.cin_pad + c] = h;
     if (d.wt) {
-      if (d.t_mode == 0) d.wt[static_cast<int64_t>(c) * d.ld_t + ((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.cout_pad + n] = h;
+      if ((d.t_mode & 1) == 0) d.wt[static_cast<int64_t>(c) * d.ld_t + ((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.cout_pad + n] = h;
       else d.wt[static_cast<int64_t>((r * d.S + s) * d.cin_pad + c) * d.ld_t + n] = h;
     }
   }

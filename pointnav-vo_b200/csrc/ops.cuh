@@ -9,6 +9,8 @@ struct ConvArgs {
   const __half* w;    // packed weights [n_total][w_ld] fp16, K-major, zero padded
   void* y;            // output [M][ldo] fp16 (or fp32 when out_fp32)
   const __half* add;  // optional [M][ldo] fp16 added before the store (dgrad accumulation)
+  const __half* x_lo; // split-fp16 mode (both or neither): residual planes x - fp16(x), w - fp16(w) in the same layouts;
+  const __half* w_lo; //   the kernel accumulates x*w + x_lo*w + x*w_lo (3 MMAs per product, ~fp32 operand precision)
   double* stats;      // optional GroupNorm partial sums [B][G][2] (sum, sum of squares), pre-zeroed; fp64 accumulators:
                       // the ORDER of the atomics then no longer shows in the fp32 mean / rstd (reproducible forward)
   int B, IH, IW, Cin;

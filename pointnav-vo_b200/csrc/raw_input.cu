@@ -27,6 +27,7 @@ struct RawArgs {
   const float* scale;
   const float* shift;
   __half* out;
+  __half* out_lo;       // split-fp16 mode (nullable): value - fp16(value); handled by the generic kernel variant
   int row_w, out_pitch;
   double* stats;        // [2C] (sum, sumsq) interleaved, accumulated
 };
@@ -130,6 +131,17 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
         h2[2] = __floats2half2_rn(fmaf(v[c + 4], sb.x, hb.x), fmaf(v[c + 5], sb.y, hb.y));
         h2[3] = __floats2half2_rn(fmaf(v[c + 6], sb.z, hb.z), fmaf(v[c + 7], sb.w, hb.w));
         *reinterpret_cast<uint4*>(out + q * 8) = u;
+        if (kGeneric && a.out_lo) {
+          const float x[8] = {fmaf(v[c], sa.x, ha.x),     fmaf(v[c + 1], sa.y, ha.y), fmaf(v[c + 2], sa.z, ha.z),
+                              fmaf(v[c + 3], sa.w, ha.w), fmaf(v[c + 4], sb.x, hb.x), fmaf(v[c + 5], sb.y, hb.y),
+                              fmaf(v[c + 6], sb.z, hb.z), fmaf(v[c + 7], sb.w, hb.w)};
+          uint4 ul;
+          __half2* l2 = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            l2[e] = __floats2half2_rn(x[2 * e] - __low2float(h2[e]), x[2 * e + 1] - __high2float(h2[e]));
+          *reinterpret_cast<uint4*>(a.out_lo + opix * a.Cpad + q * 8) = ul;
+        }
       }
     }
   }
@@ -266,8 +278,8 @@ int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
   PNVO_REQUIRE(a.out && a.Cpad % 8 == 0 && a.Cpad <= kMaxInC && a.C <= a.Cpad, "raw_assemble: bad output layout");
   if (a.n_pix <= 0) return 0;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
-  if (a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
-  else if (a.use_rgb && a.use_depth && a.n_dd == 0 && !a.use_td) raw_assemble_kernel<1, 1, 0, 0><<<blocks, 256, 0, st>>>(a);
+  if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
+  else if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 0 && !a.use_td) raw_assemble_kernel<1, 1, 0, 0><<<blocks, 256, 0, st>>>(a);
   else raw_assemble_kernel<0, 0, -1, 0><<<blocks, 256, 0, st>>>(a);
   count_launch();
   return check_launch("raw_assemble");
@@ -286,7 +298,7 @@ int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
 }
 
 int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st) {
-  // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats
+  // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats, p7 = out_lo
   // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch
   (void)f;
   RawArgs a{};
@@ -301,6 +313,7 @@ int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStrea
   a.row_w = i[8]; a.out_pitch = i[9];
   if (code == PNVO_OP_RAW_ASSEMBLE) {
     a.out = static_cast<__half*>(p[6]);
+    a.out_lo = static_cast<__half*>(p[7]);
     return raw_assemble_launch(a, st);
   }
   a.stats = static_cast<double*>(p[6]);

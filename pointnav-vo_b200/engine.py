@@ -52,12 +52,14 @@ class ConvLayer:
         self.nt_total = _ru(self.cin_pad, 16)
         # how the OIHW source is viewed by the pack kernel (Linear layers: [Cout, C, H, W] of the flatten)
         self.src_shape = src_shape or (Cout, Cin, R, S)
-        self.wp = self.wt = self.dwp = None
+        self.wp = self.wt = self.dwp = self.wp_lo = None
         self.up = None          # zero-upsampled dy (stride-2 data gradient), allocated on first use
         self.fast_s2 = True
 
-    def alloc(self, dev, training, own_dwp=True):
+    def alloc(self, dev, training, own_dwp=True, split=False):
         self.wp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
+        if split:  # residual plane w - fp16(w) of the split-fp16 representation
+            self.wp_lo = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
         if self.need_dgrad and training:
             self.wt = torch.zeros(self.nt_total, self.wt_ld, dtype=torch.float16, device=dev)
         if training and own_dwp:  # inside a plan dwp is a view of the gradient arena (one zero-fill per step)
@@ -71,10 +73,10 @@ class ConvLayer:
         return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld,
                            self.cout_pad, self.wt_ld, 0)
 
-    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False):
+    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None):
         return L.op_conv(x, self.wp, y, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
                          self.stride, self.pad, 1, self.w_ld, self.cout_pad, self.cout_pad, self.cout_pad, None, stats,
-                         cpg, G, out_fp32)
+                         cpg, G, out_fp32, x_lo=x_lo, w_lo=self.wp_lo if x_lo is not None else None)
 
     def op_dgrad(self, dy, gx, B, add=None):
         # gx[b, h, w, c] = sum_{r,s,n} dy[b, (h + pad - r)/stride, (w + pad - s)/stride, n] * W[n, c, r, s]
@@ -117,6 +119,10 @@ class ConvLayer:
                           self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld, self.cout_pad, self.wt_ld, 0,
                           self.Cin * self.R * self.S)
 
+    def pack_desc_lo(self, w):
+        return L.PackDesc(w.data_ptr(), self.wp_lo.data_ptr(), None, self.Cout, self.Cin, self.R, self.S, self.cin_pad,
+                          self.w_ld, self.cout_pad, self.wt_ld, 2, self.Cin * self.R * self.S)
+
     def unpack_desc(self, grad):
         return L.UnpackDesc(self.dwp.data_ptr(), grad.data_ptr(), self.Cout, self.Cin, self.R, self.S, self.cin_pad,
                             self.w_ld, 0, self.Cin * self.R * self.S)
@@ -145,6 +151,11 @@ class LinearLayer(ConvLayer):
         return L.PackDesc(w.data_ptr(), self.wp.data_ptr(), self.wt.data_ptr() if self.wt is not None else None,
                           self.Cout, self.fC, self.fH, self.fW, self.c_pad, self.w_ld, self.cout_pad, self.wt_ld, 1, ld)
 
+    def pack_desc_lo(self, w):
+        ld = self.src_ld or self.fC * self.fH * self.fW
+        return L.PackDesc(w.data_ptr(), self.wp_lo.data_ptr(), None, self.Cout, self.fC, self.fH, self.fW, self.c_pad,
+                          self.w_ld, self.cout_pad, self.wt_ld, 3, ld)
+
     def unpack_desc(self, grad):
         ld = self.src_ld or self.fC * self.fH * self.fW
         return L.UnpackDesc(self.dwp.data_ptr(), grad.data_ptr(), self.Cout, self.fC, self.fH, self.fW, self.c_pad,
@@ -164,10 +175,19 @@ class EncoderPlan:
 
     def __init__(self, *, params, buffers, B, H, W, in_channels, sources, backbone, baseplanes, ngroups,
                  compression_channels, prefix, head=None, training=True, avgpool_input=False, device="cuda",
-                 world_size=1, raw_fp32=False, dropout_p=0.0):
+                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False):
         """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
-        head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim)."""
+        head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim).
+        split: forward-only precision mode.  Every fp16 activation / weight tensor gets a residual plane
+        (t - fp16(t), fp16), raw conv outputs stay fp32 and each conv accumulates x*w + x_lo*w + x*w_lo: operands carry
+        ~22 mantissa bits, so outputs agree with the fp32 reference to ~1e-5 instead of ~5e-3 (3 MMAs per product,
+        generic implicit-GEMM kernel only)."""
+        self.split = bool(split)
+        if self.split:
+            assert not training, "split-fp16 precision is a forward-only mode"
+            raw_fp32 = True
+        self._lo = {}
         self.P, self.Bf = params, buffers
         self.B, self.H, self.W = B, H, W
         self.dev = torch.device(device)
@@ -267,12 +287,19 @@ class EncoderPlan:
 
     # ------------------------------------------------------------------------------------------
     def _act(self, B, H, W, C, dtype=torch.float16):
-        return torch.empty(B, H, W, C, dtype=dtype, device=self.dev)
+        t = torch.empty(B, H, W, C, dtype=dtype, device=self.dev)
+        if self.split and dtype == torch.float16:
+            self._lo[t.data_ptr()] = torch.zeros_like(t)
+        return t
+
+    def lo(self, t):
+        """Residual plane of an activation tensor in split-fp16 mode (None otherwise)."""
+        return self._lo.get(t.data_ptr()) if (self.split and t is not None) else None
 
     def _alloc(self):
         B, dev, tr = self.B, self.dev, self.training
         for c in self.all_convs():
-            c.alloc(dev, tr, own_dwp=False)
+            c.alloc(dev, tr, own_dwp=False, split=self.split)
         gns = self.all_gns()
         # one contiguous fp32 region for all GroupNorm partial sums -> a single ZERO op per forward
         tot = sum(B * g.G * 2 for g in gns)
@@ -395,7 +422,8 @@ class EncoderPlan:
     def _gn_apply(self, g, x, y, HW, relu=True, res=None):
         B = self.B
         return L.op_gn_apply(x, g.stats, self.P[g.key + ".weight"], self.P[g.key + ".bias"], y, B, g.C, g.G, g.cpg, HW,
-                             float(g.cpg_real * HW), relu, res, self.raw_fp32, 1e-5, g.C_real)
+                             float(g.cpg_real * HW), relu, res, self.raw_fp32, 1e-5, g.C_real, y_lo=self.lo(y),
+                             res_lo=self.lo(res))
 
     def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
         return L.op_gn_bwd(reduce, gin, relu_ref, x, g.stats, self.P[g.key + ".weight"], g.sums, dx, dy_out, self.B,
@@ -421,6 +449,9 @@ class EncoderPlan:
         if self.batch_small_ops:
             self._pack_tab = L.device_table([c.pack_desc(self.P[c.key]) for c in self.all_convs()], self.dev)
             pack = [L.op_multi(L.OP_PACK_W_MULTI, self._pack_tab, len(self.all_convs()))]
+            if self.split:
+                self._pack_tab_lo = L.device_table([c.pack_desc_lo(self.P[c.key]) for c in self.all_convs()], self.dev)
+                pack.append(L.op_multi(L.OP_PACK_W_MULTI, self._pack_tab_lo, len(self.all_convs())))
         else:
             pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
         if self.use_stem:
@@ -437,22 +468,23 @@ class EncoderPlan:
             ops.append(L.op_conv_stem(self.x0, self.w_stem, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg, 2))
         else:
             assert not self.use_stem, "raw_fp32 is not supported together with the stem kernel"
-            ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32))
+            ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32, x_lo=self.lo(self.x0)))
         ops.append(L.op_gn_pool(self.raw1, g1.stats, self.P[g1.key + ".weight"], self.P[g1.key + ".bias"], self.pool,
                                 self.argmax, B, g1.C, g1.G, g1.cpg, c1.OH, c1.OW, self.PH, self.PW,
-                                float(g1.cpg_real * c1.OH * c1.OW), self.raw_fp32, 1e-5, g1.C_real))
+                                float(g1.cpg_real * c1.OH * c1.OW), self.raw_fp32, 1e-5, g1.C_real,
+                                y_lo=self.lo(self.pool)))
         x = self.pool
         for blk in self.blocks:
             convs, gns = blk["convs"], blk["gns"]
             res = x
             if blk["down"]:
                 d, gd = blk["down"]
-                ops.append(d.op_fwd(x, blk["raw_d"], B, gd.stats, gd.cpg, gd.G, self.raw_fp32))
+                ops.append(d.op_fwd(x, blk["raw_d"], B, gd.stats, gd.cpg, gd.G, self.raw_fp32, x_lo=self.lo(x)))
                 ops.append(self._gn_apply(gd, blk["raw_d"], blk["res_d"], d.OH * d.OW, relu=False))
                 res = blk["res_d"]
             cur = x
             for k, (c, g) in enumerate(zip(convs, gns)):
-                ops.append(c.op_fwd(cur, blk["raw"][k], B, g.stats, g.cpg, g.G, self.raw_fp32))
+                ops.append(c.op_fwd(cur, blk["raw"][k], B, g.stats, g.cpg, g.G, self.raw_fp32, x_lo=self.lo(cur)))
                 if k < len(convs) - 1:
                     ops.append(self._gn_apply(g, blk["raw"][k], blk["mid"][k], c.OH * c.OW, relu=True))
                     cur = blk["mid"][k]
@@ -461,15 +493,17 @@ class EncoderPlan:
             blk["x_in"] = x
             x = blk["y"]
         cc, gc = self.comp, self.gnc
-        ops.append(cc.op_fwd(x, self.raw_c, B, gc.stats, gc.cpg, gc.G, self.raw_fp32))
+        ops.append(cc.op_fwd(x, self.raw_c, B, gc.stats, gc.cpg, gc.G, self.raw_fp32, x_lo=self.lo(x)))
         ops.append(self._gn_apply(gc, self.raw_c, self.feat, self.fH * self.fW, relu=True))
         p_drop = self.dropout_p
         if p_drop > 0:  # nn.Dropout in front of visual_fc (vo_cnn.py:218)
             ops.append(L.op_dropout(self.feat, self.drop_seed, 0, p_drop))
+            if self.split:  # same counter-based mask on the residual plane
+                ops.append(L.op_dropout(self.lo(self.feat), self.drop_seed, 0, p_drop))
         if self.head is not None:
             hd = self.head
             feat_flat = self.feat  # [B, 1, 1, fH*fW*c_pad] as far as the 1x1 "conv" is concerned
-            ops.append(self.fc.op_fwd(feat_flat, self.z, B, None, 0, 0, True))
+            ops.append(self.fc.op_fwd(feat_flat, self.z, B, None, 0, 0, True, x_lo=self.lo(self.feat)))
             emb = hd.get("embed")
             if emb:
                 E = self.P[emb["table"]]
@@ -596,7 +630,8 @@ class EncoderPlan:
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             assert t.shape[-1] == n
-            ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale))
+            ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale,
+                                     out_lo=self.lo(self.x0)))
             coff += n
             self._keepalive = t
         return ops

@@ -169,10 +169,10 @@ def _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix):
     return ints + words, list(pre_scale) + [1.0] * (4 - len(pre_scale))
 
 
-def op_assemble(srcs, nch, pre_scale, lut, C, Cpad, n_pix, scale, shift, out, row_w=0, out_pitch=0):
+def op_assemble(srcs, nch, pre_scale, lut, C, Cpad, n_pix, scale, shift, out, row_w=0, out_pitch=0, out_lo=None):
     ints, fl = _assemble_fields(srcs, nch, pre_scale, lut, C, Cpad, n_pix)
     ints = ints + [0] * (25 - len(ints)) + [row_w, out_pitch]
-    return _op(OP_ASSEMBLE, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [scale, shift, out])
+    return _op(OP_ASSEMBLE, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [scale, shift, out, out_lo])
 
 
 def op_input_stats(srcs, nch, pre_scale, lut, C, Cpad, n_pix, stats_f64):
@@ -191,9 +191,9 @@ def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, 
 
 
 def op_raw_assemble(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, scale, shift, out,
-                    row_w=0, out_pitch=0):
+                    row_w=0, out_pitch=0, out_lo=None):
     return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch), (),
-               [rgb_u8, depth, td, edges, scale, shift, out])
+               [rgb_u8, depth, td, edges, scale, shift, out, out_lo])
 
 
 def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv, n_batch, pix_per_sample):
@@ -202,9 +202,11 @@ def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv
 
 
 def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, add=None, stats=None,
-            cpg=0, G=0, out_fp32=False, pad_w=None):
+            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None):
+    """x_lo / w_lo: residual planes of the split-fp16 representation (x - fp16(x)); with them the kernel accumulates
+    x*w + x_lo*w + x*w_lo, i.e. products of ~fp32-precision operands (3 MMAs per product)."""
     return _op(OP_CONV, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, cpg, G,
-                         int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats])
+                         int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats, x_lo, w_lo])
 
 
 def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None, x_row_pitch=0):
@@ -213,16 +215,16 @@ def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, l
 
 
 def op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, cnt, relu=True, res=None, x_fp32=False, eps=1e-5,
-                C_real=None):
+                C_real=None, y_lo=None, res_lo=None):
     return _op(OP_GN_APPLY, [B, C, G, cpg, HW, int(relu), int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real],
-               [cnt, eps], [x, stats, gamma, beta, res, y])
+               [cnt, eps], [x, stats, gamma, beta, res, y, None, y_lo, res_lo])
 
 
 def op_gn_pool(x, stats, gamma, beta, y, argmax, B, C, G, cpg, H, W, PH, PW, cnt, x_fp32=False, eps=1e-5,
-               C_real=None):
+               C_real=None, y_lo=None):
     return _op(OP_GN_POOL, [B, C, G, cpg, H * W, 1, int(x_fp32), H, W, PH, PW, C if C_real is None else C_real],
                [cnt, eps],
-               [x, stats, gamma, beta, None, y, argmax])
+               [x, stats, gamma, beta, None, y, argmax, y_lo])
 
 
 def op_pool_bwd(g, pooled, argmax, dy, B, C, H, W, PH, PW):
@@ -322,8 +324,8 @@ def op_adam(p, g, m, v, n, step, lr, beta1, beta2, eps):
     return _op(OP_ADAM, [lo, hi, step], [lr, beta1, beta2, eps], [p, g, m, v])
 
 
-def op_avgpool2(src, out, B, H, W, C, Cpad, coff, pre_scale=1.0):
-    return _op(OP_AVGPOOL2, [B, H, W, C, Cpad, coff], [pre_scale], [src, out])
+def op_avgpool2(src, out, B, H, W, C, Cpad, coff, pre_scale=1.0, out_lo=None):
+    return _op(OP_AVGPOOL2, [B, H, W, C, Cpad, coff], [pre_scale], [src, out, out_lo])
 
 
 USE_GRAPHS = os.environ.get("PNVO_GRAPHS", "1") != "0"

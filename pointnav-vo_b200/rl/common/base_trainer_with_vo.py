@@ -22,6 +22,10 @@ from ...vo.common.common_vars import ACT_IDX2NAME
 
 class VOInferenceMixin:
     _vo_obs_transformer = None
+    # Precision of the per-step VO forward (VisualOdometryCNNBase.set_precision).  "split" = value + residual fp16
+    # planes, three tensor-core products per convolution: the deltas agree with the reference's fp32 network to ~1e-4
+    # relative, and at rollout batch sizes (one to a few dozen pairs) the step is launch-bound either way.
+    vo_precision = "split"
 
     # ---- base_trainer_with_vo.py:101-128 ------------------------------------------------------
     def _setup_vo_preproc(self):
@@ -89,6 +93,7 @@ class VOInferenceMixin:
             extra_infos["ego_top_down_map"] = obs_pairs["top_down_view"][0, :, :, 1:2]
         cfg = self.config.VO.REGRESS_MODEL
         model = self.vo_model[self._vo_key(act)]
+        model.set_precision(self.vo_precision)
         local_delta_states, local_delta_states_std = [], []
         with torch.no_grad():
             if cfg.mode == "det":
@@ -133,6 +138,7 @@ class VOInferenceMixin:
             for key in sorted({self._vo_key(int(a)) for a in acts}):
                 idx = torch.tensor([i for i, a in enumerate(acts) if self._vo_key(int(a)) == key], device=dev)
                 model = self.vo_model[key]
+                model.set_precision(self.vo_precision)
                 model.eval()
                 sub = {k: v.index_select(0, idx).contiguous() for k, v in obs.items()}
                 out.index_copy_(0, idx, model(sub)[:, :3])

@@ -121,6 +121,7 @@ class PointNavResNetNet(Net):
         self.state_encoder = RNNStateEncoder((0 if self.is_blind else self._hidden_size) + rnn_input_size,
                                              self._hidden_size, rnn_type=rnn_type, num_layers=num_recurrent_layers)
         self._plans, self._ptr_sig, self._packed_version, self._packed_plan = {}, None, None, None
+        self.precision = "fp16"  # set_precision
         self._visual_param_order = [k for k, _ in self.named_parameters()
                                     if k.startswith("visual_encoder.") or k.startswith("visual_fc.")]
         self.train()
@@ -142,6 +143,14 @@ class PointNavResNetNet(Net):
         P = dict(self.named_parameters())
         return [P[k] for k in self._visual_param_order]
 
+    def set_precision(self, mode):
+        """'fp16' (default) or 'split': no-grad forwards (rollout action selection) with value + residual fp16 planes
+        and three tensor-core products per convolution, see engine.EncoderPlan(split=True)."""
+        if mode not in ("fp16", "split"):
+            raise ValueError(mode)
+        self.precision = mode
+        return self
+
     def _plan_for(self, obs, need_grad):
         enc = self.visual_encoder
         first = obs[enc._sources[0][0]]
@@ -153,7 +162,8 @@ class PointNavResNetNet(Net):
             self._plans.clear()
             self._ptr_sig, self._packed_version = sig, None
         B, H, W = first.shape[0], first.shape[1], first.shape[2]
-        key = (B, H, W, bool(need_grad), str(first.device))
+        split = self.precision == "split" and not need_grad
+        key = (B, H, W, bool(need_grad), str(first.device), split)
         plan = self._plans.get(key)
         if plan is None:
             P = {k: p.data for k, p in self.named_parameters()}
@@ -161,7 +171,8 @@ class PointNavResNetNet(Net):
             plan = EncoderPlan(params=P, buffers={}, B=B, H=H, W=W, in_channels=enc.input_channels,
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0], prefix="visual_encoder",
-                               head=head, training=bool(need_grad), avgpool_input=True, device=first.device)
+                               head=head, training=bool(need_grad), avgpool_input=True, device=first.device,
+                               split=split)
             self._plans[key] = plan
         return plan
 

@@ -108,6 +108,8 @@ class _VOFunction(torch.autograd.Function):
 class VisualOdometryCNNBase(nn.Module):
     """vo_cnn.py:182-233."""
 
+    precision = "fp16"  # see set_precision
+
     def __init__(self, *, observation_space, observation_size, hidden_size=512, resnet_baseplanes=32,
                  backbone="resnet18", normalize_visual_inputs=False, output_dim=DEFAULT_DELTA_STATE_SIZE,
                  dropout_p=0.2, after_compression_flat_size=2048, rgb_pair_channel=RGB_PAIR_CHANNEL,
@@ -146,6 +148,17 @@ class VisualOdometryCNNBase(nn.Module):
     def _signature(self):
         return tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers())
 
+    def set_precision(self, mode):
+        """'fp16' (default): fp16 operands / activations, fp32 accumulation -- outputs within ~5e-3 of the fp32 reference.
+        'split': no-grad forwards keep every activation and weight as a pair of fp16 planes (value + residual) and run
+        three tensor-core products per convolution (engine.EncoderPlan(split=True)); outputs agree with the fp32
+        reference to ~1e-5 (the north-star 1e-3 bound) at roughly 3x the convolution time.  Forwards that record a
+        graph for backward always use 'fp16'."""
+        if mode not in ("fp16", "split"):
+            raise ValueError(mode)
+        self.precision = mode
+        return self
+
     # ---------------------------------------------------------------- raw observation pairs
     # forward() also accepts the step's inputs in the form the simulator / dataset stores them:
     #   {"rgb": uint8 [B,H,W,6], "depth": fp32 [B,H,W,2]}   (prev | cur on the channel axis)
@@ -183,7 +196,8 @@ class VisualOdometryCNNBase(nn.Module):
             self._packed_version = None
         B, H, W = first.shape[0], first.shape[1], first.shape[2]
         drop = self._dropout_p if training else 0.0  # nn.Dropout is the identity in eval mode
-        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32, drop)
+        split = self.precision == "split" and not need_grad
+        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32, drop, split)
         plan = self._plans.get(key)
         if plan is None:
             P, Bf = self._tensors()
@@ -201,7 +215,7 @@ class VisualOdometryCNNBase(nn.Module):
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0],
                                prefix="visual_encoder", head=head, training=bool(need_grad), device=first.device,
-                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop)
+                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop, split=split)
             self._plans[key] = plan
         return plan
 
@@ -262,7 +276,7 @@ class VisualOdometryCNNBase(nn.Module):
             scale = shift = None
         ops.append(L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
                                      scale, shift, plan.x0_for(parity), row_w=plan.W if plan.x0_pitch else 0,
-                                     out_pitch=plan.x0_pitch))
+                                     out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0) if parity == 0 else None))
         L.run_ops(ops, dev)
         if not prepare_only:
             self._run_backbone(plan, parity)
@@ -315,7 +329,7 @@ class VisualOdometryCNNBase(nn.Module):
         else:
             scale = shift = None
         ops.append(L.op_assemble(srcs, nch, pre, lut, C, plan.cin_pad, n_pix, scale, shift, plan.x0,
-                                 row_w=plan.W if plan.x0_pitch else 0, out_pitch=plan.x0_pitch))
+                                 row_w=plan.W if plan.x0_pitch else 0, out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0)))
         L.run_ops(ops, dev)
         self._run_backbone(plan)
 

@@ -257,3 +257,60 @@ def test_descriptor_table_layouts_match_the_c_structs():
     assert ctypes.sizeof(L.UnpackDesc) == 48 and L.UnpackDesc.Cout.offset == 16 and L.UnpackDesc.dst_ld.offset == 44
     assert ctypes.sizeof(L.GnParamDesc) == 32 and L.GnParamDesc.C.offset == 24
     assert ctypes.sizeof(L.PnvoOp) == 4 + 27 * 4 + 4 * 4 + 10 * 8
+
+
+def test_reference_checkpoint_envelopes_load(tmp_path):
+    """the three checkpoint envelopes of the reference (single-network VO file, joint VO file keyed by
+    action id, DD-PPO policy file with the 'actor_critic.' prefix) load into the modules of this package."""
+    from pointnav_vo_b200.rl.policies.resnet_policy import PointNavResNetPolicy
+    from pointnav_vo_b200.utils import checkpoint as ck
+    from pointnav_vo_b200.vo.common.common_vars import ACT_NAME2IDX
+    from pointnav_vo_b200.vo.models import vo_cnn
+    from tests.helpers import policy_spaces
+
+    def make():
+        return vo_cnn.baseline_registry.get_vo_model("vo_cnn")(
+            observation_space=["rgb", "depth"], observation_size=(341, 192), hidden_size=512, backbone="resnet18",
+            normalize_visual_inputs=True, output_dim=3, dropout_p=0.2)
+
+    torch.manual_seed(0)
+    src = {k: make() for k in ("forward", "left", "right")}
+    for i, m in enumerate(src.values()):
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.01 * (i + 1))
+            m.visual_encoder.running_mean_and_var._count.fill_(100.0 + i)
+    single = str(tmp_path / "act_forward.pth")
+    joint = str(tmp_path / "act_left_right_inv_joint.pth")
+    torch.save({"model_state": src["forward"].state_dict(), "epoch": 3}, single)
+    ck.save_vo_checkpoint(joint, {"left": src["left"], "right": src["right"]}, epoch=7)
+    written = torch.load(joint, weights_only=False)
+    assert set(written["model_states"]) == {ACT_NAME2IDX["left"], ACT_NAME2IDX["right"]}  # the reference's keys
+    dst = {k: make() for k in ("forward", "left", "right")}
+    # VO.REGRESS_MODEL.pretrained_ckpt: one path per action, left and right naming the same joint file
+    res = ck.load_vo_checkpoint({"forward": single, "left": joint, "right": joint}, dst)
+    assert set(res) == {"forward", "left", "right"}
+    for k in dst:
+        for (n1, t1), (n2, t2) in zip(src[k].state_dict().items(), dst[k].state_dict().items()):
+            assert n1 == n2 and torch.equal(t1, t2), (k, n1)
+    with pytest.raises(KeyError):
+        ck.vo_state_dict_for(written, "forward")
+    with pytest.raises(ValueError):
+        ck.vo_state_dict_for({"state_dict": {}}, "forward")
+
+    obs_space, act_space = policy_spaces()
+    pol = PointNavResNetPolicy(observation_space=obs_space, action_space=act_space, backbone="resnet18", vis_types=["depth"])
+    with torch.no_grad():
+        for p in pol.parameters():
+            p.add_(0.5)
+    path = str(tmp_path / "rl_tune_vo.pth")
+    torch.save({"state_dict": {"actor_critic." + k: v for k, v in pol.state_dict().items()}, "config": None}, path)
+    pol2 = PointNavResNetPolicy(observation_space=obs_space, action_space=act_space, backbone="resnet18", vis_types=["depth"])
+    ck.load_policy_checkpoint(path, pol2)
+    for (n1, t1), (n2, t2) in zip(pol.state_dict().items(), pol2.state_dict().items()):
+        assert n1 == n2 and torch.equal(t1, t2), n1
+    pol3 = PointNavResNetPolicy(observation_space=obs_space, action_space=act_space, backbone="resnet18", vis_types=["depth"])
+    ck.load_policy_checkpoint(path, pol3, encoder_only=True)
+    for (n, t1), (_, t3) in zip(pol.net.visual_encoder.state_dict().items(), pol3.net.visual_encoder.state_dict().items()):
+        assert torch.equal(t1, t3), n
+    assert not torch.equal(pol.critic.fc.weight, pol3.critic.fc.weight)
