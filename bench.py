@@ -239,6 +239,17 @@ def run_b200(args):
                               "value": round(world * B / (ms_f * 1e-3), 1), "unit": "pairs/s", "n_gpus": world,
                               "ms_per_step": round(ms_f, 3),
                               "forward_tflops": round(world * B * GFLOP_FWD * 1e9 / (ms_f * 1e-3) / 1e12, 1)}), flush=True)
+        # the 1e-3 precision mode (value + residual fp16 planes, 3 MMAs per product, generic kernel only)
+        model.set_precision("split")
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                model(obs)
+            ms_s = timed(lambda: model(obs), args.steps) / args.steps
+        model.set_precision("fp16")
+        if rank == 0:
+            print(json.dumps({"metric": "VO frame-pairs/sec, eval-mode forward only, split precision (within 1e-3 of fp32)",
+                              "value": round(world * B / (ms_s * 1e-3), 1), "unit": "pairs/s", "n_gpus": world,
+                              "ms_per_step": round(ms_s, 3)}), flush=True)
         model.train()
     pf = obs if prefetch else None
     for _ in range(args.warmup):

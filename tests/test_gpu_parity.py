@@ -6,9 +6,10 @@ Tolerances (also in DESIGN.md "Numerics"):
   * integer / index work (discretisation, top-down counts and maps, exact-mode GAE): bit-exact.
   * a single conv / GroupNorm op against torch fp32 on the same fp16-rounded inputs: max|d| <= 3e-3 * rms(ref)
     (one fp16 rounding of the stored result).
-  * whole-network outputs against the fp32 reference: fp16 operands/activations with fp32 accumulation give
-    max|d| <= 6e-3 * rms(ref) for ResNet-18 and 2.5e-2 for ResNet-50 (20 resp. 53 rounded layers); the
-    north-star figure of 1e-3 is not reachable with single-pass fp16 tensor-core operands.
+  * whole-network outputs against the fp32 reference, default mode: fp16 operands/activations with fp32 accumulation
+    give max|d| <= 8e-3 * rms(ref) for ResNet-18 and 2.5e-2 for ResNet-50 (20 resp. 53 rounded layers).
+  * whole-network outputs in split precision (set_precision("split"), no-grad forwards): <= 1e-3 (the north-star
+    tolerance; measured 7e-6 .. 6e-5), both as max|d| / rms(ref) and element-wise relative to |ref|.
   * gradients: ReLU masks flip where a pre-activation is within rounding distance of zero, which perturbs
     weight gradients (random-sign sums) by ~sqrt(flip fraction); relative L2 error <= 0.15 per tensor.
 """
