@@ -30,7 +30,21 @@ struct RawArgs {
   __half* out_lo;       // split-fp16 mode (nullable): value - fp16(value); handled by the generic kernel variant
   int row_w, out_pitch;
   double* stats;        // [2C] (sum, sumsq) interleaved, accumulated
+  // Geometric-invariance augmentation on the device (regression_geo_invariance_iter_dataset.py:342-420): output sample b
+  // is source pair pair_map[b] >> 1, with prev / cur swapped when pair_map[b] & 1.  n_pix then counts OUTPUT pixels and
+  // hw = pixels per sample; the raw tensors hold only the source pairs (no second copy over PCIe, no second top-down).
+  const int32_t* pair_map;
+  int hw;
 };
+
+// source pixel + swap flag of output pixel p under the pair map
+__device__ __forceinline__ int64_t mapped_pixel(const RawArgs& a, int64_t p, bool& flip) {
+  const uint32_t p32 = static_cast<uint32_t>(p), hw = static_cast<uint32_t>(a.hw);  // launchers require n_pix < 2^31
+  const uint32_t b = p32 / hw;
+  const int32_t m = __ldg(a.pair_map + b);
+  flip = (m & 1) != 0;
+  return static_cast<int64_t>(m >> 1) * a.hw + (p32 - b * hw);
+}
 
 // bin i <=> e_i <= d < e_{i+1}, last bin closed at e_n (base_trainer_with_vo.py:143-154).  floor(d * n) is at most
 // one bin off (edges are fl(i/n)); the comparisons against the actual fp32 edges make the result exact.
@@ -43,7 +57,7 @@ __device__ __forceinline__ int depth_bin(float d, const float* s_edges, int n) {
 }
 
 // RGB / DEP / TD: 0 or 1; NDD: number of one-hot bins (compile-time layout), or -1 = every flag read at run time
-template <int RGB, int DEP, int NDD, int TD>
+template <int RGB, int DEP, int NDD, int TD, bool MAP = false>
 __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
   __shared__ __align__(16) float s_scale[kMaxInC];
   __shared__ __align__(16) float s_shift[kMaxInC];
@@ -66,6 +80,9 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
     for (int c = 0; c < kMaxInC; ++c) v[c] = 0.f;
     float rgbv[6] = {0, 0, 0, 0, 0, 0};
     float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
+    const int64_t p_out = p;
+    bool flip = false;
+    if (MAP) p = mapped_pixel(a, p_out, flip);
     if (use_rgb) {
       const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
       const uint32_t w0 = r16[0], w1 = r16[1], w2 = r16[2];
@@ -79,6 +96,15 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
     }
     if (use_depth || n_dd > 0) d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
     if (use_td) t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
+    if (MAP) {
+      if (flip) {  // prev <-> cur
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const float x = rgbv[c]; rgbv[c] = rgbv[c + 3]; rgbv[c + 3] = x; }
+        d = make_float2(d.y, d.x);
+        t = make_float2(t.y, t.x);
+      }
+      p = p_out;
+    }
     // channel placement, fully unrolled so that v[] stays in registers; with a compile-time layout every
     // comparison below folds away
 #pragma unroll
@@ -176,15 +202,25 @@ __global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) fs[i] = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < a.n_pix; p += stride) {
+  for (int64_t po = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; po < a.n_pix; po += stride) {
     uint32_t w[3] = {0u, 0u, 0u};
     float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
+    bool flip = false;
+    const int64_t p = a.pair_map ? mapped_pixel(a, po, flip) : po;
     if (a.use_rgb) {
       const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
       w[0] = r16[0]; w[1] = r16[1]; w[2] = r16[2];
     }
     if (a.depth) d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
     if (a.use_td) t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
+    if (flip) {  // prev <-> cur: bytes [0 1 2 | 3 4 5] -> [3 4 5 | 0 1 2]
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      w[0] = (w1 >> 8) | ((w2 & 0xff) << 8);
+      w[1] = (w2 >> 8) | ((w0 & 0xff) << 8);
+      w[2] = (w0 >> 8) | ((w1 & 0xff) << 8);
+      d = make_float2(d.y, d.x);
+      t = make_float2(t.y, t.x);
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const uint32_t lo = w[k] & 0xff, hi = w[k] >> 8;
@@ -278,7 +314,13 @@ int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
   PNVO_REQUIRE(a.out && a.Cpad % 8 == 0 && a.Cpad <= kMaxInC && a.C <= a.Cpad, "raw_assemble: bad output layout");
   if (a.n_pix <= 0) return 0;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
-  if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
+  if (a.pair_map) {
+    PNVO_REQUIRE(a.hw > 0 && a.n_pix % a.hw == 0 && a.n_pix < (1ll << 31), "raw_assemble: pair map needs pixels per sample");
+    if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td)
+      raw_assemble_kernel<1, 1, 10, 1, true><<<blocks, 256, 0, st>>>(a);
+    else
+      raw_assemble_kernel<0, 0, -1, 0, true><<<blocks, 256, 0, st>>>(a);
+  } else if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
   else if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 0 && !a.use_td) raw_assemble_kernel<1, 1, 0, 0><<<blocks, 256, 0, st>>>(a);
   else raw_assemble_kernel<0, 0, -1, 0><<<blocks, 256, 0, st>>>(a);
   count_launch();
@@ -288,6 +330,7 @@ int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
 int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
   if (raw_check(a)) return -1;
   PNVO_REQUIRE(a.stats, "raw_stats: null accumulator");
+  PNVO_REQUIRE(!a.pair_map || (a.hw > 0 && a.n_pix % a.hw == 0 && a.n_pix < (1ll << 31)), "raw_stats: pair map needs pixels per sample");
   if (a.n_pix <= 0) return 0;
   // a thread must see <= 255 pixels (8-bit packed bin counts; 32-bit integer rgb sums are exact far beyond): <= 128
   int64_t blocks = std::max<int64_t>(148 * 8, ceil_div64(a.n_pix, 256 * 128));
@@ -298,7 +341,8 @@ int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
 }
 
 int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st) {
-  // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats, p7 = out_lo
+  // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats, p7 = out_lo,
+  // p8 = pair_map (int32 per output sample, nullable); i10 = pixels per sample (with pair_map)
   // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch
   (void)f;
   RawArgs a{};
@@ -311,6 +355,7 @@ int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStrea
   a.use_rgb = i[0]; a.use_depth = i[1]; a.n_dd = i[2]; a.use_td = i[3]; a.C = i[4]; a.Cpad = i[5];
   a.n_pix = (static_cast<int64_t>(static_cast<uint32_t>(i[7])) << 32) | static_cast<uint32_t>(i[6]);
   a.row_w = i[8]; a.out_pitch = i[9];
+  a.pair_map = static_cast<const int32_t*>(p[8]); a.hw = i[10];
   if (code == PNVO_OP_RAW_ASSEMBLE) {
     a.out = static_cast<__half*>(p[6]);
     a.out_lo = static_cast<__half*>(p[7]);

@@ -180,20 +180,22 @@ def op_input_stats(srcs, nch, pre_scale, lut, C, Cpad, n_pix, stats_f64):
     return _op(OP_INPUT_STATS, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [None, None, stats_f64])
 
 
-def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0):
-    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch]
+def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0, hw=0):
+    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch, hw]
 
 
-def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, stats_f64):
-    """Batch statistics of the assembled input straight from the raw pairs (csrc/raw_input.cu)."""
-    return _op(OP_RAW_STATS, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix), (),
-               [rgb_u8, depth, td, edges, None, None, stats_f64])
+def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, stats_f64, pair_map=None,
+                 hw=0):
+    """Batch statistics of the assembled input straight from the raw pairs (csrc/raw_input.cu).  pair_map (int32 per
+    OUTPUT sample = 2 * source pair + swap flag) expands / swaps pairs on the fly; n_pix then counts output pixels."""
+    return _op(OP_RAW_STATS, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, hw=hw), (),
+               [rgb_u8, depth, td, edges, None, None, stats_f64, None, pair_map])
 
 
 def op_raw_assemble(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, scale, shift, out,
-                    row_w=0, out_pitch=0, out_lo=None):
-    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch), (),
-               [rgb_u8, depth, td, edges, scale, shift, out, out_lo])
+                    row_w=0, out_pitch=0, out_lo=None, pair_map=None, hw=0):
+    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch, hw), (),
+               [rgb_u8, depth, td, edges, scale, shift, out, out_lo, pair_map])
 
 
 def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv, n_batch, pix_per_sample):

@@ -195,6 +195,8 @@ class VisualOdometryCNNBase(nn.Module):
             self._ptr_sig = sig
             self._packed_version = None
         B, H, W = first.shape[0], first.shape[1], first.shape[2]
+        if obs.get("pair_map") is not None:  # device-side inverse-pair augmentation: one network row per map entry
+            B = obs["pair_map"].numel()
         drop = self._dropout_p if training else 0.0  # nn.Dropout is the identity in eval mode
         split = self.precision == "split" and not need_grad
         key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32, drop, split)
@@ -235,13 +237,21 @@ class VisualOdometryCNNBase(nn.Module):
         use_td = "top_down_view" in keys
         H, W, B = plan.H, plan.W, plan.B
         rgb = depth = td = edges = None
+        # pair_map (int32 [B], entry = 2 * source pair + swap flag): the raw tensors hold B_src <= B source pairs and the
+        # kernels expand / swap them on the fly (regression_geo_invariance_iter_dataset.py:342-420 done on the device)
+        pair_map = obs.get("pair_map")
+        B_src = B
+        if pair_map is not None:
+            if pair_map.dtype != torch.int32 or not pair_map.is_cuda or pair_map.numel() != B:
+                raise L.PnvoError("pair_map must be an int32 CUDA tensor with one entry per network row")
+            B_src = self._first_tensor(obs).shape[0]
         if use_rgb:
             rgb = obs["rgb"]
-            if rgb.dtype != torch.uint8 or not rgb.is_contiguous() or tuple(rgb.shape) != (B, H, W, 6):
+            if rgb.dtype != torch.uint8 or not rgb.is_contiguous() or tuple(rgb.shape) != (B_src, H, W, 6):
                 raise L.PnvoError("raw rgb pairs must be contiguous uint8 [B, H, W, 6]")
         if use_depth or n_dd or use_td:
             depth = obs["depth"]
-            if depth.dtype != torch.float32 or not depth.is_contiguous() or tuple(depth.shape) != (B, H, W, 2):
+            if depth.dtype != torch.float32 or not depth.is_contiguous() or tuple(depth.shape) != (B_src, H, W, 2):
                 raise L.PnvoError("raw depth pairs must be contiguous fp32 [B, H, W, 2]")
         if n_dd:
             end_vals = getattr(self, "_raw_dd_end_vals", None) or gu.discretize_end_vals(n_dd)
@@ -252,8 +262,8 @@ class VisualOdometryCNNBase(nn.Module):
                 gen = getattr(self, "_raw_td_gen", None)
                 if gen is None:  # configs/vo/vo_pointnav.yaml: VO.GEOMETRY (hfov passed verbatim)
                     gen = self._raw_td_gen = gu.NormalizedDepth2TopDownViewHabitatTorch(0.1, 10.0, H, W, 70)
-                if getattr(plan, "td_pair", None) is None:
-                    plan.td_pair = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev)
+                if getattr(plan, "td_pair", None) is None or plan.td_pair.shape[0] != B_src:
+                    plan.td_pair = torch.empty(B_src, H, W, 2, dtype=torch.float32, device=dev)
                 td = gu.gen_top_down_view_pairs(gen, depth, out=plan.td_pair)
         C = enc.input_channels
         n_pix = B * H * W
@@ -264,7 +274,7 @@ class VisualOdometryCNNBase(nn.Module):
             if training:
                 ops.append(L.op_zero(plan.in_stats))
                 ops.append(L.op_raw_stats(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
-                                          plan.in_stats))
+                                          plan.in_stats, pair_map=pair_map, hw=H * W))
                 if plan.world_size > 1:
                     L.run_ops(ops, dev)
                     ops = []
@@ -276,7 +286,8 @@ class VisualOdometryCNNBase(nn.Module):
             scale = shift = None
         ops.append(L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
                                      scale, shift, plan.x0_for(parity), row_w=plan.W if plan.x0_pitch else 0,
-                                     out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0) if parity == 0 else None))
+                                     out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0) if parity == 0 else None,
+                                     pair_map=pair_map, hw=H * W))
         L.run_ops(ops, dev)
         if not prepare_only:
             self._run_backbone(plan, parity)

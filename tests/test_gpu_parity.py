@@ -507,6 +507,70 @@ def test_raw_input_pipeline_matches_reference_inputs(case):
             assert rel(y2, y1) <= 6e-3
 
 
+@pytest.mark.parametrize("case", ["r18_30ch", "r18_8ch"])
+def test_inverse_pair_augmentation_on_device(case):
+    """8f-2: `pair_map` rows (2 * source pair + swap flag) expanded by the input kernels == the reference dataset's way
+    (a second, channel-swapped copy of the frames built on the host, regression_geo_invariance_iter_dataset.py:342-366):
+    identical assembled input in eval mode, equal running statistics and outputs in training mode."""
+    import copy
+
+    from pointnav_vo_b200.vo.dataset import geo_invariance as gi
+
+    model, space, _ = _load_vo(case)
+    obs = helpers.vo_inputs(3, 23, space, "cuda")
+    rgb, dep = obs["rgb"].to(torch.uint8).contiguous(), obs["depth"].contiguous()
+    pm = gi.make_pair_map([2, 3, 2], act_type=[2, 3], geo_invariance_types=("inverse_joint_train",))
+    pm["pair_map"] = np.concatenate([pm["pair_map"], np.array([4, 1], np.int32)])  # ragged tail: repeats, odd row count
+    pmap = torch.from_numpy(pm["pair_map"]).cuda()
+    src, sw = (pmap >> 1).long(), (pmap & 1).bool()
+
+    def expand(t, half):
+        e = t[src].clone()
+        e[sw] = torch.cat([e[sw][..., half:], e[sw][..., :half]], -1)
+        return e.contiguous()
+
+    host = {"rgb": expand(rgb, 3), "depth": expand(dep, 1)}
+    devm = {"rgb": rgb, "depth": dep, "pair_map": pmap}
+    m2 = copy.deepcopy(model)
+    R = pmap.numel()
+    for train in (False, True):
+        model.train(train)
+        m2.train(train)
+        with torch.no_grad():
+            y1 = model(host)
+            x1 = model._plan_for(host, False, train).x0.clone()
+            y2 = m2(devm)
+            x2 = m2._plan_for(devm, False, train).x0.clone()
+        assert y1.shape == y2.shape == (R, 3)
+        if not train:
+            assert torch.equal(x1, x2)
+            assert torch.equal(y1, y2)
+        else:
+            r1, r2 = model.visual_encoder.running_mean_and_var, m2.visual_encoder.running_mean_and_var
+            assert rel(r2._mean, r1._mean) <= 1e-6 and rel(r2._var, r1._var) <= 1e-6
+            assert float(r1._count) == float(r2._count)
+            d = (x1.float() - x2.float()).abs()
+            assert d.max().item() <= 2e-3 and (d > 0).float().mean().item() < 0.01  # isolated fp16 ulps from the fp32 statistics
+            assert rel(y2, y1) <= 8e-3
+    # one fused optimisation step with the inversion loss on an interleaved batch: same loss either way
+    from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+    pm = gi.make_pair_map([2, 3, 2], act_type=[2, 3], geo_invariance_types=("inverse_joint_train",))
+    pmap = torch.from_numpy(pm["pair_map"]).cuda()
+    src, sw = (pmap >> 1).long(), (pmap & 1).bool()
+    host = {"rgb": expand(rgb, 3), "depth": expand(dep, 1)}
+    devm = {"rgb": rgb, "depth": dep, "pair_map": pmap}
+    rng = np.random.default_rng(5)
+    tg = torch.from_numpy(gi.expand_targets(rng.normal(0, 0.2, (3, 3)).astype(np.float32), pm)).cuda()
+    acts = torch.from_numpy(pm["actions"]).cuda()
+    losses = []
+    for m, o in ((model, host), (m2, devm)):
+        m.train()
+        t = FusedVOTrainStep(m, loss_inv_weight=1.0, move_forward_id=1)
+        losses.append([float(t.step(o, tg, acts).item()) for _ in range(2)])
+    assert np.allclose(losses[0], losses[1], rtol=2e-2), losses
+
+
 def test_geo_inversion_loss_and_gradient():
     """a6: geometric-inversion loss on the device against the oracle (pinned to the reference), value + gradient;
     the known-answer case (ground-truth inverse poses) must give ~0 (the reference's train_debug check)."""

@@ -314,3 +314,36 @@ def test_reference_checkpoint_envelopes_load(tmp_path):
     for (n, t1), (_, t3) in zip(pol.net.visual_encoder.state_dict().items(), pol3.net.visual_encoder.state_dict().items()):
         assert torch.equal(t1, t3), n
     assert not torch.equal(pol.critic.fc.weight, pol3.critic.fc.weight)
+
+
+def test_pair_map_follows_the_dataset_rules_and_inverse_targets_zero_the_inversion_loss():
+    """8f-2: device-side inverse-pair augmentation, host part.  Row selection mirrors
+    regression_geo_invariance_iter_dataset.py:290-366; the targets of the swapped rows make the reference's inversion loss
+    (oracle, pinned to the reference) vanish."""
+    from oracle import vo_oracle as vo
+    from pointnav_vo_b200.vo.common.common_vars import MOVE_FORWARD, TURN_LEFT, TURN_RIGHT
+    from pointnav_vo_b200.vo.dataset import geo_invariance as gi
+
+    acts = [TURN_LEFT, TURN_RIGHT, MOVE_FORWARD, TURN_LEFT]
+    # unified model, no augmentation: one row per pair
+    pm = gi.make_pair_map(acts, act_type=-1, geo_invariance_types=())
+    assert pm["pair_map"].tolist() == [0, 2, 4, 6] and pm["actions"].tolist() == acts
+    # joint left/right training: every turn pair followed by its swapped twin with the opposite action; forward pairs
+    # are kept (joint training) but never inverted
+    pm = gi.make_pair_map(acts, act_type=[TURN_LEFT, TURN_RIGHT], geo_invariance_types=("inverse_joint_train",))
+    assert pm["pair_map"].tolist() == [0, 1, 2, 3, 4, 6, 7]
+    assert pm["actions"].tolist() == [TURN_LEFT, TURN_RIGHT, TURN_RIGHT, TURN_LEFT, MOVE_FORWARD, TURN_LEFT, TURN_RIGHT]
+    assert pm["data_types"].tolist() == [0, 1, 0, 1, 0, 0, 1]
+    # act-specific model with augmentation only: own action as is, the OTHER turn action only as its inverse
+    pm = gi.make_pair_map(acts, act_type=TURN_LEFT, geo_invariance_types=("inverse_data_augment_only",))
+    assert pm["pair_map"].tolist() == [0, 3, 6] and pm["actions"].tolist() == [TURN_LEFT, TURN_LEFT, TURN_LEFT]
+    rng = np.random.default_rng(0)
+    d = np.concatenate([rng.normal(0, 0.2, (16, 2)), rng.normal(0, 0.3, (16, 1))], 1).astype(np.float32)
+    turn = [TURN_LEFT, TURN_RIGHT] * 8
+    pm = gi.make_pair_map(turn, act_type=[TURN_LEFT, TURN_RIGHT], geo_invariance_types=("inverse_joint_train",))
+    tg = gi.expand_targets(d, pm)
+    assert tg.shape == (32, 3) and np.array_equal(tg[0::2], d)
+    loss = vo.geo_invariance_inverse_loss(torch.from_numpy(tg).double(), torch.from_numpy(pm["actions"]))
+    assert float(loss) <= 1e-12
+    again = gi.inverse_delta_states(gi.inverse_delta_states(d))
+    assert np.allclose(again, d, atol=1e-6)
