@@ -4,6 +4,7 @@
 // (un)packing, the tiny regression head (vo_cnn.py:216-227) and a flat-bucket Adam.
 // All activation tensors are NHWC fp16 with the channel count padded to a multiple of 8, so every
 // thread moves 16-byte vectors.
+#include <cstdlib>
 #include "common.cuh"
 #include "elem.cuh"
 
@@ -373,10 +374,25 @@ __device__ __forceinline__ void store8h_lo(__half* base, int64_t idx8, const flo
 }
 
 // y = [relu]( GN(x) [+ res] )
+template <bool EARLY>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
   extern __shared__ float s_ab[];  // a_c [C], b_c [C]
   const int b = blockIdx.y;
   const int C = a.C;
+  const int c8 = C >> 3;
+  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
+  const int64_t base = static_cast<int64_t>(b) * per_sample;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // the first element's loads are issued BEFORE the statistics -> coefficient chain (two dependent global loads, fp64
+  // divide / sqrt, a barrier): the small layers are latency-bound, not bandwidth-bound
+  float v[8], r[8], rl[8];
+  const bool first = EARLY && i < per_sample;
+  if (first) {
+    load8(a.x, base + i, a.x_fp32, v);
+    if (a.res) load8(a.res, base + i, 0, r);
+    if (a.res_lo) load8(a.res_lo, base + i, 0, rl);
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     group_mean_rstd(a.stats, b, a.G, c / a.cpg, a.cnt, a.eps, mean, rstd);
@@ -385,25 +401,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
     s_ab[C + c] = (c < a.C_real) ? a.beta[c] - mean * ga : 0.f;
   }
   __syncthreads();
-  const int c8 = C >> 3;
-  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
-  const int64_t base = static_cast<int64_t>(b) * per_sample;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  bool loaded = first;
+  for (; i < per_sample; i += stride) {
     const int cc = static_cast<int>(i % c8) * 8;
-    float v[8];
-    load8(a.x, base + i, a.x_fp32, v);
+    if (!loaded) {
+      load8(a.x, base + i, a.x_fp32, v);
+      if (a.res) load8(a.res, base + i, 0, r);
+      if (a.res_lo) load8(a.res_lo, base + i, 0, rl);
+    }
+    loaded = false;
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_ab[cc + e], s_ab[C + cc + e]);
     if (a.res) {
-      float r[8];
-      load8(a.res, base + i, 0, r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += r[e];
       if (a.res_lo) {
-        load8(a.res_lo, base + i, 0, r);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += r[e];
+        for (int e = 0; e < 8; ++e) v[e] += rl[e];
       }
     }
     if (a.relu) {
@@ -549,6 +563,73 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __half* __restrict_
       }
     }
     store8h(dy, out_base + i, acc);
+  }
+}
+
+// Same gradient, one thread per 2 x 2 block of outputs x 8 channels.  Rows 2i / 2i+1 only ever belong to the window rows
+// i (taps r = 1 / 2) and i+1 (tap r = 0, odd row only), so the block needs exactly the four windows (i..i+1, j..j+1) and
+// every window is fetched by four blocks instead of by its nine outputs: 12 loads + 4 stores per 4 outputs instead of
+// 27 + 4 (the per-output gather was bound by load/store issue at 1.6 TB/s of DRAM traffic, not by HBM).
+__global__ void __launch_bounds__(256) pool_bwd2x2_kernel(const __half* __restrict__ g, const __half* __restrict__ pooled,
+                                                          const uint8_t* __restrict__ argmax, __half* __restrict__ dy,
+                                                          int H, int W, int PH, int PW, int C) {
+  const int b = blockIdx.y;
+  const int c8 = C >> 3;
+  const int BH = (H + 1) >> 1, BW = (W + 1) >> 1;
+  const int per_sample = BH * BW * c8;
+  const int64_t out_base = static_cast<int64_t>(b) * H * W * c8;
+  const int64_t p_base = static_cast<int64_t>(b) * PH * PW * c8;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < per_sample; it += gridDim.x * blockDim.x) {
+    const int q = it % c8;
+    const int blk = it / c8;
+    const int j = blk % BW;
+    const int i = blk / BW;
+    uint2 am[4];
+    uint4 gv[4], pv[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ph = i + (k >> 1), pw = j + (k & 1);
+      ok[k] = ph < PH && pw < PW;
+      am[k] = make_uint2(0xffffffffu, 0xffffffffu);
+      gv[k] = pv[k] = make_uint4(0, 0, 0, 0);
+      if (ok[k]) {
+        const int64_t pi = p_base + (static_cast<int64_t>(ph) * PW + pw) * c8 + q;
+        am[k] = __ldg(reinterpret_cast<const uint2*>(argmax) + pi);
+        gv[k] = __ldg(reinterpret_cast<const uint4*>(g) + pi);
+        pv[k] = __ldg(reinterpret_cast<const uint4*>(pooled) + pi);
+      }
+    }
+    float acc[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2* g2 = reinterpret_cast<const __half2*>(&gv[k]);
+      const __half2* p2 = reinterpret_cast<const __half2*>(&pv[k]);
+      const int a = k >> 1, bb = k & 1;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int t = ((e < 4 ? am[k].x : am[k].y) >> (8 * (e & 3))) & 0xff;  // 0xff (never a tap) when !ok
+        const float gval = (e & 1) ? __high2float(g2[e >> 1]) : __low2float(g2[e >> 1]);
+        const float pval = (e & 1) ? __high2float(p2[e >> 1]) : __low2float(p2[e >> 1]);
+        const float gm = pval > 0.f ? gval : 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int dh = o >> 1, dw = o & 1;
+          // tap of window (a, bb) that lands on output (dh, dw): row 2(i+a)-1+r = 2i+dh  ->  r = dh + 1 - 2a
+          const int r = dh + 1 - 2 * a, sx = dw + 1 - 2 * bb;
+          if (r >= 0 && sx >= 0 && t == r * 3 + sx) acc[o][e] += gm;  // r, sx fold at compile time
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int h = 2 * i + (o >> 1), w = 2 * j + (o & 1);
+      if (h < H && w < W) store8h(dy, out_base + (static_cast<int64_t>(h) * W + w) * c8 + q, acc[o]);
+    }
   }
 }
 
@@ -708,8 +789,16 @@ static int gn_grid_x(int64_t per_sample_items, int B, int c8) {
 int gn_apply_launch(const GnArgs& a, int B, cudaStream_t st) {
   PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 4096, "gn_apply: C=%d", a.C);
   if (B <= 0 || a.HW <= 0) return 0;
-  const int gx = gn_grid_x(static_cast<int64_t>(a.HW) * (a.C / 8), B, a.C / 8);
-  gn_apply_kernel<<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a);
+  // every block pays the statistics -> coefficient prologue: at least `min_items` vectors per thread
+  // (measured over the 32 launches of a ResNet-18 step at B = 256: 729 us -> 678 us with 4 vectors per thread and the
+  // early loads of the kernel's first iteration)
+  static const int min_items = getenv("PNVO_GN_MIN_ITEMS") ? atoi(getenv("PNVO_GN_MIN_ITEMS")) : 4;
+  const int64_t items = static_cast<int64_t>(a.HW) * (a.C / 8);
+  const int gx = static_cast<int>(std::min<int64_t>(gn_grid_x(items, B, a.C / 8),
+                                                    std::max<int64_t>(1, ceil_div64(items, 256 * min_items))));
+  static const int early = getenv("PNVO_GN_EARLY") ? atoi(getenv("PNVO_GN_EARLY")) : 1;
+  if (early) gn_apply_kernel<true><<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a);
+  else gn_apply_kernel<false><<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a);
   count_launch();
   return check_launch("gn_apply");
 }
@@ -724,6 +813,13 @@ int gn_pool_launch(const GnArgs& a, int B, int H, int W, int PH, int PW, uint8_t
 int pool_bwd_launch(const __half* g, const __half* pooled, const uint8_t* argmax, __half* dy, int B, int H, int W,
                     int PH, int PW, int C, cudaStream_t st) {
   if (B <= 0) return 0;
+  static const int blocked = getenv("PNVO_POOL_BWD_2X2") ? atoi(getenv("PNVO_POOL_BWD_2X2")) : 1;
+  if (blocked && PH == (H + 1) / 2 && PW == (W + 1) / 2) {  // 3x3 / stride 2 / pad 1 geometry
+    const int gx2 = gn_grid_x(static_cast<int64_t>((H + 1) / 2) * ((W + 1) / 2) * (C / 8), B, C / 8);
+    pool_bwd2x2_kernel<<<dim3(gx2, B), 256, 0, st>>>(g, pooled, argmax, dy, H, W, PH, PW, C);
+    count_launch();
+    return check_launch("pool_bwd2x2");
+  }
   const int gx = gn_grid_x(static_cast<int64_t>(H) * W * (C / 8), B, C / 8);
   pool_bwd_kernel<<<dim3(gx, B), 256, 0, st>>>(g, pooled, argmax, dy, H, W, PH, PW, C);
   count_launch();

@@ -80,6 +80,7 @@ struct TopDownArgs {
   float* out;
   int64_t out_frame_stride, out_pix_stride;
   int32_t* count;
+  int band_rows;  // rows of the crop whose horizontal blur is staged in shared memory at a time
 };
 
 __device__ __forceinline__ float blur_h(const float* row, int c, int W, int64_t ps) {
@@ -163,30 +164,42 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     ra = 0;
     rb = min(a.k.rows_around_center * 2, h);
   }
-  const int n_pts = (rb - ra) * w;
   const float fH = static_cast<float>(H), fW = static_cast<float>(W);
+  // The horizontal pass is computed ONCE per (row, column) into shared memory, band by band (band + 2 rows of the crop
+  // fit next to the histogram), and the vertical pass reads three shared-memory values: 3.1 global loads per point
+  // instead of 9, and no per-point index division (a warp owns whole rows).  Same operations in the same order as the
+  // per-point version, so the counts stay bit-exact.
   // (warp-aggregating the histogram atomics with match.any was measured slower: 0.36 vs 0.335 ms for 512 frames)
-#pragma unroll 4
-  for (int i = tid; i < n_pts; i += nt) {
-    const int rr = i / w;
-    const int cc = i - rr * w;
-    const int r = r0 + ra + rr;  // frame row
-    const int c = c0 + cc;       // frame column
-    // horizontal pass on rows r-1, r, r+1 (zero outside the crop == zero outside the frame / bbox)
-    const float hm = (r > r0) ? blur_h(D + static_cast<int64_t>(r - 1) * W * ps, c, W, ps) : 0.0f;
-    const float h0 = blur_h(D + static_cast<int64_t>(r) * W * ps, c, W, ps);
-    const float hp = (r < r1) ? blur_h(D + static_cast<int64_t>(r + 1) * W * ps, c, W, ps) : 0.0f;
-    const float v = __fadd_rn(__fmul_rn(__fadd_rn(hm, hp), 0.25f), __fmul_rn(h0, 0.5f));
-    const float z = __fadd_rn(__fmul_rn(v, a.k.depth_scale), a.k.depth_off);  // :558-560
-    const float x = __fmul_rn(__ldg(a.ray + c), z);                            // :656
-    const float nx = __fdiv_rn(__fsub_rn(x, a.k.min_x), a.k.x_den);            // :679
-    const float nz = __fdiv_rn(__fsub_rn(z, a.k.depth_off), a.k.z_den);        // :680
-    const float frow = __fsub_rn(fH, ceilf(__fmul_rn(fH, nz)));                // :689-691
-    const float fcol = floorf(__fmul_rn(fW, nx));                              // :692
-    if (frow >= 0.0f && frow < fH && fcol >= 0.0f && fcol < fW) {              // :706-711
-      const int cell = static_cast<int>(frow) * W + static_cast<int>(fcol);
-      atomicAdd(&hist[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+  float* __restrict__ hb = reinterpret_cast<float*>(s_col_any + W);
+  const int lane = tid & 31, wid = tid >> 5, n_warps = nt >> 5;
+  const int band = a.band_rows;
+  for (int b0 = ra; b0 < rb; b0 += band) {
+    const int nb = min(band, rb - b0);
+    for (int k = wid; k < nb + 2; k += n_warps) {
+      const int r = r0 + b0 - 1 + k;  // frame row; rows outside the crop are zero (== zero border of the blur)
+      const bool in = r >= r0 && r <= r1;
+      const float* row = D + static_cast<int64_t>(r) * W * ps;
+      for (int cc = lane; cc < w; cc += 32) hb[k * w + cc] = in ? blur_h(row, c0 + cc, W, ps) : 0.0f;
     }
+    __syncthreads();
+    for (int k = wid; k < nb; k += n_warps) {
+      const float* h3 = hb + k * w;
+      for (int cc = lane; cc < w; cc += 32) {
+        const float hm = h3[cc], h0 = h3[w + cc], hp = h3[2 * w + cc];
+        const float v = __fadd_rn(__fmul_rn(__fadd_rn(hm, hp), 0.25f), __fmul_rn(h0, 0.5f));
+        const float z = __fadd_rn(__fmul_rn(v, a.k.depth_scale), a.k.depth_off);  // :558-560
+        const float x = __fmul_rn(__ldg(a.ray + c0 + cc), z);                      // :656
+        const float nx = __fdiv_rn(__fsub_rn(x, a.k.min_x), a.k.x_den);            // :679
+        const float nz = __fdiv_rn(__fsub_rn(z, a.k.depth_off), a.k.z_den);        // :680
+        const float frow = __fsub_rn(fH, ceilf(__fmul_rn(fH, nz)));                // :689-691
+        const float fcol = floorf(__fmul_rn(fW, nx));                              // :692
+        if (frow >= 0.0f && frow < fH && fcol >= 0.0f && fcol < fW) {              // :706-711
+          const int cell = static_cast<int>(frow) * W + static_cast<int>(fcol);
+          atomicAdd(&hist[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+        }
+      }
+    }
+    __syncthreads();
   }
   __syncthreads();
   // phase 3: max + normalise
@@ -399,10 +412,18 @@ int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride,
   PNVO_REQUIRE(in_pix_stride >= 1, "topdown_project: in_pix_stride");
   a.depth = depth; a.in_stride = in_stride; a.in_pix = in_pix_stride; a.in_group = in_group; a.out_group = out_group; a.H = H; a.W = W; a.ray = ray; a.k = *consts;
   a.out = out; a.out_frame_stride = out_frame_stride; a.out_pix_stride = out_pix_stride; a.count = count;
-  const size_t smem = static_cast<size_t>((H * W + 1) / 2) * 4 + static_cast<size_t>(H + W) * 4;
+  const size_t smem_hist = static_cast<size_t>((H * W + 1) / 2) * 4 + static_cast<size_t>(H + W) * 4;
+  // horizontal-blur staging: as many crop rows (+2 halo rows) as fit in what the histogram leaves of 226 KB
+  const int rows_max = 2 * consts->rows_around_center;
+  int band = static_cast<int>((226 * 1024 - smem_hist) / (static_cast<size_t>(W) * 4)) - 2;
+  PNVO_REQUIRE(band >= 1, "topdown_project: no shared memory left for the blur rows (%dx%d)", H, W);
+  if (band > rows_max) band = rows_max;
+  band = (rows_max + ceil_div(rows_max, band) - 1) / ceil_div(rows_max, band);  // equal bands
+  a.band_rows = band;
+  const size_t smem = smem_hist + static_cast<size_t>(band + 2) * W * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(topdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(topdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   topdown_kernel<<<n_frames, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
