@@ -267,29 +267,36 @@ int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample
 // weights, which runs on the TMA / raster kernels instead of the divisibility-testing generic producer; for the
 // 1x1 / stride-2 downsample branch it scatters the compact 1x1 result back to the input resolution.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) upsample2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B,
-                                                        int OH, int OW, int IH, int IW, int c8) {
-  const int64_t total = static_cast<int64_t>(B) * IH * IW * c8;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int q = static_cast<int>(i % c8);
-    int64_t t = i / c8;
-    const int w = static_cast<int>(t % IW);
-    t /= IW;
-    const int h = static_cast<int>(t % IH);
-    const int b = static_cast<int>(t / IH);
+// One thread per PAIR of destination pixels (w = 2j, 2j + 1) x 8 channels of one sample (blockIdx.y): one load (even rows
+// only), two 16-byte stores, 32-bit index arithmetic (the per-destination-vector version with 64-bit div / mod ran at
+// 2 TB/s of write traffic).
+__global__ void __launch_bounds__(256) upsample2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int OH,
+                                                        int OW, int IH, int IW, int c8) {
+  const int b = blockIdx.y;
+  const int BW = (IW + 1) >> 1;
+  const int items = IH * BW * c8;
+  const uint4* __restrict__ s = src + static_cast<int64_t>(b) * OH * OW * c8;
+  uint4* __restrict__ d = dst + static_cast<int64_t>(b) * IH * IW * c8;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const int q = it % c8;
+    const int t = it / c8;
+    const int j = t % BW;
+    const int h = t / BW;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (((h | w) & 1) == 0 && (h >> 1) < OH && (w >> 1) < OW)
-      v = __ldg(src + ((static_cast<int64_t>(b) * OH + (h >> 1)) * OW + (w >> 1)) * c8 + q);
-    dst[i] = v;
+    if ((h & 1) == 0 && (h >> 1) < OH && j < OW) v = __ldg(s + ((h >> 1) * OW + j) * c8 + q);
+    const int o = (h * IW + 2 * j) * c8 + q;
+    d[o] = v;
+    if (2 * j + 1 < IW) d[o + c8] = make_uint4(0, 0, 0, 0);
   }
 }
 int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int IH, int IW, int C, cudaStream_t st) {
   PNVO_REQUIRE(src && dst && C % 8 == 0, "upsample2: bad arguments");
-  const int64_t total = static_cast<int64_t>(B) * IH * IW * (C / 8);
-  if (total <= 0) return 0;
-  upsample2_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
-      reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B, OH, OW, IH, IW, C / 8);
+  const int64_t items = static_cast<int64_t>(IH) * ((IW + 1) / 2) * (C / 8);
+  PNVO_REQUIRE(static_cast<int64_t>(IH) * IW * (C / 8) < (1ll << 30), "upsample2: sample too large");
+  if (items <= 0 || B <= 0) return 0;
+  const int gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(items, 256 * 2), (148 * 16) / std::max(1, std::min(B, 148 * 16)) + 1)));
+  upsample2_kernel<<<dim3(gx, B), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), OH, OW,
+                                                IH, IW, C / 8);
   count_launch();
   return check_launch("upsample2");
 }
@@ -373,26 +380,16 @@ __device__ __forceinline__ void store8h_lo(__half* base, int64_t idx8, const flo
   store8h(base, idx8, r);
 }
 
-// y = [relu]( GN(x) [+ res] )
-template <bool EARLY>
+// y = [relu]( GN(x) [+ res] ).  SPLIT: residual fp16 planes of res / y (split-precision forward) -- a template parameter,
+// not a run-time branch.  This kernel lives on occupancy (40 registers, 6 CTAs per SM): every variant that added
+// registers was measured slower over the 32 launches of a training step (570 us): run-time split branches in the loop
+// body 658 us, first-iteration loads hoisted above the statistics prologue 678 us, 2 / 4 explicitly batched vectors per
+// thread 797 / 1023 us, __launch_bounds__(256, 8) (32 registers, spills) 712 us.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
   extern __shared__ float s_ab[];  // a_c [C], b_c [C]
   const int b = blockIdx.y;
   const int C = a.C;
-  const int c8 = C >> 3;
-  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
-  const int64_t base = static_cast<int64_t>(b) * per_sample;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  // the first element's loads are issued BEFORE the statistics -> coefficient chain (two dependent global loads, fp64
-  // divide / sqrt, a barrier): the small layers are latency-bound, not bandwidth-bound
-  float v[8], r[8], rl[8];
-  const bool first = EARLY && i < per_sample;
-  if (first) {
-    load8(a.x, base + i, a.x_fp32, v);
-    if (a.res) load8(a.res, base + i, 0, r);
-    if (a.res_lo) load8(a.res_lo, base + i, 0, rl);
-  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     group_mean_rstd(a.stats, b, a.G, c / a.cpg, a.cnt, a.eps, mean, rstd);
@@ -401,23 +398,25 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
     s_ab[C + c] = (c < a.C_real) ? a.beta[c] - mean * ga : 0.f;
   }
   __syncthreads();
-  bool loaded = first;
-  for (; i < per_sample; i += stride) {
+  const int c8 = C >> 3;
+  const int64_t per_sample = static_cast<int64_t>(a.HW) * c8;
+  const int64_t base = static_cast<int64_t>(b) * per_sample;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int cc = static_cast<int>(i % c8) * 8;
-    if (!loaded) {
-      load8(a.x, base + i, a.x_fp32, v);
-      if (a.res) load8(a.res, base + i, 0, r);
-      if (a.res_lo) load8(a.res_lo, base + i, 0, rl);
-    }
-    loaded = false;
+    float v[8];
+    load8(a.x, base + i, a.x_fp32, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_ab[cc + e], s_ab[C + cc + e]);
     if (a.res) {
+      float r[8];
+      load8(a.res, base + i, 0, r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += r[e];
-      if (a.res_lo) {
+      if (SPLIT && a.res_lo) {
+        load8(a.res_lo, base + i, 0, r);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += rl[e];
+        for (int e = 0; e < 8; ++e) v[e] += r[e];
       }
     }
     if (a.relu) {
@@ -425,7 +424,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
       for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
     }
     store8h(a.y, base + i, v);
-    if (a.y_lo) store8h_lo(a.y_lo, base + i, v);
+    if (SPLIT && a.y_lo) store8h_lo(a.y_lo, base + i, v);
   }
 }
 
@@ -790,15 +789,14 @@ int gn_apply_launch(const GnArgs& a, int B, cudaStream_t st) {
   PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 4096, "gn_apply: C=%d", a.C);
   if (B <= 0 || a.HW <= 0) return 0;
   // every block pays the statistics -> coefficient prologue: at least `min_items` vectors per thread
-  // (measured over the 32 launches of a ResNet-18 step at B = 256: 729 us -> 678 us with 4 vectors per thread and the
-  // early loads of the kernel's first iteration)
+  // (4 vectors per thread: 579 -> 570 us over the 32 launches of a ResNet-18 step at B = 256, all of it on layer4)
   static const int min_items = getenv("PNVO_GN_MIN_ITEMS") ? atoi(getenv("PNVO_GN_MIN_ITEMS")) : 4;
   const int64_t items = static_cast<int64_t>(a.HW) * (a.C / 8);
   const int gx = static_cast<int>(std::min<int64_t>(gn_grid_x(items, B, a.C / 8),
                                                     std::max<int64_t>(1, ceil_div64(items, 256 * min_items))));
-  static const int early = getenv("PNVO_GN_EARLY") ? atoi(getenv("PNVO_GN_EARLY")) : 1;
-  if (early) gn_apply_kernel<true><<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a);
-  else gn_apply_kernel<false><<<dim3(gx, B), 256, 2 * a.C * sizeof(float), st>>>(a);
+  const size_t sm = 2 * a.C * sizeof(float);
+  if (a.y_lo || a.res_lo) gn_apply_kernel<true><<<dim3(gx, B), 256, sm, st>>>(a);
+  else gn_apply_kernel<false><<<dim3(gx, B), 256, sm, st>>>(a);
   count_launch();
   return check_launch("gn_apply");
 }
@@ -917,39 +915,94 @@ int unpack_dw_launch(const float* dwp, int Cout, int Cin, int R, int S, int cin_
 // 3-5 us launch per layer -- 22 weight packs, 22 gradient unpacks and 21 GroupNorm parameter-gradient reductions per
 // training step become three launches.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_w_multi_kernel(const PackDesc* __restrict__ tab) {
+// A block takes kPackRows consecutive output channels (x a chunk of input channels when a row exceeds the staging buffer):
+// the OIHW rows are read contiguously, converted once and staged in shared memory; the fprop layout is then written as
+// contiguous runs along c and the dgrad / transposed layout as 16-byte vectors along n (the first version walked the
+// elements in OIHW order and scattered 2-byte stores into both layouts: 109 us per step for 11 M weights).
+static constexpr int kPackRows = 8;
+static constexpr int kPackElems = 2304;  // staged elements per row (fp16): a 3x3 x 256-channel filter row
+__global__ void __launch_bounds__(256) pack_w_multi_kernel(const PackDesc* __restrict__ tab) {
+  __shared__ __align__(16) __half sm[kPackRows][kPackElems];
   const PackDesc d = tab[blockIdx.y];
-  const int64_t per = static_cast<int64_t>(d.Cin) * d.R * d.S;
-  const int64_t total = static_cast<int64_t>(d.Cout) * per;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int s = static_cast<int>(i % d.S);
-    const int r = static_cast<int>((i / d.S) % d.R);
-    const int c = static_cast<int>((i / (static_cast<int64_t>(d.S) * d.R)) % d.Cin);
-    const int n = static_cast<int>(i / per);
-    const float wv = d.w[static_cast<int64_t>(n) * d.src_ld + (i - static_cast<int64_t>(n) * per)];
-    __half h = __float2half_rn(wv);
-    if (d.t_mode & 2) h = __float2half_rn(wv - __half2float(h));  // residual plane (split-fp16 mode)
-    if (d.wp) d.wp[static_cast<int64_t>(n) * d.ld_p + (r * d.S + s) * d.cin_pad + c] = h;
+  const int RS = d.R * d.S;
+  const int per = d.Cin * RS;
+  const int CC = min(d.Cin, kPackElems / RS);          // channels per chunk (>= 1: RS <= 64)
+  const int n_chunks = (d.Cin + CC - 1) / CC;
+  const int n_groups = (d.Cout + kPackRows - 1) / kPackRows;
+  for (int u = blockIdx.x; u < n_groups * n_chunks; u += gridDim.x) {
+    const int n0 = (u / n_chunks) * kPackRows;
+    const int cb = (u % n_chunks) * CC;
+    const int cc = min(CC, d.Cin - cb);
+    const int len = cc * RS;
+    __syncthreads();  // the previous unit's readers are done with sm
+    for (int e = 0; e < kPackRows; ++e) {
+      const bool row = n0 + e < d.Cout;
+      const float* src = d.w + static_cast<int64_t>(n0 + e) * d.src_ld + cb * RS;
+      for (int j = threadIdx.x; j < len; j += blockDim.x) {
+        const float wv = row ? src[j] : 0.f;
+        __half h = __float2half_rn(wv);
+        if (d.t_mode & 2) h = __float2half_rn(wv - __half2float(h));  // residual plane (split-fp16 mode)
+        sm[e][j] = h;
+      }
+    }
+    __syncthreads();
+    if (d.wp) {
+      for (int e = 0; e < kPackRows && n0 + e < d.Cout; ++e) {
+        __half* dst = d.wp + static_cast<int64_t>(n0 + e) * d.ld_p + cb;
+        for (int k = threadIdx.x; k < len; k += blockDim.x) {
+          const int tap = k / cc, c = k - tap * cc;
+          dst[tap * d.cin_pad + c] = sm[e][c * RS + tap];
+        }
+      }
+    }
     if (d.wt) {
-      if ((d.t_mode & 1) == 0) d.wt[static_cast<int64_t>(c) * d.ld_t + ((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.cout_pad + n] = h;
-      else d.wt[static_cast<int64_t>((r * d.S + s) * d.cin_pad + c) * d.ld_t + n] = h;
+      // n0 is a multiple of 8 and cout_pad / ld_t are multiples of 8: the 8 output channels of (c, tap) are one aligned
+      // 16-byte vector (rows beyond Cout hold zeros, like the zero-initialised padding they overwrite)
+      for (int k = threadIdx.x; k < len; k += blockDim.x) {
+        const int c = k / RS, tap = k - c * RS;
+        uint4 v;
+        __half* hv = reinterpret_cast<__half*>(&v);
+#pragma unroll
+        for (int e = 0; e < kPackRows; ++e) hv[e] = sm[e][k];
+        int64_t o;
+        if ((d.t_mode & 1) == 0) {
+          const int r = tap / d.S, sx = tap - r * d.S;
+          o = static_cast<int64_t>(cb + c) * d.ld_t + ((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.cout_pad + n0;
+        } else {
+          o = static_cast<int64_t>(tap * d.cin_pad + cb + c) * d.ld_t + n0;
+        }
+        *reinterpret_cast<uint4*>(d.wt + o) = v;
+      }
     }
   }
 }
-__global__ void unpack_dw_multi_kernel(const UnpackDesc* __restrict__ tab) {
+// Gradient unpack, same staging: packed rows are read as contiguous runs along c, OIHW rows written contiguously.
+static constexpr int kUnpackRows = 4;
+__global__ void __launch_bounds__(256) unpack_dw_multi_kernel(const UnpackDesc* __restrict__ tab) {
+  __shared__ float sm[kUnpackRows][kPackElems];
   const UnpackDesc d = tab[blockIdx.y];
-  const int64_t per = static_cast<int64_t>(d.Cin) * d.R * d.S;
-  const int64_t total = static_cast<int64_t>(d.Cout) * per;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int s = static_cast<int>(i % d.S);
-    const int r = static_cast<int>((i / d.S) % d.R);
-    const int c = static_cast<int>((i / (static_cast<int64_t>(d.S) * d.R)) % d.Cin);
-    const int n = static_cast<int>(i / per);
-    const float v = d.dwp[static_cast<int64_t>(n) * d.ld_p + (r * d.S + s) * d.cin_pad + c];
-    const int64_t o = static_cast<int64_t>(n) * d.dst_ld + (i - static_cast<int64_t>(n) * per);
-    d.grad[o] = d.accumulate ? d.grad[o] + v : v;
+  const int RS = d.R * d.S;
+  const int CC = min(d.Cin, kPackElems / RS);
+  const int n_chunks = (d.Cin + CC - 1) / CC;
+  const int n_groups = (d.Cout + kUnpackRows - 1) / kUnpackRows;
+  for (int u = blockIdx.x; u < n_groups * n_chunks; u += gridDim.x) {
+    const int n0 = (u / n_chunks) * kUnpackRows;
+    const int cb = (u % n_chunks) * CC;
+    const int cc = min(CC, d.Cin - cb);
+    const int len = cc * RS;
+    __syncthreads();
+    for (int e = 0; e < kUnpackRows && n0 + e < d.Cout; ++e) {
+      const float* src = d.dwp + static_cast<int64_t>(n0 + e) * d.ld_p + cb;
+      for (int k = threadIdx.x; k < len; k += blockDim.x) {
+        const int tap = k / cc, c = k - tap * cc;
+        sm[e][c * RS + tap] = src[tap * d.cin_pad + c];
+      }
+    }
+    __syncthreads();
+    for (int e = 0; e < kUnpackRows && n0 + e < d.Cout; ++e) {
+      float* dst = d.grad + static_cast<int64_t>(n0 + e) * d.dst_ld + cb * RS;
+      for (int j = threadIdx.x; j < len; j += blockDim.x) dst[j] = d.accumulate ? dst[j] + sm[e][j] : sm[e][j];
+    }
   }
 }
 __global__ void __launch_bounds__(128) gn_param_grad_multi_kernel(const GnParamDesc* __restrict__ tab, int B) {

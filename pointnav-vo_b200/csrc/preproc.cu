@@ -413,9 +413,9 @@ int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride,
   a.depth = depth; a.in_stride = in_stride; a.in_pix = in_pix_stride; a.in_group = in_group; a.out_group = out_group; a.H = H; a.W = W; a.ray = ray; a.k = *consts;
   a.out = out; a.out_frame_stride = out_frame_stride; a.out_pix_stride = out_pix_stride; a.count = count;
   const size_t smem_hist = static_cast<size_t>((H * W + 1) / 2) * 4 + static_cast<size_t>(H + W) * 4;
-  // horizontal-blur staging: as many crop rows (+2 halo rows) as fit in what the histogram leaves of 226 KB
+  // horizontal-blur staging: as many crop rows (+2 halo rows) as fit in what the histogram leaves of 224 KB
   const int rows_max = 2 * consts->rows_around_center;
-  int band = static_cast<int>((226 * 1024 - smem_hist) / (static_cast<size_t>(W) * 4)) - 2;
+  int band = static_cast<int>((224 * 1024 - smem_hist) / (static_cast<size_t>(W) * 4)) - 2;
   PNVO_REQUIRE(band >= 1, "topdown_project: no shared memory left for the blur rows (%dx%d)", H, W);
   if (band > rows_max) band = rows_max;
   band = (rows_max + ceil_div(rows_max, band) - 1) / ceil_div(rows_max, band);  // equal bands
@@ -423,7 +423,9 @@ int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride,
   const size_t smem = smem_hist + static_cast<size_t>(band + 2) * W * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(topdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // 227 KB per CTA minus the kernel's few static words
+    const cudaError_t e = cudaFuncSetAttribute(topdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    PNVO_REQUIRE(e == cudaSuccess, "topdown_project: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   topdown_kernel<<<n_frames, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);

@@ -897,10 +897,19 @@ def test_train_step_with_prefetched_input_pipeline():
         l1.append(s1.step(obs, tgt).item())
         nxt = batches[k + 1][0] if k + 1 < len(batches) else None
         l2.append(s2.step(obs, tgt, prefetch=nxt).item())
+        # dW is flushed with fp32 atomics (last-bit differences) and Adam's first steps amplify them (measured: 0, 5e-5,
+        # 6e-4, 5e-2 relative loss difference over four free-running steps), so the second trainer is put back on the
+        # first one's weights / moments after every step: each step's forward must then agree to rounding
+        torch.cuda.synchronize()
+        drift = ((s2._flat - s1._flat).abs().max() / s1._flat.abs().max()).item()
+        assert drift <= 2 * s1.lr + 1e-6, drift  # one Adam step moves a weight by at most ~lr
+        s2._flat.copy_(s1._flat)
+        s2._m.copy_(s1._m)
+        s2._v.copy_(s1._v)
+        m2._packed_version = None
     torch.cuda.synchronize()
     for a, b in zip(l1, l2):
-        assert abs(a - b) <= 2e-2 * abs(a) + 1e-6, (l1, l2)  # dW atomics differ in the last bit; Adam amplifies sign flips
-    assert abs(l1[0] - l2[0]) <= 1e-6 * abs(l1[0])            # the first step sees identical weights: bit-equal forward
+        assert abs(a - b) <= 1e-5 * abs(a) + 1e-7, (l1, l2)
     r1, r2 = m1.visual_encoder.running_mean_and_var, m2.visual_encoder.running_mean_and_var
     assert float(r1._count) == float(r2._count) == count0 + 8.0
     assert rel(r2._mean, r1._mean) <= 1e-6 and rel(r2._var, r1._var) <= 1e-6
