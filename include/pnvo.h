@@ -64,6 +64,13 @@ int pnvo_topdown_project_strided(const float* depth, int64_t in_frame_stride, in
                                  int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
                                  int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
 
+/* Same with fp16 depth (the type the reference's HDF5 datasets store, vo/dataset/regression_iter_dataset.py:47-58 and
+ * regression_geo_invariance_iter_dataset.py:229-236): widened exactly to fp32 on load, so the result equals
+ * pnvo_topdown_project_strided on the widened tensor.  Strides are in elements. */
+int pnvo_topdown_project_strided_f16(const uint16_t* depth, int64_t in_frame_stride, int64_t in_pix_stride, int n_frames,
+                                     int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
+                                     int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a13 GAE / discounted returns -- RolloutStorage.compute_returns
  *     (pointnav_vo/rl/common/rollout_storage.py:102-120).

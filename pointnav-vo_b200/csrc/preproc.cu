@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) discretize_kernel(const float* __restrict
 //   reading the frame itself with zero padding at the frame edge.
 // ------------------------------------------------------------------------------------------------
 struct TopDownArgs {
-  const float* depth;
+  const void* depth;  // fp32, or fp16 (the dataset's storage type) with the templated kernel
   int64_t in_stride;
   int64_t in_pix;  // floats between consecutive pixels of one frame (1, or 2 for a [.., 2] depth-pair tensor)
   int in_group, out_group;  // frames interleaved per group: frame n starts at (n / g) * stride + n % g
@@ -83,13 +83,18 @@ struct TopDownArgs {
   int band_rows;  // rows of the crop whose horizontal blur is staged in shared memory at a time
 };
 
-__device__ __forceinline__ float blur_h(const float* row, int c, int W, int64_t ps) {
-  const float a = (c > 0) ? row[(c - 1) * ps] : 0.0f;
-  const float b = row[c * ps];
-  const float d = (c + 1 < W) ? row[(c + 1) * ps] : 0.0f;
+__device__ __forceinline__ float td_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float td_ld(const __half* p) { return __half2float(__ldg(p)); }  // exact widening
+
+template <typename T>
+__device__ __forceinline__ float blur_h(const T* row, int c, int W, int64_t ps) {
+  const float a = (c > 0) ? td_ld(row + (c - 1) * ps) : 0.0f;
+  const float b = td_ld(row + c * ps);
+  const float d = (c + 1 < W) ? td_ld(row + (c + 1) * ps) : 0.0f;
   return __fadd_rn(__fmul_rn(__fadd_rn(a, d), 0.25f), __fmul_rn(b, 0.5f));
 }
 
+template <typename T>
 __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = a.H, W = a.W;
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
   __shared__ int s_bbox[4];
   __shared__ int s_max;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const float* __restrict__ D = a.depth + static_cast<int64_t>(blockIdx.x / a.in_group) * a.in_stride + blockIdx.x % a.in_group;
+  const T* __restrict__ D = static_cast<const T*>(a.depth) + static_cast<int64_t>(blockIdx.x / a.in_group) * a.in_stride + blockIdx.x % a.in_group;
   const int64_t ps = a.in_pix;
 
   for (int i = tid; i < hist_words; i += nt) hist[i] = 0u;
@@ -120,12 +125,12 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     constexpr int kColChunks = 16;  // up to 512 columns
     unsigned col_any = 0u;          // bit k: column lane + 32k of some row of this warp is > 0
     for (int r = wid; r < H; r += n_warps) {
-      const float* row = D + static_cast<int64_t>(r) * W * ps;
+      const T* row = D + static_cast<int64_t>(r) * W * ps;
       bool any = false;
 #pragma unroll 4
       for (int k = 0; k < kColChunks; ++k) {
         const int c = lane + 32 * k;
-        if (c < W && __ldg(row + static_cast<int64_t>(c) * ps) > 0.0f) {
+        if (c < W && td_ld(row + static_cast<int64_t>(c) * ps) > 0.0f) {
           any = true;
           col_any |= 1u << k;
         }
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(1024, 1) topdown_kernel(TopDownArgs a) {
     for (int k = wid; k < nb + 2; k += n_warps) {
       const int r = r0 + b0 - 1 + k;  // frame row; rows outside the crop are zero (== zero border of the blur)
       const bool in = r >= r0 && r <= r1;
-      const float* row = D + static_cast<int64_t>(r) * W * ps;
+      const T* row = D + static_cast<int64_t>(r) * W * ps;
       for (int cc = lane; cc < w; cc += 32) hb[k * w + cc] = in ? blur_h(row, c0 + cc, W, ps) : 0.0f;
     }
     __syncthreads();
@@ -361,9 +366,9 @@ __global__ void goal_update_kernel(double* __restrict__ goal, const float* __res
 }  // namespace pnvo
 
 namespace pnvo {
-int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride, int in_group, int out_group,
+int topdown_launch(const void* depth, int64_t in_stride, int64_t in_pix_stride, int in_group, int out_group,
                    int n_frames, int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
-                   int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream);
+                   int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream, int depth_fp16);
 }
 using namespace pnvo;
 
@@ -388,7 +393,7 @@ extern "C" int pnvo_topdown_project(const float* depth, int64_t in_stride, int n
                                     const float* ray, const pnvo_topdown_consts* consts, float* out,
                                     int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream) {
   return pnvo::topdown_launch(depth, in_stride, 1, 1, 1, n_frames, H, W, ray, consts, out, out_frame_stride,
-                              out_pix_stride, count, stream);
+                              out_pix_stride, count, stream, 0);
 }
 
 extern "C" int pnvo_topdown_project_strided(const float* depth, int64_t in_stride, int64_t in_pix_stride, int n_frames,
@@ -397,13 +402,22 @@ extern "C" int pnvo_topdown_project_strided(const float* depth, int64_t in_strid
                                             int32_t* count, void* stream) {
   return pnvo::topdown_launch(depth, in_stride, in_pix_stride, static_cast<int>(in_pix_stride),
                               static_cast<int>(out_pix_stride), n_frames, H, W, ray, consts, out, out_frame_stride,
-                              out_pix_stride, count, stream);
+                              out_pix_stride, count, stream, 0);
+}
+
+extern "C" int pnvo_topdown_project_strided_f16(const uint16_t* depth, int64_t in_stride, int64_t in_pix_stride,
+                                                int n_frames, int H, int W, const float* ray,
+                                                const pnvo_topdown_consts* consts, float* out, int64_t out_frame_stride,
+                                                int64_t out_pix_stride, int32_t* count, void* stream) {
+  return pnvo::topdown_launch(depth, in_stride, in_pix_stride, static_cast<int>(in_pix_stride),
+                              static_cast<int>(out_pix_stride), n_frames, H, W, ray, consts, out, out_frame_stride,
+                              out_pix_stride, count, stream, 1);
 }
 
 namespace pnvo {
-int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride, int in_group, int out_group,
+int topdown_launch(const void* depth, int64_t in_stride, int64_t in_pix_stride, int in_group, int out_group,
                    int n_frames, int H, int W, const float* ray, const pnvo_topdown_consts* consts, float* out,
-                   int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream) {
+                   int64_t out_frame_stride, int64_t out_pix_stride, int32_t* count, void* stream, int depth_fp16) {
   PNVO_REQUIRE(depth && ray && consts && out, "topdown_project: null argument");
   PNVO_REQUIRE(H > 0 && W > 0 && W <= 512 && static_cast<int64_t>(H) * W <= 110000, "topdown_project: frame %dx%d too large", H, W);
   PNVO_REQUIRE(consts->rows_around_center * 2 * W < 65535, "topdown_project: too many points for uint16 counts");
@@ -424,11 +438,13 @@ int topdown_launch(const float* depth, int64_t in_stride, int64_t in_pix_stride,
   static bool attr_set = false;
   if (!attr_set) {
     // 227 KB per CTA minus the kernel's few static words
-    const cudaError_t e = cudaFuncSetAttribute(topdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(topdown_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(topdown_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     PNVO_REQUIRE(e == cudaSuccess, "topdown_project: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  topdown_kernel<<<n_frames, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  if (depth_fp16) topdown_kernel<__half><<<n_frames, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  else topdown_kernel<float><<<n_frames, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   count_launch();
   return check_launch("topdown_project");
 }

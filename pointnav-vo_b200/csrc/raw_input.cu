@@ -18,7 +18,8 @@ static constexpr int kRawMaxBins = 16;
 
 struct RawArgs {
   const uint8_t* rgb;   // [n_pix][6] (prev rgb, cur rgb) or null
-  const float* depth;   // [n_pix][2] or null (needed for the depth and the one-hot channels)
+  const void* depth;    // [n_pix][2] fp32 (or fp16 when depth_fp16: the dataset's storage type, widened exactly) or null
+  int depth_fp16;
   const float* td;      // [n_pix][2] or null
   const float* edges;   // n_dd + 1 fp32 bin edges (device)
   int use_rgb, use_depth, n_dd, use_td;
@@ -38,6 +39,11 @@ struct RawArgs {
 };
 
 // source pixel + swap flag of output pixel p under the pair map
+__device__ __forceinline__ float2 ld_depth_pair(const RawArgs& a, int64_t p) {
+  if (a.depth_fp16) return __half22float2(__ldg(reinterpret_cast<const __half2*>(a.depth) + p));
+  return __ldg(reinterpret_cast<const float2*>(a.depth) + p);
+}
+
 __device__ __forceinline__ int64_t mapped_pixel(const RawArgs& a, int64_t p, bool& flip) {
   const uint32_t p32 = static_cast<uint32_t>(p), hw = static_cast<uint32_t>(a.hw);  // launchers require n_pix < 2^31
   const uint32_t b = p32 / hw;
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
       rgbv[4] = __fdiv_rn(static_cast<float>(w2 & 0xff), 255.f);
       rgbv[5] = __fdiv_rn(static_cast<float>(w2 >> 8), 255.f);
     }
-    if (use_depth || n_dd > 0) d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
+    if (use_depth || n_dd > 0) d = ld_depth_pair(a, p);
     if (use_td) t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
     if (MAP) {
       if (flip) {  // prev <-> cur
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
       const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
       w[0] = r16[0]; w[1] = r16[1]; w[2] = r16[2];
     }
-    if (a.depth) d = __ldg(reinterpret_cast<const float2*>(a.depth) + p);
+    if (a.depth) d = ld_depth_pair(a, p);
     if (a.use_td) t = __ldg(reinterpret_cast<const float2*>(a.td) + p);
     if (flip) {  // prev <-> cur: bytes [0 1 2 | 3 4 5] -> [3 4 5 | 0 1 2]
       const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
@@ -342,12 +348,13 @@ int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
 
 int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st) {
   // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats, p7 = out_lo,
-  // p8 = pair_map (int32 per output sample, nullable); i10 = pixels per sample (with pair_map)
+  // p8 = pair_map (int32 per output sample, nullable); i10 = pixels per sample (with pair_map); i11 = depth is fp16
   // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch
   (void)f;
   RawArgs a{};
   a.rgb = static_cast<const uint8_t*>(p[0]);
-  a.depth = static_cast<const float*>(p[1]);
+  a.depth = p[1];
+  a.depth_fp16 = i[11];
   a.td = static_cast<const float*>(p[2]);
   a.edges = static_cast<const float*>(p[3]);
   a.scale = static_cast<const float*>(p[4]);

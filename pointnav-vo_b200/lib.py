@@ -62,7 +62,8 @@ _lib = None
 
 EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_discretize_depth",
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
-           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_conv_stem2_supported", "pnvo_conv_stem_wgrad2_supported", "pnvo_graph_capture", "pnvo_graph_launch",
+           "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_topdown_project_strided_f16",
+           "pnvo_conv_stem2_supported", "pnvo_conv_stem_wgrad2_supported", "pnvo_graph_capture", "pnvo_graph_launch",
            "pnvo_graph_destroy"]
 
 
@@ -93,6 +94,8 @@ def load():
     lib.pnvo_topdown_project_strided.argtypes = [vp, i64, i64, i32, i32, i32, vp, ctypes.POINTER(TopdownConsts), vp, i64,
                                                  i64, vp, vp]
     lib.pnvo_topdown_project_strided.restype = i32
+    lib.pnvo_topdown_project_strided_f16.argtypes = lib.pnvo_topdown_project_strided.argtypes
+    lib.pnvo_topdown_project_strided_f16.restype = i32
     lib.pnvo_gae_scan.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
     lib.pnvo_goal_update.argtypes = [vp, vp, vp, i32, vp]
     lib.pnvo_run_ops.argtypes = [ctypes.POINTER(PnvoOp), i32, vp]
@@ -180,21 +183,22 @@ def op_input_stats(srcs, nch, pre_scale, lut, C, Cpad, n_pix, stats_f64):
     return _op(OP_INPUT_STATS, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [None, None, stats_f64])
 
 
-def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0, hw=0):
-    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch, hw]
+def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0, hw=0, depth=None):
+    depth_fp16 = int(depth is not None and depth.dtype == torch.float16)
+    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch, hw, depth_fp16]
 
 
 def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, stats_f64, pair_map=None,
                  hw=0):
     """Batch statistics of the assembled input straight from the raw pairs (csrc/raw_input.cu).  pair_map (int32 per
     OUTPUT sample = 2 * source pair + swap flag) expands / swaps pairs on the fly; n_pix then counts output pixels."""
-    return _op(OP_RAW_STATS, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, hw=hw), (),
+    return _op(OP_RAW_STATS, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, hw=hw, depth=depth), (),
                [rgb_u8, depth, td, edges, None, None, stats_f64, None, pair_map])
 
 
 def op_raw_assemble(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, scale, shift, out,
                     row_w=0, out_pitch=0, out_lo=None, pair_map=None, hw=0):
-    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch, hw), (),
+    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch, hw, depth), (),
                [rgb_u8, depth, td, edges, scale, shift, out, out_lo, pair_map])
 
 

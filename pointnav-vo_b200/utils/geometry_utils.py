@@ -145,15 +145,16 @@ def gen_top_down_view_pairs(generator, depth_pairs, out=None):
     base_trainer_with_vo.py:232-269 / regression_geo_invariance_iter_dataset.py:251-267 compute frame by frame."""
     H, W = generator._vis_size_h, generator._vis_size_w
     d = depth_pairs
-    assert d.is_cuda and d.dtype == torch.float32 and d.is_contiguous() and d.shape[1:] == (H, W, 2)
+    # fp16 pairs (the dataset's storage type) are widened exactly inside the kernel
+    assert d.is_cuda and d.dtype in (torch.float32, torch.float16) and d.is_contiguous() and d.shape[1:] == (H, W, 2)
     B = d.shape[0]
     if out is None:
         out = torch.empty((B, H, W, 2), dtype=torch.float32, device=d.device)
     assert out.is_contiguous() and out.shape == (B, H, W, 2) and out.dtype == torch.float32
     lib = _lib.load()
-    _lib.check(lib.pnvo_topdown_project_strided(_lib.ptr(d), 2 * H * W, 2, 2 * B, H, W,
-                                                _lib.ptr(generator._ray_on(d.device)), ctypes.byref(generator._consts),
-                                                _lib.ptr(out), 2 * H * W, 2, None, _lib.stream_ptr(d.device)))
+    fn = lib.pnvo_topdown_project_strided_f16 if d.dtype == torch.float16 else lib.pnvo_topdown_project_strided
+    _lib.check(fn(_lib.ptr(d), 2 * H * W, 2, 2 * B, H, W, _lib.ptr(generator._ray_on(d.device)),
+                  ctypes.byref(generator._consts), _lib.ptr(out), 2 * H * W, 2, None, _lib.stream_ptr(d.device)))
     return out
 
 

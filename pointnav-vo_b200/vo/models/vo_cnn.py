@@ -251,8 +251,9 @@ class VisualOdometryCNNBase(nn.Module):
                 raise L.PnvoError("raw rgb pairs must be contiguous uint8 [B, H, W, 6]")
         if use_depth or n_dd or use_td:
             depth = obs["depth"]
-            if depth.dtype != torch.float32 or not depth.is_contiguous() or tuple(depth.shape) != (B_src, H, W, 2):
-                raise L.PnvoError("raw depth pairs must be contiguous fp32 [B, H, W, 2]")
+            if (depth.dtype not in (torch.float32, torch.float16) or not depth.is_contiguous()
+                    or tuple(depth.shape) != (B_src, H, W, 2)):
+                raise L.PnvoError("raw depth pairs must be contiguous fp32 (or fp16, the dataset's type) [B, H, W, 2]")
         if n_dd:
             end_vals = getattr(self, "_raw_dd_end_vals", None) or gu.discretize_end_vals(n_dd)
             edges = gu._edges(end_vals, dev)

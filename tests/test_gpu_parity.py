@@ -571,6 +571,38 @@ def test_inverse_pair_augmentation_on_device(case):
     assert np.allclose(losses[0], losses[1], rtol=2e-2), losses
 
 
+def test_raw_pipeline_fp16_depth_is_exact():
+    """8f-2: depth pairs shipped in the dataset's storage type (float16, regression_geo_invariance_iter_dataset.py:229-236)
+    and widened on the device == the reference's route (widen on the host, ship fp32): identical top-down maps, identical
+    assembled input and outputs, equal running statistics."""
+    import copy
+
+    from pointnav_vo_b200.utils import geometry_utils as gu
+
+    model, space, _ = _load_vo("r18_30ch")
+    obs = helpers.vo_inputs(3, 27, space, "cuda")
+    rgb = obs["rgb"].to(torch.uint8).contiguous()
+    d16 = obs["depth"].half().contiguous()
+    d32 = d16.float().contiguous()
+    gen = gu.NormalizedDepth2TopDownViewHabitatTorch(0.1, 10.0, 192, 341, 70)
+    assert torch.equal(gu.gen_top_down_view_pairs(gen, d16), gu.gen_top_down_view_pairs(gen, d32))
+    m2 = copy.deepcopy(model)
+    for train in (False, True):
+        model.train(train)
+        m2.train(train)
+        with torch.no_grad():
+            y1 = model({"rgb": rgb, "depth": d32})
+            x1 = model._plan_for({"rgb": rgb, "depth": d32}, False, train).x0.clone()
+            y2 = m2({"rgb": rgb, "depth": d16})
+            x2 = m2._plan_for({"rgb": rgb, "depth": d16}, False, train).x0.clone()
+        if not train:
+            assert torch.equal(x1, x2) and torch.equal(y1, y2)
+        else:
+            r1, r2 = model.visual_encoder.running_mean_and_var, m2.visual_encoder.running_mean_and_var
+            assert rel(r2._mean, r1._mean) <= 1e-6 and rel(r2._var, r1._var) <= 1e-6
+            assert (x1.float() - x2.float()).abs().max().item() <= 2e-3 and rel(y2, y1) <= 8e-3
+
+
 def test_geo_inversion_loss_and_gradient():
     """a6: geometric-inversion loss on the device against the oracle (pinned to the reference), value + gradient;
     the known-answer case (ground-truth inverse poses) must give ~0 (the reference's train_debug check)."""
