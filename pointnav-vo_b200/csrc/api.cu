@@ -200,15 +200,18 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       return conv_stem_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
                                   static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
     case PNVO_OP_CONV_STEM2:
-      // p0 = W-padded x, p1 = stem2-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg
+      // p0 = W-padded x, p1 = stem2-packed weights, p2 = y, p3 = stats, p4 = x_lo (split mode), p5 = fp16 tensor added in
+      // the epilogue; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = fp32 output
       return conv_stem2_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
-                                   static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], st);
+                                   static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], st,
+                                   static_cast<const __half*>(p[4]), static_cast<const __half*>(p[5]), i[5]);
     case PNVO_OP_WGRAD_STEM2:
       // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld
       return conv_stem_wgrad2_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),
                                      static_cast<float*>(p[2]), i[3], i[0], i[1], i[2], st);
     case PNVO_OP_PACK_W_STEM2:
-      return pack_w_stem2_launch(static_cast<const float*>(p[0]), i[0], static_cast<__half*>(p[1]), st);
+      // p0 = w OIHW fp32, p1 = packed; i0 = Cin, i1 = residual plane (w - fp16(w)) instead of the value plane
+      return pack_w_stem2_launch(static_cast<const float*>(p[0]), i[0], static_cast<__half*>(p[1]), i[1], st);
     case PNVO_OP_WGRAD_STEM:
       // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld, i4 = rows per CTA
       return conv_stem_wgrad_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),

@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
     if (warp == 0 && elect_one()) {
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
+      if (split) {
+        tma_prefetch_desc(&tm.a_lo);
+        tma_prefetch_desc(&tm.b_lo);
+      }
       const int ohw = p.OH * p.OW;
       const int n_img = m0 / ohw;
       const int rem = m0 - n_img * ohw;
@@ -150,6 +154,11 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
         tma_load_im2col_4d(sA, &tm.a, bar, kf & p.cmask, w0, h0, n_img, static_cast<uint16_t>(rs.y),
                            static_cast<uint16_t>(rs.x));
         tma_load_2d(sA + a_bytes, &tm.b, bar, kf, n0);
+        if (split) {  // residual planes of both operands, same boxes (stage = {A, B, A_lo, B_lo})
+          tma_load_im2col_4d(sA + pair_bytes, &tm.a_lo, bar, kf & p.cmask, w0, h0, n_img, static_cast<uint16_t>(rs.y),
+                             static_cast<uint16_t>(rs.x));
+          tma_load_2d(sA + pair_bytes + a_bytes, &tm.b_lo, bar, kf, n0);
+        }
       }
     }
   }
@@ -383,7 +392,7 @@ int conv_plan(ConvArgs& a) {
   // TMA im2col path: unit "dilation" (div == 1), square filter / symmetric padding, channels in chunks of 32 or 64
   const bool split = a.x_lo != nullptr;
   PNVO_REQUIRE((a.x_lo != nullptr) == (a.w_lo != nullptr), "conv: split mode needs both x_lo and w_lo");
-  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1 && !split) ? 1 : 0;
+  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1) ? 1 : 0;
   a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : kTileK;
   a.nkb = ceil_div(a.K, a.chunk_k);
   PNVO_REQUIRE(a.w_ld >= a.nkb * a.chunk_k, "conv: packed weight row stride %d < padded K %d", a.w_ld, a.nkb * a.chunk_k);
@@ -416,7 +425,6 @@ int conv_plan(ConvArgs& a) {
 }
 
 int conv_launch(ConvArgs a, cudaStream_t st) {
-  if (a.x_lo || a.w_lo) a.force_generic = 1;  // split-fp16 operands: only the cp.async producer stages the lo planes
   if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster_supported(a)) return conv_raster_launch(a, st);
   if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster128_supported(a)) return conv_raster128_launch(a, st);
   if (conv_plan(a)) return -1;
@@ -432,6 +440,10 @@ int conv_launch(ConvArgs a, cudaStream_t st) {
   if (a.tma) {
     if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM)) return -1;
     if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.N, a.chunk_k)) return -1;
+    if (a.x_lo) {
+      if (tmap_im2col(&tm.a_lo, a.x_lo, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM)) return -1;
+      if (tmap_tiled2d(&tm.b_lo, a.w_lo, a.n_total, a.w_ld, a.w_ld, a.N, a.chunk_k)) return -1;
+    }
   }
   conv_igemm_kernel<<<dim3(a.grid_x, a.grid_y), 160, a.smem_bytes, st>>>(a, tm);
   count_launch();

@@ -25,7 +25,7 @@
 namespace pnvo {
 
 struct RasterArgs {
-  __half* y;
+  void* y;       // fp16, or fp32 in split mode
   const __half* add;
   double* stats;
   int B, H, W;
@@ -55,11 +55,15 @@ __device__ __forceinline__ void raster_group_sums(const float* v, float* acc) {
 static constexpr int kNG = 3;  // epilogue groups == accumulator buffers (4 would cap the kernel at 96 registers -> spills)
 static constexpr int kRasterThreads = kNG * 128 + 64;
 
-template <int C, int N>
+// SPLIT: split-fp16 forward (ConvArgs::x_lo / w_lo): the residual planes of the weights are resident next to the
+// value planes, every unit stages two rasters (x, x_lo: two TMA boxes), each tap issues x*w + x_lo*w + x*w_lo into the
+// same fp32 accumulator, and the raw conv output is stored in fp32.
+template <int C, int N, bool SPLIT>
 __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const RasterArgs p, const __grid_constant__ ConvTmaps tm) {
   constexpr int kPix = C * 2;             // bytes per pixel = operand row bytes
   constexpr int kWTap = N * kPix;         // bytes of one weight tap [N][C]
   constexpr int kWBytes = 9 * kWTap;
+  constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kKSteps = C / 16;
   constexpr int kTmemCols = kNG * N <= 128 ? 128 : (kNG * N <= 256 ? 256 : 512);
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t sW = smem_base;
-  const uint32_t sIn0 = smem_base + ((kWBytes + 1023) & ~1023);
+  const uint32_t sIn0 = smem_base + ((kPlanes * kWBytes + 1023) & ~1023);
+  const uint32_t slot_bytes = static_cast<uint32_t>(kPlanes) * p.in_bytes;
 
   if (tid == 0) {
     mbar_init(smem_u32(&s_wfull), 1);
@@ -102,9 +107,14 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
       const uint32_t wbar = smem_u32(&s_wfull);
-      mbar_arrive_expect_tx(wbar, kWBytes);
+      mbar_arrive_expect_tx(wbar, kPlanes * kWBytes);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * kWTap, &tm.b, wbar, tap * C, 0);
-      const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * kPix;
+      if (SPLIT) {
+        tma_prefetch_desc(&tm.a_lo);
+        tma_prefetch_desc(&tm.b_lo);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + kWBytes + tap * kWTap, &tm.b_lo, wbar, tap * C, 0);
+      }
+      const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * kPix * kPlanes;
       int i = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int slot = i & 1;
@@ -114,7 +124,8 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
         const uint32_t bar = smem_u32(&s_infull[slot]);
         mbar_arrive_expect_tx(bar, in_tx);
         // rows h0-1 .. h0+T, pixels -1 .. W: out-of-range rows / pixels arrive as zeros (the conv's padding)
-        tma_load_4d(sIn0 + slot * p.in_bytes, &tm.a, bar, 0, -1, h0 - 1, b);
+        tma_load_4d(sIn0 + slot * slot_bytes, &tm.a, bar, 0, -1, h0 - 1, b);
+        if (SPLIT) tma_load_4d(sIn0 + slot * slot_bytes + p.in_bytes, &tm.a_lo, bar, 0, -1, h0 - 1, b);
       }
     }
   } else if (warp == 4 * kNG) {
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
         const int slot = i & 1;
         mbar_wait(smem_u32(&s_infull[slot]), (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t in_lo = lo0 + ((sIn0 + slot * p.in_bytes) >> 4);
+        const uint32_t in_lo = lo0 + ((sIn0 + slot * slot_bytes) >> 4);
         for (int j = 0; j < n_tiles; ++j, ++tc) {
           const int ab = tc % kNG;
           if (tc >= kNG) {
@@ -147,9 +158,14 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-            for (int k = 0; k < kKSteps; ++k)
-              tc_mma_f16_lohi(d_tmem, a_lo + tap_a[tap] + 2 * k, b_lo0 + ((tap * kWTap) >> 4) + 2 * k, hi, idesc,
-                              (tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kKSteps; ++k) {
+              const uint32_t ax = a_lo + tap_a[tap] + 2 * k, bw = b_lo0 + ((tap * kWTap) >> 4) + 2 * k;
+              tc_mma_f16_lohi(d_tmem, ax, bw, hi, idesc, (tap | k) != 0 ? 1u : 0u);
+              if (SPLIT) {
+                tc_mma_f16_lohi(d_tmem, ax + (p.in_bytes >> 4), bw, hi, idesc, 1u);  // x_lo * w
+                tc_mma_f16_lohi(d_tmem, ax, bw + (kWBytes >> 4), hi, idesc, 1u);     // x * w_lo
+              }
+            }
           }
           tc_commit(smem_u32(&s_accfull[ab]));
         }
@@ -183,7 +199,7 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
         const int64_t gofs = ((static_cast<int64_t>(b) * p.H + oh) * p.W + ocol) * N;
         // identity-branch gradient to accumulate: fetched before the accumulator is waited for
         uint4 addq[N / 8];
-        if (p.add && valid) {
+        if (!SPLIT && p.add && valid) {
 #pragma unroll
           for (int q = 0; q < N / 8; ++q) addq[q] = __ldg(reinterpret_cast<const uint4*>(p.add + gofs) + q);
         }
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_accempty[ab]));
           }
-          if (p.add && valid) {
+          if (!SPLIT && p.add && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const __half2* h2 = reinterpret_cast<const __half2*>(&addq[ch * 4 + q]);
@@ -223,8 +239,14 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
               else raster_group_sums<8, 8>(v, acc);
             }
           }
-          if (valid) {
-            __half* yp = p.y + gofs + ch * 32;
+          if (SPLIT) {
+            if (valid) {
+              float4* yp = reinterpret_cast<float4*>(static_cast<float*>(p.y) + gofs + ch * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) yp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else if (valid) {
+            __half* yp = static_cast<__half*>(p.y) + gofs + ch * 32;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 uu;
@@ -267,7 +289,10 @@ static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
   if (a.R != 3 || a.S != 3 || a.mul != 1 || a.div != 1 || a.pad != 1 || a.pad_w != 1) return false;
   if (a.IH != a.OH || a.IW != a.OW) return false;
   if (!(a.Cin == 32 || a.Cin == 64) || !(a.n_total == 32 || a.n_total == 64)) return false;
-  if (a.n_store != a.n_total || a.ldo != a.n_total || a.out_fp32) return false;
+  if (a.x_lo && a.Cin != 32) return false;  // split-fp16 with 64 / 128 channels: conv_raster128.cu (streamed weights)
+  if (a.n_store != a.n_total || a.ldo != a.n_total) return false;
+  const bool split = a.x_lo != nullptr;
+  if (split ? (!a.out_fp32 || !a.w_lo || a.add) : (a.out_fp32 != 0)) return false;
   if (a.w_ld < 9 * a.Cin) return false;
   if (a.stats) {
     if (a.G * a.cpg != a.n_total || a.G > 16) return false;
@@ -276,7 +301,9 @@ static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
   const int P = a.IW + 2;
   if (P > 256 || a.IW < 8 || a.IH < 4) return false;
   const int pix = a.Cin * 2;
-  const int w_bytes = (9 * a.n_total * pix + 1023) & ~1023;
+  const int planes = split ? 2 : 1;
+  const int w_bytes = (planes * 9 * a.n_total * pix + 1023) & ~1023;
+  const int smem_limit = split ? 224 * 1024 : 200 * 1024;  // (the fp16 geometry was tuned under the 200 KB cap)
   double best = -1.0;
   for (int T = 2; T <= std::min(a.IH, 64); ++T) {
     const int rows_in = T + 2;
@@ -284,8 +311,8 @@ static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
     const int n_tiles = ceil_div(T * P, 128);
     const int positions = std::max(rows_in * P, n_tiles * 128 + 2 * P + 2);
     const int in_bytes = (positions * pix + 1023) & ~1023;
-    const int smem = w_bytes + 2 * in_bytes + 1024;
-    if (smem > 200 * 1024) break;
+    const int smem = w_bytes + 2 * planes * in_bytes + 1024;
+    if (smem > smem_limit) break;
     const int upi = ceil_div(a.IH, T);
     // useful fraction of the MMA rows, discounted by the halo re-read (T+2)/T (weakly) and unit imbalance
     const int n_units = a.B * upi;
@@ -301,7 +328,7 @@ static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
     }
   }
   if (best < 0.5) return false;
-  r.y = static_cast<__half*>(a.y); r.add = a.add; r.stats = a.stats;
+  r.y = a.y; r.add = a.add; r.stats = a.stats;
   r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
   return true;
 }
@@ -312,15 +339,15 @@ int conv_raster_supported(const ConvArgs& a) {
   return raster_plan(a, r, smem) ? 1 : 0;
 }
 
-template <int C, int N>
+template <int C, int N, bool SPLIT>
 static int raster_launch_t(const RasterArgs& r, const ConvTmaps& tm, int smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(conv_raster_kernel<C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_raster_kernel<C, N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr = true;
   }
   const int grid = std::min(r.n_units, 148);
-  conv_raster_kernel<C, N><<<grid, kRasterThreads, smem, st>>>(r, tm);
+  conv_raster_kernel<C, N, SPLIT><<<grid, kRasterThreads, smem, st>>>(r, tm);
   count_launch();
   return check_launch("conv_raster");
 }
@@ -334,10 +361,16 @@ int conv_raster_launch(const ConvArgs& a, cudaStream_t st) {
   memset(&tm, 0, sizeof(tm));
   if (tmap_tiled4d(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, r.P, a.Cin * 2 == 128 ? 128 : 64, r.rows_in)) return -1;
   if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.n_total, a.Cin)) return -1;
-  if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32>(r, tm, smem, st);
-  if (a.Cin == 32 && a.n_total == 64) return raster_launch_t<32, 64>(r, tm, smem, st);
-  if (a.Cin == 64 && a.n_total == 32) return raster_launch_t<64, 32>(r, tm, smem, st);
-  return raster_launch_t<64, 64>(r, tm, smem, st);
+  if (a.x_lo) {
+    if (tmap_tiled4d(&tm.a_lo, a.x_lo, a.B, a.IH, a.IW, a.Cin, r.P, a.Cin * 2 == 128 ? 128 : 64, r.rows_in)) return -1;
+    if (tmap_tiled2d(&tm.b_lo, a.w_lo, a.n_total, a.w_ld, a.w_ld, a.n_total, a.Cin)) return -1;
+    if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32, true>(r, tm, smem, st);
+    return raster_launch_t<32, 64, true>(r, tm, smem, st);
+  }
+  if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32, false>(r, tm, smem, st);
+  if (a.Cin == 32 && a.n_total == 64) return raster_launch_t<32, 64, false>(r, tm, smem, st);
+  if (a.Cin == 64 && a.n_total == 32) return raster_launch_t<64, 32, false>(r, tm, smem, st);
+  return raster_launch_t<64, 64, false>(r, tm, smem, st);
 }
 
 }  // namespace pnvo

@@ -9,6 +9,12 @@
 // per unit instead of once per 128 output pixels.  L2 -> smem traffic per 128 outputs: 576 KB (im2col TMA kernel,
 // measured at the L2 -> SM ingest limit) -> ~130 KB.
 //   warp 13: TMA producer    warp 12: TMEM owner + MMA issuer    warps 0-11: epilogue, warpgroup g <-> M tile g
+//
+// The same kernel runs the split-fp16 FORWARD convolutions (ConvArgs::x_lo / w_lo: value + residual fp16 planes, three
+// products x*w + x_lo*w + x*w_lo into one fp32 accumulator, fp32 output) of the 64- and 128-channel layers, whose value +
+// residual weights (147 / 590 KB) cannot be resident either: the residual plane of the input is just one more raster
+// (MODE 1: 64 channels -> rasters {x, x_lo}; MODE 2: 128 channels -> {x[0:64], x[64:128], x_lo[0:64], x_lo[64:128]})
+// and the weight ring alternates value / residual stages; a value stage multiplies both the x and the x_lo raster.
 #include "common.cuh"
 #include "ops.cuh"
 #include "tmap.cuh"
@@ -16,7 +22,7 @@
 namespace pnvo {
 
 struct Raster128Args {
-  __half* y;
+  void* y;   // fp16 (MODE 0) or fp32 (split modes)
   const __half* add;
   double* stats;
   int B, H, W;
@@ -45,9 +51,31 @@ __device__ __forceinline__ void r128_group_sums(const float* v, float* acc) {
   }
 }
 
-template <int N>
+// MODE 0: fp16, 128 channels (stage = (tap, channel half));  MODE 1: split, 64 channels (stage = (tap, w / w_lo));
+// MODE 2: split, 128 channels (stage = (tap, channel half, w / w_lo))
+template <int MODE>
+struct R128Mode {
+  static constexpr int kPlanes = MODE == 2 ? 4 : 2;
+  static constexpr int kStages = MODE == 2 ? 36 : 18;
+  static constexpr bool kSplit = MODE != 0;
+  // weight matrix (0 = value, 1 = residual), K offset of the stage's [N][64] tile, first / second raster it multiplies
+  __device__ static __forceinline__ void stage(int st, int& wsel, int& koff, int& tap, int& pa, int& pb) {
+    if (MODE == 0) {
+      wsel = 0; koff = st * 64; tap = st >> 1; pa = st & 1; pb = -1;
+    } else if (MODE == 1) {
+      wsel = st & 1; tap = st >> 1; koff = tap * 64; pa = 0; pb = wsel ? -1 : 1;
+    } else {
+      wsel = st & 1; tap = st >> 2;
+      const int half = (st >> 1) & 1;
+      koff = tap * 128 + half * 64; pa = half; pb = wsel ? -1 : 2 + half;
+    }
+  }
+};
+
+template <int N, int MODE>
 __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Raster128Args p,
                                                                        const __grid_constant__ ConvTmaps tm) {
+  using Md = R128Mode<MODE>;
   constexpr int kWStage = N * 128;                 // one weight stage: [N][64 channels] fp16
   constexpr int kTmemCols = 3 * N <= 256 ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -57,8 +85,8 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t sIn = smem_base;                                   // two channel-half rasters
-  const uint32_t sW = smem_base + 2 * p.in_bytes;                   // weight ring
+  const uint32_t sIn = smem_base;                                   // kPlanes rasters
+  const uint32_t sW = smem_base + Md::kPlanes * p.in_bytes;         // weight ring
   const int ws = p.w_stages;
 
   if (tid == 0) {
@@ -87,7 +115,11 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
     if (elect_one()) {
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
-      const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * 128u * 2u;
+      if (Md::kSplit) {
+        tma_prefetch_desc(&tm.a_lo);
+        tma_prefetch_desc(&tm.b_lo);
+      }
+      const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * 128u * Md::kPlanes;
       int i = 0, wctr = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         if (i >= 1) mbar_wait(smem_u32(&s_inempty), (i - 1) & 1);
@@ -95,14 +127,26 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
         const int h0 = (u - b * p.units_per_img) * p.T;
         const uint32_t bar = smem_u32(&s_infull);
         mbar_arrive_expect_tx(bar, in_tx);
-        tma_load_4d(sIn, &tm.a, bar, 0, -1, h0 - 1, b);                 // channels 0..63
-        tma_load_4d(sIn + p.in_bytes, &tm.a, bar, 64, -1, h0 - 1, b);   // channels 64..127
-        for (int st = 0; st < 18; ++st, ++wctr) {                       // (tap, channel half) stages
+        if (MODE == 0) {
+          tma_load_4d(sIn, &tm.a, bar, 0, -1, h0 - 1, b);                 // channels 0..63
+          tma_load_4d(sIn + p.in_bytes, &tm.a, bar, 64, -1, h0 - 1, b);   // channels 64..127
+        } else if (MODE == 1) {
+          tma_load_4d(sIn, &tm.a, bar, 0, -1, h0 - 1, b);                 // x
+          tma_load_4d(sIn + p.in_bytes, &tm.a_lo, bar, 0, -1, h0 - 1, b); // x_lo
+        } else {
+          tma_load_4d(sIn, &tm.a, bar, 0, -1, h0 - 1, b);
+          tma_load_4d(sIn + p.in_bytes, &tm.a, bar, 64, -1, h0 - 1, b);
+          tma_load_4d(sIn + 2 * p.in_bytes, &tm.a_lo, bar, 0, -1, h0 - 1, b);
+          tma_load_4d(sIn + 3 * p.in_bytes, &tm.a_lo, bar, 64, -1, h0 - 1, b);
+        }
+        for (int st = 0; st < Md::kStages; ++st, ++wctr) {
           const int s = wctr % ws;
           if (wctr >= ws) mbar_wait(smem_u32(&s_wempty[s]), ((wctr / ws) & 1) ^ 1);
           const uint32_t wbar = smem_u32(&s_wfull[s]);
           mbar_arrive_expect_tx(wbar, kWStage);
-          tma_load_2d(sW + s * kWStage, &tm.b, wbar, st * 64, 0);       // K offset (tap * 128 + half * 64) == st * 64
+          int wsel, koff, tap, pa, pb;
+          Md::stage(st, wsel, koff, tap, pa, pb);
+          tma_load_2d(sW + s * kWStage, wsel ? &tm.b_lo : &tm.b, wbar, koff, 0);
         }
       }
     }
@@ -118,18 +162,28 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
         if (i >= 1) mbar_wait(smem_u32(&s_accempty), (i - 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int st = 0; st < 18; ++st, ++wctr) {
+        for (int st = 0; st < Md::kStages; ++st, ++wctr) {
           const int s = wctr % ws;
           mbar_wait(smem_u32(&s_wfull[s]), (wctr / ws) & 1);
           tc_fence_after();
-          const int tap = st >> 1, half = st & 1;
-          const uint32_t a_lo = lo0 + ((sIn + half * p.in_bytes) >> 4) + static_cast<uint32_t>((tap / 3) * p.P + (tap % 3)) * 8u;
+          int wsel, koff, tap, pa, pb;
+          Md::stage(st, wsel, koff, tap, pa, pb);
+          const uint32_t tap_off = static_cast<uint32_t>((tap / 3) * p.P + (tap % 3)) * 8u;
+          const uint32_t a_lo = lo0 + ((sIn + pa * p.in_bytes) >> 4) + tap_off;
           const uint32_t b_lo = lo0 + ((sW + s * kWStage) >> 4);
           for (int t = 0; t < n_tiles; ++t) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc_mma_f16_lohi(tmem_base + t * N, a_lo + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc,
                               (st | k) != 0 ? 1u : 0u);
+          }
+          if (Md::kSplit && pb >= 0) {  // the residual raster against the same (value) weight stage
+            const uint32_t a2 = lo0 + ((sIn + pb * p.in_bytes) >> 4) + tap_off;
+            for (int t = 0; t < n_tiles; ++t) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f16_lohi(tmem_base + t * N, a2 + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc, 1u);
+            }
           }
           tc_commit(smem_u32(&s_wempty[s]));
         }
@@ -166,7 +220,7 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
           float v[32];
           tmem_ld32(tmem_base + t_lane + grp * N + ch * 32, v);
           tmem_ld_wait();
-          if (p.add && valid) {
+          if (!Md::kSplit && p.add && valid) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.add + gofs + ch * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -192,8 +246,14 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
               else r128_group_sums<4, 16>(v, acc);
             }
           }
-          if (valid) {
-            __half* yp = p.y + gofs + ch * 32;
+          if (Md::kSplit) {
+            if (valid) {
+              float4* yp = reinterpret_cast<float4*>(static_cast<float*>(p.y) + gofs + ch * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) yp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else if (valid) {
+            __half* yp = static_cast<__half*>(p.y) + gofs + ch * 32;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 uu;
@@ -234,18 +294,29 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
   }
 }
 
-static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes) {
+static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes, int& mode) {
   if (a.R != 3 || a.S != 3 || a.mul != 1 || a.div != 1 || a.pad != 1 || a.pad_w != 1) return false;
   if (a.IH != a.OH || a.IW != a.OW) return false;
   // N = 64 (the zero-upsampled data gradient of layer3.0 at 24x43) was measured slower here than on the im2col kernel
   // (95 vs 86 us at B = 256: single-buffered accumulators + the accumulate-input reads in the epilogue): N = 128 only
-  if (a.Cin != 128 || a.n_total != 128) return false;
-  if (a.n_store != a.n_total || a.ldo != a.n_total || a.out_fp32) return false;
+  const bool split = a.x_lo != nullptr;
+  if (split) {
+    if (!a.w_lo || !a.out_fp32 || a.add) return false;
+    if (a.Cin == 64 && a.n_total == 64) mode = 1;
+    else if (a.Cin == 128 && a.n_total == 128) mode = 2;
+    else return false;
+  } else {
+    if (a.Cin != 128 || a.n_total != 128 || a.out_fp32) return false;
+    mode = 0;
+  }
+  if (a.n_store != a.n_total || a.ldo != a.n_total) return false;
   if (a.w_ld < 9 * a.Cin) return false;
   if (a.stats && (a.G != 16 || a.G * a.cpg != a.n_total)) return false;
   const int P = a.IW + 2;
   if (P > 256 || a.IW < 8 || a.IH < 4) return false;
   const int w_stage = a.n_total * 128;
+  const int planes = mode == 2 ? 4 : 2;
+  const int smem_limit = split ? 222 * 1024 : 200 * 1024;  // (the fp16 geometry was tuned under the 200 KB cap)
   double best = -1.0;
   for (int T = 2; T <= std::min(a.IH, 64); ++T) {
     const int rows_in = T + 2;
@@ -253,7 +324,7 @@ static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes)
     if (n_tiles > 3) break;
     const int positions = std::max(rows_in * P, n_tiles * 128 + 2 * P + 2);
     const int in_bytes = (positions * 128 + 1023) & ~1023;
-    const int stages = std::min(8, (200 * 1024 - 2 * in_bytes) / w_stage);
+    const int stages = std::min(8, (smem_limit - planes * in_bytes) / w_stage);
     if (stages < 3) break;
     const int upi = ceil_div(a.IH, T);
     const int n_units = a.B * upi;
@@ -265,44 +336,49 @@ static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes)
       best = eff;
       r.P = P; r.T = T; r.n_tiles = n_tiles; r.rows_in = rows_in; r.units_per_img = upi; r.n_units = n_units;
       r.in_bytes = in_bytes; r.w_stages = stages;
-      smem_bytes = 2 * in_bytes + stages * w_stage + 1024;
+      smem_bytes = planes * in_bytes + stages * w_stage + 1024;
     }
   }
   if (best < 0.5) return false;
-  r.y = static_cast<__half*>(a.y); r.add = a.add; r.stats = a.stats;
+  r.y = a.y; r.add = a.add; r.stats = a.stats;
   r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
   return true;
 }
 
 int conv_raster128_supported(const ConvArgs& a) {
   Raster128Args r{};
-  int smem = 0;
-  return raster128_plan(a, r, smem) ? 1 : 0;
+  int smem = 0, mode = 0;
+  return raster128_plan(a, r, smem, mode) ? 1 : 0;
 }
 
-template <int N>
+template <int N, int MODE>
 static int raster128_launch_t(const Raster128Args& r, const ConvTmaps& tm, int smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(conv_raster128_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    cudaFuncSetAttribute(conv_raster128_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr = true;
   }
-  conv_raster128_kernel<N><<<std::min(r.n_units, 148), kR128Threads, smem, st>>>(r, tm);
+  conv_raster128_kernel<N, MODE><<<std::min(r.n_units, 148), kR128Threads, smem, st>>>(r, tm);
   count_launch();
   return check_launch("conv_raster128");
 }
 
 int conv_raster128_launch(const ConvArgs& a, cudaStream_t st) {
   Raster128Args r{};
-  int smem = 0;
-  PNVO_REQUIRE(raster128_plan(a, r, smem), "conv_raster128: unsupported geometry");
+  int smem = 0, mode = 0;
+  PNVO_REQUIRE(raster128_plan(a, r, smem, mode), "conv_raster128: unsupported geometry");
   if (a.B <= 0) return 0;
   alignas(64) ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
   if (tmap_tiled4d(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, r.P, 128, r.rows_in, 64)) return -1;
   if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.n_total, 64)) return -1;
-  if (a.n_total == 64) return raster128_launch_t<64>(r, tm, smem, st);
-  return raster128_launch_t<128>(r, tm, smem, st);
+  if (mode != 0) {
+    if (tmap_tiled4d(&tm.a_lo, a.x_lo, a.B, a.IH, a.IW, a.Cin, r.P, 128, r.rows_in, 64)) return -1;
+    if (tmap_tiled2d(&tm.b_lo, a.w_lo, a.n_total, a.w_ld, a.w_ld, a.n_total, 64)) return -1;
+  }
+  if (mode == 1) return raster128_launch_t<64, 1>(r, tm, smem, st);
+  if (mode == 2) return raster128_launch_t<128, 2>(r, tm, smem, st);
+  return raster128_launch_t<128, 0>(r, tm, smem, st);
 }
 
 }  // namespace pnvo

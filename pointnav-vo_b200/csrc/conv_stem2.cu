@@ -23,7 +23,10 @@
 namespace pnvo {
 
 struct Stem2Args {
-  __half* y;      // [B, OH, OW, 32] fp16
+  void* y;        // [B, OH, OW, 32] fp16 (fp32 when out_fp32)
+  const __half* add;  // optional [B, OH, OW, 32] fp16 added before the store (split mode: the w_lo * x product)
+  int out_fp32;
+  int x_planes;   // 1, or 2 in split mode: every input row is staged twice (x through tm.a, x_lo through tm.a_lo)
   double* stats;  // [B][G][2]
   int B, IH, OH, OW;
   int G, cpg;
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
     if (elect_one()) {
       tma_prefetch_desc(&tm.a);
       tma_prefetch_desc(&tm.b);
+      if (p.x_planes > 1) tma_prefetch_desc(&tm.a_lo);
       const uint32_t wbar = smem_u32(&s_wfull);
       mbar_arrive_expect_tx(wbar, kS2W);
       for (int j = 0; j < 4; ++j) tma_load_2d(sW + j * kS2Plane, &tm.b, wbar, 0, j * 224);
@@ -108,12 +112,15 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           const int d = stem2_row(k);
           const int h = 2 * oh0 - 3 + d;
           if (k != 0 && (h < 0 || h >= p.IH)) continue;  // all-zero row: nothing to add
-          const int s = ctr % stages;
-          if (ctr >= stages) mbar_wait(smem_u32(&s_xempty[s]), ((ctr / stages) & 1) ^ 1);
-          const uint32_t bar = smem_u32(&s_xfull[s]);
-          mbar_arrive_expect_tx(bar, x_tx);
-          tma_load_4d(stage_addr(s), &tm.a, bar, 0, 0, h, b);  // whole W-padded row as pixel pairs; outside the image: zeros
-          ++ctr;
+          for (int pl = 0; pl < p.x_planes; ++pl) {
+            const int s = ctr % stages;
+            if (ctr >= stages) mbar_wait(smem_u32(&s_xempty[s]), ((ctr / stages) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&s_xfull[s]);
+            mbar_arrive_expect_tx(bar, x_tx);
+            // whole W-padded row as pixel pairs; outside the image: zeros
+            tma_load_4d(stage_addr(s), pl ? &tm.a_lo : &tm.a, bar, 0, 0, h, b);
+            ++ctr;
+          }
         }
       }
     }
@@ -138,9 +145,6 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           const int d = stem2_row(k);
           const int h = 2 * oh0 - 3 + d;
           if (k != 0 && (h < 0 || h >= p.IH)) continue;
-          const int s = ctr % stages;
-          mbar_wait(smem_u32(&s_xfull[s]), (ctr / stages) & 1);
-          tc_fence_after();
           // window of 4 filter rows: even d -> [6,4,2,0] from position (6-d)/2, odd d -> [5,3,1] from (5-d)/2
           const int odd = d & 1;
           const int p0 = odd ? (5 - d) / 2 : (6 - d) / 2;   // exact divisions (numerators are even)
@@ -150,16 +154,21 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           for (int q = 0; q < 4; ++q) m[q] = (p0 + q >= 0 && p0 + q < npos) ? 0u : 0xFFFFFFFFu;
           const int a_off = (odd ? 4 * 4096 : 0) + p0 * 4096;  // may be negative: masked lanes, valid addresses
           const uint32_t a_lo = lo0 + (static_cast<uint32_t>(static_cast<int>(sW) + a_off) >> 4);
-          const uint32_t b_lo = lo0 + (stage_addr(s) >> 4);
+          for (int pl = 0; pl < p.x_planes; ++pl) {
+            const int s = ctr % stages;
+            mbar_wait(smem_u32(&s_xfull[s]), (ctr / stages) & 1);
+            tc_fence_after();
+            const uint32_t b_lo = lo0 + (stage_addr(s) >> 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              tc_mma_f16_masked(d_tmem, a_lo + j * (kS2Plane >> 4) + kk * 2, b_lo + j * 8 + kk * 2, hi, idesc, m[0], m[1],
-                                m[2], m[3], (k | j | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma_f16_masked(d_tmem, a_lo + j * (kS2Plane >> 4) + kk * 2, b_lo + j * 8 + kk * 2, hi, idesc, m[0], m[1],
+                                  m[2], m[3], (k | j | kk | pl) != 0 ? 1u : 0u);
+            }
+            tc_commit(smem_u32(&s_xempty[s]));
+            ++ctr;
           }
-          tc_commit(smem_u32(&s_xempty[s]));
-          ++ctr;
         }
         tc_commit(smem_u32(&s_accfull[ab]));
       }
@@ -175,7 +184,10 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
       const int oh = (g - b * p.groups_per_img) * 4 + warp;
       const int ab = i & 1;
       const bool row_valid = oh < p.OH;
-      __half* yrow = p.y + (static_cast<int64_t>(b) * p.OH + oh) * p.OW * 32 + lane;
+      const int64_t row_ofs = (static_cast<int64_t>(b) * p.OH + oh) * p.OW * 32 + lane;
+      __half* yrow = static_cast<__half*>(p.y) + row_ofs;
+      float* yrow32 = static_cast<float*>(p.y) + row_ofs;
+      const __half* arow = p.add ? p.add + row_ofs : nullptr;
       float sum = 0.f, ssq = 0.f;
       mbar_wait(smem_u32(&s_accfull[ab]), (i >> 1) & 1);
       tc_fence_after();
@@ -194,9 +206,12 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           for (int e = 0; e < 32; ++e) {
             const int ow = ch * 32 + e;
             if (ow < p.OW) {
-              yrow[static_cast<int64_t>(ow) * 32] = __float2half_rn(v[e]);
-              sum += v[e];
-              ssq = fmaf(v[e], v[e], ssq);
+              float val = v[e];
+              if (arow) val += __half2float(arow[static_cast<int64_t>(ow) * 32]);
+              if (p.out_fp32) yrow32[static_cast<int64_t>(ow) * 32] = val;
+              else yrow[static_cast<int64_t>(ow) * 32] = __float2half_rn(val);
+              sum += val;
+              ssq = fmaf(val, val, ssq);
             }
           }
         }
@@ -224,18 +239,21 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
 
 // OIHW fp32 [32][Cin][7][7] -> [pair j][position][cout][64] fp16: positions 0..3 = filter rows 6,4,2,0, positions 4..6 =
 // rows 5,3,1; column = (s & 1) * 32 + c with s = 2j + (s & 1); tap s = 7 and channels >= Cin stay zero.
-__global__ void pack_w_stem2_kernel(const float* __restrict__ w, int Cin, __half* __restrict__ wr) {
+// lo != 0: the residual plane w - fp16(w) of the split-fp16 representation
+__global__ void pack_w_stem2_kernel(const float* __restrict__ w, int Cin, __half* __restrict__ wr, int lo) {
   const int total = 32 * Cin * 49;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int s = i % 7, r = (i / 7) % 7, c = (i / 49) % Cin, n = i / (49 * Cin);
     const int pos = (r & 1) ? 4 + (5 - r) / 2 : (6 - r) / 2;
-    wr[(((s >> 1) * 7 + pos) * 32 + n) * 64 + (s & 1) * 32 + c] = __float2half_rn(w[i]);
+    const float x = w[i];
+    const __half h = __float2half_rn(x);
+    wr[(((s >> 1) * 7 + pos) * 32 + n) * 64 + (s & 1) * 32 + c] = lo ? __float2half_rn(x - __half2float(h)) : h;
   }
 }
 
-int pack_w_stem2_launch(const float* w, int Cin, __half* wr, cudaStream_t st) {
+int pack_w_stem2_launch(const float* w, int Cin, __half* wr, int lo, cudaStream_t st) {
   PNVO_REQUIRE(w && wr && Cin <= 32, "pack_w_stem2: bad arguments");
-  pack_w_stem2_kernel<<<ceil_div(32 * Cin * 49, 256), 256, 0, st>>>(w, Cin, wr);
+  pack_w_stem2_kernel<<<ceil_div(32 * Cin * 49, 256), 256, 0, st>>>(w, Cin, wr, lo);
   count_launch();
   return check_launch("pack_w_stem2");
 }
@@ -247,12 +265,13 @@ int conv_stem2_supported(int IH, int IW) {
 }
 
 int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
-                          cudaStream_t st) {
+                          cudaStream_t st, const __half* x_lo, const __half* add, int out_fp32) {
   PNVO_REQUIRE(x && wr && y, "conv_stem2: null pointer");
   PNVO_REQUIRE(conv_stem2_supported(IH, IW), "conv_stem2: unsupported geometry %dx%d", IH, IW);
   PNVO_REQUIRE(!stats || (cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && G * cpg == 32), "conv_stem2: bad group config");
   Stem2Args a{};
-  a.y = static_cast<__half*>(y); a.stats = stats; a.B = B; a.IH = IH;
+  a.y = y; a.stats = stats; a.B = B; a.IH = IH;
+  a.add = add; a.out_fp32 = out_fp32; a.x_planes = x_lo ? 2 : 1;
   a.OH = (IH + 6 - 7) / 2 + 1;
   a.OW = (IW + 6 - 7) / 2 + 1;
   a.G = G; a.cpg = cpg;
@@ -268,6 +287,7 @@ int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* st
   memset(&tm, 0, sizeof(tm));
   // pixel pairs as the innermost 128-byte dimension: [B, IH, Wp/2, 64]; the box may run past Wp/2 (zero fill)
   if (tmap_tiled4d(&tm.a, x, B, IH, Wp / 2, 64, a.n_cols + 8)) return -1;
+  if (x_lo && tmap_tiled4d(&tm.a_lo, x_lo, B, IH, Wp / 2, 64, a.n_cols + 8)) return -1;
   if (tmap_tiled2d(&tm.b, wr, 4 * 7 * 32, 64, 64, 224, 64)) return -1;
   static bool attr = false;
   if (!attr) {

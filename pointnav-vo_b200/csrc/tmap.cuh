@@ -10,8 +10,10 @@
 namespace pnvo {
 
 struct ConvTmaps {
-  CUtensorMap a;  // activations: im2col map (fprop / wgrad A operand)
-  CUtensorMap b;  // weights (fprop) or output gradient (wgrad): 2-D tiled map
+  CUtensorMap a;     // activations: im2col map (fprop / wgrad A operand)
+  CUtensorMap b;     // weights (fprop) or output gradient (wgrad): 2-D tiled map
+  CUtensorMap a_lo;  // split-fp16 forward: the residual planes x - fp16(x), w - fp16(w) (same geometry as a / b)
+  CUtensorMap b_lo;
 };
 
 // NHWC fp16 activations [N, H, W, C]; a load fetches `pixels` consecutive output positions (w fastest,

@@ -179,13 +179,13 @@ class EncoderPlan:
         """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
         head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim).
-        split: forward-only precision mode.  Every fp16 activation / weight tensor gets a residual plane
+        split: precision mode of the FORWARD pass.  Every fp16 activation / weight tensor gets a residual plane
         (t - fp16(t), fp16), raw conv outputs stay fp32 and each conv accumulates x*w + x_lo*w + x*w_lo: operands carry
-        ~22 mantissa bits, so outputs agree with the fp32 reference to ~1e-5 instead of ~5e-3 (3 MMAs per product,
-        generic implicit-GEMM kernel only)."""
+        ~22 mantissa bits, so outputs agree with the fp32 reference to ~1e-5 instead of ~5e-3 (3 MMAs per product; the
+        stem / raster / implicit-GEMM kernels all have a split variant).  The backward pass of a split plan reads the
+        value planes only (single-pass fp16 operands, fp32 accumulation) and the fp32 raw conv outputs."""
         self.split = bool(split)
         if self.split:
-            assert not training, "split-fp16 precision is a forward-only mode"
             raw_fp32 = True
         self._lo = {}
         self.P, self.Bf = params, buffers
@@ -217,7 +217,7 @@ class EncoderPlan:
         self.inH, self.inW = H, W
         self.cin_pad = _pow2(self.in_channels)
         ow1 = (W + 6 - 7) // 2 + 1
-        if (not self.avgpool_input and not self.raw_fp32 and self.in_channels <= 32 and baseplanes == 32
+        if (not self.avgpool_input and (self.split or not self.raw_fp32) and self.in_channels <= 32 and baseplanes == 32
                 and 128 <= ow1 <= 256):
             # the stem kernels (conv_stem2.cu) work on 64-byte pixels: an 8-channel input (rgb + depth) is padded to 32
             # zero channels rather than sent through the generic cp.async producer (measured 2.5 ms vs 0.5 ms at B=256)
@@ -327,16 +327,27 @@ class EncoderPlan:
                 off += n
         raw_dt = torch.float32 if self.raw_fp32 else torch.float16
         # stem kernel (conv_stem.cu): needs 64-byte pixels, 32 output channels and W-padded rows with a zero halo
-        self.use_stem = (not self.avgpool_input and not self.raw_fp32 and self.cin_pad == 32 and self.conv1.cout_pad == 32
-                         and self.conv1.Cout == 32 and self.conv1.OW <= 256 and self.conv1.OW >= 128)
+        self.use_stem = (not self.avgpool_input and (self.split or not self.raw_fp32) and self.cin_pad == 32
+                         and self.conv1.cout_pad == 32 and self.conv1.Cout == 32 and self.conv1.OW <= 256
+                         and self.conv1.OW >= 128)
+        if self.use_stem and self.split:  # only the pixels-as-N stem kernel has a split variant
+            self.use_stem = bool(self.stem_version >= 2 and L.load().pnvo_conv_stem2_supported(self.inH, self.inW)
+                                 and (not tr or L.load().pnvo_conv_stem_wgrad2_supported(self.inH, self.inW)))
         if self.use_stem:
             self.x0_pitch = L.load().pnvo_stem_padded_width(self.inW)
             self.x0 = torch.zeros(B, self.inH, self.x0_pitch, self.cin_pad, dtype=torch.float16, device=dev)
+            if self.split:
+                self._lo[self.x0.data_ptr()] = torch.zeros_like(self.x0)
             self.x0_img = self.x0[:, :, 3:, :]  # view whose data_ptr is the first image pixel
             self.w_stem = torch.zeros(7 * 4 * 32, 64, dtype=torch.float16, device=dev)
             # pixels-as-N stem kernel (conv_stem2.cu): full-rate MMAs, resident weights
             self.use_stem2 = bool(self.stem_version >= 2 and L.load().pnvo_conv_stem2_supported(self.inH, self.inW))
             self.w_stem2 = torch.zeros(4 * 7 * 32, 64, dtype=torch.float16, device=dev) if self.use_stem2 else None
+            if self.split:
+                # residual plane of the stem weights + the fp16 tensor that carries the w_lo * x product between the two
+                # launches of the split stem (value + residual weights do not fit in shared memory together)
+                self.w_stem2_lo = torch.zeros(4 * 7 * 32, 64, dtype=torch.float16, device=dev)
+                self.stem_corr = torch.empty(B, self.conv1.OH, self.conv1.OW, 32, dtype=torch.float16, device=dev)
         else:
             self.x0_pitch = 0
             self.x0 = self._act(B, self.inH, self.inW, self.cin_pad)
@@ -455,14 +466,23 @@ class EncoderPlan:
         else:
             pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
         if self.use_stem:
-            pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
+            if not self.split:
+                pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
             if self.use_stem2:
                 pack.append(L.op_pack_w_stem2(self.P[self.conv1.key], self.w_stem2, self.conv1.Cin))
+                if self.split:
+                    pack.append(L.op_pack_w_stem2(self.P[self.conv1.key], self.w_stem2_lo, self.conv1.Cin, lo=True))
         self.pack_prog = L.Program(pack, graph=True)
         # ---- forward (after the input tensor x0 has been produced) ----
         ops = [L.op_zero(self.stats_all)]
         c1, g1 = self.conv1, self.gn1
-        if self.use_stem2 and not self.raw_fp32:
+        if self.use_stem2 and self.split:
+            # raw1 = w * (x + x_lo) + (w_lo * x): the residual-weight product first, as an fp16 tensor (it is ~2^-11 of
+            # the result), then the value weights against both input planes with that tensor added in the epilogue
+            ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, self.stem_corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
+            ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg,
+                                       x_lo=self.lo(self.x0), add=self.stem_corr, out_fp32=True))
+        elif self.use_stem2 and not self.raw_fp32:
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg))
         elif self.use_stem and not self.raw_fp32:
             ops.append(L.op_conv_stem(self.x0, self.w_stem, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg, 2))
@@ -607,6 +627,8 @@ class EncoderPlan:
             return self.x0
         if getattr(self, "x0_alt", None) is None:
             self.x0_alt = torch.zeros_like(self.x0)
+            if self.split:
+                self._lo[self.x0_alt.data_ptr()] = torch.zeros_like(self.x0)
         return self.x0_alt
 
     def programs_for(self, parity):
@@ -616,6 +638,8 @@ class EncoderPlan:
             alt = self.x0_for(1)
             off = self.x0_img.data_ptr() - self.x0.data_ptr()
             mapping = {self.x0.data_ptr(): alt.data_ptr(), self.x0.data_ptr() + off: alt.data_ptr() + off}
+            if self.split:
+                mapping[self.lo(self.x0).data_ptr()] = self.lo(alt).data_ptr()
             fwd = L.Program(L.patch_ops(self.fwd_ops, mapping), graph=True)
             bwd = L.Program(L.patch_ops(self.bwd_ops, mapping), graph=True) if self.training else None
             self._alt_progs = (fwd, bwd)

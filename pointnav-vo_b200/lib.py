@@ -305,16 +305,18 @@ def op_conv_stem(x, wr, y, stats, B, IH, IW, G, cpg, stages=4):
     return _op(OP_CONV_STEM, [B, IH, IW, G, cpg, stages], (), [x, wr, y, stats])
 
 
-def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg):
-    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg], (), [x, wr, y, stats])
+def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg, x_lo=None, add=None, out_fp32=False):
+    """x_lo: residual plane of x (split mode: every row is multiplied twice against the same weights); add: fp16
+    [B, OH, OW, 32] added in the epilogue; out_fp32: y is fp32."""
+    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg, int(out_fp32)], (), [x, wr, y, stats, x_lo, add])
 
 
 def op_wgrad_stem2(x, dy, dw, B, IH, IW, w_ld):
     return _op(OP_WGRAD_STEM2, [B, IH, IW, w_ld], (), [x, dy, dw])
 
 
-def op_pack_w_stem2(w, wr, Cin):
-    return _op(OP_PACK_W_STEM2, [Cin], (), [w, wr])
+def op_pack_w_stem2(w, wr, Cin, lo=False):
+    return _op(OP_PACK_W_STEM2, [Cin, int(lo)], (), [w, wr])
 
 
 def op_wgrad_stem(x, dy, dw, B, IH, IW, w_ld, rows_per_cta=32):
