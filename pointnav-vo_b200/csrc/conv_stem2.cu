@@ -193,6 +193,16 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
       tc_fence_after();
       const int n_chunks = (p.n_cols + 31) >> 5;
       for (int ch = 0; ch < n_chunks; ++ch) {
+        // the tensor added in the epilogue (split mode): all 32 loads of the chunk are issued before the accumulator is
+        // read -- interleaved with the stores they serialised on the memory latency (2.76 ms instead of 1.0 ms per launch)
+        __half av[32];
+        if (arow && row_valid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int ow = ch * 32 + e;
+            av[e] = (ow < p.OW) ? __ldg(arow + static_cast<int64_t>(ow) * 32) : __half(0.f);
+          }
+        }
         float v[32];
         tmem_ld32(tmem_base + t_lane + ab * 256 + ch * 32, v);
         tmem_ld_wait();
@@ -202,16 +212,18 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           if (lane == 0) mbar_arrive(smem_u32(&s_accempty[ab]));
         }
         if (row_valid) {
+          if (arow) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += __half2float(av[e]);
+          }
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int ow = ch * 32 + e;
             if (ow < p.OW) {
-              float val = v[e];
-              if (arow) val += __half2float(arow[static_cast<int64_t>(ow) * 32]);
-              if (p.out_fp32) yrow32[static_cast<int64_t>(ow) * 32] = val;
-              else yrow[static_cast<int64_t>(ow) * 32] = __float2half_rn(val);
-              sum += val;
-              ssq = fmaf(val, val, ssq);
+              if (p.out_fp32) yrow32[static_cast<int64_t>(ow) * 32] = v[e];
+              else yrow[static_cast<int64_t>(ow) * 32] = __float2half_rn(v[e]);
+              sum += v[e];
+              ssq = fmaf(v[e], v[e], ssq);
             }
           }
         }

@@ -63,7 +63,8 @@ __device__ __forceinline__ int depth_bin(float d, const float* s_edges, int n) {
 }
 
 // RGB / DEP / TD: 0 or 1; NDD: number of one-hot bins (compile-time layout), or -1 = every flag read at run time
-template <int RGB, int DEP, int NDD, int TD, bool MAP = false>
+// LO: also write the residual plane value - fp16(value) (split-fp16 forward); the generic variant tests a.out_lo at run time
+template <int RGB, int DEP, int NDD, int TD, bool MAP = false, bool LO = false>
 __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
   __shared__ __align__(16) float s_scale[kMaxInC];
   __shared__ __align__(16) float s_shift[kMaxInC];
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
         h2[2] = __floats2half2_rn(fmaf(v[c + 4], sb.x, hb.x), fmaf(v[c + 5], sb.y, hb.y));
         h2[3] = __floats2half2_rn(fmaf(v[c + 6], sb.z, hb.z), fmaf(v[c + 7], sb.w, hb.w));
         *reinterpret_cast<uint4*>(out + q * 8) = u;
-        if (kGeneric && a.out_lo) {
+        if ((kGeneric || LO) && a.out_lo) {
           const float x[8] = {fmaf(v[c], sa.x, ha.x),     fmaf(v[c + 1], sa.y, ha.y), fmaf(v[c + 2], sa.z, ha.z),
                               fmaf(v[c + 3], sa.w, ha.w), fmaf(v[c + 4], sb.x, hb.x), fmaf(v[c + 5], sb.y, hb.y),
                               fmaf(v[c + 6], sb.z, hb.z), fmaf(v[c + 7], sb.w, hb.w)};
@@ -322,13 +323,21 @@ int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
   if (a.pair_map) {
     PNVO_REQUIRE(a.hw > 0 && a.n_pix % a.hw == 0 && a.n_pix < (1ll << 31), "raw_assemble: pair map needs pixels per sample");
-    if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td)
-      raw_assemble_kernel<1, 1, 10, 1, true><<<blocks, 256, 0, st>>>(a);
-    else
+    if (a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) {
+      if (a.out_lo) raw_assemble_kernel<1, 1, 10, 1, true, true><<<blocks, 256, 0, st>>>(a);
+      else raw_assemble_kernel<1, 1, 10, 1, true><<<blocks, 256, 0, st>>>(a);
+    } else {
       raw_assemble_kernel<0, 0, -1, 0, true><<<blocks, 256, 0, st>>>(a);
-  } else if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
-  else if (!a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 0 && !a.use_td) raw_assemble_kernel<1, 1, 0, 0><<<blocks, 256, 0, st>>>(a);
-  else raw_assemble_kernel<0, 0, -1, 0><<<blocks, 256, 0, st>>>(a);
+    }
+  } else if (a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) {
+    if (a.out_lo) raw_assemble_kernel<1, 1, 10, 1, false, true><<<blocks, 256, 0, st>>>(a);
+    else raw_assemble_kernel<1, 1, 10, 1><<<blocks, 256, 0, st>>>(a);
+  } else if (a.use_rgb && a.use_depth && a.n_dd == 0 && !a.use_td) {
+    if (a.out_lo) raw_assemble_kernel<1, 1, 0, 0, false, true><<<blocks, 256, 0, st>>>(a);
+    else raw_assemble_kernel<1, 1, 0, 0><<<blocks, 256, 0, st>>>(a);
+  } else {
+    raw_assemble_kernel<0, 0, -1, 0><<<blocks, 256, 0, st>>>(a);
+  }
   count_launch();
   return check_launch("raw_assemble");
 }
