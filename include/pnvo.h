@@ -84,6 +84,18 @@ int pnvo_gae_scan(const float* rewards, float* value_preds, const float* masks, 
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a14 / 8f-3  PPO clipped-surrogate + clipped-value loss with its gradient, one pass -- PPO.update
+ *     (pointnav_vo/rl/ppo/ppo.py:101-126).  All arrays [n] fp32 on the device (n = T * N' rows of a minibatch).
+ * losses[0] = value_loss, losses[1] = action_loss (written; no pre-zeroing needed);
+ * d_values = value_loss_coef * d(value_loss)/d(values), d_log_probs = d(action_loss)/d(log_probs): the gradient of
+ * `value_loss * value_loss_coef + action_loss`; the entropy term of the total loss stays with the caller.
+ */
+int pnvo_ppo_loss(const float* values, const float* log_probs, const float* value_preds, const float* returns,
+                  const float* old_log_probs, const float* adv_targ, int64_t n, float clip_param,
+                  int use_clipped_value_loss, float value_loss_coef, float* losses, float* d_values,
+                  float* d_log_probs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a10 batched goal update -- compute_goal_pos (pointnav_vo/utils/geometry_utils.py:115-144), fp64.
  * goal_xyz [n,3] f64 in/out (cartesian), delta [n,3] f32 (dx, dz, dyaw), polar [n,2] f32 out (rho, -phi).
  */

@@ -16,6 +16,8 @@ Reference (paths relative to /root/reference/pointnav_vo):
   vo_forward           vo/models/vo_cnn.py:82-95,176-179,216-233 ; vo_cnn_act_embed.py:65-75
   rl_encoder_forward   rl/policies/resnet_policy.py:146-174
   vo_losses            vo/engine/vo_cnn_engine.py:135-198 ; vo_cnn_regression_geo_invariance_engine.py:367-449
+  vo_total_loss        vo/engine/vo_cnn_regression_geo_invariance_engine.py:676-792 (_process_one_batch's loss)
+  ppo_losses           rl/ppo/ppo.py:86-126 (clipped surrogate / clipped value / entropy)
 """
 import torch
 import torch.nn.functional as F
@@ -212,3 +214,54 @@ def geo_invariance_inverse_loss(deltas, actions, move_forward=1):
         mask[fwd, 1] = 0.0
         pos = mask * pos
     return loss_rot + torch.mean(pos)
+
+
+def vo_total_loss(pred, target, actions=None, data_types=None, loss_weights=(1.0, 1.0, 1.0), dz_regress_masks=None,
+                  loss_inv_weight=0.0, turn_ids=(2, 3), move_forward=1):
+    """Training loss of ONE VO model over its rows, as _process_one_batch composes it
+    (vo_cnn_regression_geo_invariance_engine.py:676-792):
+      * no geometric-invariance types (data_types is None): sum over dx/dz/dyaw of mean((gt - pred)^2 * w) (:676-699);
+      * with data types: the same sum evaluated SEPARATELY on the cur-rel-to-prev rows and on the prev-rel-to-cur rows,
+        and added (:700-750) -- each mean is over the rows of its own type;
+      * inverse_joint_train: + loss_inv_weight * inversion loss over the rows whose action is TURN_LEFT / TURN_RIGHT,
+        which must alternate [cur_rel_to_prev, prev_rel_to_cur, ...] (:781-792, :373-374)."""
+    if data_types is None:
+        loss = sum(vo_losses(pred, target, loss_weights, dz_regress_masks))
+    else:
+        data_types = data_types.reshape(-1)
+        loss = pred.new_zeros(())
+        for t in (0, 1):
+            idx = torch.nonzero(data_types == t, as_tuple=True)[0]
+            if idx.numel() == 0:
+                continue
+            m = dz_regress_masks[idx] if dz_regress_masks is not None else None
+            loss = loss + sum(vo_losses(pred[idx], target[idx], loss_weights, m))
+    if loss_inv_weight > 0:
+        a = actions.reshape(-1)
+        if data_types is None:
+            valid = torch.arange(a.numel())
+        else:
+            valid = torch.nonzero((a == turn_ids[0]) | (a == turn_ids[1]), as_tuple=True)[0]
+            vt = data_types[valid]
+            assert bool((vt[0::2] == 0).all()) and bool((vt[1::2] == 1).all())
+        if valid.numel():
+            loss = loss + loss_inv_weight * geo_invariance_inverse_loss(pred[valid], a[valid], move_forward)
+    return loss
+
+
+def ppo_losses(values, action_log_probs, dist_entropy, value_preds, returns, old_action_log_probs, adv_targ,
+               clip_param=0.2, use_clipped_value_loss=True):
+    """rl/ppo/ppo.py:86-126 -> (value_loss, action_loss, dist_entropy.mean()); total = value_loss * value_loss_coef +
+    action_loss - entropy * entropy_coef (:127-133)."""
+    ratio = torch.exp(action_log_probs - old_action_log_probs)
+    surr1 = ratio * adv_targ
+    surr2 = torch.clamp(ratio, 1.0 - clip_param, 1.0 + clip_param) * adv_targ
+    action_loss = -torch.min(surr1, surr2).mean()
+    if use_clipped_value_loss:
+        value_pred_clipped = value_preds + (values - value_preds).clamp(-clip_param, clip_param)
+        value_losses = (values - returns).pow(2)
+        value_losses_clipped = (value_pred_clipped - returns).pow(2)
+        value_loss = 0.5 * torch.max(value_losses, value_losses_clipped).mean()
+    else:
+        value_loss = 0.5 * (returns - values).pow(2).mean()
+    return value_loss, action_loss, dist_entropy.mean()

@@ -80,10 +80,12 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       // p0 = device table of PackDesc / UnpackDesc / GnParamDesc (elem.cuh); i0 = entries, i1 = B (param grad)
       return multi_launch(op.code, p[0], i[0], i[1], st);
     case PNVO_OP_GEO_INV_LOSS:
-      // p0 = pred [B][O], p1 = actions int64 [B], p2 = dout (nullable, accumulated), p3 = loss[3] (total+=, rot, pos)
-      // i0 = B, i1 = O, i2 = MOVE_FORWARD id; f0 = loss_inv_weight, f1 = gradient scale
-      return geo_inv_loss_launch(static_cast<const float*>(p[0]), static_cast<const int64_t*>(p[1]), i[0], i[1], i[2], f[0],
-                                 f[1], static_cast<float*>(p[2]), static_cast<float*>(p[3]), st);
+      // p0 = pred [B][O], p1 = actions int64 [B], p2 = dout (nullable, accumulated), p3 = loss[3] (total+=, rot, pos),
+      // p4 = data types int64 [B] (nullable: every row, interleaved pairs), p5 = int32 error flag (nullable)
+      // i0 = B, i1 = O, i2 = MOVE_FORWARD id, i3 = TURN_LEFT id, i4 = TURN_RIGHT id; f0 = loss_inv_weight, f1 = gradient scale
+      return geo_inv_loss_launch(static_cast<const float*>(p[0]), static_cast<const int64_t*>(p[1]),
+                                 static_cast<const int64_t*>(p[4]), i[0], i[1], i[2], i[3], i[4], f[0], f[1],
+                                 static_cast<float*>(p[2]), static_cast<float*>(p[3]), static_cast<int*>(p[5]), st);
     case PNVO_OP_UPSAMPLE2:
       // p0 = src [B,OH,OW,C] fp16, p1 = dst [B,IH,IW,C] fp16; i0 = B, i1 = OH, i2 = OW, i3 = IH, i4 = IW, i5 = C
       return upsample2_launch(static_cast<const __half*>(p[0]), static_cast<__half*>(p[1]), i[0], i[1], i[2], i[3], i[4],
@@ -190,11 +192,11 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                              static_cast<float*>(p[4]), static_cast<__half*>(p[5]), static_cast<float*>(p[6]), i[3],
                              (f[0] == 0.f) ? 1.f : f[0], st);
     case PNVO_OP_MSE_LOSS:
-      // p0 = pred, p1 = target, p2 = dz mask (nullable), p3 = dout (nullable), p4 = loss; i0 = B, i1 = O;
-      // f0..f2 = loss weights, f3 = gradient scale
+      // p0 = pred, p1 = target, p2 = dz mask (nullable), p3 = dout (nullable), p4 = loss, p5 = data types int64 [B]
+      // (nullable; with them: one mean per data type, summed); i0 = B, i1 = O; f0..f2 = loss weights, f3 = gradient scale
       return mse_loss_launch(static_cast<const float*>(p[0]), static_cast<const float*>(p[1]),
-                             static_cast<const float*>(p[2]), i[0], i[1], f[0], f[1], f[2], f[3],
-                             static_cast<float*>(p[3]), static_cast<float*>(p[4]), st);
+                             static_cast<const float*>(p[2]), static_cast<const int64_t*>(p[5]), i[0], i[1], f[0], f[1],
+                             f[2], f[3], static_cast<float*>(p[3]), static_cast<float*>(p[4]), st);
     case PNVO_OP_CONV_STEM:
       // p0 = x [B,IH,IW,32] fp16, p1 = stem-packed weights, p2 = y, p3 = stats; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = stages
       return conv_stem_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
@@ -230,10 +232,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                          (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), f[0],
                          f[1], f[2], f[3], i[2], 1.0f, st);
     case PNVO_OP_AVGPOOL2:
-      // p0 = src fp32 NHWC, p1 = out fp16, p2 = out_lo (split-fp16 residual plane, nullable);
-      // i0 = B, i1 = H, i2 = W, i3 = C, i4 = Cpad, i5 = coff; f0 = pre_scale
+      // p0 = src fp32 NHWC, p1 = out fp16 (nullable), p2 = out_lo (split-fp16 residual plane, nullable), p3 = fp32 pooled
+      // output [.., ld32] (nullable); i0 = B, i1 = H, i2 = W, i3 = C, i4 = Cpad, i5 = coff, i6 = ld32; f0 = pre_scale
       return avgpool2_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], f[0], static_cast<__half*>(p[1]),
-                             i[4], i[5], st, static_cast<__half*>(p[2]));
+                             i[4], i[5], st, static_cast<__half*>(p[2]), static_cast<float*>(p[3]), i[6]);
     default:
       set_error("run_ops: unknown opcode %d", op.code);
       return -3;

@@ -26,7 +26,7 @@ int input_stats_launch(const AssembleArgs& a, double* stats, cudaStream_t st);
 int rmv_update_launch(const double* stats, double n_batch, double pix_per_sample, float* mean, float* var,
                       float* count, int C, int update, int have_rmv, float* scale, float* shift, cudaStream_t st);
 int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
-                    cudaStream_t st, __half* out_lo = nullptr);
+                    cudaStream_t st, __half* out_lo = nullptr, float* out32 = nullptr, int ld32 = 0);
 int zero_launch(void* p, int64_t bytes, cudaStream_t st);
 int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int IH, int IW, int C, cudaStream_t st);
 // raw_input.cu: PNVO_OP_RAW_STATS / PNVO_OP_RAW_ASSEMBLE (field layout documented there)
@@ -109,10 +109,11 @@ int head_fwd_launch(const float* h, const float* W, const float* bias, int B, in
 int head_bwd_launch(const float* dout, const float* h, const float* W, int B, int K, int O, float* dW, float* db2,
                     __half* dz16, float* db1, int accumulate, float dh_scale, cudaStream_t st);
 int dropout_launch(void* buf, int64_t n, int is_fp16, uint64_t* seed, int site, float p, int advance, cudaStream_t st);
-int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, int B, int O, float w0, float w1,
-                    float w2, float grad_scale, float* dout, float* loss, cudaStream_t st);
-int geo_inv_loss_launch(const float* pred, const int64_t* actions, int B, int O, int move_forward, float weight,
-                        float grad_scale, float* dout, float* loss, cudaStream_t st);
+int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, const int64_t* data_types, int B, int O,
+                    float w0, float w1, float w2, float grad_scale, float* dout, float* loss, cudaStream_t st);
+int geo_inv_loss_launch(const float* pred, const int64_t* actions, const int64_t* data_types, int B, int O,
+                        int move_forward, int turn_left, int turn_right, float weight, float grad_scale, float* dout,
+                        float* loss, int* err, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                 int step, float grad_scale, cudaStream_t st);
 

@@ -304,9 +304,11 @@ int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int 
 // ------------------------------------------------------------------------------------------------
 // 2x2 average pool of fp32 NHWC sources -> fp16 NHWC (policy encoder, resnet_policy.py:146-168)
 // ------------------------------------------------------------------------------------------------
+// out32 (nullable): the pooled values in fp32, [B, OH, OW, ld32] at channel offset coff -- the input of the RunningMeanAndVar
+// statistics / normalisation ops when the encoder normalises its visual inputs (resnet_policy.py:170)
 __global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ src, int B, int H, int W, int C,
                                                        float pre_scale, __half* __restrict__ out, int Cpad, int coff,
-                                                       __half* __restrict__ out_lo) {
+                                                       __half* __restrict__ out_lo, float* __restrict__ out32, int ld32) {
   const int OH = H / 2, OW = W / 2;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(B) * OH * OW;
@@ -315,21 +317,34 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__
   const int oh = static_cast<int>((idx / OW) % OH);
   const int b = static_cast<int>(idx / (static_cast<int64_t>(OW) * OH));
   const float* p = src + ((static_cast<int64_t>(b) * H + 2 * oh) * W + 2 * ow) * C;
+  const bool div255 = pre_scale == 1.f / 255.f;
   for (int c = 0; c < C; ++c) {
-    // F.avg_pool2d sums the window then multiplies by 1/4
-    const float s = ((p[c] + p[C + c]) + p[static_cast<int64_t>(W) * C + c]) + p[static_cast<int64_t>(W) * C + C + c];
-    const float v = s * 0.25f * pre_scale;
-    const __half h = __float2half_rn(v);
-    out[idx * Cpad + coff + c] = h;
-    if (out_lo) out_lo[idx * Cpad + coff + c] = __float2half_rn(v - __half2float(h));  // split-fp16 residual plane
+    // the reference scales (rgb / 255) before pooling; F.avg_pool2d sums the window then multiplies by 1/4
+    float q[4] = {p[c], p[C + c], p[static_cast<int64_t>(W) * C + c], p[static_cast<int64_t>(W) * C + C + c]};
+    if (div255) {  // rgb / 255.0: a true division, as the reference does (resnet_policy.py:155)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = __fdiv_rn(q[k], 255.f);
+    } else if (pre_scale != 1.f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] *= pre_scale;
+    }
+    const float s = ((q[0] + q[1]) + q[2]) + q[3];
+    const float v = s * 0.25f;
+    if (out32) out32[idx * ld32 + coff + c] = v;
+    if (out) {
+      const __half h = __float2half_rn(v);
+      out[idx * Cpad + coff + c] = h;
+      if (out_lo) out_lo[idx * Cpad + coff + c] = __float2half_rn(v - __half2float(h));  // split-fp16 residual plane
+    }
   }
 }
 int avgpool2_launch(const float* src, int B, int H, int W, int C, float pre_scale, __half* out, int Cpad, int coff,
-                    cudaStream_t st, __half* out_lo) {
+                    cudaStream_t st, __half* out_lo, float* out32, int ld32) {
   const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2);
   if (total <= 0) return 0;
+  PNVO_REQUIRE(out || out32, "avgpool2: no output");
   avgpool2_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, st>>>(src, B, H, W, C, pre_scale, out, Cpad, coff,
-                                                                            out_lo);
+                                                                            out_lo, out32, ld32);
   count_launch();
   return check_launch("avgpool2");
 }
@@ -1200,21 +1215,41 @@ int dropout_launch(void* buf, int64_t n, int is_fp16, uint64_t* seed, int site, 
 // ------------------------------------------------------------------------------------------------
 // VO regression loss (vo_cnn_engine.py:135-198): loss = sum_i w_i * mean_b (t_bi - p_bi)^2 (dz optionally
 // masked), and its gradient dout_bi = 2 w_i mask_bi (p_bi - t_bi) / B (scaled by grad_scale, e.g. 1/world).
-// One block; B is a few hundred.
+// With per-row data types (geometric-invariance batches, vo_cnn_regression_geo_invariance_engine.py:676-750) the
+// reference sums a SEPARATE mean per data type (cur-rel-to-prev rows, prev-rel-to-cur rows): every row is then
+// normalised by the number of rows of its own type.  One block; B is a few hundred.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
-                                                       const float* __restrict__ dz_mask, int B, int O, float w0,
+                                                       const float* __restrict__ dz_mask,
+                                                       const int64_t* __restrict__ data_types, int B, int O, float w0,
                                                        float w1, float w2, float grad_scale, float* __restrict__ dout,
                                                        float* __restrict__ loss) {
   __shared__ float s_part[8];
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (data_types) {
+    int c1 = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) c1 += (data_types[b] != 0) ? 1 : 0;
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt[1], c1);
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt[0] = B - s_cnt[1];
+  } else if (threadIdx.x == 0) {
+    s_cnt[0] = B;
+  }
+  __syncthreads();
+  const float inv0 = s_cnt[0] > 0 ? 1.f / static_cast<float>(s_cnt[0]) : 0.f;
+  const float inv1 = s_cnt[1] > 0 ? 1.f / static_cast<float>(s_cnt[1]) : 0.f;
   float acc = 0.f;
   for (int i = threadIdx.x; i < B * O; i += blockDim.x) {
     const int b = i / O, o = i - b * O;
     float w = (o == 0) ? w0 : ((o == 1) ? w1 : w2);
     if (o == 1 && dz_mask) w *= dz_mask[b];
+    w *= (data_types && data_types[b] != 0) ? inv1 : inv0;
     const float d = pred[i] - tgt[i];
     acc = fmaf(w * d, d, acc);
-    if (dout) dout[i] = 2.f * w * d * grad_scale / static_cast<float>(B);
+    if (dout) dout[i] = 2.f * w * d * grad_scale;
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -1222,37 +1257,66 @@ __global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += s_part[k];
-    *loss = t / static_cast<float>(B);
+    *loss = t;
   }
 }
-int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, int B, int O, float w0, float w1,
-                    float w2, float grad_scale, float* dout, float* loss, cudaStream_t st) {
+int mse_loss_launch(const float* pred, const float* tgt, const float* dz_mask, const int64_t* data_types, int B, int O,
+                    float w0, float w1, float w2, float grad_scale, float* dout, float* loss, cudaStream_t st) {
   PNVO_REQUIRE(pred && tgt && loss, "mse_loss: null argument");
-  mse_loss_kernel<<<1, 256, 0, st>>>(pred, tgt, dz_mask, B, O, w0, w1, w2, grad_scale, dout, loss);
+  mse_loss_kernel<<<1, 256, 0, st>>>(pred, tgt, dz_mask, data_types, B, O, w0, w1, w2, grad_scale, dout, loss);
   count_launch();
   return check_launch("mse_loss");
 }
 
 // ------------------------------------------------------------------------------------------------
-// Geometric-inversion loss (vo_cnn_regression_geo_invariance_engine.py:367-449) on predictions interleaved
-// [a0, b0, a1, b1, ...] (a = cur relative to prev, b = prev relative to cur), n = B/2 pairs:
+// Geometric-inversion loss (vo_cnn_regression_geo_invariance_engine.py:367-449,781-792) over n pairs (a = cur relative
+// to prev, b = prev relative to cur):
 //   rot = mean_i (a.yaw + b.yaw)^2
 //   pos = mean_{i,k} m_ik (b.xz + R(b.yaw) a.xz)_k^2,  R = [[c, s], [-s, c]] (left-handed), m_i1 = 0 for MOVE_FORWARD
 // loss[0] += weight * (rot + pos) (added to the regression loss already there), loss[1] = rot, loss[2] = pos;
 // dout += weight * grad_scale * d(rot + pos)/d(pred).
+// Which rows pair up: with data_types == null the batch is taken as interleaved [a0, b0, a1, b1, ...] (every row);
+// with data_types the reference's selection is reproduced (:781-792): only rows whose action is TURN_LEFT / TURN_RIGHT
+// take part, in batch order, and that sub-sequence must alternate [cur-rel-to-prev, prev-rel-to-cur, ...] (:373-374
+// asserts it) -- a violation (or an odd count) sets *err and contributes nothing.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) geo_inv_loss_kernel(const float* __restrict__ pred,
-                                                           const int64_t* __restrict__ actions, int B, int O,
-                                                           int move_forward, float weight, float grad_scale,
-                                                           float* __restrict__ dout, float* __restrict__ loss) {
+                                                           const int64_t* __restrict__ actions,
+                                                           const int64_t* __restrict__ data_types, int B, int O,
+                                                           int move_forward, int turn_left, int turn_right, float weight,
+                                                           float grad_scale, float* __restrict__ dout,
+                                                           float* __restrict__ loss, int* __restrict__ err) {
+  extern __shared__ int s_rows[];  // valid rows in batch order
   __shared__ float s_rot[8], s_pos[8];
-  const int n = B / 2;
+  __shared__ int s_nvalid, s_bad;
+  if (threadIdx.x == 0) {
+    int nv = 0, bad = 0;
+    if (data_types) {
+      for (int b = 0; b < B; ++b) {
+        const int64_t a = actions[b];
+        if (a == turn_left || a == turn_right) {
+          if (data_types[b] != (nv & 1)) bad = 1;
+          s_rows[nv++] = b;
+        }
+      }
+      if (nv & 1) bad = 1;
+    } else {
+      for (int b = 0; b < B; ++b) s_rows[b] = b;
+      nv = B;
+    }
+    s_nvalid = bad ? 0 : nv;
+    s_bad = bad;
+    if (bad && err) *err = 1;
+  }
+  __syncthreads();
+  const int n = s_nvalid / 2;
   float acc_rot = 0.f, acc_pos = 0.f;
-  const float inv_n = 1.f / static_cast<float>(n);
+  const float inv_n = n > 0 ? 1.f / static_cast<float>(n) : 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float* a = pred + static_cast<int64_t>(2 * i) * O;
-    const float* b = a + O;
-    const float m = (actions[2 * i] == move_forward) ? 0.f : 1.f;
+    const int ra = s_rows[2 * i], rb = s_rows[2 * i + 1];
+    const float* a = pred + static_cast<int64_t>(ra) * O;
+    const float* b = pred + static_cast<int64_t>(rb) * O;
+    const float m = (actions[ra] == move_forward) ? 0.f : 1.f;
     const float yaw = a[2] + b[2];
     const float c = cosf(b[2]), s = sinf(b[2]);
     const float p0 = c * a[0] + s * a[1], p1 = -s * a[0] + c * a[1];
@@ -1261,8 +1325,8 @@ __global__ void __launch_bounds__(256) geo_inv_loss_kernel(const float* __restri
     acc_pos += e0 * e0 + m * e1 * e1;
     if (dout) {
       const float k = weight * grad_scale * inv_n;
-      float* da = dout + static_cast<int64_t>(2 * i) * O;
-      float* db = da + O;
+      float* da = dout + static_cast<int64_t>(ra) * O;
+      float* db = dout + static_cast<int64_t>(rb) * O;
       da[0] += k * (e0 * c - m * e1 * s);
       da[1] += k * (e0 * s + m * e1 * c);
       da[2] += k * 2.f * yaw;
@@ -1288,11 +1352,15 @@ __global__ void __launch_bounds__(256) geo_inv_loss_kernel(const float* __restri
     loss[2] = q;
   }
 }
-int geo_inv_loss_launch(const float* pred, const int64_t* actions, int B, int O, int move_forward, float weight,
-                        float grad_scale, float* dout, float* loss, cudaStream_t st) {
-  PNVO_REQUIRE(pred && actions && loss && O >= 3 && B % 2 == 0, "geo_inv_loss: bad arguments (B must be even: interleaved pairs)");
+int geo_inv_loss_launch(const float* pred, const int64_t* actions, const int64_t* data_types, int B, int O,
+                        int move_forward, int turn_left, int turn_right, float weight, float grad_scale, float* dout,
+                        float* loss, int* err, cudaStream_t st) {
+  PNVO_REQUIRE(pred && actions && loss && O >= 3, "geo_inv_loss: bad arguments");
+  PNVO_REQUIRE(data_types || B % 2 == 0, "geo_inv_loss: B must be even without data types (interleaved pairs)");
+  PNVO_REQUIRE(B <= 8192, "geo_inv_loss: at most 8192 rows");
   if (B == 0) return 0;
-  geo_inv_loss_kernel<<<1, 256, 0, st>>>(pred, actions, B, O, move_forward, weight, grad_scale, dout, loss);
+  geo_inv_loss_kernel<<<1, 256, B * sizeof(int), st>>>(pred, actions, data_types, B, O, move_forward, turn_left,
+                                                       turn_right, weight, grad_scale, dout, loss, err);
   count_launch();
   return check_launch("geo_inv_loss");
 }

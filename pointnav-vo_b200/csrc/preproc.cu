@@ -3,6 +3,7 @@
 //   batched goal update (a10).  All arithmetic that feeds an index map uses explicit round-to-nearest
 //   intrinsics (no FMA contraction) so the maps are bit-identical to the reference's fp32 torch path.
 #include "common.cuh"
+#include "elem.cuh"
 
 namespace pnvo {
 
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(128) gae_seq_kernel(const float* __restrict__ 
   if (n >= N) return;
   const float nv = next_value[n];
   if (use_gae) {
-    values[static_cast<int64_t>(T) * N + n] = nv;
-    returns[static_cast<int64_t>(T) * N + n] = 0.0f;
+    values[static_cast<int64_t>(T) * N + n] = nv;  // (returns[T] is left untouched, as the reference does)
+    if (T == 0) return;
     float gae = 0.0f;
     float v_next = nv;
     // software-pipelined: loads of step t-1 are independent of the recurrence
@@ -294,7 +295,6 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float* __restrict__
   if (lane == 0) {
     if (use_gae) {
       values[static_cast<int64_t>(T) * N + n] = nv;
-      returns[static_cast<int64_t>(T) * N + n] = 0.0f;
     } else {
       returns[static_cast<int64_t>(T) * N + n] = nv;
     }
@@ -449,6 +449,85 @@ int topdown_launch(const void* depth, int64_t in_stride, int64_t in_pix_stride, 
   return check_launch("topdown_project");
 }
 }  // namespace pnvo
+
+// ------------------------------------------------------------------------------------------------
+// a14 / 8f-3: PPO clipped-surrogate + clipped-value loss and its gradient in one pass (rl/ppo/ppo.py:101-126).
+//   ratio = exp(lp - old_lp); action_loss = -mean(min(ratio * adv, clamp(ratio, 1-c, 1+c) * adv))
+//   value_loss = 0.5 * mean(max((v - R)^2, (vp + clamp(v - vp, -c, c) - R)^2))        (or 0.5 * mean((R - v)^2))
+// losses[0] = value_loss, losses[1] = action_loss (atomics into a pre-zeroed pair);
+// d_values = value_loss_coef * d value_loss / d v,  d_log_probs = d action_loss / d lp  -- ties of min / max split the
+// gradient evenly and clamp passes it on its closed interval, as torch.min / torch.max / torch.clamp do.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const float* __restrict__ values, const float* __restrict__ lp,
+                                                       const float* __restrict__ value_preds,
+                                                       const float* __restrict__ returns, const float* __restrict__ old_lp,
+                                                       const float* __restrict__ adv, int64_t n, float clip,
+                                                       int use_clipped_value, float value_coef,
+                                                       float* __restrict__ losses, float* __restrict__ d_values,
+                                                       float* __restrict__ d_lp) {
+  __shared__ float s_v[8], s_a[8];
+  const float inv_n = 1.f / static_cast<float>(n);
+  float acc_v = 0.f, acc_a = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float a = adv[i];
+    const float ratio = expf(lp[i] - old_lp[i]);
+    const float rc = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+    const float s1 = ratio * a, s2 = rc * a;
+    acc_a -= fminf(s1, s2);
+    const float in_range = (ratio >= 1.f - clip && ratio <= 1.f + clip) ? 1.f : 0.f;
+    // d min(s1, s2) / d ratio: s1 carries a, s2 carries a * in_range; a tie splits evenly
+    float g = (s1 < s2) ? a : ((s1 > s2) ? a * in_range : 0.5f * (a + a * in_range));
+    d_lp[i] = -g * ratio * inv_n;
+    const float v = values[i], R = returns[i];
+    const float e1 = v - R;
+    float dv;
+    if (use_clipped_value) {
+      const float vp = value_preds[i];
+      const float dvp = v - vp;
+      const float vc = vp + fminf(fmaxf(dvp, -clip), clip);
+      const float e2 = vc - R;
+      const float l1 = e1 * e1, l2 = e2 * e2;
+      acc_v += 0.5f * fmaxf(l1, l2);
+      const float inr = (dvp >= -clip && dvp <= clip) ? 1.f : 0.f;
+      dv = (l1 > l2) ? e1 : ((l1 < l2) ? e2 * inr : 0.5f * (e1 + e2 * inr));
+    } else {
+      acc_v += 0.5f * e1 * e1;
+      dv = e1;
+    }
+    d_values[i] = value_coef * dv * inv_n;
+  }
+  acc_v = warp_sum(acc_v);
+  acc_a = warp_sum(acc_a);
+  if ((threadIdx.x & 31) == 0) {
+    s_v[threadIdx.x >> 5] = acc_v;
+    s_a[threadIdx.x >> 5] = acc_a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tv = 0.f, ta = 0.f;
+    for (int k = 0; k < 8; ++k) { tv += s_v[k]; ta += s_a[k]; }
+    atomicAdd(losses, tv * inv_n);
+    atomicAdd(losses + 1, ta * inv_n);
+  }
+}
+
+extern "C" int pnvo_ppo_loss(const float* values, const float* log_probs, const float* value_preds, const float* returns,
+                             const float* old_log_probs, const float* adv_targ, int64_t n, float clip_param,
+                             int use_clipped_value_loss, float value_loss_coef, float* losses, float* d_values,
+                             float* d_log_probs, void* stream) {
+  PNVO_REQUIRE(values && log_probs && returns && old_log_probs && adv_targ && losses && d_values && d_log_probs,
+               "ppo_loss: null argument");
+  PNVO_REQUIRE(!use_clipped_value_loss || value_preds, "ppo_loss: the clipped value loss needs value_preds");
+  PNVO_REQUIRE(n > 0, "ppo_loss: empty minibatch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (zero_launch(losses, 2 * sizeof(float), st)) return -1;
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 148));
+  ppo_loss_kernel<<<blocks, 256, 0, st>>>(values, log_probs, value_preds, returns, old_log_probs, adv_targ, n, clip_param,
+                                          use_clipped_value_loss, value_loss_coef, losses, d_values, d_log_probs);
+  count_launch();
+  return check_launch("ppo_loss");
+}
 
 extern "C" int pnvo_gae_scan(const float* rewards, float* value_preds, const float* masks, const float* next_value,
                              float* returns, int T, int N, int use_gae, float gamma, float gamma_tau, int mode,

@@ -645,19 +645,26 @@ class EncoderPlan:
             self._alt_progs = (fwd, bwd)
         return self._alt_progs
 
-    def input_ops(self, obs):
+    def input_ops(self, obs, out32=None):
         """avg-pool input path of the RL encoder (resnet_policy.py:146-168): sources are pooled 2x2 and written
-        into the channel slots of x0 (pad channels stay zero)."""
+        into the channel slots of x0 (pad channels stay zero) -- or, with out32, into an fp32 [B, h, w, C] tensor that
+        the RunningMeanAndVar ops then normalise into x0."""
         ops, coff = [], 0
+        keep = []
         for k, n, scale in self.sources:
             t = obs[k]
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             assert t.shape[-1] == n
-            ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale,
-                                     out_lo=self.lo(self.x0)))
+            if out32 is not None:
+                ops.append(L.op_avgpool2(t, None, self.B, self.H, self.W, n, self.cin_pad, coff, scale, out32=out32,
+                                         ld32=self.in_channels))
+            else:
+                ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale,
+                                         out_lo=self.lo(self.x0)))
             coff += n
-            self._keepalive = t
+            keep.append(t)
+        self._keepalive = keep
         return ops
 
     def conv_flops(self, backward=False):

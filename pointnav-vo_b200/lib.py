@@ -64,7 +64,7 @@ EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_dis
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
            "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_topdown_project_strided_f16",
            "pnvo_conv_stem2_supported", "pnvo_conv_stem_wgrad2_supported", "pnvo_graph_capture", "pnvo_graph_launch",
-           "pnvo_graph_destroy"]
+           "pnvo_graph_destroy", "pnvo_ppo_loss"]
 
 
 def load():
@@ -98,6 +98,8 @@ def load():
     lib.pnvo_topdown_project_strided_f16.restype = i32
     lib.pnvo_gae_scan.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
     lib.pnvo_goal_update.argtypes = [vp, vp, vp, i32, vp]
+    lib.pnvo_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, i32, f32, vp, vp, vp, vp]
+    lib.pnvo_ppo_loss.restype = i32
     lib.pnvo_run_ops.argtypes = [ctypes.POINTER(PnvoOp), i32, vp]
     lib.pnvo_graph_capture.argtypes = [ctypes.POINTER(PnvoOp), i32, ctypes.POINTER(ctypes.c_void_p)]
     lib.pnvo_graph_launch.argtypes = [vp, vp]
@@ -257,9 +259,13 @@ def op_unpack_dw(dwp, grad, Cout, Cin, R, S, cin_pad, ld_p, accumulate=False, ds
     return _op(OP_UNPACK_DW, [Cout, Cin, R, S, cin_pad, ld_p, int(accumulate), dst_ld], (), [dwp, grad])
 
 
-def op_geo_inv_loss(pred, actions, dout, loss3, B, O, weight, grad_scale=1.0, move_forward=1):
-    """loss3[0] += weight * (rot + pos), loss3[1] = rot, loss3[2] = pos; dout += weight * grad_scale * gradient."""
-    return _op(OP_GEO_INV_LOSS, [B, O, move_forward], [weight, grad_scale], [pred, actions, dout, loss3])
+def op_geo_inv_loss(pred, actions, dout, loss3, B, O, weight, grad_scale=1.0, move_forward=1, data_types=None, err=None,
+                    turn_left=2, turn_right=3):
+    """loss3[0] += weight * (rot + pos), loss3[1] = rot, loss3[2] = pos; dout += weight * grad_scale * gradient.
+    data_types (int64 per row): only TURN_LEFT / TURN_RIGHT rows pair up, in batch order, and must alternate
+    [cur-rel-to-prev, prev-rel-to-cur] (else *err = 1); None: every row, interleaved."""
+    return _op(OP_GEO_INV_LOSS, [B, O, move_forward, turn_left, turn_right], [weight, grad_scale],
+               [pred, actions, dout, loss3, data_types, err])
 
 
 def op_upsample2(src, dst, B, OH, OW, IH, IW, C):
@@ -297,8 +303,10 @@ def op_dropout(buf, seed, site, p, advance=False):
     return _op(OP_DROPOUT, [lo, hi, int(buf.dtype == torch.float16), site, int(advance)], [p], [buf, seed])
 
 
-def op_mse_loss(pred, target, dz_mask, dout, loss, B, O, weights=(1.0, 1.0, 1.0), grad_scale=1.0):
-    return _op(OP_MSE_LOSS, [B, O], [weights[0], weights[1], weights[2], grad_scale], [pred, target, dz_mask, dout, loss])
+def op_mse_loss(pred, target, dz_mask, dout, loss, B, O, weights=(1.0, 1.0, 1.0), grad_scale=1.0, data_types=None):
+    """data_types (int64 per row, 0 = cur-rel-to-prev, 1 = prev-rel-to-cur): one mean per data type, summed."""
+    return _op(OP_MSE_LOSS, [B, O], [weights[0], weights[1], weights[2], grad_scale],
+               [pred, target, dz_mask, dout, loss, data_types])
 
 
 def op_conv_stem(x, wr, y, stats, B, IH, IW, G, cpg, stages=4):
@@ -332,8 +340,8 @@ def op_adam(p, g, m, v, n, step, lr, beta1, beta2, eps):
     return _op(OP_ADAM, [lo, hi, step], [lr, beta1, beta2, eps], [p, g, m, v])
 
 
-def op_avgpool2(src, out, B, H, W, C, Cpad, coff, pre_scale=1.0, out_lo=None):
-    return _op(OP_AVGPOOL2, [B, H, W, C, Cpad, coff], [pre_scale], [src, out, out_lo])
+def op_avgpool2(src, out, B, H, W, C, Cpad, coff, pre_scale=1.0, out_lo=None, out32=None, ld32=0):
+    return _op(OP_AVGPOOL2, [B, H, W, C, Cpad, coff, ld32], [pre_scale], [src, out, out_lo, out32])
 
 
 USE_GRAPHS = os.environ.get("PNVO_GRAPHS", "1") != "0"

@@ -70,7 +70,8 @@ class RolloutStorage:
                                      f"the number of trainer mini batches ({num_mini_batch}).")
         per = N // num_mini_batch
         T = self.step
-        perm = torch.randperm(N, device=self.rewards.device)
+        fixed = getattr(self, "fixed_perms", None)  # tests: replay a recorded sequence of env permutations
+        perm = fixed.pop(0) if fixed else torch.randperm(N, device=self.rewards.device)
         for start in range(0, N, per):
             ind = perm[start:start + per]
             n = ind.numel()

@@ -14,6 +14,7 @@ from ... import lib as L
 from ...engine import EncoderPlan
 from ...model_utils import resnet
 from ...model_utils.rnns.rnn_state_encoder import RNNStateEncoder
+from ...model_utils.running_mean_and_var import RunningMeanAndVar
 from ...utils.baseline_registry import baseline_registry
 from ...vo.models.vo_cnn import Flatten
 from .policy import Net, Policy
@@ -41,11 +42,11 @@ class ResNetEncoder(nn.Module):
             self._n_input_depth = spaces["depth"].shape[2]
             spatial_size_w, spatial_size_h = spaces["depth"].shape[0] // 2, spaces["depth"].shape[1] // 2
             self._sources.append(("depth", self._n_input_depth, 1.0))
-        if normalize_visual_inputs:
-            raise NotImplementedError("normalize_visual_inputs for the RL encoder is not implemented on the B200 path "
-                                      "(the shipped depth-only policy builds it with False, ddppo_trainer.py:118-121)")
-        self.running_mean_and_var = nn.Sequential()
         self.baseplanes, self.ngroups = baseplanes, ngroups
+        if normalize_visual_inputs:  # applied to the 2x2-pooled input (resnet_policy.py:168-170)
+            self.running_mean_and_var = RunningMeanAndVar(self._n_input_depth + self._n_input_rgb)
+        else:
+            self.running_mean_and_var = nn.Sequential()
         if not self.is_blind:
             input_channels = self._n_input_depth + self._n_input_rgb
             self.input_channels = input_channels
@@ -80,12 +81,16 @@ class _VisualFunction(torch.autograd.Function):
     def forward(ctx, net, obs, need_grad, *params):
         plan = net._plan_for(obs, need_grad)
         net._run_visual(plan, obs)
-        ctx.net, ctx.plan = net, plan
+        plan.generation = getattr(plan, "generation", 0) + 1  # see _VOFunction: one set of activation buffers per shape
+        ctx.net, ctx.plan, ctx.generation = net, plan, plan.generation
         return plan.h32.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         net, plan = ctx.net, ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("backward of a policy forward whose activations were overwritten by a later forward of the "
+                               "same shape: call backward before the next forward of that shape")
         plan.dout.copy_(grad_out)
         plan.bwd_prog.run(plan.dev)
         flat = plan.grad_flat.clone()
@@ -169,7 +174,11 @@ class PointNavResNetNet(Net):
         if plan is None:
             P = {k: p.data for k, p in self.named_parameters()}
             head = dict(fc_w="visual_fc.1.weight", fc_b="visual_fc.1.bias", hidden=self._hidden_size, out_dim=None)
-            plan = EncoderPlan(params=P, buffers={}, B=B, H=H, W=W, in_channels=enc.input_channels,
+            rmv = enc.running_mean_and_var
+            world = 1
+            if isinstance(rmv, RunningMeanAndVar) and rmv._distributed:
+                world = torch.distributed.get_world_size()
+            plan = EncoderPlan(params=P, buffers={}, B=B, H=H, W=W, in_channels=enc.input_channels, world_size=world,
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0], prefix="visual_encoder",
                                head=head, training=bool(need_grad), avgpool_input=True, device=first.device,
@@ -178,12 +187,39 @@ class PointNavResNetNet(Net):
         return plan
 
     def _run_visual(self, plan, obs):
-        L.run_ops(plan.input_ops(obs), plan.dev)
+        rmv = self.visual_encoder.running_mean_and_var
+        if isinstance(rmv, RunningMeanAndVar):
+            self._run_normalised_input(plan, obs, rmv)
+        else:
+            L.run_ops(plan.input_ops(obs), plan.dev)
         ver = sum(p._version for p in self._visual_params())
         if ver != self._packed_version or plan is not self._packed_plan:
             plan.pack_prog.run(plan.dev)
             self._packed_version, self._packed_plan = ver, plan
         plan.fwd_prog.run(plan.dev)
+
+    def _run_normalised_input(self, plan, obs, rmv):
+        """avg_pool2d -> RunningMeanAndVar -> x0 (resnet_policy.py:168-170): pooled values in fp32, batch statistics and
+        the Chan merge in training mode (one packed all-reduce in a process group), then normalise into the fp16 planes."""
+        dev = plan.dev
+        C, B, h, w = plan.in_channels, plan.B, plan.inH, plan.inW
+        if getattr(plan, "pooled32", None) is None:
+            plan.pooled32 = torch.empty(B, h, w, C, dtype=torch.float32, device=dev)
+        ops = plan.input_ops(obs, out32=plan.pooled32)
+        lut = [(0, c) for c in range(C)]
+        n_pix = B * h * w
+        if self.training:
+            ops.append(L.op_zero(plan.in_stats))
+            ops.append(L.op_input_stats([plan.pooled32], [C], [1.0], lut, C, plan.cin_pad, n_pix, plan.in_stats))
+            if plan.world_size > 1:
+                L.run_ops(ops, dev)
+                ops = []
+                torch.distributed.all_reduce(plan.in_stats)
+        ops.append(L.op_rmv_update(plan.in_stats, rmv._mean, rmv._var, rmv._count, plan.in_scale, plan.in_shift, C,
+                                   self.training, True, B * plan.world_size, h * w))
+        ops.append(L.op_assemble([plan.pooled32], [C], [1.0], lut, C, plan.cin_pad, n_pix, plan.in_scale, plan.in_shift,
+                                 plan.x0, out_lo=plan.lo(plan.x0)))
+        L.run_ops(ops, dev)
 
     def visual_features(self, observations):
         """[N, hidden] = ReLU(visual_fc(Flatten(visual_encoder(obs)))) (resnet_policy.py:246-256)."""

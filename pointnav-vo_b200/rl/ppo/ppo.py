@@ -1,14 +1,46 @@
 """PPO / DD-PPO update around the B200 actor-critic (pointnav_vo/rl/ppo/ppo.py:14-160,
 pointnav_vo/rl/ddppo/algo/ddppo.py:18-96).  Same constructor keywords, `update(rollouts)` contract and return
-values.  The clipped-surrogate / clipped-value / entropy terms act on [T*N, 1] tensors (negligible); the policy's
-visual encoder forward/backward -- where the time goes (8192 frames per minibatch at the shipped config) -- runs as a
+values.  The clipped-surrogate / clipped-value terms and their gradient are ONE libpnvo launch (pnvo_ppo_loss,
+SURVEY 8f-3); the policy's visual encoder forward/backward -- where the time goes (8192 frames per minibatch at the shipped config) -- runs as a
 libpnvo op program behind `evaluate_actions`.  Data parallelism: instead of borrowing DistributedDataParallel's reducer
 (ddppo.py:68-90) the gradients are flattened into one bucket and summed with ONE all-reduce."""
 import torch
 import torch.nn as nn
 import torch.optim as optim
 
+from ... import lib as L
+
 EPS_PPO = 1e-5
+
+
+class _FusedPPOLoss(torch.autograd.Function):
+    """value_loss * value_loss_coef + action_loss of ppo.py:101-126 with its gradient, one libpnvo launch
+    (pnvo_ppo_loss) instead of ~25 elementwise kernels forward and as many backward.  Returns (partial total,
+    value_loss, action_loss); only the first output is differentiable."""
+
+    @staticmethod
+    def forward(ctx, values, log_probs, value_preds, returns, old_log_probs, adv, clip, use_clipped, value_coef):
+        f = [t.detach().reshape(-1).contiguous().float() for t in (values, log_probs, value_preds, returns, old_log_probs, adv)]
+        n = f[0].numel()
+        for t in f:
+            assert t.numel() == n and t.is_cuda, "PPO loss terms must be CUDA tensors of one length (no CPU fallback)"
+        losses = torch.empty(2, dtype=torch.float32, device=f[0].device)
+        d_v, d_lp = torch.empty_like(f[0]), torch.empty_like(f[1])
+        L.check(L.load().pnvo_ppo_loss(L.ptr(f[0]), L.ptr(f[1]), L.ptr(f[2]), L.ptr(f[3]), L.ptr(f[4]), L.ptr(f[5]), n,
+                                       float(clip), int(bool(use_clipped)), float(value_coef), L.ptr(losses), L.ptr(d_v),
+                                       L.ptr(d_lp), L.stream_ptr(f[0].device)))
+        ctx.save_for_backward(d_v, d_lp)
+        ctx.shapes = (values.shape, log_probs.shape)
+        value_loss, action_loss = losses[0], losses[1]
+        total = value_loss * value_coef + action_loss
+        ctx.mark_non_differentiable(value_loss, action_loss)
+        return total, value_loss, action_loss
+
+    @staticmethod
+    def backward(ctx, g_total, _gv, _ga):
+        d_v, d_lp = ctx.saved_tensors
+        return (g_total * d_v.view(ctx.shapes[0]), g_total * d_lp.view(ctx.shapes[1]), None, None, None, None, None, None,
+                None)
 
 
 def distributed_mean_and_var(values):
@@ -45,26 +77,21 @@ class PPO(nn.Module):
         return (adv - adv.mean()) / (adv.std() + EPS_PPO)
 
     def _losses(self, sample):
+        """(total loss, value_loss, action_loss, entropy) of one minibatch (ppo.py:86-133)."""
         (obs, hidden, actions, prev_actions, value_preds, returns, masks, old_log_probs, adv) = sample
         values, log_probs, entropy, _ = self.actor_critic.evaluate_actions(obs, hidden, prev_actions, masks, actions)
-        ratio = torch.exp(log_probs - old_log_probs)
-        clipped = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)
-        action_loss = -torch.min(ratio * adv, clipped * adv).mean()
-        if self.use_clipped_value_loss:
-            v_clip = value_preds + (values - value_preds).clamp(-self.clip_param, self.clip_param)
-            value_loss = 0.5 * torch.max((values - returns).pow(2), (v_clip - returns).pow(2)).mean()
-        else:
-            value_loss = 0.5 * (returns - values).pow(2).mean()
-        return value_loss, action_loss, entropy
+        partial, value_loss, action_loss = _FusedPPOLoss.apply(values, log_probs, value_preds, returns, old_log_probs, adv,
+                                                               self.clip_param, self.use_clipped_value_loss,
+                                                               self.value_loss_coef)
+        return partial - entropy * self.entropy_coef, value_loss, action_loss, entropy
 
     def update(self, rollouts):
         advantages = self.get_advantages(rollouts)
         sums = torch.zeros(3, device=advantages.device)
         for _ in range(self.ppo_epoch):
             for sample in rollouts.recurrent_generator(advantages, self.num_mini_batch):
-                value_loss, action_loss, entropy = self._losses(sample)
+                total, value_loss, action_loss, entropy = self._losses(sample)
                 self.optimizer.zero_grad()
-                total = value_loss * self.value_loss_coef + action_loss - entropy * self.entropy_coef
                 self.before_backward(total)
                 total.backward()
                 self.after_backward(total)

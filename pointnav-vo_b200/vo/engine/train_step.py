@@ -4,7 +4,9 @@
     bucket] -> Adam over the flat parameter bucket
 
 Semantics follow the reference's engine: per-delta mean((gt - pred)^2 * w) summed over dx/dz/dyaw
-(vo/engine/vo_cnn_engine.py:135-198), optimiser Adam(lr=2.5e-4, eps=1e-8, weight_decay=0)
+(vo/engine/vo_cnn_engine.py:135-198) -- one such mean PER DATA TYPE when the batch carries geometric-invariance rows
+(vo_cnn_regression_geo_invariance_engine.py:676-750), plus loss_inv_weight times the inversion loss over the TURN rows
+(:781-792) -- optimiser Adam(lr=2.5e-4, eps=1e-8, weight_decay=0)
 (vo_cnn_regression_geo_invariance_engine.py:122-133, configs/vo/vo_pointnav.yaml:36-40).
 Data-parallel training (new capability; the reference trains VO on one GPU): every rank
 holds a replica, the flat gradient bucket is summed with ONE all-reduce and scaled by 1/world inside the
@@ -73,9 +75,9 @@ class PrefetchedBatches:
 class FusedVOTrainStep:
     def __init__(self, model, lr=2.5e-4, betas=(0.9, 0.999), eps=1e-8, loss_weights=(1.0, 1.0, 1.0),
                  process_group=None, loss_inv_weight=0.0, move_forward_id=1):
-        """loss_inv_weight > 0 adds the geometric-inversion loss (VO.TRAIN.loss_inv_weight,
-        vo_cnn_regression_geo_invariance_engine.py:367-449,792): batches are then interleaved pairs
-        [cur->prev, prev->cur, ...] and step() needs the per-row action ids."""
+        """loss_inv_weight > 0 adds the geometric-inversion loss (VO.GEOMETRY.loss_inv_weight,
+        vo_cnn_regression_geo_invariance_engine.py:367-449,781-792); step() then needs the per-row action ids and
+        data types (CUR_REL_TO_PREV / PREV_REL_TO_CUR, vo/dataset/geo_invariance.make_pair_map emits both)."""
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.loss_weights = tuple(float(w) for w in loss_weights)
@@ -92,7 +94,6 @@ class FusedVOTrainStep:
         self._parity = 0
         self._prefetched = None   # (obs identity, parity) prepared ahead on the side stream
         self._staged = [None, None]   # event: input buffer `parity` holds a prepared batch
-        self._consumed = [None, None]  # event: the step that read input buffer `parity` has finished
 
     # parameters are re-pointed into one flat fp32 buffer ordered like the plan's gradient bucket, so the
     # optimiser and the all-reduce each touch a single contiguous range
@@ -126,16 +127,50 @@ class FusedVOTrainStep:
             plan = model._plan_for(obs, True, model.training)  # rebuilt on the flat storage
         if plan is not self._plan:
             B, O = plan.B, plan.head["out_dim"]
-            self._target = torch.zeros(B, O, dtype=torch.float32, device=plan.dev)
-            ops = [L.op_mse_loss(plan.out, self._target, None, plan.dout, self._loss, B, O, self.loss_weights,
-                                 1.0 / self.world)]
-            if self.loss_inv_weight > 0:
-                self._actions = torch.zeros(B, dtype=torch.int64, device=plan.dev)
-                ops.append(L.op_geo_inv_loss(plan.out, self._actions, plan.dout, self._loss, B, O, self.loss_inv_weight,
-                                             1.0 / self.world, self.move_forward_id))
-            self._loss_prog = L.Program(ops)
+            dev = plan.dev
+            self._target = torch.zeros(B, O, dtype=torch.float32, device=dev)
+            self._actions = torch.zeros(B, dtype=torch.int64, device=dev)
+            self._data_types = torch.zeros(B, dtype=torch.int64, device=dev)
+            self._dz_mask = torch.ones(B, dtype=torch.float32, device=dev)
+            self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._loss_progs = {}
             self._plan = plan
         return plan
+
+    def _loss_prog_for(self, plan, typed, masked):
+        """Loss + d(loss)/d(pred) program: `typed` = per-data-type means (+ the inversion loss over the turn rows when
+        loss_inv_weight > 0); untyped batches with loss_inv_weight > 0 are taken as interleaved pairs (every row)."""
+        key = (typed, masked)
+        prog = self._loss_progs.get(key)
+        if prog is None:
+            B, O = plan.B, plan.head["out_dim"]
+            types = self._data_types if typed else None
+            ops = [L.op_mse_loss(plan.out, self._target, self._dz_mask if masked else None, plan.dout, self._loss, B, O,
+                                 self.loss_weights, 1.0 / self.world, data_types=types)]
+            if self.loss_inv_weight > 0:
+                ops.append(L.op_geo_inv_loss(plan.out, self._actions, plan.dout, self._loss, B, O, self.loss_inv_weight,
+                                             1.0 / self.world, self.move_forward_id, data_types=types, err=self._err))
+            prog = self._loss_progs[key] = L.Program(ops)
+        return prog
+
+    @staticmethod
+    def _check_pairing(actions, data_types, turn_ids=(2, 3)):
+        """The reference's assertion (vo_cnn_regression_geo_invariance_engine.py:373-374) on host-side metadata: the TURN
+        rows, in batch order, alternate [cur-rel-to-prev, prev-rel-to-cur]."""
+        import numpy as np
+
+        a = np.asarray(actions).reshape(-1)
+        t = np.asarray(data_types).reshape(-1)
+        v = t[(a == turn_ids[0]) | (a == turn_ids[1])]
+        if v.size % 2 or (v[0::2] != 0).any() or (v[1::2] != 1).any():
+            raise L.PnvoError("geometric-inversion loss: the TURN rows of the batch must alternate "
+                              "[cur_rel_to_prev, prev_rel_to_cur, ...] (vo_cnn_regression_geo_invariance_engine.py:373-374)")
+
+    def check(self):
+        """Raises if a device-side pairing check of an earlier step failed (only CUDA-resident metadata is checked on the
+        device; numpy / CPU metadata is validated on the host inside step())."""
+        if self._plan is not None and int(self._err.item()) != 0:
+            raise L.PnvoError("geometric-inversion loss: TURN rows did not alternate [cur_rel_to_prev, prev_rel_to_cur]")
 
     def _prefetch(self, plan, obs, parity, ready=None):
         """Input pipeline (top-down, statistics, assembly) of a FUTURE batch into staging buffer `parity`, on the side
@@ -143,10 +178,10 @@ class FusedVOTrainStep:
         dev = plan.dev
         if self._side is None:
             self._side = torch.cuda.Stream(dev)
-        if self._consumed[parity] is not None:
-            self._side.wait_event(self._consumed[parity])  # the step that read this buffer last is done with it
-        else:
-            self._side.wait_stream(torch.cuda.current_stream(dev))
+        # Everything the compute stream has enqueued so far comes first: the step that last read staging buffer `parity`
+        # AND -- when this step fell back to the non-prefetched path -- the current batch's own input pipeline, which
+        # shares plan.in_stats / in_scale / in_shift / td_pair and the RunningMeanAndVar buffers with this one.
+        self._side.wait_stream(torch.cuda.current_stream(dev))
         if ready is not None:
             self._side.wait_event(ready)  # e.g. the host->device copy of that batch
         with torch.cuda.stream(self._side):
@@ -156,22 +191,38 @@ class FusedVOTrainStep:
         self._staged[parity] = ev
         self._prefetched = (tuple(id(v) for v in obs.values()), parity)
 
-    def step(self, obs, target, actions=None, prefetch=None, prefetch_ready=None):
+    def step(self, obs, target, actions=None, prefetch=None, prefetch_ready=None, data_types=None, dz_regress_masks=None):
         """obs: dict of NHWC fp32 CUDA tensors (the model's forward input), or the raw pairs
         {"rgb": uint8 [B,H,W,6], "depth": fp32 [B,H,W,2]} (derived channels computed on the device);
         target: [B, 3] fp32 CUDA.  prefetch: the NEXT step's raw pairs -- their input pipeline is started on a side
         stream into the alternate staging buffer and overlaps this step (the next call must pass the same tensors as
         `obs`); prefetch_ready: optional event the side stream waits for first (the batch's host->device copy).
+        actions / data_types: per-row action ids and CUR_REL_TO_PREV / PREV_REL_TO_CUR flags (numpy, CPU or CUDA);
+        dz_regress_masks: optional [B] weights of the dz term (vo_cnn_engine.py:160-166).
         Returns the (device) loss tensor of this rank's batch."""
         model = self.model
         plan = self._get_plan(obs)
         dev = plan.dev
         main = torch.cuda.current_stream(dev)
-        self._target.copy_(target)
+        self._target.copy_(target, non_blocking=True)
+
+        def put(dst, src):
+            if not isinstance(src, torch.Tensor):
+                src = torch.as_tensor(src)
+            dst.copy_(src.reshape(-1), non_blocking=True)
+
+        typed = data_types is not None
         if self.loss_inv_weight > 0:
             if actions is None:
                 raise L.PnvoError("the geometric-inversion loss needs the per-row action ids")
-            self._actions.copy_(actions.reshape(-1))
+            if typed and not (isinstance(actions, torch.Tensor) and actions.is_cuda):
+                dt = data_types.cpu() if isinstance(data_types, torch.Tensor) else data_types
+                self._check_pairing(actions, dt)
+            put(self._actions, actions)
+        if typed:
+            put(self._data_types, data_types)
+        if dz_regress_masks is not None:
+            put(self._dz_mask, dz_regress_masks)
         key = tuple(id(v) for v in obs.values())
         if self._prefetched is not None and self._prefetched[0] == key and model._is_raw(obs):
             parity = self._prefetched[1]
@@ -192,11 +243,8 @@ class FusedVOTrainStep:
                 parity = 0
                 model._run_forward(plan, obs, model.training)
         self._parity = 1 - parity if prefetch is not None else parity
-        self._loss_prog.run(dev)
+        self._loss_prog_for(plan, typed, dz_regress_masks is not None).run(dev)
         plan.programs_for(parity)[1].run(dev)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        self._consumed[parity] = ev
         if self.world > 1:
             torch.distributed.all_reduce(plan.grad_flat, group=self.group)
         self.step_count += 1

@@ -83,7 +83,9 @@ class _VOFunction(torch.autograd.Function):
     def forward(ctx, model, obs, training, need_grad, *params):
         plan = model._plan_for(obs, need_grad, training)
         model._run_forward(plan, obs, training)
-        ctx.model, ctx.plan = model, plan
+        # the plan's activation buffers are shared by every forward of this shape: remember which forward filled them
+        plan.generation = getattr(plan, "generation", 0) + 1
+        ctx.model, ctx.plan, ctx.generation = model, plan, plan.generation
         return plan.out.clone()
 
     @staticmethod
@@ -91,6 +93,10 @@ class _VOFunction(torch.autograd.Function):
         model, plan = ctx.model, ctx.plan
         if not plan.training:
             raise RuntimeError("backward through a plan built without gradient buffers")
+        if plan.generation != ctx.generation:
+            raise RuntimeError("backward of a VO forward whose activations were overwritten by a later forward of the same "
+                               "shape (the op program keeps ONE set of activation buffers per batch shape): call "
+                               "backward before the next forward, or give the second forward its own module copy")
         plan.dout.copy_(grad_out)
         plan.bwd_prog.run(plan.dev)
         flat = plan.grad_flat.clone()  # detach from the plan's reusable bucket

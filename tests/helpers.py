@@ -13,6 +13,8 @@ VO_CASES = {
     "r18_8ch": ("vo_cnn", ["rgb", "depth"], "resnet18", {}),
     "r50_8ch": ("base", ["rgb", "depth"], "resnet50", {}),
     "r18_8ch_act_embed": ("vo_cnn_act_embed", ["rgb", "depth"], "resnet18", {}),
+    "r18_wider": ("vo_cnn_wider", ["rgb", "depth"], "resnet18", {}),        # 64 base planes (vo_cnn.py:308-340)
+    "r101_deeper": ("vo_cnn_deeper", ["rgb", "depth"], "resnet101", {}),    # vo_cnn.py:343-375
 }
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -80,6 +82,8 @@ def vo_state_dict(case, seed=7, device="cpu"):
 def vo_state_shapes(case):
     from pointnav_vo_b200.vo.models.shapes import vo_state_dict_shapes
     name, space, backbone, kw = VO_CASES[case]
+    if case == "r18_wider":
+        kw = dict(kw, resnet_baseplanes=64)
     return vo_state_dict_shapes(space, backbone, act_embed="act_embed" in case, **kw)
 
 
@@ -98,17 +102,22 @@ class _Discrete:
         self.n = n
 
 
-def policy_spaces():
+def policy_spaces(vis_types=("depth",)):
     """gym-like observation / action spaces of the shipped depth-only policy (ddppo_pointnav.yaml)."""
-    return _Dict({"depth": _Box((192, 341, 1)), "pointgoal_with_gps_compass": _Box((2,))}), _Discrete(4)
+    sp = {"pointgoal_with_gps_compass": _Box((2,))}
+    if "depth" in vis_types:
+        sp["depth"] = _Box((192, 341, 1))
+    if "rgb" in vis_types:
+        sp["rgb"] = _Box((192, 341, 3))
+    return _Dict(sp), _Discrete(4)
 
 
-def policy_state_dict(seed=9, device="cpu"):
+def policy_state_dict(seed=9, device="cpu", vis_types=("depth",), normalize=False):
     from pointnav_vo_b200.rl.policies.resnet_policy import PointNavResNetPolicy
 
-    obs_space, act_space = policy_spaces()
+    obs_space, act_space = policy_spaces(vis_types)
     pol = PointNavResNetPolicy(observation_space=obs_space, action_space=act_space, backbone="resnet18",
-                               vis_types=["depth"])
+                               vis_types=list(vis_types), normalize_visual_inputs=normalize)
     proto = {k: np.empty(tuple(v.shape), dtype=np.float32) for k, v in pol.state_dict().items()}
     sd = synth.fill_state_dict(proto, seed=seed)
     pol.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})

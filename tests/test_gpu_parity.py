@@ -433,8 +433,9 @@ FWD_TOL = {"r18_30ch": 8e-3, "r18_8ch": 8e-3, "r50_8ch": 2.5e-2, "r18_8ch_act_em
 GRAD_TOL = {"r18_30ch": 0.15, "r18_8ch": 0.15, "r50_8ch": 0.35, "r18_8ch_act_embed": 0.15}  # relative L2 per tensor (ReLU-flip noise, 53 layers)
 
 
-@pytest.mark.parametrize("precision", ["split", "fp16"])
-@pytest.mark.parametrize("case", ["r18_30ch", "r18_8ch", "r50_8ch", "r18_8ch_act_embed"])
+@pytest.mark.parametrize("case,precision", [(c, p) for c in ("r18_30ch", "r18_8ch", "r50_8ch", "r18_8ch_act_embed")
+                                            for p in ("split", "fp16")] +
+                         [("r18_wider", "split"), ("r101_deeper", "split")])  # vo_cnn_wider / vo_cnn_deeper (vo_cnn.py:308-375)
 def test_vo_model_against_reference_golden(case, precision, golden_dir):
     g = np.load(os.path.join(golden_dir, f"vo_{case}.npz"))
     m, space, backbone = _load_vo(case)
@@ -791,18 +792,48 @@ def test_policy_against_reference_golden(golden_dir):
     with torch.no_grad():
         value, action, logp, new_hid = pol.act(obs, hid, prev_a, masks, deterministic=True)
         plan = list(pol.net._plans.values())[0]
-        enc = plan.feat[..., :114].permute(0, 3, 1, 2)
-    assert rel(enc, torch.from_numpy(g["encoder_out"])) <= 3e-2  # max over 6k values after 21 fp16-rounded layers
-    assert rel(value, torch.from_numpy(g["value"])) <= 2e-2
-    assert rel(new_hid, torch.from_numpy(g["new_hidden"])) <= 2e-2
+        enc = (plan.feat.float() + plan.lo(plan.feat).float())[..., :114].permute(0, 3, 1, 2)
+    # default precision = split (value + residual planes): the north-star bound
+    assert rel(enc, torch.from_numpy(g["encoder_out"])) <= SPLIT_TOL
+    assert rel(value, torch.from_numpy(g["value"])) <= SPLIT_TOL
+    assert rel(new_hid, torch.from_numpy(g["new_hidden"])) <= SPLIT_TOL
     assert np.array_equal(action.cpu().numpy(), g["action"])
-    assert np.allclose(logp.cpu().numpy(), g["logp"], atol=1e-3)
-    # backward through the visual path runs and produces finite gradients
+    assert np.allclose(logp.cpu().numpy(), g["logp"], atol=1e-4)
+    pol.net.set_precision("fp16")  # the single-pass throughput mode: 21 fp16-rounded layers
+    with torch.no_grad():
+        value16, action16, _, hid16 = pol.act(obs, hid, prev_a, masks, deterministic=True)
+    assert rel(value16, torch.from_numpy(g["value"])) <= 2e-2 and rel(hid16, torch.from_numpy(g["new_hidden"])) <= 2e-2
+
+
+def test_policy_rgbd_with_input_normalisation(golden_dir):
+    """a11 with rgb + depth and normalize_visual_inputs=True (resnet_policy.py:61-174): RunningMeanAndVar acts on the
+    2x2-pooled input; eval-mode act() and a training-mode forward (statistics update) against the reference golden."""
+    g = np.load(os.path.join(golden_dir, "policy_r18_rgbd_norm.npz"))
+    pol = helpers.policy_state_dict(device="cuda", vis_types=("rgb", "depth"), normalize=True).eval()
+    assert [str(k) for k in g["keys"]] == list(pol.state_dict().keys())
+    obs = {"rgb": torch.from_numpy(synth.rgb_frames(3, seed=32).astype(np.float32)).cuda(),
+           "depth": torch.from_numpy(synth.depth_frames(3, seed=31)[..., None]).cuda(),
+           "pointgoal_with_gps_compass": torch.from_numpy(g["goal"]).cuda()}
+    hid, prev_a, masks = (torch.from_numpy(g[k]).cuda() for k in ("hidden", "prev_actions", "masks"))
+    with torch.no_grad():
+        value, action, logp, new_hid = pol.act(obs, hid, prev_a, masks, deterministic=True)
+        plan = list(pol.net._plans.values())[0]
+        C = g["encoder_out"].shape[1]
+        enc = (plan.feat.float() + plan.lo(plan.feat).float())[..., :C].permute(0, 3, 1, 2)
+    print("policy rgbd+norm:", rel(enc, torch.from_numpy(g["encoder_out"])), rel(value, torch.from_numpy(g["value"])))
+    assert rel(enc, torch.from_numpy(g["encoder_out"])) <= SPLIT_TOL
+    assert rel(value, torch.from_numpy(g["value"])) <= SPLIT_TOL
+    assert rel(new_hid, torch.from_numpy(g["new_hidden"])) <= SPLIT_TOL
+    assert np.array_equal(action.cpu().numpy(), g["action"])
     pol.train()
-    v, lp, ent, _ = pol.evaluate_actions(obs, hid, prev_a, masks, action)
-    (v.mean() + lp.mean() + ent).backward()
-    gw = pol.net.visual_encoder.backbone.conv1[0].weight.grad
-    assert gw is not None and torch.isfinite(gw).all() and gw.abs().sum() > 0
+    with torch.no_grad():
+        pol.net.visual_features(obs)
+        plan = [p for p in pol.net._plans.values()][-1]
+        enc_tr = (plan.feat.float() + plan.lo(plan.feat).float())[..., :C].permute(0, 3, 1, 2)
+    rm = pol.net.visual_encoder.running_mean_and_var
+    assert rel(rm._mean, torch.from_numpy(g["train_mean"])) <= 1e-5 and rel(rm._var, torch.from_numpy(g["train_var"])) <= 1e-5
+    assert float(rm._count) == float(g["train_count"])
+    assert rel(enc_tr, torch.from_numpy(g["train_encoder_out"])) <= SPLIT_TOL
 
 
 def test_policy_split_precision_within_north_star_tolerance(golden_dir):
@@ -905,6 +936,149 @@ def test_ppo_update_on_device():
     moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, pol.parameters()))
     assert moved >= len(before) - 2
     rs.after_update()
+
+
+def test_ppo_update_against_reference_golden(golden_dir):
+    """a14 / 8f-3: PPO.update through the B200 actor-critic and the fused loss kernel (pnvo_ppo_loss) against the
+    UNMODIFIED reference's PPO.update on the same seeded rollout (tests/golden/make_golden.py: gen_ppo; 2 epochs x 2
+    minibatches with the reference's recorded env permutations): GAE returns bit-exact, first-minibatch loss terms and
+    total <= 1e-3, first-minibatch gradient norms <= 2e-2 per tensor, reported losses, and every parameter after the
+    four Adam steps."""
+    from pointnav_vo_b200.rl.common.rollout_storage import RolloutStorage
+    from pointnav_vo_b200.rl.ppo.ppo import PPO
+
+    g = np.load(os.path.join(golden_dir, "ppo_update.npz"))
+    T, N = 4, 4
+    pol = helpers.policy_state_dict(device="cuda")
+    assert [str(k) for k in g["keys"]] == list(pol.state_dict().keys())
+    before = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    obs_space, act_space = helpers.policy_spaces()
+    rs = RolloutStorage(T, N, obs_space, act_space, 512, num_recurrent_layers=4)
+    rs.to("cuda")
+    dep = synth.depth_frames((T + 1) * N, seed=42).reshape(T + 1, N, 192, 341, 1)
+    rs.observations["depth"].copy_(torch.from_numpy(dep))
+    rs.observations["pointgoal_with_gps_compass"].copy_(torch.from_numpy(g["in/goal"]))
+    rs.recurrent_hidden_states[0].copy_(torch.from_numpy(g["in/hidden0"]))
+    for k in ("actions", "prev_actions", "masks", "rewards", "value_preds", "action_log_probs"):
+        getattr(rs, k).copy_(torch.from_numpy(g["in/" + k]))
+    rs.step = T
+    rs.compute_returns(torch.from_numpy(g["in/next_value"]).cuda(), True, 0.99, 0.95)
+    assert np.array_equal(rs.returns.cpu().numpy(), g["returns"])
+    rs.fixed_perms = [torch.from_numpy(p).cuda() for p in g["perms"]]
+    agent = PPO(pol, clip_param=0.2, ppo_epoch=2, num_mini_batch=2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
+    first = {}
+    real_before_step, real_losses = agent.before_step, agent._losses
+
+    def before_step():
+        if "grads" not in first:
+            first["grads"] = {k: p.grad.norm().item() for k, p in pol.named_parameters() if p.grad is not None}
+        real_before_step()
+
+    def losses(sample):
+        out = real_losses(sample)
+        first.setdefault("terms", tuple(float(x.detach()) for x in out))
+        return out
+
+    agent.before_step, agent._losses = before_step, losses
+    pol.train()
+    vl, al, ent = agent.update(rs)
+    # first minibatch, before any parameter moved: total, value_loss, action_loss, entropy
+    t = {k[4:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("mb0/")}
+    vl0, al0, ent0 = vo.ppo_losses(t["values"], t["log_probs"], t["entropy"], t["value_preds"], t["returns"],
+                                   t["old_log_probs"], t["adv"], 0.2, True)
+    total, v0, a0, e0 = first["terms"]
+    print("ppo first minibatch:", first["terms"], "reference:", float(g["mb0/total"]), vl0.item(), al0.item(), ent0.item())
+    assert abs(total - float(g["mb0/total"])) <= 1e-3 * abs(float(g["mb0/total"]))
+    assert abs(v0 - vl0.item()) <= 1e-3 * abs(vl0.item()) and abs(a0 - al0.item()) <= 1e-3 * abs(al0.item())
+    assert abs(e0 - ent0.item()) <= 1e-3 * abs(ent0.item())
+    worst = 0.0
+    for k, n in zip([str(k) for k in g["grad_keys"]], g["grad_norms"]):
+        if n > 1e-6:
+            worst = max(worst, abs(first["grads"][k] - n) / n)
+            assert abs(first["grads"][k] - n) <= 2e-2 * n, (k, first["grads"][k], n)
+    print("ppo first-minibatch gradient norms: worst relative deviation", worst)
+    ref_losses = g["losses"]
+    print("ppo update losses:", (vl, al, ent), "reference:", ref_losses)
+    for got, want in zip((vl, al, ent), ref_losses):
+        assert abs(got - want) <= 5e-3 * abs(want)
+    # parameters after 4 Adam steps: the update of every tensor has the reference's size, and the small tensors
+    # (biases, GroupNorm affine parameters: stored in full) move the same way
+    after = pol.state_dict()
+    for k, dn in zip([str(k) for k in g["keys"]], g["delta_norms"]):
+        d = (after[k] - before[k]).float()
+        if dn > 0:
+            assert abs(d.norm().item() - dn) <= 0.1 * dn, (k, d.norm().item(), dn)
+        if "delta/" + k in g.files and dn > 0:
+            assert rel_l2(d, torch.from_numpy(g["delta/" + k])) <= 0.25, k
+
+
+def test_losses_against_reference_golden(golden_dir):
+    """a6: PNVO_OP_MSE_LOSS / PNVO_OP_GEO_INV_LOSS against the reference's loss composition (_process_one_batch,
+    vo_cnn_regression_geo_invariance_engine.py:676-792; golden from the reference's own functions): plain batches,
+    per-data-type means, and the inversion loss restricted to the TURN rows with unpaired MOVE_FORWARD rows in between.
+    Value and d(loss)/d(pred) <= 1e-5."""
+    from pointnav_vo_b200 import lib as L
+
+    g = np.load(os.path.join(golden_dir, "vo_losses.npz"))
+    w = tuple(float(x) for x in g["loss_weights"])
+    for name in ("plain", "types_only", "joint"):
+        pred = torch.from_numpy(g[f"{name}/pred"]).cuda()
+        tgt = torch.from_numpy(g[f"{name}/target"]).cuda()
+        acts = torch.from_numpy(g[f"{name}/actions"]).cuda()
+        dzm = torch.from_numpy(g[f"{name}/dz_mask"]).cuda()
+        types = torch.from_numpy(g[f"{name}/data_types"]).cuda() if f"{name}/data_types" in g.files else None
+        B = pred.shape[0]
+        dout = torch.zeros(B, 3, device="cuda")
+        loss = torch.zeros(3, device="cuda")
+        err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops = [L.op_mse_loss(pred, tgt, dzm, dout, loss, B, 3, w, 1.0, data_types=types)]
+        inv_w = float(g[f"{name}/inv_w"])
+        if inv_w > 0:
+            ops.append(L.op_geo_inv_loss(pred, acts, dout, loss, B, 3, inv_w, 1.0, 1, data_types=types, err=err))
+        L.run_ops(ops)
+        assert int(err.item()) == 0
+        assert abs(loss[0].item() - float(g[f"{name}/loss"])) <= 1e-5 * abs(float(g[f"{name}/loss"])), name
+        assert rel(dout, torch.from_numpy(g[f"{name}/grad"])) <= 1e-5, name
+    # misaligned TURN rows: the device flags them (the reference asserts, :373-374) and the host check raises
+    from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+    bad_a, bad_t = torch.tensor([2, 2, 3, 3]).cuda(), torch.tensor([0, 0, 1, 1]).cuda()
+    pred = torch.zeros(4, 3, device="cuda")
+    L.run_ops([L.op_geo_inv_loss(pred, bad_a, None, loss, 4, 3, 1.0, 1.0, 1, data_types=bad_t, err=err)])
+    assert int(err.item()) == 1
+    with pytest.raises(L.PnvoError):
+        FusedVOTrainStep._check_pairing(bad_a.cpu().numpy(), bad_t.cpu().numpy())
+
+
+def test_fused_train_step_matches_reference_loss_composition():
+    """The whole fused step on an inverse_joint_train batch (pair map with unpaired MOVE_FORWARD rows between the TURN
+    pairs): the loss it reports and the gradient it feeds to the backward program equal the oracle of the reference's
+    _process_one_batch evaluated on the step's own predictions."""
+    from pointnav_vo_b200.vo.dataset import geo_invariance as gi
+    from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+    model, space, _ = _load_vo("r18_8ch")
+    obs = helpers.vo_inputs(4, 23, space, "cuda")
+    rgb, dep = obs["rgb"].to(torch.uint8).contiguous(), obs["depth"].contiguous()
+    pm = gi.make_pair_map([2, 1, 3, 2], act_type=2, geo_invariance_types=("inverse_joint_train",))
+    assert list(pm["actions"]) == [2, 3, 1, 3, 2, 2, 3] and list(pm["data_types"]) == [0, 1, 0, 0, 1, 0, 1]
+    rng = np.random.default_rng(5)
+    tg = torch.from_numpy(gi.expand_targets(rng.normal(0, 0.2, (4, 3)).astype(np.float32), pm)).cuda()
+    batch = {"rgb": rgb, "depth": dep, "pair_map": torch.from_numpy(pm["pair_map"]).cuda()}
+    model.train()
+    tr = FusedVOTrainStep(model, loss_weights=(1.0, 2.0, 0.5), loss_inv_weight=0.7)
+    loss = tr.step(batch, tg, actions=pm["actions"], data_types=pm["data_types"])
+    plan = tr._plan
+    pred = plan.out.detach().float().cpu().requires_grad_(True)
+    want = vo.vo_total_loss(pred, tg.cpu(), torch.from_numpy(pm["actions"]), torch.from_numpy(pm["data_types"]),
+                            (1.0, 2.0, 0.5), None, 0.7)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert rel(plan.dout, pred.grad) <= 1e-5
+    tr.check()
+    with pytest.raises(Exception):  # rows out of order: TURN rows no longer alternate
+        tr.step(batch, tg, actions=pm["actions"][::-1].copy(), data_types=pm["data_types"])
 
 
 def test_vo_inference_in_the_rl_loop():

@@ -63,17 +63,18 @@ def test_goal_update_known_answers():
     assert np.allclose(out["polar"], [1.0, -np.pi / 2], atol=1e-6)
 
 
-@pytest.mark.parametrize("case", ["r18_30ch", "r18_8ch", "r50_8ch", "r18_8ch_act_embed"])
+@pytest.mark.parametrize("case", ["r18_30ch", "r18_8ch", "r50_8ch", "r18_8ch_act_embed", "r18_wider", "r101_deeper"])
 def test_vo_oracle_matches_reference(golden_dir, case):
     g = np.load(os.path.join(golden_dir, f"vo_{case}.npz"))
     space, backbone = helpers.VO_CASES[case][1], helpers.VO_CASES[case][2]
+    ng = int(g["ngroups"]) if "ngroups" in g.files else 16
     sd = helpers.vo_state_dict(case)
     obs = helpers.vo_inputs(2, 11, space)
     actions = torch.from_numpy(g["actions"]) if "actions" in g.files else None
     with torch.no_grad():
-        y, _ = vo.vo_forward(obs, sd, space, backbone, training=False, actions=actions)
+        y, _ = vo.vo_forward(obs, sd, space, backbone, ngroups=ng, training=False, actions=actions)
     assert np.allclose(y.numpy(), g["eval_out"], rtol=1e-5, atol=2e-6)
-    y, st = vo.vo_forward(obs, sd, space, backbone, training=True, actions=actions)
+    y, st = vo.vo_forward(obs, sd, space, backbone, ngroups=ng, training=True, actions=actions)
     assert np.allclose(y.detach().numpy(), g["train_out"], rtol=1e-5, atol=2e-6)
     assert np.allclose(st[0].numpy(), g["train_mean"], rtol=1e-6, atol=1e-7)
     assert np.allclose(st[1].numpy(), g["train_var"], rtol=1e-6, atol=1e-7)
@@ -92,3 +93,36 @@ def test_geo_inverse_loss_is_zero_on_consistent_pairs():
     deltas = torch.stack((a, b), 1).reshape(2 * n, 3)
     actions = torch.from_numpy(rng.integers(1, 4, size=2 * n))
     assert float(vo.geo_invariance_inverse_loss(deltas, actions)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["plain", "types_only", "joint"])
+def test_total_loss_oracle_matches_reference_composition(golden_dir, name):
+    """vo_total_loss == the reference's _compute_loss / _compute_geo_invariance_inverse_loss composed as
+    _process_one_batch does (vo_cnn_regression_geo_invariance_engine.py:676-792): value and gradient."""
+    g = np.load(os.path.join(golden_dir, "vo_losses.npz"))
+    pred = torch.from_numpy(g[f"{name}/pred"]).requires_grad_(True)
+    types = torch.from_numpy(g[f"{name}/data_types"]) if f"{name}/data_types" in g.files else None
+    loss = vo.vo_total_loss(pred, torch.from_numpy(g[f"{name}/target"]), torch.from_numpy(g[f"{name}/actions"]), types,
+                            tuple(float(w) for w in g["loss_weights"]), torch.from_numpy(g[f"{name}/dz_mask"])[:, None],
+                            float(g[f"{name}/inv_w"]))
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{name}/loss"])) <= 1e-6 * abs(float(g[f"{name}/loss"]))
+    assert np.allclose(pred.grad.numpy(), g[f"{name}/grad"], rtol=1e-5, atol=1e-8)
+
+
+def test_total_loss_oracle_rejects_misaligned_pairs():
+    # the reference asserts the [cur_rel_to_prev, prev_rel_to_cur] alternation of the TURN rows (:373-374)
+    pred = torch.zeros(4, 3)
+    with pytest.raises(AssertionError):
+        vo.vo_total_loss(pred, pred, torch.tensor([2, 2, 3, 3]), torch.tensor([0, 0, 1, 1]), loss_inv_weight=1.0)
+
+
+def test_ppo_loss_oracle_matches_reference_first_minibatch(golden_dir):
+    """ppo_losses on the tensors the reference's PPO.update fed to its loss (first minibatch) reproduces the total loss
+    it handed to backward (ppo.py:86-135)."""
+    g = np.load(os.path.join(golden_dir, "ppo_update.npz"))
+    t = {k[4:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("mb0/")}
+    vl, al, ent = vo.ppo_losses(t["values"], t["log_probs"], t["entropy"], t["value_preds"], t["returns"],
+                                t["old_log_probs"], t["adv"], 0.2, True)
+    total = (vl * 0.5 + al - ent * 0.01).item()
+    assert abs(total - float(g["mb0/total"])) <= 1e-6 * abs(float(g["mb0/total"]))
