@@ -12,7 +12,17 @@ discretised-depth and top-down channels are derived on the device inside the ste
 every step's H2D copy (double-buffered on a side stream, overlapping the previous step's kernels) and a D2H
 read of the loss inside the timed region.  `--inputs dict` feeds the reference's four fp32 tensors instead.
 `--impl reference` times the reference algorithm's CPU path (oracle/vo_oracle.py: the plain-PyTorch fp32
-restatement pinned against the unmodified reference) on the host cores.
+restatement pinned against the unmodified reference, plus the oracle's discretise / top-down preprocessing of every
+frame, as the reference's DataLoader workers do) on the host cores.
+
+Precision: the model's default ("split": value + residual fp16 operand planes in every FORWARD convolution, 3 tensor-core
+products per conv, fp32 accumulation; single-pass fp16 operands in the backward pass) -- the mode whose outputs match the
+fp32 reference within the north-star 1e-3 (tests/test_gpu_parity.py: measured 6e-6 .. 6e-5) and whose gradients stay within
+2e-2 relative L2 per tensor.  `--precision fp16` times the single-pass throughput mode (outputs ~5e-3: outside the bound).
+
+On one GPU the JSON line also carries `extra`: eval-mode forward, the ResNet-50 step (BASELINE configs[2]), and K4 (policy
+act() at 128 envs, a PPO update over 128 envs x 128 steps = 2 minibatches of 8192 frames, the GAE scan, and the achieved
+HBM GB/s of the discretisation / top-down / GAE kernels).
 """
 import argparse
 import json
@@ -30,11 +40,19 @@ import torch  # noqa: E402
 
 H, W = 192, 341
 GFLOP_FWD, GFLOP_FWDBWD = 2.6845, 6.509  # per pair, BASELINE.md section 2
-# dram__bytes_read.sum + dram__bytes_write.sum of the stem kernel at B=256 from the committed `ncu --set full` capture
-# (profiles/r01_ncu_stem2_fwd.txt); None until that capture exists
-STEM_DRAM_BYTES = 1347959832  # 1.095 GB read (= the W-padded fp16 input, once) + 0.253 GB written
 METRIC = "VO frame-pairs/sec (341x192 RGB-D, bs256 per GPU, ResNet-18 fwd+bwd+Adam)"
 SPACE = ["rgb", "depth", "discretized_depth", "top_down_view"]
+
+
+def stem_dram_bytes(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the stem convolution's launch(es) at B=256, read from the committed
+    `ncu --set full` summary (profiles/r02_stem_traffic.json, written by tools/ncu_metrics.py from the capture); None
+    when that file is absent."""
+    p = os.path.join(ROOT, "profiles", "r02_stem_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d.get(precision, {}).get("dram_bytes")
 
 
 def peaks():
@@ -159,6 +177,7 @@ def run_b200(args):
     from pointnav_vo_b200.vo.engine.train_step import PrefetchedBatches
 
     model = build_model(dev, model=args.model)
+    model.set_precision(args.precision)
     trainer = FusedVOTrainStep(model)
     rgb, dep, tgt = synth_batch(B, seed=1 + rank)
     depth_fp16 = args.depth == "fp16" and args.inputs == "raw"
@@ -235,29 +254,6 @@ def run_b200(args):
         sync_all()
         return ms
 
-    if args.forward_only:
-        model.eval()
-        with torch.no_grad():
-            for _ in range(args.warmup):
-                model(obs)
-            ms_f = timed(lambda: model(obs), args.steps) / args.steps
-        if rank == 0:
-            print(json.dumps({"metric": "VO frame-pairs/sec, eval-mode forward only (same model, batch 256 per GPU)",
-                              "value": round(world * B / (ms_f * 1e-3), 1), "unit": "pairs/s", "n_gpus": world,
-                              "ms_per_step": round(ms_f, 3),
-                              "forward_tflops": round(world * B * GFLOP_FWD * 1e9 / (ms_f * 1e-3) / 1e12, 1)}), flush=True)
-        # the 1e-3 precision mode (value + residual fp16 planes, 3 MMAs per product, generic kernel only)
-        model.set_precision("split")
-        with torch.no_grad():
-            for _ in range(args.warmup):
-                model(obs)
-            ms_s = timed(lambda: model(obs), args.steps) / args.steps
-        model.set_precision("fp16")
-        if rank == 0:
-            print(json.dumps({"metric": "VO frame-pairs/sec, eval-mode forward only, split precision (within 1e-3 of fp32)",
-                              "value": round(world * B / (ms_s * 1e-3), 1), "unit": "pairs/s", "n_gpus": world,
-                              "ms_per_step": round(ms_s, 3)}), flush=True)
-        model.train()
     pf = obs if prefetch else None
     for _ in range(args.warmup):
         trainer.step(obs, d_tgt, prefetch=pf)
@@ -279,37 +275,60 @@ def run_b200(args):
             torch.distributed.destroy_process_group()
         return
 
-    # dominant kernel: the stem convolution (57 % of the forward FLOPs), timed alone with CUDA events
+    # dominant kernel: the stem convolution (57 % of the forward FLOPs), timed alone with CUDA events.  In split precision it
+    # is two launches of conv_stem2_fwd_kernel (w_lo * x into an fp16 tensor, then w * (x, x_lo) + that tensor -> fp32):
+    # `achieved` divides the ALGORITHMIC FLOPs of the convolution (one product per MAC) by the time of both launches;
+    # the tensor pipe issues three products per MAC (`issued_tflops`).
     plan = trainer._plan
     pk, how = peaks()
-    conv_op = plan.fwd_ops[1]
-    prog = L.Program([conv_op])
-    for _ in range(3):
-        prog.run(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    reps = 10
-    for _ in range(reps):
-        prog.run(dev)
-    e1.record()
-    torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / reps
+    split = bool(plan.split)
+    stem_ops = [op for op in plan.fwd_ops if op.code in (L.OP_CONV_STEM2, L.OP_CONV_STEM, L.OP_CONV)][:2 if split else 1]
+    if not (getattr(plan, "use_stem2", False) or getattr(plan, "use_stem", False)):
+        stem_ops = stem_ops[:1]
+
+    def time_ops(ops, reps=10):
+        prog = L.Program(list(ops))
+        for _ in range(3):
+            prog.run(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            prog.run(dev)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    k_ms = time_ops(stem_ops)
+    k_parts = [round(time_ops([op]), 4) for op in stem_ops]
     k_flop = plan.conv1.flops(B)
     achieved = k_flop / (k_ms * 1e-3) / 1e12
     kname = "conv_stem2_fwd_kernel" if getattr(plan, "use_stem2", False) else "conv_stem_fwd_kernel"
-    roofline = {"kernel": "%s (conv1 7x7/s2 30->32, B=%d): 57 %% of the forward FLOPs" % (kname, B), "bound": "tensor",
-                "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": STEM_DRAM_BYTES, "peak_source": how + " (burst)",
-                "algorithmic_flop": "2 * 49 taps * 30 ch * 32 cout per output pixel x B*96*171 pixels",
-                "launch_ms": round(k_ms, 4), "flop_per_launch": k_flop,
-                "step_tflops": round(world * B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12, 2),
-                "step_frac_of_sustained": round(B * GFLOP_FWDBWD * 1e9 / (ms_per_step * 1e-3) / 1e12
+    gflop_step = GFLOP_FWDBWD if args.model == "r18_30ch" else 8.880
+    roofline = {"kernel": "%s (conv1 7x7/s2 30->32, B=%d): 57 %% of the forward FLOPs; %s" %
+                          (kname, B, "2 launches in split precision (residual-weight product, then value weights x "
+                                     "(x, x_lo))" if split else "1 launch"),
+                "bound": "tensor", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": stem_dram_bytes("split" if split else "fp16"),
+                "peak_source": how + " (burst)",
+                "algorithmic_flop": "2 * 49 taps * 30 ch * 32 cout per output pixel x B*96*171 pixels (one product per MAC)",
+                "launch_ms": round(k_ms, 4), "launch_ms_parts": k_parts, "flop_per_launch": k_flop,
+                "issued_tflops": round(achieved * (3 if split else 1), 2),
+                "issued_frac": round(achieved * (3 if split else 1) / pk["bf16_tflops"], 4),
+                "step_tflops": round(world * B * gflop_step * 1e9 / (ms_per_step * 1e-3) / 1e12, 2),
+                "step_frac_of_sustained": round(B * gflop_step * 1e9 / (ms_per_step * 1e-3) / 1e12
                                                 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), 4)}
+    extra = None
+    if world == 1 and not args.no_extras:
+        extra = run_extras(args, dev, model, obs, timed, pk)
     cpu = cpu_baseline(seconds=args.cpu_seconds) if world == 1 and not args.no_cpu and args.model == "r18_30ch" else None
+    prec = model.precision
     out = {"metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+           "vs_baseline": None,
+           "dtype": ("f16x3: value + residual fp16 operand planes (3 tensor-core products per forward conv), f32 accumulate; "
+                     "single-pass f16 operands in backward" if prec == "split" else "f16 operands / f32 accumulate"),
+           "data": "synthetic",
            "config": {"workload": ("VO ResNet-50 (rgb + depth, 8 ch; BASELINE configs[2]) forward+backward+Adam, "
                                    if args.model == "r50_8ch" else
                                    "VO ResNet-18 (vo_cnn_rgb_d_dd_top_down, 30 ch) forward+backward+Adam, ") +
@@ -317,8 +336,10 @@ def run_b200(args):
                                   + (f"uint8 rgb + {dname} depth pairs, discretised-depth / top-down channels derived "
                                      "on the device inside the step" if pre is None else
                                      "the reference's four fp32 NHWC tensors"),
+                      "precision": prec + (" (outputs within 1e-3 of the fp32 reference: the parity-tested mode)"
+                                           if prec == "split" else " (throughput mode, outputs ~5e-3 from the fp32 reference)"),
                       "global_batch": world * B, "parallelism": f"dp{world}",
-                      "l2": f"step inputs ({h2d / 1e6:.0f} MB raw, 1.07 GB assembled) and every activation tensor exceed "
+                      "l2": f"step inputs ({h2d / 1e6:.0f} MB raw, 2.1 GB assembled) and every activation tensor exceed "
                             "the 126 MB L2; no flush needed"},
            "e2e": {"value": round(e2e_value, 1), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": 4, "ms_per_step": round(t_e2e / args.steps, 3),
@@ -327,20 +348,193 @@ def run_b200(args):
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val}
     if cpu:
         out["cpu_baseline"] = cpu
+    if extra:
+        out["extra"] = extra
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+def run_extras(args, dev, model, obs, timed, pk):
+    """Secondary measurements on one GPU (BASELINE configs[2] and [4]).  Every entry is wrapped: a
+    failure is reported in place and never hides the headline line."""
+    from pointnav_vo_b200 import lib as L
+
+    extra = {}
+    B = args.batch
+    hbm = pk.get("hbm_gbs", 6551.4)
+
+    def ev_time(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def guarded(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.synchronize()
+
+    # ---- eval-mode forward of the headline model (inference), both precisions
+    def fwd_only():
+        out = {}
+        was = model.precision
+        model.eval()
+        with torch.no_grad():
+            for prec in ("split", "fp16"):
+                model.set_precision(prec)
+                ms = ev_time(lambda: model(obs), reps=10)
+                out[prec] = {"ms": round(ms, 3), "pairs_per_s": round(B / (ms * 1e-3), 1),
+                             "tflops_algorithmic": round(B * GFLOP_FWD * 1e9 / (ms * 1e-3) / 1e12, 1)}
+        model.set_precision(was)
+        model.train()
+        model._plans = {k: v for k, v in model._plans.items() if v.training}  # drop the inference plans' buffers
+        return out
+
+    if args.model == "r18_30ch":
+        guarded("forward_only_b256", fwd_only)
+
+    # ---- K2: ResNet-50 rgb + depth, B = 256, training step
+    def r50():
+        from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+        m = build_model(dev, model="r50_8ch")
+        tr = FusedVOTrainStep(m)
+        raw = {"rgb": obs["rgb"], "depth": obs["depth"]}
+        tgt = torch.zeros(B, 3, device=dev)
+        ms = ev_time(lambda: tr.step(raw, tgt), reps=5, warm=3)
+        del tr, m
+        torch.cuda.empty_cache()
+        return {"workload": "VO ResNet-50 rgb+depth (8 ch) fwd+bwd+Adam, B=256 (BASELINE configs[2])", "ms_per_step": round(ms, 3),
+                "pairs_per_s": round(B / (ms * 1e-3), 1), "tflops_algorithmic": round(B * 8.880e9 / (ms * 1e-3) / 1e12, 1)}
+
+    if args.model == "r18_30ch" and "rgb" in obs and obs["rgb"].dtype == torch.uint8:
+        guarded("k2_resnet50_b256", r50)
+
+    # ---- K4: policy encoder + PPO over 128 envs x 128 steps
+    def k4():
+        import types
+
+        from pointnav_vo_b200.rl.common.rollout_storage import RolloutStorage
+        from pointnav_vo_b200.rl.policies.resnet_policy import PointNavResNetPolicy
+        from pointnav_vo_b200.rl.ppo.ppo import PPO
+
+        T = N = 128
+        box = lambda *sh: types.SimpleNamespace(shape=tuple(sh))  # noqa: E731
+        obs_space = types.SimpleNamespace(spaces={"depth": box(H, W, 1), "pointgoal_with_gps_compass": box(2)})
+
+        class ActionSpace:
+            n = 4
+
+        torch.manual_seed(0)
+        pol = PointNavResNetPolicy(observation_space=obs_space, action_space=ActionSpace(), backbone="resnet18",
+                                   vis_types=["depth"]).to(dev)
+        rs = RolloutStorage(T, N, obs_space, ActionSpace(), 512, num_recurrent_layers=pol.net.num_recurrent_layers)
+        rs.to(dev)
+        g = torch.Generator(device=dev).manual_seed(1)
+        rs.observations["depth"].copy_(torch.rand(T + 1, N, H, W, 1, device=dev, generator=g))
+        rs.observations["pointgoal_with_gps_compass"].copy_(torch.rand(T + 1, N, 2, device=dev, generator=g) * 4 - 2)
+        rs.rewards.copy_(torch.randn(T, N, 1, device=dev, generator=g))
+        rs.value_preds.copy_(torch.randn(T + 1, N, 1, device=dev, generator=g))
+        rs.masks.copy_((torch.rand(T + 1, N, 1, device=dev, generator=g) < 0.98).float())
+        rs.actions.copy_(torch.randint(0, 4, (T, N, 1), device=dev, generator=g))
+        rs.prev_actions.copy_(torch.randint(0, 4, (T + 1, N, 1), device=dev, generator=g))
+        rs.action_log_probs.copy_(-1.4 + 0.1 * torch.randn(T, N, 1, device=dev, generator=g))
+        rs.step = T
+        out = {"workload": "depth-only ResNet-18 policy (ddppo_pointnav.yaml), 128 envs x 128 steps, 341x192 depth"}
+        pol.eval()
+        step_obs = {k: v[0] for k, v in rs.observations.items()}
+        with torch.no_grad():
+            ms = ev_time(lambda: pol.act(step_obs, rs.recurrent_hidden_states[0], rs.prev_actions[0], rs.masks[0]), reps=20)
+        out["policy_act_n128"] = {"ms": round(ms, 3), "frames_per_s": round(N / (ms * 1e-3), 1)}
+        nv = torch.randn(N, 1, device=dev, generator=g)
+        for mode in ("exact", "scan"):
+            ms = ev_time(lambda: rs.compute_returns(nv, True, 0.99, 0.95, mode=mode), reps=50)
+            # rollout_storage.py:102-120: rewards, values, masks read + returns written = 16 B per (step, env)
+            out["gae_" + mode] = {"us": round(ms * 1e3, 2), "algorithmic_bytes": 16 * T * N,
+                                  "achieved_gbs": round(16 * T * N / (ms * 1e-3) / 1e9, 2),
+                                  "note": "latency-bound: 262 KB per launch"}
+        agent = PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                    eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
+        pol.train()
+        agent.update(rs)  # warm-up: builds the B = 8192 plan
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            agent.update(rs)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        frames = T * N
+        out["ppo_update"] = {"ms": round(ms, 2), "minibatches": "1 epoch x 2 minibatches x 8192 frames",
+                             "frames_per_s": round(frames / (ms * 1e-3), 1),
+                             "encoder_tflops_algorithmic": round(frames * 3 * 0.3122e9 / (ms * 1e-3) / 1e12, 1)}
+        del agent, pol, rs
+        torch.cuda.empty_cache()
+        return out
+
+    if args.model == "r18_30ch":
+        guarded("k4_policy_ppo", k4)
+
+    # ---- HBM-bound preprocessing kernels on 512 frames (one batch of 256 pairs): achieved GB/s on algorithmic bytes
+    def preproc():
+        from pointnav_vo_b200.utils import geometry_utils as gu
+
+        out = {}
+        n = 2 * B
+        d = torch.rand(n, H, W, device=dev)
+        ms = ev_time(lambda: gu.discretize_depth_index(d), reps=20)
+        by = n * H * W * 5  # 4 B depth in + 1 B bin index out per pixel (SURVEY 8d)
+        out["discretize_index"] = {"us": round(ms * 1e3, 1), "algorithmic_bytes": by, "achieved_gbs": round(by / (ms * 1e-3) / 1e9, 1),
+                                   "frac_of_hbm_peak": round(by / (ms * 1e-3) / 1e9 / hbm, 3)}
+        gen = gu.NormalizedDepth2TopDownViewHabitatTorch(0.1, 10.0, H, W, 70)
+        td = torch.empty(n, H, W, 1, device=dev)
+        dd = d[..., None].contiguous()
+        ms = ev_time(lambda: gen.gen_top_down_view(dd, out=td), reps=20)
+        by = int(n * 0.66e6)  # SURVEY 8d: bbox scan 262 KB + 100-row crop 136 KB + map write 262 KB per frame
+        out["topdown"] = {"us": round(ms * 1e3, 1), "frames": n, "algorithmic_bytes": by,
+                          "achieved_gbs": round(by / (ms * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(by / (ms * 1e-3) / 1e9 / hbm, 3),
+                          "note": "atomic / issue-bound (one CTA per frame, shared-memory histogram)"}
+        return out
+
+    guarded("preproc_kernels_512_frames", preproc)
+    return extra
+
+
+def _preproc_pair(dep_pair):
+    """Worker: the reference DataLoader's per-sample preprocessing (regression_geo_invariance_iter_dataset.py:237-267) on one
+    depth pair, through the pinned oracle: 2 x (10-bin discretisation + top-down projection)."""
+    from oracle import preproc_oracle as po
+
+    orc = _preproc_pair.orc = getattr(_preproc_pair, "orc", None) or po.TopDownOracle()
+    oh = po.discretize_depth_onehot(dep_pair)
+    td = np.stack([orc.gen_top_down_view(dep_pair[j])[..., 0] for j in range(2)], -1)
+    return np.concatenate([oh[0], oh[1]], -1), td
+
+
 def cpu_baseline(seconds=15.0, batch=4, threads=None):
-    """The reference algorithm on the host cores: oracle/vo_oracle.py (fp32 PyTorch-CPU restatement pinned
-    against the unmodified reference), forward + backward + Adam on batches of 4 pairs."""
+    """The reference algorithm on the host cores: the oracle port (oracle/*.py, pinned against the unmodified reference) of
+    the reference's whole K0/K1 path -- per-sample preprocessing (depth discretisation + top-down projection of both frames,
+    what its DataLoader workers do; here a process pool over all cores), then forward + backward + Adam of the fp32
+    PyTorch-CPU model on batches of 4 pairs with all host threads.  Also reports the top-down and GAE timings BASELINE.md
+    section 3 lists."""
+    import multiprocessing as mp
+
     from oracle import preproc_oracle as po  # noqa: F401  (checker-side import, allowed in bench's cpu leg)
     from oracle import vo_oracle as vo
     from pointnav_vo_b200.vo.models.shapes import vo_state_dict_shapes
     from pointnav_vo_b200.utils import synth
 
     threads = threads or os.cpu_count()
+    pool = mp.get_context("fork").Pool(min(threads, 2 * batch))  # forked before torch spins up its thread pool
     torch.set_num_threads(threads)
     shapes = vo_state_dict_shapes(SPACE, "resnet18", discretized_depth_channels=10)
     sd = synth.fill_state_dict({k: np.empty(s, np.float32) for k, s in shapes.items()}, seed=7)
@@ -348,27 +542,49 @@ def cpu_baseline(seconds=15.0, batch=4, threads=None):
     params = [v.requires_grad_(True) for k, v in sd.items() if "running" not in k]
     opt = torch.optim.Adam(params, lr=2.5e-4, eps=1e-8)
     rng = np.random.default_rng(0)
-    obs = {"rgb": torch.from_numpy(rng.integers(0, 256, size=(batch, H, W, 6)).astype(np.float32)),
-           "depth": torch.rand(batch, H, W, 2), "discretized_depth": torch.zeros(batch, H, W, 20),
-           "top_down_view": torch.rand(batch, H, W, 2)}
-    obs["discretized_depth"][..., 3] = 1
-    obs["discretized_depth"][..., 13] = 1
+    rgb = torch.from_numpy(rng.integers(0, 256, size=(batch, H, W, 6)).astype(np.float32))
+    dep = synth.depth_frames(2 * batch, seed=3).reshape(batch, 2, H, W)
     tgt = torch.randn(batch, 3) * 0.1
+    t_pre = [0.0]
 
     def step():
+        t0 = time.perf_counter()
+        res = pool.map(_preproc_pair, [dep[b] for b in range(batch)])
+        t_pre[0] += time.perf_counter() - t0
+        obs = {"rgb": rgb, "depth": torch.from_numpy(np.stack([dep[:, 0], dep[:, 1]], -1)),
+               "discretized_depth": torch.from_numpy(np.stack([r[0] for r in res])),
+               "top_down_view": torch.from_numpy(np.stack([r[1] for r in res]))}
         opt.zero_grad()
         y, _ = vo.vo_forward(obs, sd, SPACE, "resnet18", training=True)
         sum(vo.vo_losses(y, tgt)).backward()
         opt.step()
 
     step()
+    t_pre[0] = 0.0
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         step()
         n += 1
     dt = time.perf_counter() - t0
+    pool.close()
+    # BASELINE.md section 3 extras: top-down projection per frame (single thread, the oracle's numpy restatement of the
+    # fp32 Torch variant) and GAE over 128 envs x 128 steps (numpy restatement of the reference loop)
+    orc = po.TopDownOracle()
+    t1 = time.perf_counter()
+    for j in range(4):
+        orc.gen_top_down_view(dep[j % batch, 0])
+    td_ms = (time.perf_counter() - t1) * 1e3 / 4
+    r, v, m, nv = synth.gae_inputs(128, 128, 4)
+    t1 = time.perf_counter()
+    for _ in range(3):
+        po.gae_returns(r, v, m, nv, True, 0.99, 0.95)
+    gae_ms = (time.perf_counter() - t1) * 1e3 / 3
     return {"value": round(n * batch / dt, 2), "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": f"{n} fwd+bwd+Adam steps of batch {batch} (same model, 341x192, fp32 PyTorch-CPU oracle), {dt:.1f} s"}
+            "sample": f"{n} steps of batch {batch}: oracle preprocessing of the 8 depth frames (discretise + top-down, process "
+                      f"pool) + fwd+bwd+Adam of the same model (341x192, fp32 PyTorch-CPU oracle), {dt:.1f} s; preprocessing "
+                      f"took {100 * t_pre[0] / dt:.0f} % of it",
+            "topdown_ms_per_frame": round(td_ms, 1), "gae_128x128_ms": round(gae_ms, 2),
+            "model_only_pairs_per_s": round(n * batch / max(dt - t_pre[0], 1e-9), 2)}
 
 
 def run_reference(args):
@@ -389,7 +605,8 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(256 / v * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "VO ResNet-18 (vo_cnn_rgb_d_dd_top_down, 30 ch) forward+backward+Adam on the host "
-                                  "CPU, batch 4 samples of the batch-256 workload (BASELINE configs[0]/[1])"},
+                                  "CPU incl. the per-sample discretise / top-down preprocessing, batch 4 samples of the "
+                                  "batch-256 workload (BASELINE configs[0]/[1])"},
            "cpu_baseline": cb, "e2e": {"value": round(v, 2), "unit": "pairs/s", "h2d_bytes_per_step": 0,
                                        "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1)}
@@ -413,8 +630,10 @@ def main():
     ap.add_argument("--depth", choices=["fp16", "fp32"], default="fp16",
                     help="type of the depth pairs in the host batch (raw inputs only): fp16 = the type the reference's HDF5 "
                          "datasets store; fp32 = what its DataLoader hands to _transfer_batch")
-    ap.add_argument("--forward-only", action="store_true",
-                    help="extra line: eval-mode forward (inference) throughput of the same model / batch, device-resident inputs")
+    ap.add_argument("--precision", default="split", choices=["split", "fp16"],
+                    help="split (default) = the parity mode: value + residual fp16 operand planes in the forward convolutions, "
+                         "outputs within 1e-3 of the fp32 reference; fp16 = single-pass throughput mode (~5e-3)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (`extra` in the JSON line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -402,50 +402,6 @@ int conv_stem_wgrad_launch(const __half* x, const __half* dy, float* dw, int w_l
 }  // namespace pnvo
 
 // ---------------------------------------------------------------------------------------------------------
-// debug: TMA-load two boxes of one input row and dump the raw shared-memory bytes (layout inspection)
-// ---------------------------------------------------------------------------------------------------------
-namespace pnvo {
-__global__ void tma_dump_kernel(const __grid_constant__ ConvTmaps tm, int box_px, int ih, int b, int w0, uint4* out,
-                                int n16) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
-  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
-  for (int i = threadIdx.x; i < n16; i += blockDim.x)
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "r"(0xFFFFFFFFu) : "memory");
-  if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bar), 1);
-    fence_mbar_init();
-  }
-  fence_proxy_async_smem();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(smem_u32(&bar), 2 * box_px * 64);
-    tma_load_4d(base, &tm.a, smem_u32(&bar), 0, w0, ih, b);
-    tma_load_4d(base + box_px * 64, &tm.a, smem_u32(&bar), 0, w0 + box_px, ih, b);
-  }
-  mbar_wait(smem_u32(&bar), 0);
-  __syncthreads();
-  for (int i = threadIdx.x; i < n16; i += blockDim.x) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + i * 16));
-    out[i] = v;
-  }
-}
-}  // namespace pnvo
-
-extern "C" int pnvo_debug_tma_dump(const void* x, int B, int IH, int IW, int box_px, int ih, int b, int w0, void* out,
-                                   int n16, void* stream) {
-  using namespace pnvo;
-  alignas(64) ConvTmaps tm;
-  memset(&tm, 0, sizeof(tm));
-  if (tmap_tiled4d(&tm.a, x, B, IH, IW, 32, box_px)) return -1;
-  cudaFuncSetAttribute(tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  tma_dump_kernel<<<1, 256, n16 * 16 + 1024, static_cast<cudaStream_t>(stream)>>>(tm, box_px, ih, b, w0,
-                                                                                static_cast<uint4*>(out), n16);
-  return check_launch("tma_dump");
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // debug / measurement: issue rate of tcgen05.mma (M = 128, K = 16, fp16) as a function of N, the swizzle mode and the
 // byte shift of the A descriptor's start address relative to the swizzle atom (the raster kernels shift it by whole
 // pixels).  One CTA per SM issues `n_mma` MMAs back to back on fixed shared-memory operands and reports cycles / MMA.

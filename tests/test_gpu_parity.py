@@ -716,6 +716,64 @@ def test_vo_backward_block_by_block():
             assert rel_l2(P[k].grad, sd[k].grad) <= 0.08, k
 
 
+@pytest.mark.parametrize("case", ["r18_30ch", "r50_8ch"])
+def test_vo_layer_taps_against_oracle(case):
+    """Per-layer taps (promoted from the bring-up harness tests/selftest_gpu.py): every stage of the default-precision
+    plan against the fp32 oracle run on the same inputs -- forward activations (value + residual planes) within the
+    north-star 1e-3 of each tap's rms, and the gradient buffers of a training step within 2e-2 (max|d| / rms).  Separates
+    "which layer" from "how much" when a whole-network bound fails."""
+    m, space, backbone = _load_vo(case)
+    obs = helpers.vo_inputs(2, 11, space, "cuda")
+    sd = {k: v.cuda() for k, v in helpers.vo_state_dict(case).items()}
+    m.eval()
+    with torch.no_grad():
+        m(obs)
+        taps = {}
+        vo.vo_forward(obs, sd, space, backbone, training=False, taps=taps)
+    plan = [p for p in m._plans.values() if not p.training][0]
+    full = lambda t: t.float() + plan.lo(t).float()  # noqa: E731
+    C = m.visual_encoder.input_channels
+    fwd = {"input": full(plan.x0)[:, :, 3:3 + plan.W, :C] if plan.x0_pitch else full(plan.x0)[..., :C],
+           "conv1_raw": plan.raw1, "pool": full(plan.pool)}
+    li = 0
+    for bi, blk in enumerate(plan.blocks):
+        nxt = plan.blocks[bi + 1]["name"] if bi + 1 < len(plan.blocks) else None
+        if nxt is None or nxt.split(".")[-2] != blk["name"].split(".")[-2]:
+            li += 1
+            fwd[f"layer{li}"] = full(blk["y"])
+    cc = m.visual_encoder.output_shape[0]
+    fwd["compression"] = full(plan.feat)[..., :cc]
+    for k, t in fwd.items():
+        e = rel(t.permute(0, 3, 1, 2), taps[k])
+        assert e <= SPLIT_TOL, (case, k, e)
+    # training step: gradient taps against fp32 autograd through the oracle
+    m.train()
+    target = torch.from_numpy(np.random.default_rng(5).normal(0, 0.1, size=(2, 3)).astype(np.float32)).cuda()
+    y = m(obs)
+    sum(vo.vo_losses(y, target)).backward()
+    sdg = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    taps = {}
+    yo, _ = vo.vo_forward(obs, sdg, space, backbone, training=True, taps=taps)
+    for t in taps.values():
+        if t.requires_grad:
+            t.retain_grad()
+    sum(vo.vo_losses(yo, target)).backward()
+    plan = [p for p in m._plans.values() if p.training][0]
+    bwd = {"compression": plan.g_feat[..., :cc], "pool": plan.g_pool, "conv1_raw": plan.dx1}
+    li = 0
+    for bi, blk in enumerate(plan.blocks):
+        nxt = plan.blocks[bi + 1]["name"] if bi + 1 < len(plan.blocks) else None
+        if nxt is None or nxt.split(".")[-2] != blk["name"].split(".")[-2]:
+            li += 1
+            bwd[f"layer{li}"] = blk["g_y"]
+    worst = 0.0
+    for k, t in bwd.items():
+        e = rel(t.permute(0, 3, 1, 2), taps[k].grad)
+        worst = max(worst, e)
+        assert e <= 2e-2, (case, "grad tap", k, e)
+    print(case, "worst gradient tap max|d|/rms", worst)
+
+
 def test_vo_forward_is_reproducible_run_to_run():
     """GroupNorm statistics are accumulated with fp64 atomics, so their order no longer reaches the fp32 mean / rstd:
     two eval-mode forwards of the same batch are bit-identical (with fp32 atomics they differed at the 4e-3 level)."""
