@@ -148,7 +148,11 @@ enum pnvo_opcode {
   PNVO_OP_PACK_W_MULTI = 37,  /* PACK_W over a device table of descriptors (one launch for every layer) */
   PNVO_OP_UNPACK_DW_MULTI = 38,
   PNVO_OP_GN_PARAM_GRAD_MULTI = 39,
-  PNVO_OP_MAX = 40
+  PNVO_OP_STEM_EXACT_PREP = 40,   /* exact-input stem: per-channel (scale, shift, a, b, weight source) from the input statistics */
+  PNVO_OP_STEM_EXACT_PACK = 41,   /* W' = a_c W in the stem layout (value + residual planes) + the [5][5][32] border bias table */
+  PNVO_OP_STEM_DY_SUMS = 42,      /* per-border-class sums of the stem's output gradient */
+  PNVO_OP_STEM_EXACT_UNPACK = 43, /* conv1 weight gradient from the exact-tensor gradient and the border-class sums */
+  PNVO_OP_MAX = 44
 };
 
 typedef struct {

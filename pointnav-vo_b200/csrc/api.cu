@@ -96,6 +96,11 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
     case PNVO_OP_RAW_STATS:
     case PNVO_OP_RAW_ASSEMBLE:
       return raw_op(op.code, i, f, p, st);
+    case PNVO_OP_STEM_EXACT_PREP:
+    case PNVO_OP_STEM_EXACT_PACK:
+    case PNVO_OP_STEM_DY_SUMS:
+    case PNVO_OP_STEM_EXACT_UNPACK:
+      return stem_exact_op(op.code, i, f, p, st);
     case PNVO_OP_RMV_UPDATE:
       // p0 = fp64 stats, p1 = _mean, p2 = _var, p3 = _count, p4 = scale, p5 = shift
       // i0 = C, i1 = update, i2 = have_rmv; f0 = batch samples (all ranks), f1 = pixels per sample
@@ -203,10 +208,12 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                                   static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], i[5], st);
     case PNVO_OP_CONV_STEM2:
       // p0 = W-padded x, p1 = stem2-packed weights, p2 = y, p3 = stats, p4 = x_lo (split mode), p5 = fp16 tensor added in
-      // the epilogue; i0 = B, i1 = IH, i2 = IW, i3 = G, i4 = cpg, i5 = fp32 output
+      // the epilogue, p6 = border-class bias table [5][5][32] fp32 (exact-input stem); i0 = B, i1 = IH, i2 = IW, i3 = G,
+      // i4 = cpg, i5 = fp32 output
       return conv_stem2_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
                                    static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], st,
-                                   static_cast<const __half*>(p[4]), static_cast<const __half*>(p[5]), i[5]);
+                                   static_cast<const __half*>(p[4]), static_cast<const __half*>(p[5]), i[5],
+                                   static_cast<const float*>(p[6]));
     case PNVO_OP_WGRAD_STEM2:
       // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld
       return conv_stem_wgrad2_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),

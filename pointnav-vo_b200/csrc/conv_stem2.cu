@@ -25,6 +25,7 @@ namespace pnvo {
 struct Stem2Args {
   void* y;        // [B, OH, OW, 32] fp16 (fp32 when out_fp32)
   const __half* add;  // optional [B, OH, OW, 32] fp16 added before the store (split mode: the w_lo * x product)
+  const float* bias5; // optional [5][5][32] fp32: bias per (row class, column class, cout) of the exact-input stem (stem_exact.cu)
   int out_fp32;
   int x_planes;   // 1, or 2 in split mode: every input row is staged twice (x through tm.a, x_lo through tm.a_lo)
   double* stats;  // [B][G][2]
@@ -188,6 +189,13 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
       __half* yrow = static_cast<__half*>(p.y) + row_ofs;
       float* yrow32 = static_cast<float*>(p.y) + row_ofs;
       const __half* arow = p.add ? p.add + row_ofs : nullptr;
+      // exact-input stem: the normalisation shift folded into a bias that depends on which taps lie inside the image
+      float bcol[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.bias5 && row_valid) {
+        const int rc = oh < 2 ? oh : (oh <= p.OH - 3 ? 2 : 3 + oh - (p.OH - 2));
+#pragma unroll
+        for (int k = 0; k < 5; ++k) bcol[k] = __ldg(p.bias5 + (rc * 5 + k) * 32 + lane);
+      }
       float sum = 0.f, ssq = 0.f;
       mbar_wait(smem_u32(&s_accfull[ab]), (i >> 1) & 1);
       tc_fence_after();
@@ -215,6 +223,13 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           if (arow) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] += __half2float(av[e]);
+          }
+          if (p.bias5) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int ow = ch * 32 + e;
+              v[e] += ow < 2 ? (ow == 0 ? bcol[0] : bcol[1]) : (ow <= p.OW - 3 ? bcol[2] : (ow == p.OW - 2 ? bcol[3] : bcol[4]));
+            }
           }
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -277,16 +292,18 @@ int conv_stem2_supported(int IH, int IW) {
 }
 
 int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
-                          cudaStream_t st, const __half* x_lo, const __half* add, int out_fp32) {
+                          cudaStream_t st, const __half* x_lo, const __half* add, int out_fp32, const float* bias5) {
   PNVO_REQUIRE(x && wr && y, "conv_stem2: null pointer");
   PNVO_REQUIRE(conv_stem2_supported(IH, IW), "conv_stem2: unsupported geometry %dx%d", IH, IW);
   PNVO_REQUIRE(!stats || (cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && G * cpg == 32), "conv_stem2: bad group config");
   Stem2Args a{};
   a.y = y; a.stats = stats; a.B = B; a.IH = IH;
   a.add = add; a.out_fp32 = out_fp32; a.x_planes = x_lo ? 2 : 1;
+  a.bias5 = bias5;
   a.OH = (IH + 6 - 7) / 2 + 1;
   a.OW = (IW + 6 - 7) / 2 + 1;
   a.G = G; a.cpg = cpg;
+  PNVO_REQUIRE(!bias5 || (a.OH >= 4 && a.OW >= 4), "conv_stem2: the border bias needs >= 4 outputs per axis");
   a.n_cols = ceil_div(a.OW, 16) * 16;
   a.xrow_bytes = ((a.n_cols + 8) * 128 + 1023) & ~1023;
   a.groups_per_img = ceil_div(a.OH, 4);

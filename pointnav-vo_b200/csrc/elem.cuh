@@ -33,6 +33,8 @@ int upsample2_launch(const __half* src, __half* dst, int B, int OH, int OW, int 
 // act_embed.cu: PNVO_OP_ACT_EMBED_FWD / PNVO_OP_ACT_EMBED_BWD
 int act_embed_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st);
 int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st);
+// stem_exact.cu: PNVO_OP_STEM_EXACT_PREP / _PACK / PNVO_OP_STEM_DY_SUMS / PNVO_OP_STEM_EXACT_UNPACK
+int stem_exact_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st);
 
 struct GnArgs {
   const void* x;       // raw conv output [B*HW][C] fp16 (or fp32 when x_fp32)

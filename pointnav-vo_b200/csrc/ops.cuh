@@ -59,7 +59,8 @@ int conv_stem2_supported(int IH, int IW);
 // x_lo (split-fp16 mode): residual plane of x, staged row by row next to x against the same weights; add: fp16
 // [B,OH,OW,32] added in the epilogue (the separately computed w_lo * x product); out_fp32: fp32 raw output
 int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
-                          cudaStream_t st, const __half* x_lo = nullptr, const __half* add = nullptr, int out_fp32 = 0);
+                          cudaStream_t st, const __half* x_lo = nullptr, const __half* add = nullptr, int out_fp32 = 0,
+                          const float* bias5 = nullptr);
 int pack_w_stem2_launch(const float* w, int Cin, __half* wr, int lo, cudaStream_t st);
 int conv_stem_wgrad2_supported(int IH, int IW);
 int conv_stem_wgrad2_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW, cudaStream_t st);

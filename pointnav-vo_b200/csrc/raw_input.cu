@@ -30,6 +30,7 @@ struct RawArgs {
   __half* out;
   __half* out_lo;       // split-fp16 mode (nullable): value - fp16(value); handled by the generic kernel variant
   int row_w, out_pitch;
+  int n_lo;             // exact-input stem: 2 extra channels C, C+1 = residuals t - fp16(t) of the two top-down values
   double* stats;        // [2C] (sum, sumsq) interleaved, accumulated
   // Geometric-invariance augmentation on the device (regression_geo_invariance_iter_dataset.py:342-420): output sample b
   // is source pair pair_map[b] >> 1, with prev / cur swapped when pair_map[b] & 1.  n_pix then counts OUTPUT pixels and
@@ -71,8 +72,8 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
   __shared__ float s_edges[kRawMaxBins + 1];
   if (threadIdx.x < kMaxInC) {
     const int c = threadIdx.x;
-    s_scale[c] = (c < a.C) ? (a.scale ? a.scale[c] : 1.f) : 0.f;
-    s_shift[c] = (c < a.C && a.shift) ? a.shift[c] : 0.f;
+    s_scale[c] = (c < a.C + a.n_lo) ? (a.scale ? a.scale[c] : 1.f) : 0.f;
+    s_shift[c] = (c < a.C + a.n_lo && a.shift) ? a.shift[c] : 0.f;
   }
   if (threadIdx.x <= a.n_dd && a.n_dd > 0) s_edges[threadIdx.x] = a.edges[threadIdx.x];
   __syncthreads();
@@ -145,6 +146,12 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
 #pragma unroll
         for (int c = 0; c < kMaxInC; ++c)
           if (c == cur) v[c] = tv;
+        if (a.n_lo) {  // exact-input stem: the fp16 rounding residual of the top-down value rides in channel C + f
+          const float lo = tv - __half2float(__float2half_rn(tv));
+#pragma unroll
+          for (int c = 0; c < kMaxInC; ++c)
+            if (c == 2 * cf + f) v[c] = lo;
+        }
       }
     }
     int64_t opix = p;
@@ -318,7 +325,8 @@ static int raw_check(const RawArgs& a) {
 
 int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
   if (raw_check(a)) return -1;
-  PNVO_REQUIRE(a.out && a.Cpad % 8 == 0 && a.Cpad <= kMaxInC && a.C <= a.Cpad, "raw_assemble: bad output layout");
+  PNVO_REQUIRE(a.out && a.Cpad % 8 == 0 && a.Cpad <= kMaxInC && a.C + a.n_lo <= a.Cpad, "raw_assemble: bad output layout");
+  PNVO_REQUIRE(a.n_lo == 0 || (a.n_lo == 2 && a.use_td && !a.out_lo), "raw_assemble: n_lo is 0, or 2 with top-down channels and no residual plane");
   if (a.n_pix <= 0) return 0;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
   if (a.pair_map) {
@@ -358,7 +366,8 @@ int raw_stats_launch(const RawArgs& a, cudaStream_t st) {
 int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStream_t st) {
   // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats, p7 = out_lo,
   // p8 = pair_map (int32 per output sample, nullable); i10 = pixels per sample (with pair_map); i11 = depth is fp16
-  // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch
+  // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch,
+  // i12 = n_lo (exact-input stem: top-down residual channels)
   (void)f;
   RawArgs a{};
   a.rgb = static_cast<const uint8_t*>(p[0]);
@@ -372,6 +381,7 @@ int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStrea
   a.n_pix = (static_cast<int64_t>(static_cast<uint32_t>(i[7])) << 32) | static_cast<uint32_t>(i[6]);
   a.row_w = i[8]; a.out_pitch = i[9];
   a.pair_map = static_cast<const int32_t*>(p[8]); a.hw = i[10];
+  a.n_lo = i[12];
   if (code == PNVO_OP_RAW_ASSEMBLE) {
     a.out = static_cast<__half*>(p[6]);
     a.out_lo = static_cast<__half*>(p[7]);

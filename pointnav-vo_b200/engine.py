@@ -175,7 +175,7 @@ class EncoderPlan:
 
     def __init__(self, *, params, buffers, B, H, W, in_channels, sources, backbone, baseplanes, ngroups,
                  compression_channels, prefix, head=None, training=True, avgpool_input=False, device="cuda",
-                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False):
+                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False, exact_stem=False):
         """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
         head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim).
@@ -187,6 +187,10 @@ class EncoderPlan:
         self.split = bool(split)
         if self.split:
             raw_fp32 = True
+        # exact_stem (split plans fed with raw uint8 rgb / fp16 depth pairs): the input tensor holds the EXACT raw values
+        # (no residual plane) and the normalisation is folded into the stem weights + a border bias (csrc/stem_exact.cu);
+        # _alloc clears the flag when the stem kernels cannot take the geometry
+        self.exact_stem = bool(exact_stem) and self.split
         self._lo = {}
         self.P, self.Bf = params, buffers
         self.B, self.H, self.W = B, H, W
@@ -314,7 +318,8 @@ class EncoderPlan:
             # GroupNorm per-(sample, channel) sums -> ONE zero-fill launch per step
             tot = sum(B * g.C * 2 for g in gns)
             n_dw = sum(c.cout_pad * c.w_ld for c in self.all_convs())
-            self.bwd_arena = torch.zeros(_ru(tot, 4) + n_dw, dtype=torch.float32, device=dev)
+            self.bwd_arena = torch.zeros(_ru(tot, 4) + n_dw + 5 * 5 * 32, dtype=torch.float32, device=dev)
+            self.stem_S = self.bwd_arena[_ru(tot, 4) + n_dw:]  # border-class sums of the stem's output gradient
             self.sums_all = self.bwd_arena[:_ru(tot, 4)]
             off = 0
             for g in gns:
@@ -333,11 +338,15 @@ class EncoderPlan:
         if self.use_stem and self.split:  # only the pixels-as-N stem kernel has a split variant
             self.use_stem = bool(self.stem_version >= 2 and L.load().pnvo_conv_stem2_supported(self.inH, self.inW)
                                  and (not tr or L.load().pnvo_conv_stem_wgrad2_supported(self.inH, self.inW)))
+        self.exact_stem = bool(self.exact_stem and self.use_stem and self.conv1.OH >= 4 and self.conv1.OW >= 4)
         if self.use_stem:
             self.x0_pitch = L.load().pnvo_stem_padded_width(self.inW)
             self.x0 = torch.zeros(B, self.inH, self.x0_pitch, self.cin_pad, dtype=torch.float16, device=dev)
-            if self.split:
+            if self.split and not self.exact_stem:
                 self._lo[self.x0.data_ptr()] = torch.zeros_like(self.x0)
+            if self.exact_stem:
+                self.xp = torch.zeros(6 * 32, dtype=torch.float32, device=dev)       # per-channel constants (stem_exact.cu)
+                self.bias5 = torch.zeros(5 * 5 * 32, dtype=torch.float32, device=dev)
             self.x0_img = self.x0[:, :, 3:, :]  # view whose data_ptr is the first image pixel
             self.w_stem = torch.zeros(7 * 4 * 32, 64, dtype=torch.float16, device=dev)
             # pixels-as-N stem kernel (conv_stem2.cu): full-rate MMAs, resident weights
@@ -465,7 +474,7 @@ class EncoderPlan:
                 pack.append(L.op_multi(L.OP_PACK_W_MULTI, self._pack_tab_lo, len(self.all_convs())))
         else:
             pack = [c.op_pack(self.P[c.key]) for c in self.all_convs()]
-        if self.use_stem:
+        if self.use_stem and not self.exact_stem:  # (the exact-input stem packs a_c * W inside the forward program)
             if not self.split:
                 pack.append(L.op_pack_w_stem(self.P[self.conv1.key], self.w_stem, self.conv1.Cin))
             if self.use_stem2:
@@ -476,7 +485,15 @@ class EncoderPlan:
         # ---- forward (after the input tensor x0 has been produced) ----
         ops = [L.op_zero(self.stats_all)]
         c1, g1 = self.conv1, self.gn1
-        if self.use_stem2 and self.split:
+        if self.exact_stem:
+            # exact raw values in x0, normalisation folded into W' = a_c * W (packed here: a_c follows the running
+            # statistics) and the border bias; W'_lo * x as an fp16 tensor first, then W' * x + that tensor + bias
+            ops.append(L.op_stem_exact_pack(self.P[c1.key], self.xp, self.w_stem2, self.w_stem2_lo, self.bias5, c1.Cin,
+                                            self.inH, self.inW))
+            ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, self.stem_corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
+            ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg,
+                                       add=self.stem_corr, out_fp32=True, bias5=self.bias5))
+        elif self.use_stem2 and self.split:
             # raw1 = w * (x + x_lo) + (w_lo * x): the residual-weight product first, as an fp16 tensor (it is ~2^-11 of
             # the result), then the value weights against both input planes with that tensor added in the epilogue
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, self.stem_corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
@@ -603,9 +620,14 @@ class EncoderPlan:
             ops.append(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48))
         else:
             ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
+        if self.exact_stem:
+            ops.append(L.op_stem_dy_sums(self.dx1, self.stem_S, B, c1.OH, c1.OW))
+            ops.append(L.op_stem_exact_unpack(c1.dwp, self.stem_S, self.xp, self.grads[c1.key], c1.w_ld, c1.Cin, self.inH,
+                                              self.inW))
         if self.batch_small_ops:
-            self._unpack_tab = L.device_table([c.unpack_desc(self.grads[c.key]) for c in self.all_convs()], self.dev)
-            ops.append(L.op_multi(L.OP_UNPACK_DW_MULTI, self._unpack_tab, len(self.all_convs())))
+            tab_convs = [c for c in self.all_convs() if not (self.exact_stem and c is c1)]
+            self._unpack_tab = L.device_table([c.unpack_desc(self.grads[c.key]) for c in tab_convs], self.dev)
+            ops.append(L.op_multi(L.OP_UNPACK_DW_MULTI, self._unpack_tab, len(tab_convs)))
             gns = self.all_gns()
             self._gnp_tab = L.device_table(
                 [L.GnParamDesc(g.sums.data_ptr(), self.grads[g.key + ".weight"].data_ptr(),
@@ -613,7 +635,8 @@ class EncoderPlan:
             ops.append(L.op_multi(L.OP_GN_PARAM_GRAD_MULTI, self._gnp_tab, len(gns), B))
         else:
             for c in self.all_convs():
-                ops.append(c.op_unpack(self.grads[c.key]))
+                if not (self.exact_stem and c is c1):
+                    ops.append(c.op_unpack(self.grads[c.key]))
         self.bwd_ops = ops
         self.bwd_prog = L.Program(ops, graph=True)
 
@@ -627,9 +650,17 @@ class EncoderPlan:
             return self.x0
         if getattr(self, "x0_alt", None) is None:
             self.x0_alt = torch.zeros_like(self.x0)
-            if self.split:
+            if self.split and not self.exact_stem:
                 self._lo[self.x0_alt.data_ptr()] = torch.zeros_like(self.x0)
         return self.x0_alt
+
+    def xp_for(self, parity):
+        """Per-channel constants of the exact-input stem that belong to staging buffer `parity`."""
+        if parity == 0:
+            return self.xp
+        if getattr(self, "xp_alt", None) is None:
+            self.xp_alt = torch.zeros_like(self.xp)
+        return self.xp_alt
 
     def programs_for(self, parity):
         if parity == 0:
@@ -638,8 +669,10 @@ class EncoderPlan:
             alt = self.x0_for(1)
             off = self.x0_img.data_ptr() - self.x0.data_ptr()
             mapping = {self.x0.data_ptr(): alt.data_ptr(), self.x0.data_ptr() + off: alt.data_ptr() + off}
-            if self.split:
+            if self.split and not self.exact_stem:
                 mapping[self.lo(self.x0).data_ptr()] = self.lo(alt).data_ptr()
+            if self.exact_stem:
+                mapping[self.xp.data_ptr()] = self.xp_for(1).data_ptr()
             fwd = L.Program(L.patch_ops(self.fwd_ops, mapping), graph=True)
             bwd = L.Program(L.patch_ops(self.bwd_ops, mapping), graph=True) if self.training else None
             self._alt_progs = (fwd, bwd)

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnvo.so")
 OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_APPLY, OP_GN_POOL = range(1, 9)
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
 OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2, OP_WGRAD_STEM2, OP_PACK_W_MULTI, OP_UNPACK_DW_MULTI, OP_GN_PARAM_GRAD_MULTI = range(16, 40)
+OP_STEM_EXACT_PREP, OP_STEM_EXACT_PACK, OP_STEM_DY_SUMS, OP_STEM_EXACT_UNPACK = range(40, 44)
 
 
 class PnvoOp(ctypes.Structure):
@@ -185,9 +186,10 @@ def op_input_stats(srcs, nch, pre_scale, lut, C, Cpad, n_pix, stats_f64):
     return _op(OP_INPUT_STATS, ints, fl, list(srcs) + [None] * (4 - len(srcs)) + [None, None, stats_f64])
 
 
-def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0, hw=0, depth=None):
+def _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w=0, out_pitch=0, hw=0, depth=None, n_lo=0):
     depth_fp16 = int(depth is not None and depth.dtype == torch.float16)
-    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch, hw, depth_fp16]
+    return [int(use_rgb), int(use_depth), int(n_dd), int(use_td), C, Cpad, *_lohi(n_pix), row_w, out_pitch, hw, depth_fp16,
+            int(n_lo)]
 
 
 def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, stats_f64, pair_map=None,
@@ -199,9 +201,30 @@ def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, 
 
 
 def op_raw_assemble(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, scale, shift, out,
-                    row_w=0, out_pitch=0, out_lo=None, pair_map=None, hw=0):
-    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch, hw, depth), (),
+                    row_w=0, out_pitch=0, out_lo=None, pair_map=None, hw=0, n_lo=0):
+    """n_lo = 2 (exact-input stem): channels C, C+1 carry the fp16 residuals of the two top-down values; scale / shift then
+    have C + 2 entries (op_stem_exact_prep)."""
+    return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch, hw, depth,
+                                            n_lo), (),
                [rgb_u8, depth, td, edges, scale, shift, out, out_lo, pair_map])
+
+
+def op_stem_exact_prep(scale, shift, xp, use_rgb, use_depth, n_dd, use_td):
+    """xp [6][32] fp32 <- per-channel constants of the exact-input stem (csrc/stem_exact.cu) from the normaliser's
+    scale = 1/std, shift = -mean/std (None: identity)."""
+    return _op(OP_STEM_EXACT_PREP, [int(use_rgb), int(use_depth), int(n_dd), int(use_td)], (), [scale, shift, xp])
+
+
+def op_stem_exact_pack(w, xp, wr, wr_lo, bias5, Cin, IH, IW):
+    return _op(OP_STEM_EXACT_PACK, [Cin, IH, IW], (), [w, xp, wr, wr_lo, bias5])
+
+
+def op_stem_dy_sums(dy, S, B, OH, OW):
+    return _op(OP_STEM_DY_SUMS, [B, OH, OW], (), [dy, S])
+
+
+def op_stem_exact_unpack(dwp, S, xp, grad, w_ld, Cin, IH, IW):
+    return _op(OP_STEM_EXACT_UNPACK, [w_ld, Cin, IH, IW], (), [dwp, S, xp, grad])
 
 
 def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv, n_batch, pix_per_sample):
@@ -313,10 +336,10 @@ def op_conv_stem(x, wr, y, stats, B, IH, IW, G, cpg, stages=4):
     return _op(OP_CONV_STEM, [B, IH, IW, G, cpg, stages], (), [x, wr, y, stats])
 
 
-def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg, x_lo=None, add=None, out_fp32=False):
+def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg, x_lo=None, add=None, out_fp32=False, bias5=None):
     """x_lo: residual plane of x (split mode: every row is multiplied twice against the same weights); add: fp16
-    [B, OH, OW, 32] added in the epilogue; out_fp32: y is fp32."""
-    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg, int(out_fp32)], (), [x, wr, y, stats, x_lo, add])
+    [B, OH, OW, 32] added in the epilogue; out_fp32: y is fp32; bias5: [5][5][32] fp32 border-class bias (exact-input stem)."""
+    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg, int(out_fp32)], (), [x, wr, y, stats, x_lo, add, bias5])
 
 
 def op_wgrad_stem2(x, dy, dw, B, IH, IW, w_ld):

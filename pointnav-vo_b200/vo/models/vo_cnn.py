@@ -115,6 +115,7 @@ class VisualOdometryCNNBase(nn.Module):
     """vo_cnn.py:182-233."""
 
     precision = "split"  # see set_precision
+    exact_stem = True    # split plans on raw uint8 / fp16 inputs use the exact-input stem (csrc/stem_exact.cu)
 
     def __init__(self, *, observation_space, observation_size, hidden_size=512, resnet_baseplanes=32,
                  backbone="resnet18", normalize_visual_inputs=False, output_dim=DEFAULT_DELTA_STATE_SIZE,
@@ -207,7 +208,12 @@ class VisualOdometryCNNBase(nn.Module):
             B = obs["pair_map"].numel()
         drop = self._dropout_p if training else 0.0  # nn.Dropout is the identity in eval mode
         split = self.precision == "split"
-        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32, drop, split)
+        # exact-input stem (engine.EncoderPlan(exact_stem=True)): raw uint8 rgb / fp16 depth pairs are exactly representable
+        # in fp16, so split plans fed with them fold the normalisation into the stem weights instead of carrying a residual
+        # plane of the assembled input (fp32 depth, or the reference's four fp32 tensors, keep the residual plane)
+        exact = bool(split and self.exact_stem and self._is_raw(obs)
+                     and (obs.get("depth") is None or obs["depth"].dtype == torch.float16))
+        key = (B, H, W, bool(need_grad), str(first.device), self.raw_fp32, drop, split, exact)
         plan = self._plans.get(key)
         if plan is None:
             P, Bf = self._tensors()
@@ -225,7 +231,7 @@ class VisualOdometryCNNBase(nn.Module):
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0],
                                prefix="visual_encoder", head=head, training=bool(need_grad), device=first.device,
-                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop, split=split)
+                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop, split=split, exact_stem=exact)
             self._plans[key] = plan
         return plan
 
@@ -293,10 +299,15 @@ class VisualOdometryCNNBase(nn.Module):
             scale, shift = plan.in_scale, plan.in_shift
         else:
             scale = shift = None
+        n_lo = 0
+        if plan.exact_stem:
+            xp = plan.xp_for(parity)
+            ops.append(L.op_stem_exact_prep(scale, shift, xp, use_rgb, use_depth, n_dd, use_td))
+            scale, shift, n_lo = xp[:32], xp[32:64], (2 if use_td else 0)
         ops.append(L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
                                      scale, shift, plan.x0_for(parity), row_w=plan.W if plan.x0_pitch else 0,
                                      out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0_for(parity)),
-                                     pair_map=pair_map, hw=H * W))
+                                     pair_map=pair_map, hw=H * W, n_lo=n_lo))
         L.run_ops(ops, dev)
         if not prepare_only:
             self._run_backbone(plan, parity)
