@@ -108,10 +108,12 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                                static_cast<float*>(p[2]), static_cast<float*>(p[3]), i[0], i[1], i[2],
                                static_cast<float*>(p[4]), static_cast<float*>(p[5]), st);
     case PNVO_OP_CONV: {
-      // p0 = x, p1 = w, p2 = y, p3 = add, p4 = stats, p5 = x_lo, p6 = w_lo (split-fp16 mode)
+      // p0 = x, p1 = w, p2 = y, p3 = add, p4 = stats, p5 = x_lo, p6 = w_lo (split-fp16 mode), p7 = y_lo (output as value +
+      // residual fp16 planes)
       ConvArgs a{};
       a.x_lo = static_cast<const __half*>(p[5]);
       a.w_lo = static_cast<const __half*>(p[6]);
+      a.y_lo = static_cast<__half*>(p[7]);
       a.x = static_cast<const __half*>(p[0]);
       a.w = static_cast<const __half*>(p[1]);
       a.y = p[2];
@@ -141,6 +143,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.beta = static_cast<const float*>(p[3]); a.res = static_cast<const __half*>(p[4]);
       a.y = static_cast<__half*>(p[5]);
       a.y_lo = static_cast<__half*>(p[7]); a.res_lo = static_cast<const __half*>(p[8]);  // split-fp16 planes (nullable)
+      a.x_lo = static_cast<const __half*>(p[9]);  // residual plane of a raw conv output stored as value + residual
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.relu = i[5]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1];
       if (op.code == PNVO_OP_GN_APPLY) return gn_apply_launch(a, i[0], st);
@@ -213,7 +216,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       return conv_stem2_fwd_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]), p[2],
                                    static_cast<double*>(p[3]), i[0], i[1], i[2], i[3], i[4], st,
                                    static_cast<const __half*>(p[4]), static_cast<const __half*>(p[5]), i[5],
-                                   static_cast<const float*>(p[6]));
+                                   static_cast<const float*>(p[6]), static_cast<__half*>(p[7]));
     case PNVO_OP_WGRAD_STEM2:
       // p0 = W-padded x, p1 = dy [B,OH,OW,32], p2 = packed fp32 dW; i0 = B, i1 = IH, i2 = IW, i3 = w_ld
       return conv_stem_wgrad2_launch(static_cast<const __half*>(p[0]), static_cast<const __half*>(p[1]),

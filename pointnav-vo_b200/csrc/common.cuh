@@ -165,6 +165,17 @@ __device__ __forceinline__ void tc_mma_f16_parts(uint32_t d_tmem, uint32_t a_lo,
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// value + residual fp16 planes of 8 fp32 values (split-fp16 representation): hi = fp16(v), lo = fp16(v - hi)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __half2* h2 = reinterpret_cast<__half2*>(&hi);
+  __half2* l2 = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const float2 f = __half22float2(h2[e]);
+    l2[e] = __floats2half2_rn(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+  }
+}
 // 32 lanes x 32 consecutive fp32 columns: thread (lane) gets its row's 32 columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);

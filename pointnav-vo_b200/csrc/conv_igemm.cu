@@ -305,7 +305,19 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
         }
       }
       if (row_valid) {
-        if (p.out_fp32) {
+        if (p.y_lo) {  // value + residual fp16 planes
+          __half* yh = reinterpret_cast<__half*>(p.y) + static_cast<int64_t>(m) * p.ldo + col0;
+          __half* yl = p.y_lo + static_cast<int64_t>(m) * p.ldo + col0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (col0 + q * 8 < p.n_store) {
+              uint4 hi, lo;
+              split8(v + 8 * q, hi, lo);
+              *reinterpret_cast<uint4*>(yh + q * 8) = hi;
+              *reinterpret_cast<uint4*>(yl + q * 8) = lo;
+            }
+          }
+        } else if (p.out_fp32) {
           float* yp = reinterpret_cast<float*>(p.y) + static_cast<int64_t>(m) * p.ldo + col0;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -392,6 +404,7 @@ int conv_plan(ConvArgs& a) {
   // TMA im2col path: unit "dilation" (div == 1), square filter / symmetric padding, channels in chunks of 32 or 64
   const bool split = a.x_lo != nullptr;
   PNVO_REQUIRE((a.x_lo != nullptr) == (a.w_lo != nullptr), "conv: split mode needs both x_lo and w_lo");
+  PNVO_REQUIRE(!a.y_lo || !a.out_fp32, "conv: y_lo (value + residual fp16 output) excludes out_fp32");
   a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1) ? 1 : 0;
   a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : kTileK;
   a.nkb = ceil_div(a.K, a.chunk_k);

@@ -25,7 +25,8 @@
 namespace pnvo {
 
 struct RasterArgs {
-  void* y;       // fp16, or fp32 in split mode
+  void* y;       // fp16, or fp32 in split mode without y_lo
+  __half* y_lo;  // split mode: residual plane of the output (then y is its fp16 value plane)
   const __half* add;
   double* stats;
   int B, H, W;
@@ -240,7 +241,17 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
             }
           }
           if (SPLIT) {
-            if (valid) {
+            if (valid && p.y_lo) {
+              uint4* yh = reinterpret_cast<uint4*>(static_cast<__half*>(p.y) + gofs + ch * 32);
+              uint4* yl = reinterpret_cast<uint4*>(p.y_lo + gofs + ch * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 hi, lo;
+                split8(v + 8 * q, hi, lo);
+                yh[q] = hi;
+                yl[q] = lo;
+              }
+            } else if (valid) {
               float4* yp = reinterpret_cast<float4*>(static_cast<float*>(p.y) + gofs + ch * 32);
 #pragma unroll
               for (int q = 0; q < 8; ++q) yp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -292,7 +303,7 @@ static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
   if (a.x_lo && a.Cin != 32) return false;  // split-fp16 with 64 / 128 channels: conv_raster128.cu (streamed weights)
   if (a.n_store != a.n_total || a.ldo != a.n_total) return false;
   const bool split = a.x_lo != nullptr;
-  if (split ? (!a.out_fp32 || !a.w_lo || a.add) : (a.out_fp32 != 0)) return false;
+  if (split ? (!(a.out_fp32 || a.y_lo) || (a.out_fp32 && a.y_lo) || !a.w_lo || a.add) : (a.out_fp32 != 0 || a.y_lo)) return false;
   if (a.w_ld < 9 * a.Cin) return false;
   if (a.stats) {
     if (a.G * a.cpg != a.n_total || a.G > 16) return false;
@@ -328,7 +339,7 @@ static bool raster_plan(const ConvArgs& a, RasterArgs& r, int& smem_bytes) {
     }
   }
   if (best < 0.5) return false;
-  r.y = a.y; r.add = a.add; r.stats = a.stats;
+  r.y = a.y; r.y_lo = a.y_lo; r.add = a.add; r.stats = a.stats;
   r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
   return true;
 }

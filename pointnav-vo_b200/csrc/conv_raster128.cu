@@ -22,7 +22,8 @@
 namespace pnvo {
 
 struct Raster128Args {
-  void* y;   // fp16 (MODE 0) or fp32 (split modes)
+  void* y;   // fp16 (MODE 0) or fp32 (split modes without y_lo)
+  __half* y_lo;  // split modes: residual plane of the output (then y is its fp16 value plane)
   const __half* add;
   double* stats;
   int B, H, W;
@@ -247,7 +248,17 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
             }
           }
           if (Md::kSplit) {
-            if (valid) {
+            if (valid && p.y_lo) {
+              uint4* yh = reinterpret_cast<uint4*>(static_cast<__half*>(p.y) + gofs + ch * 32);
+              uint4* yl = reinterpret_cast<uint4*>(p.y_lo + gofs + ch * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 hi, lo;
+                split8(v + 8 * q, hi, lo);
+                yh[q] = hi;
+                yl[q] = lo;
+              }
+            } else if (valid) {
               float4* yp = reinterpret_cast<float4*>(static_cast<float*>(p.y) + gofs + ch * 32);
 #pragma unroll
               for (int q = 0; q < 8; ++q) yp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -301,12 +312,12 @@ static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes,
   // (95 vs 86 us at B = 256: single-buffered accumulators + the accumulate-input reads in the epilogue): N = 128 only
   const bool split = a.x_lo != nullptr;
   if (split) {
-    if (!a.w_lo || !a.out_fp32 || a.add) return false;
+    if (!a.w_lo || !(a.out_fp32 || a.y_lo) || (a.out_fp32 && a.y_lo) || a.add) return false;
     if (a.Cin == 64 && a.n_total == 64) mode = 1;
     else if (a.Cin == 128 && a.n_total == 128) mode = 2;
     else return false;
   } else {
-    if (a.Cin != 128 || a.n_total != 128 || a.out_fp32) return false;
+    if (a.Cin != 128 || a.n_total != 128 || a.out_fp32 || a.y_lo) return false;
     mode = 0;
   }
   if (a.n_store != a.n_total || a.ldo != a.n_total) return false;
@@ -340,7 +351,7 @@ static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes,
     }
   }
   if (best < 0.5) return false;
-  r.y = a.y; r.add = a.add; r.stats = a.stats;
+  r.y = a.y; r.y_lo = a.y_lo; r.add = a.add; r.stats = a.stats;
   r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
   return true;
 }

@@ -24,6 +24,7 @@ namespace pnvo {
 
 struct Stem2Args {
   void* y;        // [B, OH, OW, 32] fp16 (fp32 when out_fp32)
+  __half* y_lo;   // optional residual plane of the output (y then holds fp16(acc), y_lo fp16(acc - y))
   const __half* add;  // optional [B, OH, OW, 32] fp16 added before the store (split mode: the w_lo * x product)
   const float* bias5; // optional [5][5][32] fp32: bias per (row class, column class, cout) of the exact-input stem (stem_exact.cu)
   int out_fp32;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
   auto stage_addr = [&](int s) -> uint32_t {
     return s == 0 ? smem_base : sW + kS2W + static_cast<uint32_t>(s - 1) * p.xrow_bytes;
   };
+  const uint32_t sStage = sW + kS2W + static_cast<uint32_t>(stages - 1) * p.xrow_bytes;  // epilogue tiles: 4 warps x 4 KB
 
   if (tid == 0) {
     mbar_init(smem_u32(&s_wfull), 1);
@@ -185,10 +187,9 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
       const int oh = (g - b * p.groups_per_img) * 4 + warp;
       const int ab = i & 1;
       const bool row_valid = oh < p.OH;
-      const int64_t row_ofs = (static_cast<int64_t>(b) * p.OH + oh) * p.OW * 32 + lane;
-      __half* yrow = static_cast<__half*>(p.y) + row_ofs;
-      float* yrow32 = static_cast<float*>(p.y) + row_ofs;
-      const __half* arow = p.add ? p.add + row_ofs : nullptr;
+      const int64_t row_base = (static_cast<int64_t>(b) * p.OH + oh) * p.OW * 32;
+      float* yrow32 = static_cast<float*>(p.y) + row_base + lane;
+      const bool arow = p.add != nullptr;
       // exact-input stem: the normalisation shift folded into a bias that depends on which taps lie inside the image
       float bcol[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       if (p.bias5 && row_valid) {
@@ -200,16 +201,27 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
       mbar_wait(smem_u32(&s_accfull[ab]), (i >> 1) & 1);
       tc_fence_after();
       const int n_chunks = (p.n_cols + 31) >> 5;
+      // fp16 outputs (and the fp16 tensor added in split mode) pass through a per-warp shared-memory tile [32 pixels][32
+      // channels]: the accumulator arrives channel-per-lane (64-byte stores per pixel: 0.85 ms per launch with a residual
+      // plane), the tile turns it into 16-byte vectors, 512 contiguous bytes per warp instruction.
+      __half* s_hi = reinterpret_cast<__half*>(smem + (sStage - smem_u32(smem))) + warp * 2048;
+      __half* s_lo = s_hi + 1024;
+      const int px4 = lane >> 2, c4 = lane & 3;
       for (int ch = 0; ch < n_chunks; ++ch) {
-        // the tensor added in the epilogue (split mode): all 32 loads of the chunk are issued before the accumulator is
-        // read -- interleaved with the stores they serialised on the memory latency (2.76 ms instead of 1.0 ms per launch)
-        __half av[32];
+        float av[32];
         if (arow && row_valid) {
+          // four 16-byte loads per lane (8 pixels x 64 B per instruction), staged, then read back channel-per-lane
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int ow = ch * 32 + e;
-            av[e] = (ow < p.OW) ? __ldg(arow + static_cast<int64_t>(ow) * 32) : __half(0.f);
+          for (int k = 0; k < 4; ++k) {
+            const int px = px4 + 8 * k, ow = ch * 32 + px;
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (ow < p.OW) u = __ldg(reinterpret_cast<const uint4*>(p.add + row_base + static_cast<int64_t>(ow) * 32) + c4);
+            *reinterpret_cast<uint4*>(s_hi + px * 32 + c4 * 8) = u;
           }
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) av[e] = __half2float(s_hi[e * 32 + lane]);
+          __syncwarp();
         }
         float v[32];
         tmem_ld32(tmem_base + t_lane + ab * 256 + ch * 32, v);
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
         if (row_valid) {
           if (arow) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] += __half2float(av[e]);
+            for (int e = 0; e < 32; ++e) v[e] += av[e];
           }
           if (p.bias5) {
 #pragma unroll
@@ -233,14 +245,38 @@ __global__ void __launch_bounds__(192) conv_stem2_fwd_kernel(const Stem2Args p, 
           }
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const int ow = ch * 32 + e;
-            if (ow < p.OW) {
-              if (p.out_fp32) yrow32[static_cast<int64_t>(ow) * 32] = v[e];
-              else yrow[static_cast<int64_t>(ow) * 32] = __float2half_rn(v[e]);
+            if (ch * 32 + e < p.OW) {
               sum += v[e];
               ssq = fmaf(v[e], v[e], ssq);
             }
           }
+        }
+        if (p.out_fp32) {
+          if (row_valid) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (ch * 32 + e < p.OW) yrow32[static_cast<int64_t>(ch * 32 + e) * 32] = v[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const __half h = __float2half_rn(v[e]);
+            s_hi[e * 32 + lane] = h;
+            if (p.y_lo) s_lo[e * 32 + lane] = __float2half_rn(v[e] - __half2float(h));
+          }
+          __syncwarp();
+          if (row_valid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int px = px4 + 8 * k, ow = ch * 32 + px;
+              if (ow < p.OW) {
+                const int64_t o = row_base + static_cast<int64_t>(ow) * 32 + c4 * 8;
+                *reinterpret_cast<uint4*>(static_cast<__half*>(p.y) + o) = *reinterpret_cast<const uint4*>(s_hi + px * 32 + c4 * 8);
+                if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + o) = *reinterpret_cast<const uint4*>(s_lo + px * 32 + c4 * 8);
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       if (p.stats) {
@@ -292,7 +328,8 @@ int conv_stem2_supported(int IH, int IW) {
 }
 
 int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
-                          cudaStream_t st, const __half* x_lo, const __half* add, int out_fp32, const float* bias5) {
+                          cudaStream_t st, const __half* x_lo, const __half* add, int out_fp32, const float* bias5,
+                          __half* y_lo) {
   PNVO_REQUIRE(x && wr && y, "conv_stem2: null pointer");
   PNVO_REQUIRE(conv_stem2_supported(IH, IW), "conv_stem2: unsupported geometry %dx%d", IH, IW);
   PNVO_REQUIRE(!stats || (cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && G * cpg == 32), "conv_stem2: bad group config");
@@ -300,6 +337,8 @@ int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* st
   a.y = y; a.stats = stats; a.B = B; a.IH = IH;
   a.add = add; a.out_fp32 = out_fp32; a.x_planes = x_lo ? 2 : 1;
   a.bias5 = bias5;
+  a.y_lo = y_lo;
+  PNVO_REQUIRE(!(y_lo && out_fp32), "conv_stem2: y_lo excludes out_fp32");
   a.OH = (IH + 6 - 7) / 2 + 1;
   a.OW = (IW + 6 - 7) / 2 + 1;
   a.G = G; a.cpg = cpg;
@@ -308,9 +347,10 @@ int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* st
   a.xrow_bytes = ((a.n_cols + 8) * 128 + 1023) & ~1023;
   a.groups_per_img = ceil_div(a.OH, 4);
   a.n_groups = B * a.groups_per_img;
-  a.stages = std::min(4, (210 * 1024 - kS2W) / a.xrow_bytes);
+  constexpr int kEpiBytes = 4 * 4096;  // per-warp output staging tiles (value + residual planes)
+  a.stages = std::min(4, (231000 - 1024 - kEpiBytes - kS2W) / a.xrow_bytes);
   PNVO_REQUIRE(a.stages >= 2, "conv_stem2: input rows too wide for the shared-memory ring");
-  const int smem_bytes = a.stages * a.xrow_bytes + kS2W + 1024;
+  const int smem_bytes = a.stages * a.xrow_bytes + kS2W + 1024 + kEpiBytes;
   const int Wp = stem_padded_width(IW);
   alignas(64) ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
@@ -320,7 +360,7 @@ int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* st
   if (tmap_tiled2d(&tm.b, wr, 4 * 7 * 32, 64, 64, 224, 64)) return -1;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(conv_stem2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    cudaFuncSetAttribute(conv_stem2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231000);
     attr = true;
   }
   if (B <= 0) return 0;

@@ -38,6 +38,7 @@ int stem_exact_op(int code, const int32_t* i, const float* f, void* const* p, cu
 
 struct GnArgs {
   const void* x;       // raw conv output [B*HW][C] fp16 (or fp32 when x_fp32)
+  const __half* x_lo;  // optional residual plane of x (raw outputs of split-precision convs: x = value + residual)
   int x_fp32;
   const double* stats; // [B][G][2] fp64 (sum, sum of squares)
   const float* gamma;  // [C] (padded channels: 0)

@@ -421,6 +421,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnArgs a) {
     const int cc = static_cast<int>(i % c8) * 8;
     float v[8];
     load8(a.x, base + i, a.x_fp32, v);
+    if (SPLIT && a.x_lo) {
+      float r[8];
+      load8(a.x_lo, base + i, 0, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_ab[cc + e], s_ab[C + cc + e]);
     if (a.res) {
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int
     float ga[8], gb[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { ga[e] = s_ab[cc + e]; gb[e] = s_ab[C + cc + e]; }
-    if (!a.x_fp32) {
+    if (!a.x_fp32 && !a.x_lo) {
       uint4 tapv[9];
       bool ok[9];
 #pragma unroll
@@ -507,6 +513,12 @@ __global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int
           if (w < 0 || w >= W) continue;
           float v[8];
           load8(a.x, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, a.x_fp32, v);
+          if (a.x_lo) {
+            float r8[8];
+            load8(a.x_lo, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, 0, r8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += r8[e];
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float y = fmaxf(fmaf(v[e], ga[e], gb[e]), 0.f);
@@ -810,7 +822,7 @@ int gn_apply_launch(const GnArgs& a, int B, cudaStream_t st) {
   const int gx = static_cast<int>(std::min<int64_t>(gn_grid_x(items, B, a.C / 8),
                                                     std::max<int64_t>(1, ceil_div64(items, 256 * min_items))));
   const size_t sm = 2 * a.C * sizeof(float);
-  if (a.y_lo || a.res_lo) gn_apply_kernel<true><<<dim3(gx, B), 256, sm, st>>>(a);
+  if (a.y_lo || a.res_lo || a.x_lo) gn_apply_kernel<true><<<dim3(gx, B), 256, sm, st>>>(a);
   else gn_apply_kernel<false><<<dim3(gx, B), 256, sm, st>>>(a);
   count_launch();
   return check_launch("gn_apply");

@@ -8,6 +8,8 @@ struct ConvArgs {
   const __half* x;    // input NHWC [B, IH, IW, Cin] fp16
   const __half* w;    // packed weights [n_total][w_ld] fp16, K-major, zero padded
   void* y;            // output [M][ldo] fp16 (or fp32 when out_fp32)
+  __half* y_lo;       // split-fp16 mode, optional: the output as value + residual fp16 planes (y = fp16(acc), y_lo =
+                      // fp16(acc - y)) instead of fp32 -- same bytes, but the backward pass can read the value plane alone
   const __half* add;  // optional [M][ldo] fp16 added before the store (dgrad accumulation)
   const __half* x_lo; // split-fp16 mode (both or neither): residual planes x - fp16(x), w - fp16(w) in the same layouts;
   const __half* w_lo; //   the kernel accumulates x*w + x_lo*w + x*w_lo (3 MMAs per product, ~fp32 operand precision)
@@ -60,7 +62,7 @@ int conv_stem2_supported(int IH, int IW);
 // [B,OH,OW,32] added in the epilogue (the separately computed w_lo * x product); out_fp32: fp32 raw output
 int conv_stem2_fwd_launch(const __half* x, const __half* wr, void* y, double* stats, int B, int IH, int IW, int G, int cpg,
                           cudaStream_t st, const __half* x_lo = nullptr, const __half* add = nullptr, int out_fp32 = 0,
-                          const float* bias5 = nullptr);
+                          const float* bias5 = nullptr, __half* y_lo = nullptr);
 int pack_w_stem2_launch(const float* w, int Cin, __half* wr, int lo, cudaStream_t st);
 int conv_stem_wgrad2_supported(int IH, int IW);
 int conv_stem_wgrad2_launch(const __half* x, const __half* dy, float* dw, int w_ld, int B, int IH, int IW, cudaStream_t st);

@@ -73,10 +73,10 @@ class ConvLayer:
         return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld,
                            self.cout_pad, self.wt_ld, 0)
 
-    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None):
+    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None, y_lo=None):
         return L.op_conv(x, self.wp, y, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
                          self.stride, self.pad, 1, self.w_ld, self.cout_pad, self.cout_pad, self.cout_pad, None, stats,
-                         cpg, G, out_fp32, x_lo=x_lo, w_lo=self.wp_lo if x_lo is not None else None)
+                         cpg, G, out_fp32, x_lo=x_lo, w_lo=self.wp_lo if x_lo is not None else None, y_lo=y_lo)
 
     def op_dgrad(self, dy, gx, B, add=None):
         # gx[b, h, w, c] = sum_{r,s,n} dy[b, (h + pad - r)/stride, (w + pad - s)/stride, n] * W[n, c, r, s]
@@ -180,13 +180,13 @@ class EncoderPlan:
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
         head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim).
         split: precision mode of the FORWARD pass.  Every fp16 activation / weight tensor gets a residual plane
-        (t - fp16(t), fp16), raw conv outputs stay fp32 and each conv accumulates x*w + x_lo*w + x*w_lo: operands carry
+        (t - fp16(t), fp16) -- the raw conv outputs too -- and each conv accumulates x*w + x_lo*w + x*w_lo: operands carry
         ~22 mantissa bits, so outputs agree with the fp32 reference to ~1e-5 instead of ~5e-3 (3 MMAs per product; the
         stem / raster / implicit-GEMM kernels all have a split variant).  The backward pass of a split plan reads the
-        value planes only (single-pass fp16 operands, fp32 accumulation) and the fp32 raw conv outputs."""
+        value planes only (single-pass fp16 operands, fp32 accumulation), also of the raw conv outputs (GroupNorm backward)."""
         self.split = bool(split)
         if self.split:
-            raw_fp32 = True
+            raw_fp32 = False  # raw conv outputs are value + residual fp16 planes: same bytes, and backward reads one plane
         # exact_stem (split plans fed with raw uint8 rgb / fp16 depth pairs): the input tensor holds the EXACT raw values
         # (no residual plane) and the normalisation is folded into the stem weights + a border bias (csrc/stem_exact.cu);
         # _alloc clears the flag when the stem kernels cannot take the geometry
@@ -443,7 +443,7 @@ class EncoderPlan:
         B = self.B
         return L.op_gn_apply(x, g.stats, self.P[g.key + ".weight"], self.P[g.key + ".bias"], y, B, g.C, g.G, g.cpg, HW,
                              float(g.cpg_real * HW), relu, res, self.raw_fp32, 1e-5, g.C_real, y_lo=self.lo(y),
-                             res_lo=self.lo(res))
+                             res_lo=self.lo(res), x_lo=self.lo(x))
 
     def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
         return L.op_gn_bwd(reduce, gin, relu_ref, x, g.stats, self.P[g.key + ".weight"], g.sums, dx, dy_out, self.B,
@@ -492,36 +492,39 @@ class EncoderPlan:
                                             self.inH, self.inW))
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, self.stem_corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg,
-                                       add=self.stem_corr, out_fp32=True, bias5=self.bias5))
+                                       add=self.stem_corr, bias5=self.bias5, y_lo=self.lo(self.raw1)))
         elif self.use_stem2 and self.split:
             # raw1 = w * (x + x_lo) + (w_lo * x): the residual-weight product first, as an fp16 tensor (it is ~2^-11 of
             # the result), then the value weights against both input planes with that tensor added in the epilogue
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, self.stem_corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg,
-                                       x_lo=self.lo(self.x0), add=self.stem_corr, out_fp32=True))
+                                       x_lo=self.lo(self.x0), add=self.stem_corr, y_lo=self.lo(self.raw1)))
         elif self.use_stem2 and not self.raw_fp32:
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg))
         elif self.use_stem and not self.raw_fp32:
             ops.append(L.op_conv_stem(self.x0, self.w_stem, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg, 2))
         else:
             assert not self.use_stem, "raw_fp32 is not supported together with the stem kernel"
-            ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32, x_lo=self.lo(self.x0)))
+            ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32, x_lo=self.lo(self.x0),
+                                 y_lo=self.lo(self.raw1)))
         ops.append(L.op_gn_pool(self.raw1, g1.stats, self.P[g1.key + ".weight"], self.P[g1.key + ".bias"], self.pool,
                                 self.argmax, B, g1.C, g1.G, g1.cpg, c1.OH, c1.OW, self.PH, self.PW,
                                 float(g1.cpg_real * c1.OH * c1.OW), self.raw_fp32, 1e-5, g1.C_real,
-                                y_lo=self.lo(self.pool)))
+                                y_lo=self.lo(self.pool), x_lo=self.lo(self.raw1)))
         x = self.pool
         for blk in self.blocks:
             convs, gns = blk["convs"], blk["gns"]
             res = x
             if blk["down"]:
                 d, gd = blk["down"]
-                ops.append(d.op_fwd(x, blk["raw_d"], B, gd.stats, gd.cpg, gd.G, self.raw_fp32, x_lo=self.lo(x)))
+                ops.append(d.op_fwd(x, blk["raw_d"], B, gd.stats, gd.cpg, gd.G, self.raw_fp32, x_lo=self.lo(x),
+                                    y_lo=self.lo(blk["raw_d"])))
                 ops.append(self._gn_apply(gd, blk["raw_d"], blk["res_d"], d.OH * d.OW, relu=False))
                 res = blk["res_d"]
             cur = x
             for k, (c, g) in enumerate(zip(convs, gns)):
-                ops.append(c.op_fwd(cur, blk["raw"][k], B, g.stats, g.cpg, g.G, self.raw_fp32, x_lo=self.lo(cur)))
+                ops.append(c.op_fwd(cur, blk["raw"][k], B, g.stats, g.cpg, g.G, self.raw_fp32, x_lo=self.lo(cur),
+                                    y_lo=self.lo(blk["raw"][k])))
                 if k < len(convs) - 1:
                     ops.append(self._gn_apply(g, blk["raw"][k], blk["mid"][k], c.OH * c.OW, relu=True))
                     cur = blk["mid"][k]
@@ -530,7 +533,8 @@ class EncoderPlan:
             blk["x_in"] = x
             x = blk["y"]
         cc, gc = self.comp, self.gnc
-        ops.append(cc.op_fwd(x, self.raw_c, B, gc.stats, gc.cpg, gc.G, self.raw_fp32, x_lo=self.lo(x)))
+        ops.append(cc.op_fwd(x, self.raw_c, B, gc.stats, gc.cpg, gc.G, self.raw_fp32, x_lo=self.lo(x),
+                             y_lo=self.lo(self.raw_c)))
         ops.append(self._gn_apply(gc, self.raw_c, self.feat, self.fH * self.fW, relu=True))
         p_drop = self.dropout_p
         if p_drop > 0:  # nn.Dropout in front of visual_fc (vo_cnn.py:218)

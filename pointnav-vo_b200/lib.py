@@ -233,11 +233,11 @@ def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv
 
 
 def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, add=None, stats=None,
-            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None):
+            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None, y_lo=None):
     """x_lo / w_lo: residual planes of the split-fp16 representation (x - fp16(x)); with them the kernel accumulates
     x*w + x_lo*w + x*w_lo, i.e. products of ~fp32-precision operands (3 MMAs per product)."""
     return _op(OP_CONV, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, cpg, G,
-                         int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats, x_lo, w_lo])
+                         int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats, x_lo, w_lo, y_lo])
 
 
 def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None, x_row_pitch=0):
@@ -246,16 +246,16 @@ def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, l
 
 
 def op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, cnt, relu=True, res=None, x_fp32=False, eps=1e-5,
-                C_real=None, y_lo=None, res_lo=None):
+                C_real=None, y_lo=None, res_lo=None, x_lo=None):
     return _op(OP_GN_APPLY, [B, C, G, cpg, HW, int(relu), int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real],
-               [cnt, eps], [x, stats, gamma, beta, res, y, None, y_lo, res_lo])
+               [cnt, eps], [x, stats, gamma, beta, res, y, None, y_lo, res_lo, x_lo])
 
 
 def op_gn_pool(x, stats, gamma, beta, y, argmax, B, C, G, cpg, H, W, PH, PW, cnt, x_fp32=False, eps=1e-5,
-               C_real=None, y_lo=None):
+               C_real=None, y_lo=None, x_lo=None):
     return _op(OP_GN_POOL, [B, C, G, cpg, H * W, 1, int(x_fp32), H, W, PH, PW, C if C_real is None else C_real],
                [cnt, eps],
-               [x, stats, gamma, beta, None, y, argmax, y_lo])
+               [x, stats, gamma, beta, None, y, argmax, y_lo, None, x_lo])
 
 
 def op_pool_bwd(g, pooled, argmax, dy, B, C, H, W, PH, PW):
@@ -336,10 +336,10 @@ def op_conv_stem(x, wr, y, stats, B, IH, IW, G, cpg, stages=4):
     return _op(OP_CONV_STEM, [B, IH, IW, G, cpg, stages], (), [x, wr, y, stats])
 
 
-def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg, x_lo=None, add=None, out_fp32=False, bias5=None):
+def op_conv_stem2(x, wr, y, stats, B, IH, IW, G, cpg, x_lo=None, add=None, out_fp32=False, bias5=None, y_lo=None):
     """x_lo: residual plane of x (split mode: every row is multiplied twice against the same weights); add: fp16
     [B, OH, OW, 32] added in the epilogue; out_fp32: y is fp32; bias5: [5][5][32] fp32 border-class bias (exact-input stem)."""
-    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg, int(out_fp32)], (), [x, wr, y, stats, x_lo, add, bias5])
+    return _op(OP_CONV_STEM2, [B, IH, IW, G, cpg, int(out_fp32)], (), [x, wr, y, stats, x_lo, add, bias5, y_lo])
 
 
 def op_wgrad_stem2(x, dy, dw, B, IH, IW, w_ld):

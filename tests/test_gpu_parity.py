@@ -232,6 +232,14 @@ def test_conv_split_fp16_operands(case, force_generic):
     if c.cout_pad == Cout:
         rs = ref.reshape(B, G, -1)
         assert rel(stats, torch.stack((rs.sum(-1), rs.pow(2).sum(-1)), -1)) <= 1e-4  # truncating accumulation: ~1e-5 low
+    # the same output as value + residual fp16 planes (what the plans store: backward reads the value plane alone)
+    yh = torch.full((B, c.OH, c.OW, c.cout_pad), float("nan"), dtype=torch.float16, device=dev)
+    yl = torch.full_like(yh, float("nan"))
+    fwd2 = c.op_fwd(x_hi, yh, B, None, 0, 0, False, x_lo=x_lo, y_lo=yl)
+    fwd2.i[19] = force_generic
+    L.run_ops([fwd2])
+    assert torch.equal(yh, y.half())
+    assert rel(yh.float() + yl.float(), y) <= 1e-6
 
 
 @pytest.mark.parametrize("version", [1, 2])
@@ -287,6 +295,9 @@ def test_stem_conv_kernels(version, B, IH, IW, Cin):
         err = rel(y32.permute(0, 3, 1, 2).double(), ref64)
         print("split stem max|d|/rms", err)
         assert err <= 1e-4
+        yh, yl = torch.empty_like(y), torch.empty_like(y)
+        L.run_ops([L.op_conv_stem2(xp_hi, wr, yh, None, B, IH, IW, 16, 2, x_lo=xp_lo, add=corr, y_lo=yl)])
+        assert torch.equal(yh, y32.half()) and rel(yh.float() + yl.float(), y32) <= 1e-6
         rs = ref64.reshape(B, 16, -1)
         assert rel(stats, torch.stack((rs.sum(-1), rs.pow(2).sum(-1)), -1)) <= 1e-4
     # weight gradient on the same staged rows
@@ -788,7 +799,7 @@ def test_vo_layer_taps_against_oracle(case):
     full = lambda t: t.float() + plan.lo(t).float()  # noqa: E731
     C = m.visual_encoder.input_channels
     fwd = {"input": full(plan.x0)[:, :, 3:3 + plan.W, :C] if plan.x0_pitch else full(plan.x0)[..., :C],
-           "conv1_raw": plan.raw1, "pool": full(plan.pool)}
+           "conv1_raw": full(plan.raw1), "pool": full(plan.pool)}
     li = 0
     for bi, blk in enumerate(plan.blocks):
         nxt = plan.blocks[bi + 1]["name"] if bi + 1 < len(plan.blocks) else None
