@@ -152,8 +152,15 @@ enum pnvo_opcode {
   PNVO_OP_STEM_EXACT_PACK = 41,   /* W' = a_c W in the stem layout (value + residual planes) + the [5][5][32] border bias table */
   PNVO_OP_STEM_DY_SUMS = 42,      /* per-border-class sums of the stem's output gradient */
   PNVO_OP_STEM_EXACT_UNPACK = 43, /* conv1 weight gradient from the exact-tensor gradient and the border-class sums */
-  PNVO_OP_MAX = 44
+  PNVO_OP_JOIN = 44,              /* graph replay: everything issued on the side lane so far completes before the next op */
+  PNVO_OP_MAX = 45
 };
+
+/* `code` may carry a lane in bits 16+: PNVO_OP_SIDE_LANE marks an op whose result is not needed until the next
+ * PNVO_OP_JOIN (or the end of the program).  pnvo_run_ops ignores lanes (strictly sequential); a captured graph puts such
+ * ops on a forked branch that depends on every op before them, so they overlap the ops that follow (weight gradients
+ * under the data-gradient / GroupNorm-backward chain). */
+#define PNVO_OP_SIDE_LANE (1 << 16)
 
 typedef struct {
   int32_t code;

@@ -34,7 +34,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
   const int32_t* i = op.i;
   const float* f = op.f;
   void* const* p = op.p;
-  switch (op.code) {
+  const int code = op.code & 0xffff;  // bits 16+: lane (PNVO_OP_SIDE_LANE)
+  switch (code) {
+    case PNVO_OP_JOIN:
+      return 0;  // only meaningful to the graph capture
     case PNVO_OP_ZERO:
       // p0 = buffer; i0|i1 = byte count (lo, hi)
       return zero_launch(p[0], (static_cast<int64_t>(static_cast<uint32_t>(i[1])) << 32) | static_cast<uint32_t>(i[0]), st);
@@ -67,7 +70,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       }
       a.scale = static_cast<const float*>(p[4]);
       a.shift = static_cast<const float*>(p[5]);
-      if (op.code == PNVO_OP_ASSEMBLE) {
+      if (code == PNVO_OP_ASSEMBLE) {
         a.out = static_cast<__half*>(p[6]);
         a.out_lo = static_cast<__half*>(p[7]);  // split-fp16 residual plane (nullable)
         return assemble_launch(a, st);
@@ -78,7 +81,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
     case PNVO_OP_UNPACK_DW_MULTI:
     case PNVO_OP_GN_PARAM_GRAD_MULTI:
       // p0 = device table of PackDesc / UnpackDesc / GnParamDesc (elem.cuh); i0 = entries, i1 = B (param grad)
-      return multi_launch(op.code, p[0], i[0], i[1], st);
+      return multi_launch(code, p[0], i[0], i[1], st);
     case PNVO_OP_GEO_INV_LOSS:
       // p0 = pred [B][O], p1 = actions int64 [B], p2 = dout (nullable, accumulated), p3 = loss[3] (total+=, rot, pos),
       // p4 = data types int64 [B] (nullable: every row, interleaved pairs), p5 = int32 error flag (nullable)
@@ -92,15 +95,15 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
                               i[5], st);
     case PNVO_OP_ACT_EMBED_FWD:
     case PNVO_OP_ACT_EMBED_BWD:
-      return act_embed_op(op.code, i, f, p, st);
+      return act_embed_op(code, i, f, p, st);
     case PNVO_OP_RAW_STATS:
     case PNVO_OP_RAW_ASSEMBLE:
-      return raw_op(op.code, i, f, p, st);
+      return raw_op(code, i, f, p, st);
     case PNVO_OP_STEM_EXACT_PREP:
     case PNVO_OP_STEM_EXACT_PACK:
     case PNVO_OP_STEM_DY_SUMS:
     case PNVO_OP_STEM_EXACT_UNPACK:
-      return stem_exact_op(op.code, i, f, p, st);
+      return stem_exact_op(code, i, f, p, st);
     case PNVO_OP_RMV_UPDATE:
       // p0 = fp64 stats, p1 = _mean, p2 = _var, p3 = _count, p4 = scale, p5 = shift
       // i0 = C, i1 = update, i2 = have_rmv; f0 = batch samples (all ranks), f1 = pixels per sample
@@ -146,7 +149,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.x_lo = static_cast<const __half*>(p[9]);  // residual plane of a raw conv output stored as value + residual
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.relu = i[5]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1];
-      if (op.code == PNVO_OP_GN_APPLY) return gn_apply_launch(a, i[0], st);
+      if (code == PNVO_OP_GN_APPLY) return gn_apply_launch(a, i[0], st);
       return gn_pool_launch(a, i[0], i[7], i[8], i[9], i[10], static_cast<uint8_t*>(p[6]), st);
     }
     case PNVO_OP_GN_POOL_BWD:
@@ -164,8 +167,8 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.sums = static_cast<float*>(p[5]); a.dx = static_cast<__half*>(p[6]); a.dy_out = static_cast<__half*>(p[7]);
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1]; a.g_scale = (f[2] == 0.f) ? 1.f : f[2];
-      if (op.code == PNVO_OP_GN_BWD_REDUCE) return gn_bwd_reduce_launch(a, i[0], st);
-      if (op.code == PNVO_OP_GN_BWD_FUSED) return gn_bwd_fused_launch(a, i[0], st);
+      if (code == PNVO_OP_GN_BWD_REDUCE) return gn_bwd_reduce_launch(a, i[0], st);
+      if (code == PNVO_OP_GN_BWD_FUSED) return gn_bwd_fused_launch(a, i[0], st);
       return gn_bwd_apply_launch(a, i[0], st);
     }
     case PNVO_OP_GN_PARAM_GRAD:
@@ -247,7 +250,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       return avgpool2_launch(static_cast<const float*>(p[0]), i[0], i[1], i[2], i[3], f[0], static_cast<__half*>(p[1]),
                              i[4], i[5], st, static_cast<__half*>(p[2]), static_cast<float*>(p[3]), i[6]);
     default:
-      set_error("run_ops: unknown opcode %d", op.code);
+      set_error("run_ops: unknown opcode %d", code);
       return -3;
   }
 }
@@ -327,12 +330,48 @@ extern "C" int pnvo_graph_capture(const pnvo_op* ops, int n_ops, void** handle_o
   }
   const int64_t before = g_launches.load();
   int rc = 0;
-  for (int k = 0; k < n_ops && rc == 0; ++k) rc = run_op(ops[k], s);
+  // side lane: a forked branch of the graph.  Every side op depends on all main-lane ops issued before it and on the
+  // previous side op; the main lane picks the branch up again at PNVO_OP_JOIN / the end of the program.
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_open = false;
+  auto join = [&]() {
+    if (!side_open) return;
+    cudaEventRecord(ev_join, s2);
+    cudaStreamWaitEvent(s, ev_join, 0);
+    side_open = false;
+  };
+  for (int k = 0; k < n_ops && rc == 0; ++k) {
+    const int code = ops[k].code & 0xffff;
+    if (code == PNVO_OP_JOIN) {
+      join();
+      continue;
+    }
+    if (ops[k].code & PNVO_OP_SIDE_LANE) {
+      if (!s2) {
+        cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+      }
+      cudaEventRecord(ev_fork, s);
+      cudaStreamWaitEvent(s2, ev_fork, 0);
+      side_open = true;
+      rc = run_op(ops[k], s2);
+    } else {
+      rc = run_op(ops[k], s);
+    }
+  }
+  join();
   const int n_kernels = static_cast<int>(g_launches.load() - before);
   g_launches.fetch_sub(n_kernels);  // nothing ran yet: launches are counted per replay
   cudaGraph_t graph = nullptr;
   e = cudaStreamEndCapture(s, &graph);
   cudaStreamDestroy(s);
+  if (s2) {
+    cudaStreamDestroy(s2);
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+  }
   if (rc != 0) {
     if (graph) cudaGraphDestroy(graph);
     return rc;
@@ -365,9 +404,10 @@ extern "C" int pnvo_graph_destroy(void* handle) {
 
 extern "C" int pnvo_conv_launch_info(const pnvo_op* op, int32_t* grid_x, int32_t* grid_y, int32_t* smem_bytes,
                                      int32_t* tmem_cols, int32_t* stages) {
-  PNVO_REQUIRE(op && (op->code == PNVO_OP_CONV || op->code == PNVO_OP_WGRAD), "conv_launch_info: not a conv op");
+  const int code = op ? (op->code & 0xffff) : 0;
+  PNVO_REQUIRE(code == PNVO_OP_CONV || code == PNVO_OP_WGRAD, "conv_launch_info: not a conv op");
   const int32_t* i = op->i;
-  if (op->code == PNVO_OP_CONV) {
+  if (code == PNVO_OP_CONV) {
     ConvArgs a{};
     a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
     a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];

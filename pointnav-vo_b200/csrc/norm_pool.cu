@@ -502,6 +502,39 @@ __global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int
           if (y > best[e]) { best[e] = y; arg[e] = t; }
         }
       }
+    } else if (a.x_lo && !a.x_fp32) {
+      // value + residual planes (split-precision plans): the six loads of a window row are issued together
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int h = 2 * ph - 1 + r;
+        if (h < 0 || h >= H) continue;
+        uint4 hv[3], lv[3];
+        bool ok[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int w = 2 * pw - 1 + s;
+          ok[s] = w >= 0 && w < W;
+          hv[s] = lv[s] = make_uint4(0, 0, 0, 0);
+          if (ok[s]) {
+            const int64_t o = in_base + (static_cast<int64_t>(h) * W + w) * c8 + q;
+            hv[s] = __ldg(reinterpret_cast<const uint4*>(a.x) + o);
+            lv[s] = __ldg(reinterpret_cast<const uint4*>(a.x_lo) + o);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          if (!ok[s]) continue;
+          const __half2* h2 = reinterpret_cast<const __half2*>(&hv[s]);
+          const __half2* l2 = reinterpret_cast<const __half2*>(&lv[s]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float v = ((e & 1) ? __high2float(h2[e >> 1]) : __low2float(h2[e >> 1])) +
+                            ((e & 1) ? __high2float(l2[e >> 1]) : __low2float(l2[e >> 1]));
+            const float y = fmaxf(fmaf(v, ga[e], gb[e]), 0.f);
+            if (y > best[e]) { best[e] = y; arg[e] = r * 3 + s; }
+          }
+        }
+      }
     } else {
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
@@ -513,12 +546,6 @@ __global__ void __launch_bounds__(256) gn_pool_kernel(const GnArgs a, int H, int
           if (w < 0 || w >= W) continue;
           float v[8];
           load8(a.x, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, a.x_fp32, v);
-          if (a.x_lo) {
-            float r8[8];
-            load8(a.x_lo, in_base + (static_cast<int64_t>(h) * W + w) * c8 + q, 0, r8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += r8[e];
-          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float y = fmaxf(fmaf(v[e], ga[e], gb[e]), 0.f);

@@ -11,6 +11,7 @@ Data layout: activations NHWC fp16 (channels padded to a multiple of 8, conv out
 outputs fp16 (fp32 accumulate / GroupNorm statistics), weights [Cout][R][S][Cin] fp16.
 """
 import math
+import os
 
 import torch
 
@@ -205,6 +206,7 @@ class EncoderPlan:
         self.head = head
         self.dropout_p = float(dropout_p) if head is not None and head.get("out_dim") else 0.0
         self.fuse_gn_bwd = True
+        self.side_lane_wgrad = os.environ.get("PNVO_SIDE_LANE", "1") != "0"
         self.stem_version = 2
         self.batch_small_ops = True  # one launch for all weight packs / gradient unpacks / GN parameter gradients
         self.use_stem2 = False
@@ -562,6 +564,10 @@ class EncoderPlan:
         if not self.training:
             return
         # ---- backward ----
+        # Weight gradients only feed the gradient unpack at the end: in the captured graph they run on a side lane, under
+        # the data-gradient / GroupNorm-backward chain that follows them (their inputs -- forward activations and the dx
+        # buffers -- are written once per step)
+        W = L.side if self.side_lane_wgrad else (lambda op: op)
         ops = [L.op_zero(self.bwd_arena)]
         if self.head is not None:
             hd = self.head
@@ -579,12 +585,12 @@ class EncoderPlan:
                                               self.grads[hd["fc_w"]], self.grads[emb["table"]], B, hd["hidden"],
                                               emb["dim"], E.shape[0], self.fc.src_ld, self.fc.src_ld - emb["dim"],
                                               self.fc.cout_pad))
-            ops.append(self.fc.op_wgrad(self.feat, self.dz16, B))
+            ops.append(W(self.fc.op_wgrad(self.feat, self.dz16, B)))
             ops.append(self.fc.op_dgrad(self.dz16, self.g_feat, B))
         HWf = self.fH * self.fW
         self._gn_bwd_all(ops, gc, self.g_feat, self.feat, self.raw_c, self.dx_c, None, HWf,
                          g_scale=1.0 / (1.0 - self.dropout_p))
-        ops.append(cc.op_wgrad(x, self.dx_c, B))
+        ops.append(W(cc.op_wgrad(x, self.dx_c, B)))
         ops.append(cc.op_dgrad(self.dx_c, self.blocks[-1]["g_y"], B))
         for bi in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[bi]
@@ -599,13 +605,13 @@ class EncoderPlan:
             if blk["down"]:
                 d, gd = blk["down"]
                 self._gn_bwd_all(ops, gd, blk["dy_last"], None, blk["raw_d"], blk["dx_d"], None, d.OH * d.OW)
-                ops.append(d.op_wgrad(blk["x_in"], blk["dx_d"], B))
+                ops.append(W(d.op_wgrad(blk["x_in"], blk["dx_d"], B)))
                 ops += d.ops_dgrad(blk["dx_d"], g_x, B)
                 add = g_x
             for k in range(n - 1, -1, -1):
                 c, g = convs[k], gns[k]
                 xin = blk["x_in"] if k == 0 else blk["mid"][k - 1]
-                ops.append(c.op_wgrad(xin, blk["dx"][k], B))
+                ops.append(W(c.op_wgrad(xin, blk["dx"][k], B)))
                 if k > 0:
                     ops += c.ops_dgrad(blk["dx"][k], blk["g_mid"][k - 1], B)
                     cp, gp = convs[k - 1], gns[k - 1]
@@ -619,13 +625,15 @@ class EncoderPlan:
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
         self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
         if self.use_stem and self.stem_version >= 2 and L.load().pnvo_conv_stem_wgrad2_supported(self.inH, self.inW):
-            ops.append(L.op_wgrad_stem2(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld))
+            ops.append(W(L.op_wgrad_stem2(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld)))
         elif self.use_stem and 96 < c1.OW <= 176:
-            ops.append(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48))
+            ops.append(W(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48)))
         else:
-            ops.append(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch))
+            ops.append(W(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch)))
         if self.exact_stem:
-            ops.append(L.op_stem_dy_sums(self.dx1, self.stem_S, B, c1.OH, c1.OW))
+            ops.append(W(L.op_stem_dy_sums(self.dx1, self.stem_S, B, c1.OH, c1.OW)))
+        ops.append(L.op_join())
+        if self.exact_stem:
             ops.append(L.op_stem_exact_unpack(c1.dwp, self.stem_S, self.xp, self.grads[c1.key], c1.w_ld, c1.Cin, self.inH,
                                               self.inW))
         if self.batch_small_ops:

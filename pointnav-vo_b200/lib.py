@@ -16,6 +16,18 @@ OP_ZERO, OP_ASSEMBLE, OP_INPUT_STATS, OP_RMV_UPDATE, OP_CONV, OP_WGRAD, OP_GN_AP
 OP_GN_BWD_REDUCE, OP_GN_BWD_APPLY, OP_GN_POOL_BWD, OP_PACK_W, OP_UNPACK_DW, OP_HEAD_FWD, OP_HEAD_BWD = range(9, 16)
 OP_BIAS_RELU, OP_BIAS_RELU_BWD, OP_MSE_LOSS, OP_ADAM, OP_AVGPOOL2, OP_GN_PARAM_GRAD, OP_CAST, OP_DROPOUT, OP_CONV_STEM, OP_PACK_W_STEM, OP_WGRAD_STEM, OP_GN_BWD_FUSED, OP_RAW_STATS, OP_RAW_ASSEMBLE, OP_ACT_EMBED_FWD, OP_ACT_EMBED_BWD, OP_UPSAMPLE2, OP_GEO_INV_LOSS, OP_CONV_STEM2, OP_PACK_W_STEM2, OP_WGRAD_STEM2, OP_PACK_W_MULTI, OP_UNPACK_DW_MULTI, OP_GN_PARAM_GRAD_MULTI = range(16, 40)
 OP_STEM_EXACT_PREP, OP_STEM_EXACT_PACK, OP_STEM_DY_SUMS, OP_STEM_EXACT_UNPACK = range(40, 44)
+OP_JOIN = 44
+SIDE_LANE = 1 << 16  # include/pnvo.h: PNVO_OP_SIDE_LANE
+
+
+def side(op):
+    """Marks an op for the side lane of a captured graph: it may overlap the ops that follow until the next op_join()."""
+    op.code |= SIDE_LANE
+    return op
+
+
+def op_join():
+    return _op(OP_JOIN)
 
 
 class PnvoOp(ctypes.Structure):
