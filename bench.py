@@ -278,10 +278,12 @@ def run_b200(args):
     # dominant kernel: the stem convolution (57 % of the forward FLOPs), timed alone with CUDA events.  In split precision it
     # is two launches of conv_stem2_fwd_kernel (w_lo * x into an fp16 tensor, then w * (x, x_lo) + that tensor -> fp32):
     # `achieved` divides the ALGORITHMIC FLOPs of the convolution (one product per MAC) by the time of both launches;
-    # the tensor pipe issues three products per MAC (`issued_tflops`).
+    # the tensor pipe issues two (exact-input stem) or three products per MAC (`issued_tflops`).
     plan = trainer._plan
     pk, how = peaks()
     split = bool(plan.split)
+    exact = bool(getattr(plan, "exact_stem", False))
+    products = 2 if exact else (3 if split else 1)  # tensor-core products issued per MAC of the stem
     stem_ops = [op for op in plan.fwd_ops if op.code in (L.OP_CONV_STEM2, L.OP_CONV_STEM, L.OP_CONV)][:2 if split else 1]
     if not (getattr(plan, "use_stem2", False) or getattr(plan, "use_stem", False)):
         stem_ops = stem_ops[:1]
@@ -306,15 +308,18 @@ def run_b200(args):
     kname = "conv_stem2_fwd_kernel" if getattr(plan, "use_stem2", False) else "conv_stem_fwd_kernel"
     gflop_step = GFLOP_FWDBWD if args.model == "r18_30ch" else 8.880
     roofline = {"kernel": "%s (conv1 7x7/s2 30->32, B=%d): 57 %% of the forward FLOPs; %s" %
-                          (kname, B, "2 launches in split precision (residual-weight product, then value weights x "
-                                     "(x, x_lo))" if split else "1 launch"),
+                          (kname, B, ("2 launches: exact-input stem (raw uint8 / fp16 values held exactly in fp16, "
+                                      "normalisation folded into value + residual weights): residual-weight product, then "
+                                      "value weights + that + border bias" if exact else
+                                      "2 launches in split precision (residual-weight product, then value weights x "
+                                      "(x, x_lo))") if split else "1 launch"),
                 "bound": "tensor", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": stem_dram_bytes("split" if split else "fp16"),
+                "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": stem_dram_bytes("exact" if exact else ("split" if split else "fp16")),
                 "peak_source": how + " (burst)",
                 "algorithmic_flop": "2 * 49 taps * 30 ch * 32 cout per output pixel x B*96*171 pixels (one product per MAC)",
                 "launch_ms": round(k_ms, 4), "launch_ms_parts": k_parts, "flop_per_launch": k_flop,
-                "issued_tflops": round(achieved * (3 if split else 1), 2),
-                "issued_frac": round(achieved * (3 if split else 1) / pk["bf16_tflops"], 4),
+                "products_per_mac": products, "issued_tflops": round(achieved * products, 2),
+                "issued_frac": round(achieved * products / pk["bf16_tflops"], 4),
                 "step_tflops": round(world * B * gflop_step * 1e9 / (ms_per_step * 1e-3) / 1e12, 2),
                 "step_frac_of_sustained": round(B * gflop_step * 1e9 / (ms_per_step * 1e-3) / 1e12
                                                 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), 4)}
