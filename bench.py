@@ -64,46 +64,125 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock + throttle reasons sampled DURING the timed region.  Primary: an NVML polling thread (2 ms period, first
+    sample taken immediately, so a 100 ms timed region still yields ~50 samples); fallback: `nvidia-smi -lms 10` started
+    ahead of the warm-up (its start-up latency exceeds a short timed region) with samples filtered to the timed window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, torch_device_index):
+        import threading
+
+        self.samples = []   # (t, sm_mhz, reasons bitmask or tuple of names)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        self._smi = None
+        self._h = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "10"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[torch_device_index]) if vis and vis.split(",")[0].isdigit() else torch_device_index
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self._h = None
+        if self._h is None:
+            try:
+                self._f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(torch_device_index), f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "10"], stdout=self._f,
+                                             stderr=subprocess.DEVNULL)
+            except Exception:
+                self._smi = None
+        self.t0 = self.t1 = None
+
+    def _poll(self):
+        nv = self._nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    r = int(get_reasons(self._h))
+                    self.samples.append((time.time(), mhz, tuple(n for n, b in bits.items() if r & b)))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            else:
+                time.sleep(0.0005)
+
+    def begin(self):
+        """Call right before the timed region starts."""
+        self.t0 = time.time()
+        self._active.set()
+
+    def end(self):
+        """Call right after the timed region ended (device synchronised)."""
+        self.t1 = time.time()
+        self._active.clear()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        for r in rows:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        sm, reasons = [], set()
+        if self._h is not None:
+            for _, mhz, rs in self.samples:
+                sm.append(mhz)
+                reasons.update(rs)
+        elif self._smi is None:
+            out["source"] = "unavailable"
+        else:
+            import datetime
+
+            out["source"] = "nvidia-smi"
+            self._smi.terminate()
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
+                self._smi.wait(timeout=5)
             except Exception:
-                continue
+                self._smi.kill()
+            self._f.flush()
+            rows = [[c.strip() for c in r.split(",")] for r in open(self._f.name).read().strip().splitlines() if r.strip()]
+            os.unlink(self._f.name)
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for n, v in zip(names, r[5:9]):
-                if "Active" in v and "Not" not in v:
-                    reasons.add(n)
+            parsed = []
+            for r in rows:
+                try:
+                    t = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    parsed.append((t, float(r[1]), float(r[2]),
+                                   tuple(n for n, v in zip(names, r[3:7]) if "Active" in v and "Not" not in v)))
+                except Exception:
+                    continue
+            inside = [q for q in parsed if self.t0 is not None and self.t0 - 0.005 <= q[0] <= (self.t1 or q[0]) + 0.005]
+            if not inside and parsed and self.t0 is not None:
+                # none landed inside a short timed region: take the samples nearest to it (warm-up runs the same kernels)
+                inside = sorted(parsed, key=lambda q: abs(q[0] - self.t0))[:3]
+                out["note"] = "no nvidia-smi sample inside the timed region; nearest samples under the same load used"
+            for _, mhz, mx, rs in inside:
+                sm.append(mhz)
+                reasons.update(rs)
+                out["sm_max_mhz"] = max(out["sm_max_mhz"] or 0.0, mx)
         if sm:
             out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(max(mx))
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
         return out
@@ -255,11 +334,15 @@ def run_b200(args):
         return ms
 
     pf = obs if prefetch else None
+    sampler = ClockSampler(local) if rank == 0 else None   # created ahead of the warm-up; samples only between begin()/end()
     for _ in range(args.warmup):
         trainer.step(obs, d_tgt, prefetch=pf)
-    sampler = ClockSampler(local) if rank == 0 else None
     n0 = L.launch_count()
+    if sampler:
+        sampler.begin()
     ms = timed(lambda: trainer.step(obs, d_tgt, prefetch=pf), args.steps)
+    if sampler:
+        sampler.end()
     launches = L.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     loss_val = float(trainer._loss[0].item())
@@ -270,6 +353,17 @@ def run_b200(args):
     t_e2e = timed(e2e_steps, args.steps, whole=True)
     e2e_value = world * B / (t_e2e / args.steps * 1e-3)
     h2d = pipe.bytes_per_batch
+    # the gradient exchange + Adam alone (everything between the backward program and the next step), all ranks in lock step
+    exch = None
+    if world > 1:
+        reps = 20
+        t_x = timed(lambda: trainer._exchange_and_update(trainer._plan), reps)
+        peer = getattr(trainer, "_peer", None)
+        exch = {"kind": ("peer-memory kernel: reduce-scatter over NVLink + Adam on the owned slice + all-gather of the "
+                         "updated parameters (csrc/peer_reduce.cu)" if peer is not None else
+                         "NCCL all-reduce of the flat fp32 bucket + adam_kernel"),
+                "us": round(t_x / reps * 1e3, 1), "bucket_bytes": int(trainer._plan.grad_flat.numel() * 4),
+                "timed_out": bool(peer.timed_out()) if peer is not None else False}
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -351,6 +445,8 @@ def run_b200(args):
                    "path": f"pinned uint8 rgb + {dname} depth -> H2D (double-buffered side stream) -> top-down + "
                            "discretise + normalise on device -> train step -> loss D2H (async, read one step later)"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val}
+    if exch:
+        out["grad_exchange"] = exch
     if cpu:
         out["cpu_baseline"] = cpu
     if extra:

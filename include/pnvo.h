@@ -194,6 +194,40 @@ int pnvo_conv_stem_wgrad2_supported(int IH, int IW);
 /* 1 when PNVO_OP_GN_BWD_FUSED can take a [HW, C] fp16 sample (else use GN_BWD_REDUCE + GN_BWD_APPLY). */
 int pnvo_gn_bwd_fused_supported(int C, int HW, int x_fp32);
 
+/* ---------------------------------------------------------------------------------------------
+ * e  multi-GPU (one process per GPU on one NVLink / NVSwitch node): the data-parallel gradient exchange fused with the
+ *    optimiser step over peer memory.  Replaces, for the flat parameter / gradient buckets of the VO and PPO trainers,
+ *    DistributedDataParallel's bucketed all-reduce + torch.optim.Adam.step()
+ *    (pointnav_vo/rl/ddppo/algo/ddppo.py:55-96; optimiser: vo/engine/vo_cnn_regression_geo_invariance_engine.py:122-133,
+ *    rl/ppo/ppo.py:53-58).
+ * pnvo_peer_alloc: the one place the library allocates: a zero-filled cudaMalloc region that other processes can map,
+ *   and its 64-byte CUDA IPC handle (exchanged by the caller, e.g. with torch.distributed.all_gather).
+ * pnvo_peer_open / pnvo_peer_close: map / unmap a peer's region in this process (enables peer access lazily).
+ * pnvo_peer_reduce_adam: ONE kernel per rank and step.  grads / params / flags are HOST arrays of `world` device
+ *   pointers (entry `rank` = this rank's own buffers, the others = mapped peer regions).  Rank r reduces slice r of the
+ *   gradient buckets of all ranks in rank order (loads over NVLink), applies torch.optim.Adam (weight_decay 0) to its
+ *   slice of m / v / params and stores the new parameters into every rank's parameter bucket (stores over NVLink).
+ *   n: bucket length in floats (multiple of 4; buckets 16-byte aligned); flags: >= 128 zero-initialised bytes per rank;
+ *   seq: 1, 2, 3, ... (the same on every rank per call; sequence flags are never reset); step: Adam's t.
+ *   On return of the KERNEL every rank's parameters are updated and every rank's gradient bucket may be overwritten.
+ *   A peer that does not arrive within ~4 s sets flags[rank][17] != 0 instead of hanging the device.
+ */
+int pnvo_peer_alloc(int64_t bytes, void** ptr_out, void* handle64_out);
+int pnvo_peer_open(const void* handle64, void** ptr_out);
+int pnvo_peer_close(void* ptr);
+int pnvo_peer_free(void* ptr);
+int pnvo_peer_reduce_adam(const void* const* grads, void* const* params, void* const* flags, float* m, float* v,
+                          int64_t n, int rank, int world, uint32_t seq, float lr, float beta1, float beta2, float eps,
+                          int step, void* stream);
+
+/* All-reduce (sum, fixed rank order) of a small fp64 vector through peer memory -- the packed RunningMeanAndVar batch
+ * statistics (pointnav_vo/model_utils/running_mean_and_var.py:28-38: three distrib.all_reduce calls there).
+ * slots / flags: HOST arrays of `world` device pointers; every rank provides a zero-initialised exchange area of
+ * world * 2 * 1024 doubles and a flag block of >= 128 bytes (peer-mapped for the other ranks).  data: n <= 1024 doubles on
+ * this rank, replaced by the sum over ranks.  seq: 1, 2, 3, ... per call, equal on every rank. */
+int pnvo_peer_sum_f64(void* const* slots, void* const* flags, double* data, int n, int rank, int world, uint32_t seq,
+                      void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t pnvo_launch_count(void);
 

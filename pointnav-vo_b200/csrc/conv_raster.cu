@@ -56,17 +56,25 @@ __device__ __forceinline__ void raster_group_sums(const float* v, float* acc) {
 static constexpr int kNG = 3;  // epilogue groups == accumulator buffers (4 would cap the kernel at 96 registers -> spills)
 static constexpr int kRasterThreads = kNG * 128 + 64;
 
-// SPLIT: split-fp16 forward (ConvArgs::x_lo / w_lo): the residual planes of the weights are resident next to the
-// value planes, every unit stages two rasters (x, x_lo: two TMA boxes), each tap issues x*w + x_lo*w + x*w_lo into the
-// same fp32 accumulator, and the raw conv output is stored in fp32.
-template <int C, int N, bool SPLIT>
+// SPLIT != 0: split-fp16 forward (ConvArgs::x_lo / w_lo): the residual planes of the weights are resident next to the
+// value planes, every unit stages two rasters (x, x_lo: two TMA boxes), and the raw conv output is stored in fp32 or as
+// value + residual fp16 planes.
+//   SPLIT == 1: each tap issues x*w + x_lo*w + x*w_lo into the same fp32 accumulator (three N-wide MMAs per K step).
+//   SPLIT == 2: the value and residual taps are interleaved in shared memory ([tap][w | w_lo][N][C]), so ONE MMA of width
+//     2N computes x*[w | w_lo] (columns 0..N-1: x*w, columns N..2N-1: x*w_lo) and a second N-wide MMA adds x_lo*w to
+//     columns 0..N-1; the epilogue adds the two column halves.  A 128 x n x 16 MMA costs max(n/2, 32 + n/4) clocks
+//     (profiles/r01_mma_rate_microbench.txt), so a K step costs 48 + 40 instead of 3 x 40 clocks for N = 32 and
+//     64 + 48 instead of 3 x 48 for N = 64.
+template <int C, int N, int SPLIT>
 __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const RasterArgs p, const __grid_constant__ ConvTmaps tm) {
   constexpr int kPix = C * 2;             // bytes per pixel = operand row bytes
   constexpr int kWTap = N * kPix;         // bytes of one weight tap [N][C]
   constexpr int kWBytes = 9 * kWTap;
   constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kKSteps = C / 16;
-  constexpr int kTmemCols = kNG * N <= 128 ? 128 : (kNG * N <= 256 ? 256 : 512);
+  constexpr int kAccN = SPLIT == 2 ? 2 * N : N;  // accumulator columns per tile
+  constexpr int kTmemCols = kNG * kAccN <= 128 ? 128 : (kNG * kAccN <= 256 ? 256 : 512);
+  constexpr int kTapStride = SPLIT == 2 ? 2 * kWTap : kWTap;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_wfull;
   __shared__ __align__(8) uint64_t s_infull[2];
@@ -109,11 +117,12 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
       tma_prefetch_desc(&tm.b);
       const uint32_t wbar = smem_u32(&s_wfull);
       mbar_arrive_expect_tx(wbar, kPlanes * kWBytes);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * kWTap, &tm.b, wbar, tap * C, 0);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * kTapStride, &tm.b, wbar, tap * C, 0);
       if (SPLIT) {
         tma_prefetch_desc(&tm.a_lo);
         tma_prefetch_desc(&tm.b_lo);
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + kWBytes + tap * kWTap, &tm.b_lo, wbar, tap * C, 0);
+        const uint32_t lo_base = SPLIT == 2 ? sW + kWTap : sW + kWBytes;
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(lo_base + tap * kTapStride, &tm.b_lo, wbar, tap * C, 0);
       }
       const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * kPix * kPlanes;
       int i = 0;
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(128, N, 0, 0);
+      const uint32_t idesc2 = umma_idesc_f16(128, 2 * N, 0, 0);  // SPLIT == 2: x * [w | w_lo]
       // descriptors as (lo, hi): hi (SBO = 8 rows, version, swizzle mode) is shared by A and B; lo = (addr >> 4) | LBO.
       // Per-tap low-word deltas are loop invariant, so the inner loop is one add per operand + the MMA.
       const uint64_t d0 = umma_desc(0, 16, 8 * kPix, kPix);
@@ -154,15 +164,20 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
             mbar_wait(smem_u32(&s_accempty[ab]), ((tc / kNG) & 1) ^ 1);
             tc_fence_after();
           }
-          const uint32_t d_tmem = tmem_base + ab * N;
+          const uint32_t d_tmem = tmem_base + ab * kAccN;
           const uint32_t a_lo = in_lo + static_cast<uint32_t>((128 * j * kPix) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
             for (int k = 0; k < kKSteps; ++k) {
-              const uint32_t ax = a_lo + tap_a[tap] + 2 * k, bw = b_lo0 + ((tap * kWTap) >> 4) + 2 * k;
+              const uint32_t ax = a_lo + tap_a[tap] + 2 * k, bw = b_lo0 + ((tap * kTapStride) >> 4) + 2 * k;
+              if (SPLIT == 2) {
+                tc_mma_f16_lohi(d_tmem, ax, bw, hi, idesc2, (tap | k) != 0 ? 1u : 0u);       // x * [w | w_lo]
+                tc_mma_f16_lohi(d_tmem, ax + (p.in_bytes >> 4), bw, hi, idesc, 1u);           // x_lo * w
+                continue;
+              }
               tc_mma_f16_lohi(d_tmem, ax, bw, hi, idesc, (tap | k) != 0 ? 1u : 0u);
-              if (SPLIT) {
+              if (SPLIT == 1) {
                 tc_mma_f16_lohi(d_tmem, ax + (p.in_bytes >> 4), bw, hi, idesc, 1u);  // x_lo * w
                 tc_mma_f16_lohi(d_tmem, ax, bw + (kWBytes >> 4), hi, idesc, 1u);     // x * w_lo
               }
@@ -209,8 +224,16 @@ __global__ void __launch_bounds__(kRasterThreads) conv_raster_kernel(const Raste
 #pragma unroll
         for (int ch = 0; ch < N / 32; ++ch) {
           float v[32];
-          tmem_ld32(tmem_base + t_lane + ab * N + ch * 32, v);
-          tmem_ld_wait();
+          tmem_ld32(tmem_base + t_lane + ab * kAccN + ch * 32, v);
+          if (SPLIT == 2) {
+            float v2[32];
+            tmem_ld32(tmem_base + t_lane + ab * kAccN + N + ch * 32, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += v2[e];
+          } else {
+            tmem_ld_wait();
+          }
           if (ch == N / 32 - 1) {
             // accumulator buffer drained: hand it back to the MMA issuer before the (slow) global stores
             tc_fence_before();
@@ -350,7 +373,7 @@ int conv_raster_supported(const ConvArgs& a) {
   return raster_plan(a, r, smem) ? 1 : 0;
 }
 
-template <int C, int N, bool SPLIT>
+template <int C, int N, int SPLIT>
 static int raster_launch_t(const RasterArgs& r, const ConvTmaps& tm, int smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
@@ -375,13 +398,16 @@ int conv_raster_launch(const ConvArgs& a, cudaStream_t st) {
   if (a.x_lo) {
     if (tmap_tiled4d(&tm.a_lo, a.x_lo, a.B, a.IH, a.IW, a.Cin, r.P, a.Cin * 2 == 128 ? 128 : 64, r.rows_in)) return -1;
     if (tmap_tiled2d(&tm.b_lo, a.w_lo, a.n_total, a.w_ld, a.w_ld, a.n_total, a.Cin)) return -1;
-    if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32, true>(r, tm, smem, st);
-    return raster_launch_t<32, 64, true>(r, tm, smem, st);
+    // PNVO_RASTER_CONCAT=0 selects the three-MMA form (A/B measurements)
+    static const bool concat = !(getenv("PNVO_RASTER_CONCAT") && atoi(getenv("PNVO_RASTER_CONCAT")) == 0);
+    if (a.Cin == 32 && a.n_total == 32)
+      return concat ? raster_launch_t<32, 32, 2>(r, tm, smem, st) : raster_launch_t<32, 32, 1>(r, tm, smem, st);
+    return concat ? raster_launch_t<32, 64, 2>(r, tm, smem, st) : raster_launch_t<32, 64, 1>(r, tm, smem, st);
   }
-  if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32, false>(r, tm, smem, st);
-  if (a.Cin == 32 && a.n_total == 64) return raster_launch_t<32, 64, false>(r, tm, smem, st);
-  if (a.Cin == 64 && a.n_total == 32) return raster_launch_t<64, 32, false>(r, tm, smem, st);
-  return raster_launch_t<64, 64, false>(r, tm, smem, st);
+  if (a.Cin == 32 && a.n_total == 32) return raster_launch_t<32, 32, 0>(r, tm, smem, st);
+  if (a.Cin == 32 && a.n_total == 64) return raster_launch_t<32, 64, 0>(r, tm, smem, st);
+  if (a.Cin == 64 && a.n_total == 32) return raster_launch_t<64, 32, 0>(r, tm, smem, st);
+  return raster_launch_t<64, 64, 0>(r, tm, smem, st);
 }
 
 }  // namespace pnvo

@@ -32,6 +32,8 @@ struct Raster128Args {
   int units_per_img, n_units;
   int in_bytes;   // shared-memory bytes of ONE channel-half raster (multiple of 1024)
   int w_stages;
+  int acc_bufs;   // 2 when two sets of n_tiles accumulators fit the 512 TMEM columns: the epilogue of unit i then overlaps
+                  // the MMAs of unit i+1 (the input raster stays single-buffered; the next unit's boxes are prefetched to L2)
 };
 
 static constexpr int kR128Threads = 12 * 32 + 64;
@@ -78,9 +80,10 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
                                                                        const __grid_constant__ ConvTmaps tm) {
   using Md = R128Mode<MODE>;
   constexpr int kWStage = N * 128;                 // one weight stage: [N][64 channels] fp16
-  constexpr int kTmemCols = 3 * N <= 256 ? 256 : 512;
+  constexpr int kTmemCols = 512;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_infull, s_inempty, s_accfull, s_accempty;
+  __shared__ __align__(8) uint64_t s_infull, s_inempty;
+  __shared__ __align__(8) uint64_t s_accfull[2], s_accempty[2];
   __shared__ __align__(8) uint64_t s_wfull[8];
   __shared__ __align__(8) uint64_t s_wempty[8];
   __shared__ uint32_t s_tmem;
@@ -93,8 +96,10 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
   if (tid == 0) {
     mbar_init(smem_u32(&s_infull), 1);
     mbar_init(smem_u32(&s_inempty), 1);
-    mbar_init(smem_u32(&s_accfull), 1);
-    mbar_init(smem_u32(&s_accempty), 12);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_accfull[s]), 1);
+      mbar_init(smem_u32(&s_accempty[s]), 12);
+    }
     for (int s = 0; s < 8; ++s) {
       mbar_init(smem_u32(&s_wfull[s]), 1);
       mbar_init(smem_u32(&s_wempty[s]), 1);
@@ -110,6 +115,8 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
   const int n_tiles = p.n_tiles;
+  const int acc_bufs = p.acc_bufs;
+  const int acc_stride = n_tiles * N;  // TMEM columns of one accumulator set
 
   if (warp == 13) {
     // ================================ TMA producer ================================
@@ -140,6 +147,19 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
           tma_load_4d(sIn + 2 * p.in_bytes, &tm.a_lo, bar, 0, -1, h0 - 1, b);
           tma_load_4d(sIn + 3 * p.in_bytes, &tm.a_lo, bar, 64, -1, h0 - 1, b);
         }
+        {
+          // the raster is single-buffered (shared memory holds the weight ring instead): pull the NEXT unit's boxes into L2
+          // now, so that the load issued once this unit's MMAs have drained the raster is not a DRAM round trip
+          const int un = u + gridDim.x;
+          if (un < p.n_units) {
+            const int bn = un / p.units_per_img;
+            const int hn = (un - bn * p.units_per_img) * p.T;
+            tma_prefetch_4d(&tm.a, 0, -1, hn - 1, bn);
+            if (MODE != 1) tma_prefetch_4d(&tm.a, 64, -1, hn - 1, bn);
+            if (MODE != 0) tma_prefetch_4d(&tm.a_lo, 0, -1, hn - 1, bn);
+            if (MODE == 2) tma_prefetch_4d(&tm.a_lo, 64, -1, hn - 1, bn);
+          }
+        }
         for (int st = 0; st < Md::kStages; ++st, ++wctr) {
           const int s = wctr % ws;
           if (wctr >= ws) mbar_wait(smem_u32(&s_wempty[s]), ((wctr / ws) & 1) ^ 1);
@@ -159,9 +179,12 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
       const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
       int i = 0, wctr = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        const int ab = acc_bufs == 2 ? (i & 1) : 0;
+        const int use = acc_bufs == 2 ? (i >> 1) : i;  // how often accumulator set `ab` has been used before
         mbar_wait(smem_u32(&s_infull), i & 1);
-        if (i >= 1) mbar_wait(smem_u32(&s_accempty), (i - 1) & 1);
+        if (use >= 1) mbar_wait(smem_u32(&s_accempty[ab]), (use - 1) & 1);
         tc_fence_after();
+        const uint32_t acc0 = tmem_base + ab * acc_stride;
 #pragma unroll 1
         for (int st = 0; st < Md::kStages; ++st, ++wctr) {
           const int s = wctr % ws;
@@ -175,7 +198,7 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
           for (int t = 0; t < n_tiles; ++t) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_f16_lohi(tmem_base + t * N, a_lo + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc,
+              tc_mma_f16_lohi(acc0 + t * N, a_lo + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc,
                               (st | k) != 0 ? 1u : 0u);
           }
           if (Md::kSplit && pb >= 0) {  // the residual raster against the same (value) weight stage
@@ -183,12 +206,12 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
             for (int t = 0; t < n_tiles; ++t) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                tc_mma_f16_lohi(tmem_base + t * N, a2 + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc, 1u);
+                tc_mma_f16_lohi(acc0 + t * N, a2 + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc, 1u);
             }
           }
           tc_commit(smem_u32(&s_wempty[s]));
         }
-        tc_commit(smem_u32(&s_accfull));
+        tc_commit(smem_u32(&s_accfull[ab]));
         tc_commit(smem_u32(&s_inempty));
       }
     }
@@ -207,7 +230,9 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
       float acc[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-      mbar_wait(smem_u32(&s_accfull), i & 1);
+      const int ab = acc_bufs == 2 ? (i & 1) : 0;
+      const int use = acc_bufs == 2 ? (i >> 1) : i;
+      mbar_wait(smem_u32(&s_accfull[ab]), use & 1);
       tc_fence_after();
       if (grp < n_tiles) {
         const int m = 128 * grp + row;
@@ -219,7 +244,7 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
 #pragma unroll
         for (int ch = 0; ch < N / 32; ++ch) {
           float v[32];
-          tmem_ld32(tmem_base + t_lane + grp * N + ch * 32, v);
+          tmem_ld32(tmem_base + t_lane + ab * acc_stride + grp * N + ch * 32, v);
           tmem_ld_wait();
           if (!Md::kSplit && p.add && valid) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.add + gofs + ch * 32);
@@ -279,7 +304,7 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
       // accumulators drained (or not used by this group): hand them back to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_accempty));
+      if (lane == 0) mbar_arrive(smem_u32(&s_accempty[ab]));
       if (p.stats && grp < n_tiles) {
         int off = 16;
 #pragma unroll
@@ -347,6 +372,7 @@ static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes,
       best = eff;
       r.P = P; r.T = T; r.n_tiles = n_tiles; r.rows_in = rows_in; r.units_per_img = upi; r.n_units = n_units;
       r.in_bytes = in_bytes; r.w_stages = stages;
+      r.acc_bufs = 2 * n_tiles * a.n_total <= 512 ? 2 : 1;
       smem_bytes = planes * in_bytes + stages * w_stage + 1024;
     }
   }

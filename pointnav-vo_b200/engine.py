@@ -176,7 +176,7 @@ class EncoderPlan:
 
     def __init__(self, *, params, buffers, B, H, W, in_channels, sources, backbone, baseplanes, ngroups,
                  compression_channels, prefix, head=None, training=True, avgpool_input=False, device="cuda",
-                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False, exact_stem=False):
+                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False, exact_stem=False, grad_bucket=None):
         """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
         head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim).
@@ -185,6 +185,7 @@ class EncoderPlan:
         ~22 mantissa bits, so outputs agree with the fp32 reference to ~1e-5 instead of ~5e-3 (3 MMAs per product; the
         stem / raster / implicit-GEMM kernels all have a split variant).  The backward pass of a split plan reads the
         value planes only (single-pass fp16 operands, fp32 accumulation), also of the raw conv outputs (GroupNorm backward)."""
+        self._grad_bucket_arg = grad_bucket
         self.split = bool(split)
         if self.split:
             raw_fp32 = False  # raw conv outputs are value + residual fp16 planes: same bytes, and backward reads one plane
@@ -419,7 +420,16 @@ class EncoderPlan:
             # flat gradient bucket: one fp32 buffer, per-parameter views (the DDP all-reduce payload)
             names = self.param_names()
             n = sum(self.P[k].numel() for k in names)
-            self.grad_flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            grad_bucket = self._grad_bucket_arg
+            if grad_bucket is not None:
+                # caller-provided storage (parallel_utils.PeerBuckets: a peer-mapped region, so that the other ranks' fused
+                # reduce-scatter + Adam kernels can read this rank's gradients in place)
+                if grad_bucket.numel() < n or grad_bucket.dtype != torch.float32 or not grad_bucket.is_cuda:
+                    raise L.PnvoError(f"grad_bucket must be an fp32 CUDA tensor of at least {n} elements")
+                self.grad_flat = grad_bucket[:n]
+                self.grad_flat.zero_()
+            else:
+                self.grad_flat = torch.zeros(n, dtype=torch.float32, device=dev)
             off = 0
             for k in names:
                 m = self.P[k].numel()

@@ -77,7 +77,8 @@ EXPORTS = ["pnvo_last_error", "pnvo_abi_version", "pnvo_check_device", "pnvo_dis
            "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops", "pnvo_conv_launch_info",
            "pnvo_launch_count", "pnvo_stem_padded_width", "pnvo_gn_bwd_fused_supported", "pnvo_topdown_project_strided", "pnvo_topdown_project_strided_f16",
            "pnvo_conv_stem2_supported", "pnvo_conv_stem_wgrad2_supported", "pnvo_graph_capture", "pnvo_graph_launch",
-           "pnvo_graph_destroy", "pnvo_ppo_loss"]
+           "pnvo_graph_destroy", "pnvo_ppo_loss", "pnvo_peer_alloc", "pnvo_peer_open", "pnvo_peer_close", "pnvo_peer_free",
+           "pnvo_peer_reduce_adam", "pnvo_peer_sum_f64"]
 
 
 def load():
@@ -122,6 +123,16 @@ def load():
     lib.pnvo_conv_launch_info.argtypes = [ctypes.POINTER(PnvoOp)] + [ctypes.POINTER(ctypes.c_int32)] * 5
     for n in ("pnvo_discretize_depth", "pnvo_topdown_project", "pnvo_gae_scan", "pnvo_goal_update", "pnvo_run_ops",
               "pnvo_conv_launch_info"):
+        getattr(lib, n).restype = i32
+    lib.pnvo_peer_alloc.argtypes = [i64, ctypes.POINTER(ctypes.c_void_p), vp]
+    lib.pnvo_peer_open.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p)]
+    lib.pnvo_peer_close.argtypes = [vp]
+    lib.pnvo_peer_free.argtypes = [vp]
+    lib.pnvo_peer_reduce_adam.argtypes = [ctypes.POINTER(ctypes.c_void_p)] * 3 + [vp, vp, i64, i32, i32, ctypes.c_uint32,
+                                          f32, f32, f32, f32, i32, vp]
+    lib.pnvo_peer_sum_f64.argtypes = [ctypes.POINTER(ctypes.c_void_p)] * 2 + [vp, i32, i32, i32, ctypes.c_uint32, vp]
+    for n in ("pnvo_peer_alloc", "pnvo_peer_open", "pnvo_peer_close", "pnvo_peer_free", "pnvo_peer_reduce_adam",
+              "pnvo_peer_sum_f64"):
         getattr(lib, n).restype = i32
     _lib = lib
     return lib

@@ -60,11 +60,21 @@ def load_vo_checkpoint(ckpt, vo_models, map_location="cpu", strict=True):
 
 
 def save_vo_checkpoint(path, vo_models, optimizers=None, epoch=0, config=None):
-    """Writes the joint format of vo_cnn_regression_geo_invariance_engine.py:1425-1447 (readable by the reference)."""
+    """Writes the joint format of vo_cnn_regression_geo_invariance_engine.py:1425-1447 (readable by the reference),
+    including its four RNG states.  `optimizers`: torch optimisers or `FusedVOTrainStep`s -- the latter's state_dict()
+    is in torch.optim.Adam's format (moments sliced from the flat buckets), so either side can resume the other's run.
+    Files are read back with torch.load(weights_only=False), as the reference does: load trusted checkpoints only."""
+    import random
+
+    import numpy as np
+
     state = {"epoch": epoch, "config": config,
              "model_states": {ACT_NAME2IDX[k]: m.state_dict() for k, m in vo_models.items()},
              "optim_states": {ACT_NAME2IDX[k]: o.state_dict() for k, o in (optimizers or {}).items()},
-             "torch_rnd_state": torch.get_rng_state()}
+             "rnd_state": random.getstate(),
+             "np_rnd_state": np.random.get_state(),
+             "torch_rnd_state": torch.get_rng_state(),
+             "torch_cuda_rnd_state": torch.cuda.get_rng_state_all() if torch.cuda.is_available() else []}
     torch.save(state, path)
     return state
 

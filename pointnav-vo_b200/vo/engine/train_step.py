@@ -13,6 +13,8 @@ holds a replica, the flat gradient bucket is summed with ONE all-reduce and scal
 loss-gradient kernel, which equals the single-GPU gradient of the mean loss over the concatenated batch
 when every rank has the same batch size.
 """
+import os
+
 import torch
 
 from ... import lib as L
@@ -87,6 +89,7 @@ class FusedVOTrainStep:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.step_count = 0
+        self.use_peer_exchange = os.environ.get("PNVO_PEER_ADAM", "1") != "0"   # read when the flat buckets are created
         self._flat = None
         self._plan = None
         # double-buffered input staging (step(..., prefetch=next_obs)): side stream, per-buffer events
@@ -99,12 +102,32 @@ class FusedVOTrainStep:
     # optimiser and the all-reduce each touch a single contiguous range
     def _flatten(self, plan):
         names = plan.param_names()
+        self._names = list(names)
         P = dict(self.model.named_parameters())
         missing = set(P) - set(names)
         assert not missing, f"parameters without a gradient slot: {sorted(missing)}"
         n = sum(P[k].numel() for k in names)
         dev = plan.dev
-        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self._peer = None
+        if 2 <= self.world <= 8 and self.use_peer_exchange \
+                and torch.distributed.get_backend(self.group) == "nccl":
+            # gradient exchange fused with Adam over NVLink peer memory (csrc/peer_reduce.cu): parameters and gradients live
+            # in a peer-mapped region; the NCCL all-reduce + adam_kernel pair stays as the path for other world sizes
+            from ...parallel_utils import PeerBuckets
+
+            try:
+                self._peer = PeerBuckets(n, dev, self.group)
+            except L.PnvoError as e:
+                import warnings
+
+                warnings.warn(f"peer-memory gradient exchange unavailable ({e}); using the NCCL all-reduce")
+        if self._peer is not None:
+            flat = self._peer.params[:n]
+            self.model._grad_bucket = self._peer.grads
+            n_state = self._peer.n_pad
+        else:
+            flat = torch.empty(n, dtype=torch.float32, device=dev)
+            n_state = n
         off = 0
         for k in names:
             m = P[k].numel()
@@ -112,11 +135,79 @@ class FusedVOTrainStep:
             P[k].data = flat[off:off + m].view(P[k].shape)
             off += m
         self._flat = flat
-        self._m = torch.zeros_like(flat)
-        self._v = torch.zeros_like(flat)
+        self._m = torch.zeros(n_state, dtype=torch.float32, device=dev)
+        self._v = torch.zeros(n_state, dtype=torch.float32, device=dev)
         self._loss = torch.zeros(3, dtype=torch.float32, device=dev)  # [total, inversion rot, inversion pos]
         if self.world > 1:  # replicas start from rank 0's weights (as DDP does, ddppo.py:55-58)
             torch.distributed.broadcast(flat, 0, group=self.group)
+
+    # ---- optimiser state in torch.optim.Adam's format (the reference checkpoints `optim_states`,
+    # vo_cnn_regression_geo_invariance_engine.py:1425-1434): a run trained on the fused path resumes with its moments and
+    # bias-correction step, and the file loads into a plain torch.optim.Adam over model.parameters() as well
+    def _full_moments(self):
+        m, v = self._m, self._v
+        if getattr(self, "_peer", None) is not None:
+            # every rank holds the moments of its own slice only (zeros elsewhere): a sum gives the whole vectors
+            m, v = m.clone(), v.clone()
+            torch.distributed.all_reduce(m, group=self.group)
+            torch.distributed.all_reduce(v, group=self.group)
+        return m, v
+
+    def state_dict(self):
+        if self._flat is None:
+            raise L.PnvoError("state_dict() before the first step: there is no optimiser state yet")
+        m, v = self._full_moments()
+        order = [k for k, _ in self.model.named_parameters()]
+        state, off = {}, 0
+        sizes = dict(self.model.named_parameters())
+        spans = {}
+        for k in self._names:
+            n = sizes[k].numel()
+            spans[k] = (off, off + n)
+            off += n
+        for i, k in enumerate(order):
+            lo, hi = spans[k]
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": m[lo:hi].view(sizes[k].shape).clone(),
+                        "exp_avg_sq": v[lo:hi].view(sizes[k].shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(order)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd, example_obs=None):
+        """sd: state_dict() of this class or of a torch.optim.Adam over model.parameters().  The flat buckets exist after the
+        first plan is built: pass `example_obs` (a batch of the training shape) when loading before the first step."""
+        if self._flat is None:
+            if example_obs is None:
+                raise L.PnvoError("load_state_dict() before the first step needs example_obs to build the flat buckets")
+            self._get_plan(example_obs)
+        order = [k for k, _ in self.model.named_parameters()]
+        sizes = dict(self.model.named_parameters())
+        off, spans = 0, {}
+        for k in self._names:
+            spans[k] = (off, off + sizes[k].numel())
+            off += sizes[k].numel()
+        self._m.zero_()
+        self._v.zero_()
+        lo_own, hi_own = (0, self._m.numel()) if getattr(self, "_peer", None) is None else self._peer.slice_range()
+        steps = set()
+        for i, k in enumerate(order):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            lo, hi = spans[k]
+            self._m[lo:hi].copy_(st["exp_avg"].reshape(-1))
+            self._v[lo:hi].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if getattr(self, "_peer", None) is not None:  # keep the owned slice only
+            self._m[:lo_own].zero_(); self._m[hi_own:].zero_()
+            self._v[:lo_own].zero_(); self._v[hi_own:].zero_()
+        if len(steps) > 1:
+            raise L.PnvoError(f"optimizer state with differing step counts {sorted(steps)}: not a single-group Adam")
+        self.step_count = steps.pop() if steps else 0
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
 
     def _get_plan(self, obs):
         model = self.model
@@ -245,11 +336,25 @@ class FusedVOTrainStep:
         self._parity = 1 - parity if prefetch is not None else parity
         self._loss_prog_for(plan, typed, dz_regress_masks is not None).run(dev)
         plan.programs_for(parity)[1].run(dev)
-        if self.world > 1:
-            torch.distributed.all_reduce(plan.grad_flat, group=self.group)
-        self.step_count += 1
-        L.run_ops([L.op_adam(self._flat, plan.grad_flat, self._m, self._v, self._flat.numel(), self.step_count, self.lr,
-                             self.betas[0], self.betas[1], self.eps)], dev)
+        self._exchange_and_update(plan)
         # the optimiser wrote through raw pointers: tell the module its packed fp16 weights are stale
         model._packed_version = None
         return self._loss[:1]
+
+    def _exchange_and_update(self, plan):
+        """Gradient exchange between the replicas + the Adam step (everything after the backward program)."""
+        dev = plan.dev
+        self.step_count += 1
+        if os.environ.get("PNVO_DIAG_NO_EXCHANGE") == "1":   # timing diagnosis only: replicas diverge
+            L.run_ops([L.op_adam(self._flat, plan.grad_flat, self._m, self._v, self._flat.numel(), self.step_count, self.lr,
+                                 self.betas[0], self.betas[1], self.eps)], dev)
+            return
+        if self._peer is not None:
+            # ONE kernel: reduce-scatter of the gradients over NVLink + Adam on this rank's slice + all-gather of the
+            # updated parameters into every replica
+            self._peer.reduce_adam(self._m, self._v, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps)
+        else:
+            if self.world > 1:
+                torch.distributed.all_reduce(plan.grad_flat, group=self.group)
+            L.run_ops([L.op_adam(self._flat, plan.grad_flat, self._m, self._v, self._flat.numel(), self.step_count, self.lr,
+                                 self.betas[0], self.betas[1], self.eps)], dev)

@@ -21,6 +21,42 @@ from ..common.common_vars import (DEFAULT_DELTA_STATE_SIZE, DEPTH_PAIR_CHANNEL, 
 OBS_ORDER = ("rgb", "depth", "discretized_depth", "top_down_view")  # vo_cnn.py:114-166 append order
 
 
+
+_PEER_SUM = {}   # device index -> parallel_utils.PeerSmallSum, or False when peer memory is unavailable
+
+
+def _allreduce_stats(t):
+    """Packed RunningMeanAndVar batch statistics (sum, sum of squares per channel, fp64) summed over the ranks: ONE
+    exchange instead of the reference's three all-reduces (running_mean_and_var.py:28-38).  On one NVLink node it is
+    libpnvo's peer-memory kernel (parallel_utils.PeerSmallSum: a tiny CTA that co-resides with the persistent convolution
+    kernels; an NCCL kernel waiting for the slowest rank blocks their placement, 0.21 ms per step measured); otherwise
+    (gloo / other backends, PNVO_PEER_STATS=0, mapping failure) torch.distributed.all_reduce.
+    PNVO_DIAG_LOCAL_STATS=1 skips the exchange (timing diagnosis only: the replicas' running statistics diverge)."""
+    import os
+
+    if os.environ.get("PNVO_DIAG_LOCAL_STATS") == "1":
+        return
+    key = t.device.index
+    peer = _PEER_SUM.get(key)
+    if peer is None:
+        peer = False
+        if (t.is_cuda and t.dtype == torch.float64 and os.environ.get("PNVO_PEER_STATS", "1") != "0"
+                and torch.distributed.get_backend() == "nccl" and 2 <= torch.distributed.get_world_size() <= 8):
+            from ...parallel_utils import PeerSmallSum
+
+            try:
+                peer = PeerSmallSum(t.device)
+            except L.PnvoError as e:
+                import warnings
+
+                warnings.warn(f"peer-memory statistics exchange unavailable ({e}); using the NCCL all-reduce")
+        _PEER_SUM[key] = peer
+    if peer:
+        peer.sum_(t)
+    else:
+        torch.distributed.all_reduce(t)
+
+
 class Flatten(nn.Module):
     def forward(self, x):
         return x.contiguous().view(x.size(0), -1)
@@ -231,7 +267,8 @@ class VisualOdometryCNNBase(nn.Module):
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0],
                                prefix="visual_encoder", head=head, training=bool(need_grad), device=first.device,
-                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop, split=split, exact_stem=exact)
+                               world_size=world, raw_fp32=self.raw_fp32, dropout_p=drop, split=split, exact_stem=exact,
+                               grad_bucket=getattr(self, "_grad_bucket", None) if need_grad else None)
             self._plans[key] = plan
         return plan
 
@@ -293,7 +330,7 @@ class VisualOdometryCNNBase(nn.Module):
                 if plan.world_size > 1:
                     L.run_ops(ops, dev)
                     ops = []
-                    torch.distributed.all_reduce(plan.in_stats)
+                    _allreduce_stats(plan.in_stats)
             ops.append(L.op_rmv_update(plan.in_stats, rmv._mean, rmv._var, rmv._count, plan.in_scale, plan.in_shift, C,
                                        training, True, plan.B * plan.world_size, plan.H * plan.W))
             scale, shift = plan.in_scale, plan.in_shift
@@ -353,7 +390,7 @@ class VisualOdometryCNNBase(nn.Module):
                 L.run_ops(ops, dev)
                 ops = []
                 if plan.world_size > 1:
-                    torch.distributed.all_reduce(plan.in_stats)
+                    _allreduce_stats(plan.in_stats)
             ops.append(L.op_rmv_update(plan.in_stats, rmv._mean, rmv._var, rmv._count, plan.in_scale, plan.in_shift, C,
                                        training, True, plan.B * plan.world_size, plan.H * plan.W))
             scale, shift = plan.in_scale, plan.in_shift

@@ -1297,3 +1297,50 @@ def test_train_step_with_prefetched_input_pipeline():
     r1, r2 = m1.visual_encoder.running_mean_and_var, m2.visual_encoder.running_mean_and_var
     assert float(r1._count) == float(r2._count) == count0 + 8.0
     assert rel(r2._mean, r1._mean) <= 1e-6 and rel(r2._var, r1._var) <= 1e-6
+
+
+def test_fused_train_step_state_dict_resumes():
+    """The fused step's optimiser state in torch.optim.Adam's format (a run trained on the fused path must
+    resume with its moments and bias-correction step): 2 steps + save + load into a fresh trainer + 1 step == 3 steps."""
+    import copy
+
+    from pointnav_vo_b200.vo.engine.train_step import FusedVOTrainStep
+
+    case = "r18_8ch"
+    m1, space, _ = _load_vo(case)
+    obs = [helpers.vo_inputs(2, 31 + i, space, "cuda") for i in range(3)]
+    tgt = [torch.randn(2, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(i)) * 0.1 for i in range(3)]
+    m1.train()
+    t1 = FusedVOTrainStep(m1, lr=2.5e-4, eps=1e-8)
+    for i in range(2):
+        t1.step(obs[i], tgt[i])
+    sd_opt = t1.state_dict()
+    m2, _, _ = _load_vo(case)     # (a module that has run holds ctypes programs: build a fresh one instead of deepcopy)
+    m2.load_state_dict(copy.deepcopy(m1.state_dict()))
+    m2.train()
+    t2 = FusedVOTrainStep(m2, lr=1.0)      # hyper-parameters come from the file
+    t2.load_state_dict(sd_opt, example_obs=obs[2])
+    assert t2.step_count == 2 and t2.lr == 2.5e-4
+    t1.step(obs[2], tgt[2])
+    t2.step(obs[2], tgt[2])
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        d = (a - b).abs()
+        assert d.max().item() <= 2 * 2.5e-4 + 1e-7, k        # same bound as the autograd comparison: fp16-noise sign flips
+        assert (d > 1e-5).float().mean().item() <= 0.05, k
+    # the file loads into a plain torch.optim.Adam over the same parameters
+    opt = torch.optim.Adam(m1.parameters(), lr=1.0)
+    opt.load_state_dict(sd_opt)
+    assert opt.param_groups[0]["lr"] == 2.5e-4
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+def test_peer_memory_gradient_exchange_matches_nccl_world2():
+    """8e: the fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory against NCCL all-reduce + Adam."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tests", "multigpu", "peer_adam_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
