@@ -320,7 +320,16 @@ struct PnvoGraph {
 extern "C" int pnvo_graph_capture(const pnvo_op* ops, int n_ops, void** handle_out) {
   PNVO_REQUIRE(ops && n_ops > 0 && handle_out, "graph_capture: bad arguments");
   cudaStream_t s;
-  cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  // Kernel nodes inherit the priority of the stream they were captured on.  Captured programs (weight pack, forward,
+  // backward) get the GREATEST priority: when the input pipeline of the next batch runs on a side stream (default = lowest
+  // priority), free SMs go to the training step's kernels first and the input pipeline fills the SMs they leave idle
+  // (tails of the persistent kernels, small grids), instead of holding SMs the one-CTA-per-SM kernels are waiting for.
+  // PNVO_GRAPH_PRIORITY=0 captures at the default priority (A/B measurements).
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  const char* pe = getenv("PNVO_GRAPH_PRIORITY");
+  const int prio = (pe && atoi(pe) == 0) ? prio_least : prio_greatest;
+  cudaError_t e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio);
   PNVO_REQUIRE(e == cudaSuccess, "graph_capture: cudaStreamCreate: %s", cudaGetErrorString(e));
   e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) {
@@ -349,7 +358,7 @@ extern "C" int pnvo_graph_capture(const pnvo_op* ops, int n_ops, void** handle_o
     }
     if (ops[k].code & PNVO_OP_SIDE_LANE) {
       if (!s2) {
-        cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio);
         cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
       }

@@ -32,6 +32,9 @@ struct RawArgs {
   int row_w, out_pitch;
   int n_lo;             // exact-input stem: 2 extra channels C, C+1 = residuals t - fp16(t) of the two top-down values
   double* stats;        // [2C] (sum, sumsq) interleaved, accumulated
+  int exact;            // exact-input stem: the stored values are CONSTANT affine maps of the raw ones ((byte - 128) / 256
+                        // for rgb, the raw value otherwise) -- scale / shift are ignored, so the assembled tensor does not
+                        // depend on the batch statistics and the two passes can be one (raw_assemble with stats != null)
   // Geometric-invariance augmentation on the device (regression_geo_invariance_iter_dataset.py:342-420): output sample b
   // is source pair pair_map[b] >> 1, with prev / cur swapped when pair_map[b] & 1.  n_pix then counts OUTPUT pixels and
   // hw = pixels per sample; the raw tensors hold only the source pairs (no second copy over PCIe, no second top-down).
@@ -63,17 +66,137 @@ __device__ __forceinline__ int depth_bin(float d, const float* s_edges, int n) {
   return k;
 }
 
+// values per block: rgb 6 x (sum, sumsq) as uint32, depth / td 2 x (sum, sumsq) fp32, bins 2 x kRawMaxBins counts
+static constexpr int kRawVals = 12 + 4 + 4 + 2 * kRawMaxBins;
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ double warp_sum_f64(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// Per-thread accumulators of the batch statistics of the assembled (un-normalised, reference-unit) input.
+// A thread sees <= 255 pixels (launchers), so its per-bin counts fit in 8 bits: bins 0-7 / 8-15 of a frame are
+// packed into two 64-bit words and bumped with one shift-add instead of a compare chain per bin.
+struct RawAcc {
+  uint32_t ri[12];
+  float fs[8];
+  unsigned long long cb[4];  // [frame][bins 0-7 | bins 8-15]
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ri[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fs[i] = 0.f;
+    cb[0] = cb[1] = cb[2] = cb[3] = 0ull;
+  }
+  // w: the three 16-bit words of the (possibly swapped) rgb pair; d / t: depth and top-down pairs; b0 / b1: depth bins
+  __device__ __forceinline__ void add(const uint32_t* w, float2 d, float2 t, int b0, int b1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t lo = w[k] & 0xff, hi = w[k] >> 8;
+      ri[4 * k] += lo; ri[4 * k + 1] += lo * lo;
+      ri[4 * k + 2] += hi; ri[4 * k + 3] += hi * hi;
+    }
+    fs[0] += d.x; fs[1] = fmaf(d.x, d.x, fs[1]);
+    fs[2] += d.y; fs[3] = fmaf(d.y, d.y, fs[3]);
+    fs[4] += t.x; fs[5] = fmaf(t.x, t.x, fs[5]);
+    fs[6] += t.y; fs[7] = fmaf(t.y, t.y, fs[7]);
+    const unsigned long long i0 = (b0 >= 0) ? (1ull << ((b0 & 7) * 8)) : 0ull;
+    const unsigned long long i1 = (b1 >= 0) ? (1ull << ((b1 & 7) * 8)) : 0ull;
+    cb[0] += (b0 < 8) ? i0 : 0ull;
+    cb[1] += (b0 < 8) ? 0ull : i0;
+    cb[2] += (b1 < 8) ? i1 : 0ull;
+    cb[3] += (b1 < 8) ? 0ull : i1;
+  }
+  // warp reduction (integers exactly, floats in fp64), across the 8 warps through shared memory, then thread c < C gathers
+  // the (sum, sumsq) of output channel c and adds it to the global accumulator.  All 256 threads of the block must call.
+  __device__ __forceinline__ void flush(const RawArgs& a, double (*s_red)[kRawVals]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const uint32_t x = warp_sum_u32(ri[i]);
+      if (lane == 0) s_red[warp][i] = static_cast<double>(x);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double x = warp_sum_f64(static_cast<double>(fs[i]));
+      if (lane == 0) s_red[warp][12 + i] = x;
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * kRawMaxBins; ++i) {
+      const int f = i / kRawMaxBins, bin = i % kRawMaxBins;
+      const uint32_t x = warp_sum_u32(static_cast<uint32_t>((cb[2 * f + (bin >> 3)] >> ((bin & 7) * 8)) & 0xffull));
+      if (lane == 0) s_red[warp][20 + i] = static_cast<double>(x);
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c < a.C) {
+      const int cf = a.C >> 1;
+      const int f = c / cf;
+      int k = c - f * cf;
+      auto tot = [&](int i) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_red[w][i];
+        return t;
+      };
+      double s = 0.0, q = 0.0;
+      bool done = false;
+      if (a.use_rgb) {
+        if (k < 3) {
+          // rgb channel j = 3f + k lives in word j / 2, half j & 1: ri index 4*(j/2) + 2*(j&1)
+          const int j = 3 * f + k;
+          const int base = 4 * (j >> 1) + 2 * (j & 1);
+          s = tot(base) / 255.0;
+          q = tot(base + 1) / (255.0 * 255.0);
+          done = true;
+        }
+        k -= 3;
+      }
+      if (!done && a.use_depth) {
+        if (k == 0) { s = tot(12 + 2 * f); q = tot(12 + 2 * f + 1); done = true; }
+        k -= 1;
+      }
+      if (!done && a.n_dd > 0) {
+        if (k < a.n_dd) { s = q = tot(20 + f * kRawMaxBins + k); done = true; }
+        k -= a.n_dd;
+      }
+      if (!done && a.use_td && k == 0) { s = tot(16 + 2 * f); q = tot(16 + 2 * f + 1); }
+      atomicAdd(a.stats + 2 * c, s);
+      atomicAdd(a.stats + 2 * c + 1, q);
+    }
+  }
+};
+
 // RGB / DEP / TD: 0 or 1; NDD: number of one-hot bins (compile-time layout), or -1 = every flag read at run time
 // LO: also write the residual plane value - fp16(value) (split-fp16 forward); the generic variant tests a.out_lo at run time
-template <int RGB, int DEP, int NDD, int TD, bool MAP = false, bool LO = false>
-__global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
+// STATS: also accumulate the batch statistics of the reference-unit input (exact-input stem only: the stored values
+// do not depend on them), saving raw_stats' second pass over the raw tensors.
+template <int RGB, int DEP, int NDD, int TD, bool MAP = false, bool LO = false, bool STATS = false>
+__global__ void __launch_bounds__(256, STATS ? 3 : 1) raw_assemble_kernel(const RawArgs a) {
   __shared__ __align__(16) float s_scale[kMaxInC];
   __shared__ __align__(16) float s_shift[kMaxInC];
   __shared__ float s_edges[kRawMaxBins + 1];
+  __shared__ double s_red[STATS ? 8 : 1][kRawVals];
+  RawAcc acc;
+  if (STATS) acc.clear();
   if (threadIdx.x < kMaxInC) {
     const int c = threadIdx.x;
-    s_scale[c] = (c < a.C + a.n_lo) ? (a.scale ? a.scale[c] : 1.f) : 0.f;
-    s_shift[c] = (c < a.C + a.n_lo && a.shift) ? a.shift[c] : 0.f;
+    if (a.exact) {
+      // exact-input stem (stem_exact.cu): rgb is stored as (byte - 128) / 256 = (byte / 255) * (255 / 256) - 1 / 2, every
+      // other channel as its raw value; the fp16 rounding of the result is exact
+      const int cf = a.C >> 1;
+      const bool rgb = a.use_rgb && c < a.C && (c % cf) < 3;
+      s_scale[c] = (c < a.C + a.n_lo) ? (rgb ? 255.f / 256.f : 1.f) : 0.f;
+      s_shift[c] = rgb ? -0.5f : 0.f;
+    } else {
+      s_scale[c] = (c < a.C + a.n_lo) ? (a.scale ? a.scale[c] : 1.f) : 0.f;
+      s_shift[c] = (c < a.C + a.n_lo && a.shift) ? a.shift[c] : 0.f;
+    }
   }
   if (threadIdx.x <= a.n_dd && a.n_dd > 0) s_edges[threadIdx.x] = a.edges[threadIdx.x];
   __syncthreads();
@@ -91,9 +214,12 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
     const int64_t p_out = p;
     bool flip = false;
     if (MAP) p = mapped_pixel(a, p_out, flip);
+    uint32_t sw[3] = {0u, 0u, 0u};
+    int sbin[2] = {-1, -1};
     if (use_rgb) {
       const ushort* r16 = reinterpret_cast<const ushort*>(a.rgb + p * 6);
       const uint32_t w0 = r16[0], w1 = r16[1], w2 = r16[2];
+      if (STATS) { sw[0] = w0; sw[1] = w1; sw[2] = w2; }
       // rgb / 255 as the reference divides (vo_cnn.py:117-118): fp32 division
       rgbv[0] = __fdiv_rn(static_cast<float>(w0 & 0xff), 255.f);
       rgbv[1] = __fdiv_rn(static_cast<float>(w0 >> 8), 255.f);
@@ -136,6 +262,7 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
       }
       if (n_dd > 0) {
         const int bin = depth_bin(dd, s_edges, n_dd);
+        if (STATS) sbin[f] = bin;
 #pragma unroll
         for (int c = 0; c < kMaxInC; ++c)
           if (c >= cur && c < cur + n_dd && c - cur == bin) v[c] = 1.f;
@@ -154,6 +281,7 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
         }
       }
     }
+    if (STATS) acc.add(sw, d, t, sbin[0], sbin[1]);  // (the STATS variant is never MAP: no swap to undo)
     int64_t opix = p;
     if (a.out_pitch > 0) opix = (p / a.row_w) * a.out_pitch + (p % a.row_w) + 3;  // zero halo left of the image
     __half* __restrict__ out = a.out + opix * a.Cpad;
@@ -185,36 +313,16 @@ __global__ void __launch_bounds__(256) raw_assemble_kernel(const RawArgs a) {
       }
     }
   }
+  if (STATS) acc.flush(a, s_red);
 }
 
-// values per block: rgb 6 x (sum, sumsq) as uint32, depth / td 2 x (sum, sumsq) fp32, bins 2 x kRawMaxBins counts
-static constexpr int kRawVals = 12 + 4 + 4 + 2 * kRawMaxBins;
-
-__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
-}
-__device__ __forceinline__ double warp_sum_f64(double x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
-}
-
-// A thread sees <= 255 pixels (launcher), so its per-bin counts fit in 8 bits: bins 0-7 / 8-15 of a frame are
-// packed into two 64-bit words and bumped with one shift-add instead of a compare chain per bin.
 __global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
   __shared__ float s_edges[kRawMaxBins + 1];
   __shared__ double s_red[8][kRawVals];
   if (threadIdx.x <= a.n_dd && a.n_dd > 0) s_edges[threadIdx.x] = a.edges[threadIdx.x];
   __syncthreads();
-  uint32_t ri[12];
-  float fs[8];
-  unsigned long long cb[4] = {0ull, 0ull, 0ull, 0ull};  // [frame][bins 0-7 | bins 8-15]
-#pragma unroll
-  for (int i = 0; i < 12; ++i) ri[i] = 0u;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) fs[i] = 0.f;
+  RawAcc acc;
+  acc.clear();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t po = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; po < a.n_pix; po += stride) {
     uint32_t w[3] = {0u, 0u, 0u};
@@ -235,81 +343,14 @@ __global__ void __launch_bounds__(256) raw_stats_kernel(const RawArgs a) {
       d = make_float2(d.y, d.x);
       t = make_float2(t.y, t.x);
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const uint32_t lo = w[k] & 0xff, hi = w[k] >> 8;
-      ri[4 * k] += lo; ri[4 * k + 1] += lo * lo;
-      ri[4 * k + 2] += hi; ri[4 * k + 3] += hi * hi;
-    }
-    fs[0] += d.x; fs[1] = fmaf(d.x, d.x, fs[1]);
-    fs[2] += d.y; fs[3] = fmaf(d.y, d.y, fs[3]);
-    fs[4] += t.x; fs[5] = fmaf(t.x, t.x, fs[5]);
-    fs[6] += t.y; fs[7] = fmaf(t.y, t.y, fs[7]);
+    int b0 = -1, b1 = -1;
     if (a.n_dd > 0) {
-      const int b0 = depth_bin(d.x, s_edges, a.n_dd), b1 = depth_bin(d.y, s_edges, a.n_dd);
-      const unsigned long long i0 = (b0 >= 0) ? (1ull << ((b0 & 7) * 8)) : 0ull;
-      const unsigned long long i1 = (b1 >= 0) ? (1ull << ((b1 & 7) * 8)) : 0ull;
-      cb[0] += (b0 < 8) ? i0 : 0ull;
-      cb[1] += (b0 < 8) ? 0ull : i0;
-      cb[2] += (b1 < 8) ? i1 : 0ull;
-      cb[3] += (b1 < 8) ? 0ull : i1;
+      b0 = depth_bin(d.x, s_edges, a.n_dd);
+      b1 = depth_bin(d.y, s_edges, a.n_dd);
     }
+    acc.add(w, d, t, b0, b1);
   }
-  // warp reduction (integers exactly, floats in fp64), then across the 8 warps through shared memory
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const uint32_t x = warp_sum_u32(ri[i]);
-    if (lane == 0) s_red[warp][i] = static_cast<double>(x);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double x = warp_sum_f64(static_cast<double>(fs[i]));
-    if (lane == 0) s_red[warp][12 + i] = x;
-  }
-#pragma unroll
-  for (int i = 0; i < 2 * kRawMaxBins; ++i) {
-    const int f = i / kRawMaxBins, bin = i % kRawMaxBins;
-    const uint32_t x = warp_sum_u32(static_cast<uint32_t>((cb[2 * f + (bin >> 3)] >> ((bin & 7) * 8)) & 0xffull));
-    if (lane == 0) s_red[warp][20 + i] = static_cast<double>(x);
-  }
-  __syncthreads();
-  // thread c < C: gather the (sum, sumsq) of output channel c and add it to the global accumulator
-  const int c = threadIdx.x;
-  if (c < a.C) {
-    const int cf = a.C >> 1;
-    const int f = c / cf;
-    int k = c - f * cf;
-    auto tot = [&](int i) {
-      double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += s_red[w][i];
-      return t;
-    };
-    double s = 0.0, q = 0.0;
-    bool done = false;
-    if (a.use_rgb) {
-      if (k < 3) {
-        // rgb channel j = 3f + k lives in word j / 2, half j & 1: ri index 4*(j/2) + 2*(j&1)
-        const int j = 3 * f + k;
-        const int base = 4 * (j >> 1) + 2 * (j & 1);
-        s = tot(base) / 255.0;
-        q = tot(base + 1) / (255.0 * 255.0);
-        done = true;
-      }
-      k -= 3;
-    }
-    if (!done && a.use_depth) {
-      if (k == 0) { s = tot(12 + 2 * f); q = tot(12 + 2 * f + 1); done = true; }
-      k -= 1;
-    }
-    if (!done && a.n_dd > 0) {
-      if (k < a.n_dd) { s = q = tot(20 + f * kRawMaxBins + k); done = true; }
-      k -= a.n_dd;
-    }
-    if (!done && a.use_td && k == 0) { s = tot(16 + 2 * f); q = tot(16 + 2 * f + 1); }
-    atomicAdd(a.stats + 2 * c, s);
-    atomicAdd(a.stats + 2 * c + 1, q);
-  }
+  acc.flush(a, s_red);
 }
 
 static int raw_check(const RawArgs& a) {
@@ -328,7 +369,17 @@ int raw_assemble_launch(const RawArgs& a, cudaStream_t st) {
   PNVO_REQUIRE(a.out && a.Cpad % 8 == 0 && a.Cpad <= kMaxInC && a.C + a.n_lo <= a.Cpad, "raw_assemble: bad output layout");
   PNVO_REQUIRE(a.n_lo == 0 || (a.n_lo == 2 && a.use_td && !a.out_lo), "raw_assemble: n_lo is 0, or 2 with top-down channels and no residual plane");
   if (a.n_pix <= 0) return 0;
-  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
+  int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(a.n_pix, 256), 148 * 16));
+  if (a.stats) {
+    // one pass: assembled tensor + batch statistics (exact-input stem, full 30-channel layout, no pair map)
+    PNVO_REQUIRE(a.exact && !a.pair_map && !a.out_lo && a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td,
+                 "raw_assemble: the fused statistics need the exact-input stem with the rgb + depth + 10 bins + top-down layout");
+    // a thread must see <= 255 pixels (8-bit packed bin counts)
+    blocks = static_cast<int>(std::min<int64_t>(std::max<int64_t>(blocks, ceil_div64(a.n_pix, 256 * 128)), ceil_div64(a.n_pix, 256)));
+    raw_assemble_kernel<1, 1, 10, 1, false, false, true><<<blocks, 256, 0, st>>>(a);
+    count_launch();
+    return check_launch("raw_assemble+stats");
+  }
   if (a.pair_map) {
     PNVO_REQUIRE(a.hw > 0 && a.n_pix % a.hw == 0 && a.n_pix < (1ll << 31), "raw_assemble: pair map needs pixels per sample");
     if (a.use_rgb && a.use_depth && a.n_dd == 10 && a.use_td) {
@@ -367,7 +418,7 @@ int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStrea
   // p0 = rgb u8, p1 = depth, p2 = top-down, p3 = edges, p4 = scale, p5 = shift, p6 = out fp16 / fp64 stats, p7 = out_lo,
   // p8 = pair_map (int32 per output sample, nullable); i10 = pixels per sample (with pair_map); i11 = depth is fp16
   // i0 = use_rgb, i1 = use_depth, i2 = n_dd, i3 = use_td, i4 = C, i5 = Cpad, i6|i7 = n_pix, i8 = row_w, i9 = out_pitch,
-  // i12 = n_lo (exact-input stem: top-down residual channels)
+  // i12 = n_lo (exact-input stem: top-down residual channels), i13 = exact (constant storage maps), p9 = fused statistics
   (void)f;
   RawArgs a{};
   a.rgb = static_cast<const uint8_t*>(p[0]);
@@ -382,9 +433,11 @@ int raw_op(int code, const int32_t* i, const float* f, void* const* p, cudaStrea
   a.row_w = i[8]; a.out_pitch = i[9];
   a.pair_map = static_cast<const int32_t*>(p[8]); a.hw = i[10];
   a.n_lo = i[12];
+  a.exact = i[13];
   if (code == PNVO_OP_RAW_ASSEMBLE) {
     a.out = static_cast<__half*>(p[6]);
     a.out_lo = static_cast<__half*>(p[7]);
+    a.stats = static_cast<double*>(p[9]);   // nullable: fused batch statistics (exact-input stem)
     return raw_assemble_launch(a, st);
   }
   a.stats = static_cast<double*>(p[6]);

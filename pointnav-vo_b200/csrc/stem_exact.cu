@@ -6,7 +6,7 @@
 // observations are EXACTLY representable in fp16 -- rgb bytes, one-hot depth bins, fp16 depth -- so the normalisation is
 // folded into the weights instead:
 //
-//   n_c = a_c x_c + b_c      x_c = (byte - M_c) / 256 (rgb; M_c = round(255 mean_c)), the raw value otherwise
+//   n_c = a_c x_c + b_c      x_c = (byte - 128) / 256 (rgb), the raw value otherwise
 //   conv(n, W)[co, oh, ow] = sum_{taps inside the image} (a_c W)[co, c, r, s] x_c  +  sum_{taps inside} W[co, c, r, s] b_c
 //
 // The first term is the stem kernel on the zero-padded exact tensor with weights W' = a_c W (value + residual planes: two
@@ -37,8 +37,10 @@ __global__ void stem_exact_prep_kernel(const float* __restrict__ scale, const fl
     if (rgb) {
       // stored value (byte - M) / 256: exact in fp16, |x| <= 1.  (Storing byte - M itself would make a_c = 1 / (255 std)
       // and push the RESIDUAL plane of W' = a_c W into fp16 subnormals: measured 1.5e-4 instead of 8e-6 at the output.)
-      const float mean = -sh / sc;                 // shift = -mean / std, scale = 1 / std
-      const float M = rintf(mean * 255.f);
+      // M is a CONSTANT (not round(255 mean)): the stored tensor then does not depend on the batch statistics, so the
+      // statistics pass and the assembly are one kernel (raw_input.cu: raw_assemble with stats); the remainder
+      // b = (128 / 255 - mean) / std is absorbed by the border-class bias
+      const float M = 128.f;
       xs = 255.f / 256.f; xh = -M / 256.f;
       a = sc * (256.f / 255.f);
       b = sh + M * sc / 255.f;

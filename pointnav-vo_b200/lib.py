@@ -224,12 +224,14 @@ def op_raw_stats(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, 
 
 
 def op_raw_assemble(rgb_u8, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, scale, shift, out,
-                    row_w=0, out_pitch=0, out_lo=None, pair_map=None, hw=0, n_lo=0):
+                    row_w=0, out_pitch=0, out_lo=None, pair_map=None, hw=0, n_lo=0, exact=False, stats_f64=None):
     """n_lo = 2 (exact-input stem): channels C, C+1 carry the fp16 residuals of the two top-down values; scale / shift then
-    have C + 2 entries (op_stem_exact_prep)."""
+    have C + 2 entries (op_stem_exact_prep).  exact: the exact-input stem's constant storage maps ((byte - 128) / 256 for rgb,
+    raw values otherwise; scale / shift ignored).  stats_f64 (needs exact): the batch statistics are accumulated in the
+    same pass (replaces op_raw_stats)."""
     return _op(OP_RAW_ASSEMBLE, _raw_fields(use_rgb, use_depth, n_dd, use_td, C, Cpad, n_pix, row_w, out_pitch, hw, depth,
-                                            n_lo), (),
-               [rgb_u8, depth, td, edges, scale, shift, out, out_lo, pair_map])
+                                            n_lo) + [int(bool(exact))], (),
+               [rgb_u8, depth, td, edges, scale, shift, out, out_lo, pair_map, stats_f64])
 
 
 def op_stem_exact_prep(scale, shift, xp, use_rgb, use_depth, n_dd, use_td):

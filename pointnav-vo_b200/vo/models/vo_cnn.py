@@ -22,6 +22,12 @@ OBS_ORDER = ("rgb", "depth", "discretized_depth", "top_down_view")  # vo_cnn.py:
 
 
 
+# timing diagnosis only (results become stale): bit 0 skips the top-down projection, bit 1 the batch statistics, bit 2 the
+# input assembly of every batch after the first -- separates the cost of the overlapped input pipeline from the step's
+import os as _os
+
+_DIAG_SKIP = int(_os.environ.get("PNVO_DIAG_SKIP_INPUT", "0"))
+_FUSED_STATS = _os.environ.get("PNVO_FUSED_STATS", "1") != "0"   # 0: separate raw_stats pass (A/B measurements)
 _PEER_SUM = {}   # device index -> parallel_utils.PeerSmallSum, or False when peer memory is unavailable
 
 
@@ -316,17 +322,39 @@ class VisualOdometryCNNBase(nn.Module):
                     gen = self._raw_td_gen = gu.NormalizedDepth2TopDownViewHabitatTorch(0.1, 10.0, H, W, 70)
                 if getattr(plan, "td_pair", None) is None or plan.td_pair.shape[0] != B_src:
                     plan.td_pair = torch.empty(B_src, H, W, 2, dtype=torch.float32, device=dev)
-                td = gu.gen_top_down_view_pairs(gen, depth, out=plan.td_pair)
+                if _DIAG_SKIP & 1 and getattr(plan, "_td_done", False):
+                    td = plan.td_pair          # timing diagnosis only (PNVO_DIAG_SKIP_INPUT bit 0): stale top-down maps
+                else:
+                    td = gu.gen_top_down_view_pairs(gen, depth, out=plan.td_pair)
+                    plan._td_done = True
         C = enc.input_channels
         n_pix = B * H * W
         rmv = enc.running_mean_and_var
         have_rmv = isinstance(rmv, RunningMeanAndVar)
         ops = []
+        full30 = bool(use_rgb and use_depth and n_dd == 10 and use_td)
+        # exact-input stem: the stored tensor does not depend on the statistics, so ONE kernel writes it and accumulates them
+        fused_stats = bool(plan.exact_stem and have_rmv and training and full30 and pair_map is None and _FUSED_STATS)
+
+        def assemble(scale, shift, n_lo, stats=None):
+            return L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
+                                     scale, shift, plan.x0_for(parity), row_w=plan.W if plan.x0_pitch else 0,
+                                     out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0_for(parity)),
+                                     pair_map=pair_map, hw=H * W, n_lo=n_lo, exact=bool(plan.exact_stem), stats_f64=stats)
+
+        skip_asm = bool(_DIAG_SKIP & 4 and parity in getattr(plan, "_asm_done", set()))
+        if not hasattr(plan, "_asm_done"):
+            plan._asm_done = set()
+        plan._asm_done.add(parity)
         if have_rmv:
-            if training:
+            if training and not (_DIAG_SKIP & 2 and getattr(plan, "_stats_done", False)):
+                plan._stats_done = True
                 ops.append(L.op_zero(plan.in_stats))
-                ops.append(L.op_raw_stats(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
-                                          plan.in_stats, pair_map=pair_map, hw=H * W))
+                if fused_stats:
+                    ops.append(assemble(None, None, 2, stats=plan.in_stats))
+                else:
+                    ops.append(L.op_raw_stats(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
+                                              plan.in_stats, pair_map=pair_map, hw=H * W))
                 if plan.world_size > 1:
                     L.run_ops(ops, dev)
                     ops = []
@@ -341,10 +369,8 @@ class VisualOdometryCNNBase(nn.Module):
             xp = plan.xp_for(parity)
             ops.append(L.op_stem_exact_prep(scale, shift, xp, use_rgb, use_depth, n_dd, use_td))
             scale, shift, n_lo = xp[:32], xp[32:64], (2 if use_td else 0)
-        ops.append(L.op_raw_assemble(rgb, depth, td, edges, use_rgb, use_depth, n_dd, use_td, C, plan.cin_pad, n_pix,
-                                     scale, shift, plan.x0_for(parity), row_w=plan.W if plan.x0_pitch else 0,
-                                     out_pitch=plan.x0_pitch, out_lo=plan.lo(plan.x0_for(parity)),
-                                     pair_map=pair_map, hw=H * W, n_lo=n_lo))
+        if not fused_stats and not skip_asm:
+            ops.append(assemble(scale, shift, n_lo))
         L.run_ops(ops, dev)
         if not prepare_only:
             self._run_backbone(plan, parity)
