@@ -5,7 +5,8 @@
  * (SURVEY.md section 8b); these entry points are what a ctypes binding of its hot path binds.  Each
  * one cites the reference code it replaces.  Conventions:
  *   - plain pointers and sizes only; every buffer is caller-allocated DEVICE memory (the library
- *     never owns memory and keeps no global state besides the last-error string);
+ *     keeps no global state besides the last-error string and owns no memory, except the
+ *     peer-mappable regions handed out by pnvo_peer_alloc for the multi-GPU exchange);
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - return value 0 = launched; negative = error, text via pnvo_last_error();
  *   - kernels are asynchronous with respect to the host.
