@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libpnvo.so")
-SOURCES = ["api.cu", "preproc.cu", "conv_igemm.cu", "conv_wgrad.cu", "norm_pool.cu", "tmap.cu", "conv_stem.cu", "gn_bwd_fused.cu", "raw_input.cu", "conv_raster.cu", "conv_wgrad_raster.cu", "act_embed.cu", "conv_stem2.cu", "conv_raster128.cu", "stem_exact.cu", "peer_reduce.cu"]
+SOURCES = ["api.cu", "preproc.cu", "conv_igemm.cu", "conv_wgrad.cu", "norm_pool.cu", "tmap.cu", "conv_stem.cu", "gn_bwd_fused.cu", "raw_input.cu", "conv_raster.cu", "conv_wgrad_raster.cu", "act_embed.cu", "conv_stem2.cu", "conv_raster128.cu", "stem_exact.cu", "peer_reduce.cu", "conv_direct.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v",

@@ -124,7 +124,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.stats = static_cast<double*>(p[4]);
       a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
       a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];
-      a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18]; a.force_generic = i[19];
+      a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18]; a.force_generic = i[19]; a.cin_real = i[21];
       return conv_launch(a, st);
     }
     case PNVO_OP_WGRAD: {
@@ -135,6 +135,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.dw = static_cast<float*>(p[2]);
       a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
       a.mul = i[8]; a.pad = i[9]; a.w_ld = i[11]; a.n_total = i[12]; a.ld_dy = i[14]; a.pad_w = i[18]; a.force_generic = i[19]; a.x_row_pitch = i[20];
+      a.cin_real = i[21];
       return wgrad_launch(a, st);
     }
     case PNVO_OP_GN_APPLY:

@@ -438,6 +438,7 @@ int conv_plan(ConvArgs& a) {
 }
 
 int conv_launch(ConvArgs a, cudaStream_t st) {
+  if (a.force_generic == 0 && a.x && a.w && a.y && conv_direct1_supported(a)) return conv_direct1_launch(a, st);
   if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster_supported(a)) return conv_raster_launch(a, st);
   if (a.force_generic == 0 && a.x && a.w && a.y && conv_raster128_supported(a)) return conv_raster128_launch(a, st);
   if (conv_plan(a)) return -1;

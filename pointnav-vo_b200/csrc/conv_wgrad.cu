@@ -306,6 +306,7 @@ int wgrad_plan(WgradArgs& a) {
 }
 
 int wgrad_launch(WgradArgs a, cudaStream_t st) {
+  if (a.force_generic == 0 && a.x && a.dy && a.dw && wgrad_direct1_supported(a)) return wgrad_direct1_launch(a, st);
   if (a.force_generic == 0 && a.x && a.dy && a.dw && wgrad_raster_supported(a)) return wgrad_raster_launch(a, st);
   if (wgrad_plan(a)) return -1;
   PNVO_REQUIRE(a.x && a.dy && a.dw, "wgrad: null pointer");

@@ -23,6 +23,7 @@ struct ConvArgs {
   int cpg, G;
   int out_fp32;
   int force_generic;   // 0: best kernel; 1: cp.async im2col producer; 2: TMA im2col producer (A/B testing)
+  int cin_real;        // input channels that are not zero padding (0 = unknown): 1 selects the direct fp32 stem kernel
   int tma, chunk_k;    // derived: TMA producer on/off, K elements per pipeline stage (64 or 32)
   // derived by conv_plan
   int cin_log2, cmask, M, K, nkb, N, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y;
@@ -34,6 +35,9 @@ int conv_raster_launch(const ConvArgs& a, cudaStream_t st);
 // conv_raster128.cu: the same raster for 128 input channels, weights streamed through a ring shared by all M tiles
 int conv_raster128_supported(const ConvArgs& a);
 int conv_raster128_launch(const ConvArgs& a, cudaStream_t st);
+// conv_direct.cu: one-channel 7x7 / stride 2 stem (depth-only policy encoder) on the fp32 CUDA cores
+int conv_direct1_supported(const ConvArgs& a);
+int conv_direct1_launch(const ConvArgs& a, cudaStream_t st);
 int conv_launch(ConvArgs a, cudaStream_t st);
 
 struct WgradArgs {
@@ -46,6 +50,7 @@ struct WgradArgs {
   int w_ld, n_total, ld_dy;
   int x_row_pitch;     // pixels between input rows (0 = IW); TMA path only
   int force_generic;
+  int cin_real;        // as ConvArgs::cin_real
   int tma, chunk_k;
   // derived
   int cin_log2, cmask, M, K, n_mtiles, mt, N, n_ntiles, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y, grid_z, chunks_per_split;
@@ -70,6 +75,8 @@ int wgrad_plan(WgradArgs& a);
 // conv_wgrad_raster.cu: persistent no-im2col weight gradient for 3x3 / stride 1 / pad 1 with 32 or 64 channels
 int wgrad_raster_supported(const WgradArgs& a);
 int wgrad_raster_launch(const WgradArgs& a, cudaStream_t st);
+int wgrad_direct1_supported(const WgradArgs& a);
+int wgrad_direct1_launch(const WgradArgs& a, cudaStream_t st);
 int wgrad_launch(WgradArgs a, cudaStream_t st);
 
 }  // namespace pnvo

@@ -77,7 +77,8 @@ class ConvLayer:
     def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None, y_lo=None):
         return L.op_conv(x, self.wp, y, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
                          self.stride, self.pad, 1, self.w_ld, self.cout_pad, self.cout_pad, self.cout_pad, None, stats,
-                         cpg, G, out_fp32, x_lo=x_lo, w_lo=self.wp_lo if x_lo is not None else None, y_lo=y_lo)
+                         cpg, G, out_fp32, x_lo=x_lo, w_lo=self.wp_lo if x_lo is not None else None, y_lo=y_lo,
+                         cin_real=self.Cin)
 
     def op_dgrad(self, dy, gx, B, add=None):
         # gx[b, h, w, c] = sum_{r,s,n} dy[b, (h + pad - r)/stride, (w + pad - s)/stride, n] * W[n, c, r, s]
@@ -109,7 +110,8 @@ class ConvLayer:
 
     def op_wgrad(self, x, dy, B, x_row_pitch=0):
         return L.op_wgrad(x, dy, self.dwp, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
-                          self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad, x_row_pitch=x_row_pitch)
+                          self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad, x_row_pitch=x_row_pitch,
+                          cin_real=self.Cin)
 
     def op_unpack(self, grad):
         return L.op_unpack_dw(self.dwp, grad, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld)

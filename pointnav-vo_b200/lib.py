@@ -258,16 +258,19 @@ def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv
 
 
 def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, add=None, stats=None,
-            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None, y_lo=None):
+            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None, y_lo=None, cin_real=0):
     """x_lo / w_lo: residual planes of the split-fp16 representation (x - fp16(x)); with them the kernel accumulates
-    x*w + x_lo*w + x*w_lo, i.e. products of ~fp32-precision operands (3 MMAs per product)."""
+    x*w + x_lo*w + x*w_lo, i.e. products of ~fp32-precision operands (3 MMAs per product).
+    cin_real: input channels that are not zero padding (0 = unknown); 1 selects the direct fp32 stem kernel."""
     return _op(OP_CONV, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, cpg, G,
-                         int(out_fp32), pad if pad_w is None else pad_w], (), [x, w, y, add, stats, x_lo, w_lo, y_lo])
+                         int(out_fp32), pad if pad_w is None else pad_w, 0, 0, int(cin_real)], (),
+               [x, w, y, add, stats, x_lo, w_lo, y_lo])
 
 
-def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None, x_row_pitch=0):
+def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None, x_row_pitch=0,
+             cin_real=0):
     return _op(OP_WGRAD, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, 1, w_ld, n_total, 0, ld_dy, 0, 0, 0,
-                          pad if pad_w is None else pad_w, 0, x_row_pitch], (), [x, dy, dw])
+                          pad if pad_w is None else pad_w, 0, x_row_pitch, int(cin_real)], (), [x, dy, dw])
 
 
 def op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, cnt, relu=True, res=None, x_fp32=False, eps=1e-5,

@@ -138,6 +138,7 @@ CONV_CASES = [
     ("layer4 3x3s1 256->256", 3, 256, 256, 3, 3, 1, 1, 6, 11, 16, True, None),
     ("compression 256->31", 3, 256, 31, 3, 3, 1, 1, 6, 11, 1, True, None),
     ("policy conv1 1->32", 2, 1, 32, 7, 7, 2, 3, 96, 170, 16, False, None),
+    ("policy conv1 1->32 (odd sizes, partial tiles)", 5, 1, 32, 7, 7, 2, 3, 37, 53, 16, False, None),
     ("r50 1x1 256->1024", 2, 256, 1024, 1, 1, 1, 0, 6, 11, 16, True, None),
     ("fc 2112->512", 64, 2112, 512, 1, 1, 1, 0, 1, 1, 16, True, 2112),
     ("tiny 1 pixel tile", 1, 32, 32, 3, 3, 1, 1, 1, 1, 16, True, None),
