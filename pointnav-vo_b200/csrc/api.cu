@@ -125,6 +125,10 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
       a.mul = i[8]; a.pad = i[9]; a.div = i[10]; a.w_ld = i[11]; a.n_total = i[12]; a.n_store = i[13]; a.ldo = i[14];
       a.cpg = i[15]; a.G = i[16]; a.out_fp32 = i[17]; a.pad_w = i[18]; a.force_generic = i[19]; a.cin_real = i[21];
+      // i22 = output pixel stride (0 = dense), i23 = output offsets (h | w << 8), i24 / i25 = full output height / width,
+      // i26 = 0 (symmetric padding) or (pad_hi_h + 1) | (pad_hi_w + 1) << 8
+      a.o_mul = i[22]; a.o_off_h = i[23] & 0xff; a.o_off_w = (i[23] >> 8) & 0xff; a.o_H = i[24]; a.o_W = i[25];
+      a.asym = i[26] != 0; a.pad_hi_h = (i[26] & 0xff) - 1; a.pad_hi_w = ((i[26] >> 8) & 0xff) - 1;
       return conv_launch(a, st);
     }
     case PNVO_OP_WGRAD: {

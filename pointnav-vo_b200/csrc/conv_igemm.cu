@@ -261,6 +261,16 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
     const int m = m0 + row;
     const bool row_valid = m < p.M;
     const int b = row_valid ? m / ohw : 0;
+    // where the row is stored: densely at pixel m, or scattered onto a stride-o_mul lattice of a larger tensor
+    int64_t mo = m;
+    bool st_valid = row_valid;
+    if (p.o_mul) {
+      const int rem = m - b * ohw;
+      const int oh = rem / p.OW;
+      const int gh = oh * p.o_mul + p.o_off_h, gw = (rem - oh * p.OW) * p.o_mul + p.o_off_w;
+      st_valid = row_valid && gh < p.o_H && gw < p.o_W;
+      mo = (static_cast<int64_t>(b) * p.o_H + gh) * p.o_W + gw;
+    }
 
     // ==================================== epilogue ====================================
     mbar_wait(smem_u32(&s_accum), 0);
@@ -278,8 +288,8 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
 #pragma unroll
         for (int i = 16; i < 32; ++i) v[i] = 0.f;
       }
-      if (p.add && row_valid) {
-        const __half* ap = p.add + static_cast<int64_t>(m) * p.ldo + col0;
+      if (p.add && st_valid) {
+        const __half* ap = p.add + mo * p.ldo + col0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (col0 + q * 8 < p.n_store) {
@@ -304,10 +314,10 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
           default: chunk_stats<32>(v, sample, row_valid, p.stats, p.G, g0, lane); break;  // cpg >= 32
         }
       }
-      if (row_valid) {
+      if (st_valid) {
         if (p.y_lo) {  // value + residual fp16 planes
-          __half* yh = reinterpret_cast<__half*>(p.y) + static_cast<int64_t>(m) * p.ldo + col0;
-          __half* yl = p.y_lo + static_cast<int64_t>(m) * p.ldo + col0;
+          __half* yh = reinterpret_cast<__half*>(p.y) + mo * p.ldo + col0;
+          __half* yl = p.y_lo + mo * p.ldo + col0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (col0 + q * 8 < p.n_store) {
@@ -318,13 +328,13 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
             }
           }
         } else if (p.out_fp32) {
-          float* yp = reinterpret_cast<float*>(p.y) + static_cast<int64_t>(m) * p.ldo + col0;
+          float* yp = reinterpret_cast<float*>(p.y) + mo * p.ldo + col0;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (col0 + q * 4 < p.n_store)
               *reinterpret_cast<float4*>(yp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         } else {
-          __half* yp = reinterpret_cast<__half*>(p.y) + static_cast<int64_t>(m) * p.ldo + col0;
+          __half* yp = reinterpret_cast<__half*>(p.y) + mo * p.ldo + col0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (col0 + q * 8 < p.n_store) {
@@ -405,7 +415,9 @@ int conv_plan(ConvArgs& a) {
   const bool split = a.x_lo != nullptr;
   PNVO_REQUIRE((a.x_lo != nullptr) == (a.w_lo != nullptr), "conv: split mode needs both x_lo and w_lo");
   PNVO_REQUIRE(!a.y_lo || !a.out_fp32, "conv: y_lo (value + residual fp16 output) excludes out_fp32");
-  a.tma = (a.div == 1 && a.Cin % 32 == 0 && a.R == a.S && a.pad == a.pad_w && a.force_generic != 1) ? 1 : 0;
+  PNVO_REQUIRE(!a.o_mul || (!a.stats && a.o_H > 0 && a.o_W > 0), "conv: strided output excludes GroupNorm statistics");
+  // (asymmetric padding: any filter shape, the high-side corner of the TMA bounding box is given separately)
+  a.tma = (a.div == 1 && a.Cin % 32 == 0 && (a.asym || (a.R == a.S && a.pad == a.pad_w)) && a.force_generic != 1) ? 1 : 0;
   a.chunk_k = (a.tma && a.Cin % 64 != 0) ? 32 : kTileK;
   a.nkb = ceil_div(a.K, a.chunk_k);
   PNVO_REQUIRE(a.w_ld >= a.nkb * a.chunk_k, "conv: packed weight row stride %d < padded K %d", a.w_ld, a.nkb * a.chunk_k);
@@ -452,10 +464,11 @@ int conv_launch(ConvArgs a, cudaStream_t st) {
   alignas(64) ConvTmaps tm;
   memset(&tm, 0, sizeof(tm));
   if (a.tma) {
-    if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM)) return -1;
+    const int ph_hi = a.asym ? a.pad_hi_h : a.pad, pw_hi = a.asym ? a.pad_hi_w : a.pad_w;
+    if (tmap_im2col(&tm.a, a.x, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM, 0, a.pad_w, ph_hi, pw_hi)) return -1;
     if (tmap_tiled2d(&tm.b, a.w, a.n_total, a.w_ld, a.w_ld, a.N, a.chunk_k)) return -1;
     if (a.x_lo) {
-      if (tmap_im2col(&tm.a_lo, a.x_lo, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM)) return -1;
+      if (tmap_im2col(&tm.a_lo, a.x_lo, a.B, a.IH, a.IW, a.Cin, a.R, a.S, a.mul, a.pad, a.chunk_k, kTileM, 0, a.pad_w, ph_hi, pw_hi)) return -1;
       if (tmap_tiled2d(&tm.b_lo, a.w_lo, a.n_total, a.w_ld, a.w_ld, a.N, a.chunk_k)) return -1;
     }
   }

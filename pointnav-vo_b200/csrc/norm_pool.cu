@@ -908,6 +908,18 @@ int gn_param_grad_launch(const float* sums, int B, int C, int C_real, float* dga
 // layout [c][ ((R-1-r)*S + (S-1-s))*Cout_pad + n ].  Destination buffers are zero-initialised once; pad
 // entries are never written.
 // ------------------------------------------------------------------------------------------------
+// t_mode & 4: data-gradient weights of a 3x3 / stride 2 / pad 1 convolution split by the PARITY CLASS of the input pixel.
+// gx[h, w] = sum over (r, s) with (h + 1 - r), (w + 1 - s) even of dy[(h + 1 - r) / 2, (w + 1 - s) / 2] W[r, s]: for even h
+// only r = 1 contributes (dy row h / 2), for odd h the rows r = 2 (dy row (h - 1) / 2) and r = 0 (the next dy row).  Class
+// (ph, pw) is therefore a dense stride-1 convolution of dy with (1 + ph) x (1 + pw) taps -- 1 + 2 + 2 + 4 = 9 taps for four
+// input pixels instead of 9 taps per pixel over a zero-upsampled dy.  Layout: four matrices [class][ru16(cin_pad)][ld_t],
+// element (c, (r' (1 + pw) + s') cout_pad + n) with r' = 0 <-> r = 2 - ph ... (r = 1 when ph = 0; r = 2, 0 when ph = 1).
+__device__ __forceinline__ int64_t s2_class_offset(int r, int s, int c, int cin_pad, int ld_t, int cout_pad) {
+  const int ph = (r != 1) ? 1 : 0, pw = (s != 1) ? 1 : 0;
+  const int rp = (r == 0) ? 1 : 0, sp = (s == 0) ? 1 : 0;
+  const int64_t rows = (cin_pad + 15) / 16 * 16;
+  return (static_cast<int64_t>(ph * 2 + pw) * rows + c) * ld_t + (rp * (1 + pw) + sp) * cout_pad;
+}
 __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, __half* __restrict__ wp,
                               int cin_pad, int ld_p, __half* __restrict__ wt, int cout_pad, int ld_t, int t_mode,
                               int src_ld) {
@@ -924,7 +936,8 @@ __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, in
     if (t_mode & 2) h = __float2half_rn(wv - __half2float(h));  // residual plane of the split-fp16 representation
     if (wp) wp[static_cast<int64_t>(n) * ld_p + (r * S + s) * cin_pad + c] = h;
     if (wt) {
-      if ((t_mode & 1) == 0) wt[static_cast<int64_t>(c) * ld_t + ((R - 1 - r) * S + (S - 1 - s)) * cout_pad + n] = h;
+      if (t_mode & 4) wt[s2_class_offset(r, s, c, cin_pad, ld_t, cout_pad) + n] = h;
+      else if ((t_mode & 1) == 0) wt[static_cast<int64_t>(c) * ld_t + ((R - 1 - r) * S + (S - 1 - s)) * cout_pad + n] = h;
       else wt[static_cast<int64_t>((r * S + s) * cin_pad + c) * ld_t + n] = h;
     }
   }
@@ -1019,7 +1032,10 @@ __global__ void __launch_bounds__(256) pack_w_multi_kernel(const PackDesc* __res
 #pragma unroll
         for (int e = 0; e < kPackRows; ++e) hv[e] = sm[e][k];
         int64_t o;
-        if ((d.t_mode & 1) == 0) {
+        if (d.t_mode & 4) {
+          const int r = tap / d.S, sx = tap - r * d.S;
+          o = s2_class_offset(r, sx, cb + c, d.cin_pad, d.ld_t, d.cout_pad) + n0;
+        } else if ((d.t_mode & 1) == 0) {
           const int r = tap / d.S, sx = tap - r * d.S;
           o = static_cast<int64_t>(cb + c) * d.ld_t + ((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.cout_pad + n0;
         } else {

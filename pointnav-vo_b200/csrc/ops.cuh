@@ -24,6 +24,11 @@ struct ConvArgs {
   int out_fp32;
   int force_generic;   // 0: best kernel; 1: cp.async im2col producer; 2: TMA im2col producer (A/B testing)
   int cin_real;        // input channels that are not zero padding (0 = unknown): 1 selects the direct fp32 stem kernel
+  // strided output (parity-class data gradient of a stride-2 convolution): output pixel (b, oh, ow) of the GEMM is stored
+  // at (b, oh * o_mul + o_off_h, ow * o_mul + o_off_w) of a [B, o_H, o_W] tensor (skipped when outside); 0 = dense
+  int o_mul, o_off_h, o_off_w, o_H, o_W;
+  // asym != 0: padding `pad` / `pad_w` on the low side and pad_hi_h / pad_hi_w on the high side (default: symmetric)
+  int asym, pad_hi_h, pad_hi_w;
   int tma, chunk_k;    // derived: TMA producer on/off, K elements per pipeline stage (64 or 32)
   // derived by conv_plan
   int cin_log2, cmask, M, K, nkb, N, tmem_cols, stages, lookahead, smem_bytes, grid_x, grid_y;

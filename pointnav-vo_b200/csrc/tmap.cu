@@ -41,11 +41,15 @@ static int resolve() {
 }
 
 int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad,
-                int channels, int pixels, int row_pitch_px) {
+                int channels, int pixels, int row_pitch_px, int pad_w_lo, int pad_h_hi, int pad_w_hi) {
   if (row_pitch_px <= 0) row_pitch_px = W;
+  if (pad_w_lo < 0) pad_w_lo = pad;
+  if (pad_h_hi < 0) pad_h_hi = pad;
+  if (pad_w_hi < 0) pad_w_hi = pad_w_lo;
   std::lock_guard<std::mutex> lk(g_mu);
   if (resolve()) return -1;
-  std::vector<int64_t> key = {1, reinterpret_cast<int64_t>(x), N, H, W, C, R, S, stride, pad, channels, pixels, row_pitch_px};
+  std::vector<int64_t> key = {1, reinterpret_cast<int64_t>(x), N, H, W, C, R, S, stride, pad, channels, pixels, row_pitch_px,
+                              pad_w_lo, pad_h_hi, pad_w_hi};
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     *out = it->second;
@@ -56,9 +60,9 @@ int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int
                               static_cast<cuuint64_t>(N)};
   const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(row_pitch_px) * C * 2,
                                  static_cast<cuuint64_t>(H) * row_pitch_px * C * 2};
-  // bounding box of the filter origin: [-pad, dim + pad - (filter - 1)) in both W and H
-  const int lower[2] = {-pad, -pad};
-  const int upper[2] = {pad - (S - 1), pad - (R - 1)};
+  // bounding box of the filter origin: [-pad_lo, dim + pad_hi - (filter - 1)) in W and H
+  const int lower[2] = {-pad_w_lo, -pad};
+  const int upper[2] = {pad_w_hi - (S - 1), pad_h_hi - (R - 1)};
   const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   const CUtensorMapSwizzle sw = (channels * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const CUresult r = g_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,

@@ -18,8 +18,9 @@ struct ConvTmaps {
 
 // NHWC fp16 activations [N, H, W, C]; a load fetches `pixels` consecutive output positions (w fastest,
 // wrapping over h and n inside the padded bounding box) x `channels` channels of one filter tap.
+// pad = low-side padding in H (pad_w_lo in W, default pad); pad_h_hi / pad_w_hi = high-side padding (default: symmetric)
 int tmap_im2col(CUtensorMap* out, const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad,
-                int channels, int pixels, int row_pitch_px = 0);
+                int channels, int pixels, int row_pitch_px = 0, int pad_w_lo = -1, int pad_h_hi = -1, int pad_w_hi = -1);
 // NHWC fp16 activations [N, H, W, C]: plain tiled boxes of box_w pixels x C channels of one image row,
 // SWIZZLE_128B (C*2 <= 128 bytes), out-of-range pixels / rows zero-filled
 int tmap_tiled4d(CUtensorMap* out, const void* x, int N, int H, int W, int C, int box_w, int swizzle_bytes = 128,

@@ -56,13 +56,20 @@ class ConvLayer:
         self.wp = self.wt = self.dwp = self.wp_lo = None
         self.up = None          # zero-upsampled dy (stride-2 data gradient), allocated on first use
         self.fast_s2 = True
+        # 3x3 / stride 2 / pad 1: the data gradient runs as four parity-class convolutions of dy (1 + 2 + 2 + 4 taps for four
+        # input pixels instead of 9 taps per pixel over a zero-upsampled dy); wt then holds the four class matrices
+        self.s2_classes = (R == 3 and S == 3 and stride == 2 and pad == 1 and need_dgrad
+                           and os.environ.get("PNVO_S2_CLASSES", "1") != "0")
+        if self.s2_classes:
+            self.wt_ld = _ru(4 * self.cout_pad, 64)
 
     def alloc(self, dev, training, own_dwp=True, split=False):
         self.wp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
         if split:  # residual plane w - fp16(w) of the split-fp16 representation
             self.wp_lo = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float16, device=dev)
         if self.need_dgrad and training:
-            self.wt = torch.zeros(self.nt_total, self.wt_ld, dtype=torch.float16, device=dev)
+            rows = 4 * self.nt_total if self.s2_classes else self.nt_total
+            self.wt = torch.zeros(rows, self.wt_ld, dtype=torch.float16, device=dev)
         if training and own_dwp:  # inside a plan dwp is a view of the gradient arena (one zero-fill per step)
             self.dwp = torch.zeros(self.cout_pad, self.w_ld, dtype=torch.float32, device=dev)
 
@@ -72,7 +79,7 @@ class ConvLayer:
     # ---- op builders ----
     def op_pack(self, w):
         return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld,
-                           self.cout_pad, self.wt_ld, 0)
+                           self.cout_pad, self.wt_ld, 4 if self.s2_classes else 0)
 
     def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None, y_lo=None):
         return L.op_conv(x, self.wp, y, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
@@ -82,6 +89,7 @@ class ConvLayer:
 
     def op_dgrad(self, dy, gx, B, add=None):
         # gx[b, h, w, c] = sum_{r,s,n} dy[b, (h + pad - r)/stride, (w + pad - s)/stride, n] * W[n, c, r, s]
+        assert not self.s2_classes, "parity-class weights: use ops_dgrad"
         return L.op_conv(dy, self.wt, gx, B, self.OH, self.OW, self.cout_pad, self.IH, self.IW, self.R, self.S, 1,
                          self.R - 1 - self.pad, self.stride, self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, add,
                          None, 0, 0, False, pad_w=self.S - 1 - self.pad)
@@ -91,6 +99,18 @@ class ConvLayer:
         the stride-1 kernels (TMA im2col / shared-memory raster) do the work instead of the generic
         divisibility-testing producer: 3x3/s2 = 3x3/s1 conv of up2(dy) with the flipped weights; 1x1/s2 = compact
         1x1 conv of dy scattered to the even input positions."""
+        if self.s2_classes:
+            ops = []
+            for ph in (0, 1):
+                for pw in (0, 1):
+                    wk = self.wt[(ph * 2 + pw) * self.nt_total:(ph * 2 + pw + 1) * self.nt_total]
+                    # class (ph, pw): dense stride-1 conv of dy with (1 + ph) x (1 + pw) taps, zero beyond the high edge,
+                    # computed on the whole dy grid and stored at the (2i + ph, 2j + pw) pixels of gx that exist
+                    ops.append(L.op_conv(dy, wk, gx, B, self.OH, self.OW, self.cout_pad, self.OH, self.OW, 1 + ph, 1 + pw, 1,
+                                         0, 1, self.wt_ld, self.nt_total, self.cin_pad, self.cin_pad, add, None, 0, 0,
+                                         False, pad_w=0, o_mul=2, o_off=(ph, pw), o_hw=(self.IH, self.IW),
+                                         pad_hi=(ph, pw)))
+            return ops
         if self.stride == 1 or not self.fast_s2:
             return [self.op_dgrad(dy, gx, B, add=add)]
         assert self.stride == 2
@@ -119,8 +139,8 @@ class ConvLayer:
     # descriptor-table entries of the batched pack / unpack launches
     def pack_desc(self, w):
         return L.PackDesc(w.data_ptr(), self.wp.data_ptr(), self.wt.data_ptr() if self.wt is not None else None,
-                          self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld, self.cout_pad, self.wt_ld, 0,
-                          self.Cin * self.R * self.S)
+                          self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld, self.cout_pad, self.wt_ld,
+                          4 if self.s2_classes else 0, self.Cin * self.R * self.S)
 
     def pack_desc_lo(self, w):
         return L.PackDesc(w.data_ptr(), self.wp_lo.data_ptr(), None, self.Cout, self.Cin, self.R, self.S, self.cin_pad,

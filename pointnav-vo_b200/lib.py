@@ -258,12 +258,18 @@ def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv
 
 
 def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, add=None, stats=None,
-            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None, y_lo=None, cin_real=0):
+            cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None, y_lo=None, cin_real=0, o_mul=0, o_off=(0, 0),
+            o_hw=(0, 0), pad_hi=None):
     """x_lo / w_lo: residual planes of the split-fp16 representation (x - fp16(x)); with them the kernel accumulates
     x*w + x_lo*w + x*w_lo, i.e. products of ~fp32-precision operands (3 MMAs per product).
-    cin_real: input channels that are not zero padding (0 = unknown); 1 selects the direct fp32 stem kernel."""
+    cin_real: input channels that are not zero padding (0 = unknown); 1 selects the direct fp32 stem kernel.
+    o_mul / o_off / o_hw: strided output -- GEMM pixel (b, oh, ow) is stored at (b, oh * o_mul + o_off[0], ow * o_mul +
+    o_off[1]) of a [B, o_hw[0], o_hw[1]] tensor (and `add` is read there); pad_hi = (h, w): high-side padding when it differs
+    from the low-side `pad` / `pad_w` (parity-class data gradient of stride-2 convolutions)."""
+    asym = 0 if pad_hi is None else ((pad_hi[0] + 1) | ((pad_hi[1] + 1) << 8))
     return _op(OP_CONV, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, cpg, G,
-                         int(out_fp32), pad if pad_w is None else pad_w, 0, 0, int(cin_real)], (),
+                         int(out_fp32), pad if pad_w is None else pad_w, 0, 0, int(cin_real), int(o_mul),
+                         o_off[0] | (o_off[1] << 8), o_hw[0], o_hw[1], asym], (),
                [x, w, y, add, stats, x_lo, w_lo, y_lo])
 
 
