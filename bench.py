@@ -340,7 +340,13 @@ def run_b200(args):
     n0 = L.launch_count()
     if sampler:
         sampler.begin()
+    prof = os.environ.get("PNVO_PROFILE_STEP") == "1"   # ncu --profile-from-start off: capture exactly the timed steps
+    if prof:
+        torch.cuda.profiler.start()
     ms = timed(lambda: trainer.step(obs, d_tgt, prefetch=pf), args.steps)
+    if prof:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if sampler:
         sampler.end()
     launches = L.launch_count() - n0

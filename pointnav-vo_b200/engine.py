@@ -32,6 +32,11 @@ def _pow2(x):
     return p
 
 
+# exact-input stem: also issue the residual-weight product W'_lo * x (second launch of the stem kernel).  Without it the stem
+# weights carry one fp16 rounding (PNVO_STEM_WLO=0; measured effect on the network output in tools/stem_wlo_probe.py).
+STEM_WLO = os.environ.get("PNVO_STEM_WLO", "1") != "0"
+
+
 class ConvLayer:
     """Geometry + packed-weight buffers of one convolution (or Linear seen as a 1x1 convolution)."""
 
@@ -58,7 +63,9 @@ class ConvLayer:
         self.fast_s2 = True
         # 3x3 / stride 2 / pad 1: the data gradient runs as four parity-class convolutions of dy (1 + 2 + 2 + 4 taps for four
         # input pixels instead of 9 taps per pixel over a zero-upsampled dy); wt then holds the four class matrices
-        self.s2_classes = (R == 3 and S == 3 and stride == 2 and pad == 1 and need_dgrad
+        # (32 input channels: N = 32 class GEMMs with 64-byte scattered rows measured slower than the upsampled raster route,
+        # 114 vs 98 us for layer2.0 at B = 256)
+        self.s2_classes = (R == 3 and S == 3 and stride == 2 and pad == 1 and need_dgrad and self.cin_pad >= 64
                            and os.environ.get("PNVO_S2_CLASSES", "1") != "0")
         if self.s2_classes:
             self.wt_ld = _ru(4 * self.cout_pad, 64)
@@ -524,9 +531,12 @@ class EncoderPlan:
             # statistics) and the border bias; W'_lo * x as an fp16 tensor first, then W' * x + that tensor + bias
             ops.append(L.op_stem_exact_pack(self.P[c1.key], self.xp, self.w_stem2, self.w_stem2_lo, self.bias5, c1.Cin,
                                             self.inH, self.inW))
-            ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, self.stem_corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
+            corr = None
+            if STEM_WLO:
+                corr = self.stem_corr
+                ops.append(L.op_conv_stem2(self.x0, self.w_stem2_lo, corr, None, B, self.inH, self.inW, g1.G, g1.cpg))
             ops.append(L.op_conv_stem2(self.x0, self.w_stem2, self.raw1, g1.stats, B, self.inH, self.inW, g1.G, g1.cpg,
-                                       add=self.stem_corr, bias5=self.bias5, y_lo=self.lo(self.raw1)))
+                                       add=corr, bias5=self.bias5, y_lo=self.lo(self.raw1)))
         elif self.use_stem2 and self.split:
             # raw1 = w * (x + x_lo) + (w_lo * x): the residual-weight product first, as an fp16 tensor (it is ~2^-11 of
             # the result), then the value weights against both input planes with that tensor added in the epilogue

@@ -20,6 +20,11 @@ import torch
 from ... import lib as L
 
 
+# where the side-stream input pipeline of the next batch starts: "start" = with the step (under the stem / layer1 forward),
+# "bwd" = after the forward program (under the backward pass).  Measured: see DESIGN.md section 3.
+_PREFETCH_AT = os.environ.get("PNVO_PREFETCH_AT", "start")
+
+
 class PrefetchedBatches:
     """Double-buffered host -> device staging of training batches (the device-side replacement of the reference's
     `_transfer_batch`, vo_cnn_regression_geo_invariance_engine.py:283-353, which copies a list of unpinned CPU
@@ -319,9 +324,12 @@ class FusedVOTrainStep:
             parity = self._prefetched[1]
             main.wait_event(self._staged[parity])   # inputs were assembled ahead of time
             self._prefetched = None
-            if prefetch is not None:
+            late = _PREFETCH_AT == "bwd"   # start the next batch's input pipeline under the backward pass instead
+            if prefetch is not None and not late:
                 self._prefetch(plan, prefetch, 1 - parity, prefetch_ready)
             model._run_backbone(plan, parity)
+            if prefetch is not None and late:
+                self._prefetch(plan, prefetch, 1 - parity, prefetch_ready)
         else:
             parity = self._parity
             self._prefetched = None

@@ -347,3 +347,30 @@ def test_pair_map_follows_the_dataset_rules_and_inverse_targets_zero_the_inversi
     assert float(loss) <= 1e-12
     again = gi.inverse_delta_states(gi.inverse_delta_states(d))
     assert np.allclose(again, d, atol=1e-6)
+
+
+@pytest.mark.parametrize("rnn_type", ["LSTM", "GRU"])
+def test_rnn_state_encoder_packed_sequences_match_stepwise_masking(rnn_type):
+    """RNNStateEncoder.seq_forward (every env cut at its own resets, one packed-sequence RNN call) == the reference's
+    semantics (rnn_state_encoder.py:100-138: carried state multiplied by the step's mask), outputs, final state and
+    input gradient; also with no reset at all and with resets at t = 0."""
+    from pointnav_vo_b200.model_utils.rnns.rnn_state_encoder import RNNStateEncoder
+
+    torch.manual_seed(0)
+    enc = RNNStateEncoder(24, 16, num_layers=2, rnn_type=rnn_type)
+    T, N = 13, 5
+    x = torch.randn(T * N, 24, requires_grad=True)
+    h = torch.randn(enc.num_recurrent_layers, N, 16)
+    xs = x.view(T, N, -1)
+    for p_reset in (0.25, 0.0, 1.0):
+        masks = (torch.rand(T * N, 1) >= p_reset).float()
+        y, hn = enc.seq_forward(x, h, masks)
+        hs, outs, ms = enc._unpack_hidden(h), [], masks.view(T, N, 1)
+        for t in range(T):
+            o, hs = enc.rnn(xs[t:t + 1], enc._mask_hidden(hs, ms[t:t + 1]))
+            outs.append(o)
+        yr, hr = torch.cat(outs, 0).view(T * N, -1), enc._pack_hidden(hs)
+        assert torch.allclose(y, yr, atol=1e-6) and torch.allclose(hn, hr, atol=1e-6)
+        g1, = torch.autograd.grad(y.sum() + hn.sum(), x, retain_graph=True)
+        g2, = torch.autograd.grad(yr.sum() + hr.sum(), x)
+        assert torch.allclose(g1, g2, atol=1e-6)

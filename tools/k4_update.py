@@ -50,7 +50,7 @@ def main(reps=1):
     for _ in range(reps):
         agent.update(rs)
     torch.cuda.synchronize()
-    print("ppo_update ms", (time.perf_counter() - t0) * 1e3 / reps)
+    print("ppo_update ms", (time.perf_counter() - t0) * 1e3 / max(reps, 1))
 
 
 if __name__ == "__main__":
