@@ -351,31 +351,48 @@ __global__ void __launch_bounds__(160) conv_igemm_kernel(const ConvArgs p, const
     tc_fence_before();
   } else {
     // ================================ MMA issuer (warp 4) ================================
+    // One thread issues every MMA: descriptors are (lo, hi) words with a loop-invariant hi, the stage base is a counter
+    // and the accumulate flag is a compile-time constant except for the very first MMA (the first version rebuilt two to
+    // four 64-bit descriptors per stage and tested the flag per MMA: at N <= 64 the thread, not the pipe, set the pace).
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(kTileM, p.N, 0, 0);
       const int nkb = p.nkb;
+      const uint64_t d0 = umma_desc(0, 16, 8 * row_bytes, row_bytes);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32);
+      const uint32_t base = static_cast<uint32_t>(d0) + (smem_base >> 4);
+      const uint32_t a16 = a_bytes >> 4, pair16 = pair_bytes >> 4, stage16 = stage_bytes >> 4;
+      const bool k4 = (p.chunk_k >> 4) == 4;   // 4 (64-element chunks) or 2 (32-element chunks) K steps per stage
+      uint32_t slot = 0, phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % stages;
-        mbar_wait(smem_u32(&s_full[s]), (kb / stages) & 1);
+        mbar_wait(smem_u32(&s_full[slot]), phase);
         tc_fence_after();
-        const uint32_t sA = smem_base + s * stage_bytes;
-        const uint64_t adesc = umma_desc(sA, 16, 8 * row_bytes, row_bytes);
-        const uint64_t bdesc = umma_desc(sA + a_bytes, 16, 8 * row_bytes, row_bytes);
-        const int ksteps = p.chunk_k >> 4;
-        for (int k = 0; k < ksteps; ++k) {
-          // +32 bytes (16 fp16 of K) inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
-          tc_mma_f16(tmem_base, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+        const uint32_t lo = base + slot * stage16;
+        tc_mma_f16_lohi(tmem_base, lo, lo + a16, hi, idesc, kb != 0 ? 1u : 0u);
+        tc_mma_f16_lohi_c<true>(tmem_base, lo + 2, lo + a16 + 2, hi, idesc);
+        if (k4) {
+          tc_mma_f16_lohi_c<true>(tmem_base, lo + 4, lo + a16 + 4, hi, idesc);
+          tc_mma_f16_lohi_c<true>(tmem_base, lo + 6, lo + a16 + 6, hi, idesc);
         }
         if (split) {  // + x_lo * w + x * w_lo (the lo * lo term is below fp32 resolution)
-          const uint64_t alo = umma_desc(sA + pair_bytes, 16, 8 * row_bytes, row_bytes);
-          const uint64_t blo = umma_desc(sA + pair_bytes + a_bytes, 16, 8 * row_bytes, row_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            tc_mma_f16(tmem_base, alo + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc, 1u);
-            tc_mma_f16(tmem_base, adesc + static_cast<uint64_t>(k * 2), blo + static_cast<uint64_t>(k * 2), idesc, 1u);
+          const uint32_t alo = lo + pair16, blo = lo + pair16 + a16;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            tc_mma_f16_lohi_c<true>(tmem_base, alo + 2 * k, lo + a16 + 2 * k, hi, idesc);
+            tc_mma_f16_lohi_c<true>(tmem_base, lo + 2 * k, blo + 2 * k, hi, idesc);
+          }
+          if (k4) {
+#pragma unroll
+            for (int k = 2; k < 4; ++k) {
+              tc_mma_f16_lohi_c<true>(tmem_base, alo + 2 * k, lo + a16 + 2 * k, hi, idesc);
+              tc_mma_f16_lohi_c<true>(tmem_base, lo + 2 * k, blo + 2 * k, hi, idesc);
+            }
           }
         }
-        tc_commit(smem_u32(&s_empty[s]));  // frees the smem stage once these MMAs have read it
+        tc_commit(smem_u32(&s_empty[slot]));  // frees the smem stage once these MMAs have read it
+        if (++slot == static_cast<uint32_t>(stages)) {
+          slot = 0;
+          phase ^= 1u;
+        }
       }
       tc_commit(smem_u32(&s_accum));  // accumulator complete -> epilogue
     }

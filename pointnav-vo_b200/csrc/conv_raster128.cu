@@ -33,7 +33,9 @@ struct Raster128Args {
   int in_bytes;   // shared-memory bytes of ONE channel-half raster (multiple of 1024)
   int w_stages;
   int acc_bufs;   // 2 when two sets of n_tiles accumulators fit the 512 TMEM columns: the epilogue of unit i then overlaps
-                  // the MMAs of unit i+1 (the input raster stays single-buffered; the next unit's boxes are prefetched to L2)
+                  // the MMAs of unit i+1
+  int in_bufs;    // 2 when two sets of rasters fit next to a >= 4-stage weight ring: the TMA of unit i+1 then overlaps the
+                  // MMAs of unit i; otherwise 1 (the next unit's boxes are prefetched to L2 instead)
 };
 
 static constexpr int kR128Threads = 12 * 32 + 64;
@@ -75,6 +77,89 @@ struct R128Mode {
   }
 };
 
+// NT x 4 MMAs of one weight stage against one raster plane: tile t reads the raster 128 positions further on
+template <int N, int NT, bool FIRST>
+__device__ __forceinline__ void r128_issue_stage(uint32_t acc0, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (FIRST && k == 0) tc_mma_f16_lohi_c<false>(acc0 + t * N, a_lo + t * 1024 + 2 * k, b_lo + 2 * k, hi, idesc);
+      else tc_mma_f16_lohi_c<true>(acc0 + t * N, a_lo + t * 1024 + 2 * k, b_lo + 2 * k, hi, idesc);
+    }
+  }
+}
+
+// all weight stages of one unit, in the order the producer streams them (R128Mode<MODE>::stage):
+//   MODE 0: (tap, channel half);  MODE 1: (tap, value | residual);  MODE 2: (tap, channel half, value | residual)
+template <int N, int MODE, int NT>
+__device__ __forceinline__ void r128_issue_unit(uint32_t acc0, uint32_t in_lo, uint32_t plane16, uint32_t row16, uint32_t w_lo0,
+                                                uint32_t hi, uint32_t idesc, uint64_t* s_wfull, uint64_t* s_wempty, int ws,
+                                                uint32_t& slot, uint32_t& wphase) {
+  constexpr uint32_t kStage16 = (N * 128) >> 4;
+  auto next_stage = [&]() -> uint32_t {   // waits for the ring slot, returns the low descriptor word of its weights
+    mbar_wait(smem_u32(&s_wfull[slot]), wphase);
+    tc_fence_after();
+    return w_lo0 + slot * kStage16;
+  };
+  auto release = [&]() {
+    tc_commit(smem_u32(&s_wempty[slot]));
+    if (++slot == static_cast<uint32_t>(ws)) {
+      slot = 0;
+      wphase ^= 1u;
+    }
+  };
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx) {
+      const uint32_t tap_off = static_cast<uint32_t>(r) * row16 + static_cast<uint32_t>(sx) * 8u;
+      const bool first_tap = (r == 0 && sx == 0);
+      if (MODE == 0) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t b_lo = next_stage();
+          const uint32_t a_lo = in_lo + half * plane16 + tap_off;
+          if (first_tap && half == 0) r128_issue_stage<N, NT, true>(acc0, a_lo, b_lo, hi, idesc);
+          else r128_issue_stage<N, NT, false>(acc0, a_lo, b_lo, hi, idesc);
+          release();
+        }
+      } else if (MODE == 1) {
+        {  // value weights against x and x_lo
+          const uint32_t b_lo = next_stage();
+          const uint32_t a_lo = in_lo + tap_off;
+          if (first_tap) r128_issue_stage<N, NT, true>(acc0, a_lo, b_lo, hi, idesc);
+          else r128_issue_stage<N, NT, false>(acc0, a_lo, b_lo, hi, idesc);
+          r128_issue_stage<N, NT, false>(acc0, a_lo + plane16, b_lo, hi, idesc);
+          release();
+        }
+        {  // residual weights against x
+          const uint32_t b_lo = next_stage();
+          r128_issue_stage<N, NT, false>(acc0, in_lo + tap_off, b_lo, hi, idesc);
+          release();
+        }
+      } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t a_lo = in_lo + half * plane16 + tap_off;
+          {
+            const uint32_t b_lo = next_stage();
+            if (first_tap && half == 0) r128_issue_stage<N, NT, true>(acc0, a_lo, b_lo, hi, idesc);
+            else r128_issue_stage<N, NT, false>(acc0, a_lo, b_lo, hi, idesc);
+            r128_issue_stage<N, NT, false>(acc0, a_lo + 2 * plane16, b_lo, hi, idesc);   // x_lo of the same channel half
+            release();
+          }
+          {
+            const uint32_t b_lo = next_stage();
+            r128_issue_stage<N, NT, false>(acc0, a_lo, b_lo, hi, idesc);
+            release();
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int N, int MODE>
 __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Raster128Args p,
                                                                        const __grid_constant__ ConvTmaps tm) {
@@ -82,20 +167,24 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
   constexpr int kWStage = N * 128;                 // one weight stage: [N][64 channels] fp16
   constexpr int kTmemCols = 512;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_infull, s_inempty;
+  __shared__ __align__(8) uint64_t s_infull[2], s_inempty[2];
   __shared__ __align__(8) uint64_t s_accfull[2], s_accempty[2];
   __shared__ __align__(8) uint64_t s_wfull[8];
   __shared__ __align__(8) uint64_t s_wempty[8];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t sIn = smem_base;                                   // kPlanes rasters
-  const uint32_t sW = smem_base + Md::kPlanes * p.in_bytes;         // weight ring
+  const uint32_t sIn0 = smem_base;                                  // in_bufs x kPlanes rasters
+  const uint32_t in_slot = static_cast<uint32_t>(Md::kPlanes) * p.in_bytes;
+  const int in_bufs = p.in_bufs;
+  const uint32_t sW = smem_base + in_bufs * in_slot;                // weight ring
   const int ws = p.w_stages;
 
   if (tid == 0) {
-    mbar_init(smem_u32(&s_infull), 1);
-    mbar_init(smem_u32(&s_inempty), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_infull[s]), 1);
+      mbar_init(smem_u32(&s_inempty[s]), 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&s_accfull[s]), 1);
       mbar_init(smem_u32(&s_accempty[s]), 12);
@@ -128,12 +217,17 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
         tma_prefetch_desc(&tm.b_lo);
       }
       const uint32_t in_tx = static_cast<uint32_t>(p.rows_in) * p.P * 128u * Md::kPlanes;
-      int i = 0, wctr = 0;
+      int i = 0;
+      uint32_t pslot = 0, pphase = 0;
+      bool wfill = false;   // the ring has wrapped at least once: slots must be waited for
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
-        if (i >= 1) mbar_wait(smem_u32(&s_inempty), (i - 1) & 1);
+        const int is = in_bufs == 2 ? (i & 1) : 0;
+        const int iuse = in_bufs == 2 ? (i >> 1) : i;   // how often raster slot `is` has been filled before
+        if (iuse >= 1) mbar_wait(smem_u32(&s_inempty[is]), (iuse - 1) & 1);
         const int b = u / p.units_per_img;
         const int h0 = (u - b * p.units_per_img) * p.T;
-        const uint32_t bar = smem_u32(&s_infull);
+        const uint32_t bar = smem_u32(&s_infull[is]);
+        const uint32_t sIn = sIn0 + is * in_slot;
         mbar_arrive_expect_tx(bar, in_tx);
         if (MODE == 0) {
           tma_load_4d(sIn, &tm.a, bar, 0, -1, h0 - 1, b);                 // channels 0..63
@@ -151,7 +245,7 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
           // the raster is single-buffered (shared memory holds the weight ring instead): pull the NEXT unit's boxes into L2
           // now, so that the load issued once this unit's MMAs have drained the raster is not a DRAM round trip
           const int un = u + gridDim.x;
-          if (un < p.n_units) {
+          if (in_bufs == 1 && un < p.n_units) {
             const int bn = un / p.units_per_img;
             const int hn = (un - bn * p.units_per_img) * p.T;
             tma_prefetch_4d(&tm.a, 0, -1, hn - 1, bn);
@@ -160,59 +254,69 @@ __global__ void __launch_bounds__(kR128Threads) conv_raster128_kernel(const Rast
             if (MODE == 2) tma_prefetch_4d(&tm.a_lo, 64, -1, hn - 1, bn);
           }
         }
-        for (int st = 0; st < Md::kStages; ++st, ++wctr) {
-          const int s = wctr % ws;
-          if (wctr >= ws) mbar_wait(smem_u32(&s_wempty[s]), ((wctr / ws) & 1) ^ 1);
-          const uint32_t wbar = smem_u32(&s_wfull[s]);
+        // weight stages in R128Mode<MODE>::stage order, with counters instead of divisions (the producer must stay ahead of
+        // an MMA issuer that retires a 4-MMA residual stage in ~256 clocks)
+        auto put = [&](const CUtensorMap* map, int koff) {
+          if (wfill) mbar_wait(smem_u32(&s_wempty[pslot]), pphase ^ 1u);
+          const uint32_t wbar = smem_u32(&s_wfull[pslot]);
           mbar_arrive_expect_tx(wbar, kWStage);
-          int wsel, koff, tap, pa, pb;
-          Md::stage(st, wsel, koff, tap, pa, pb);
-          tma_load_2d(sW + s * kWStage, wsel ? &tm.b_lo : &tm.b, wbar, koff, 0);
+          tma_load_2d(sW + pslot * kWStage, map, wbar, koff, 0);
+          if (++pslot == static_cast<uint32_t>(ws)) {
+            pslot = 0;
+            pphase ^= 1u;
+            wfill = true;
+          }
+        };
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if (MODE == 0) {
+            put(&tm.b, tap * 128);
+            put(&tm.b, tap * 128 + 64);
+          } else if (MODE == 1) {
+            put(&tm.b, tap * 64);
+            put(&tm.b_lo, tap * 64);
+          } else {
+            put(&tm.b, tap * 128);
+            put(&tm.b_lo, tap * 128);
+            put(&tm.b, tap * 128 + 64);
+            put(&tm.b_lo, tap * 128 + 64);
+          }
         }
       }
     }
   } else if (warp == 12) {
     // ================================ MMA issuer ================================
+    // The single issuing thread is the critical resource: an MMA occupies the pipe for 48-64 clocks, so the thread must
+    // spend less than that per MMA including its share of the per-stage work (barrier wait, descriptors).  The first
+    // version decoded (tap, channel half, value / residual) from a stage counter with divisions and looped over a run-time
+    // tile count: ~100 clocks per MMA measured (tensor pipe 32-42 % active).  Here the stage structure is nested
+    // compile-time loops, the tile loop is unrolled by a template parameter and ring slot / phase are counters.
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(128, N, 0, 0);
       const uint64_t d0 = umma_desc(0, 16, 1024, 128);
       const uint32_t hi = static_cast<uint32_t>(d0 >> 32), lo0 = static_cast<uint32_t>(d0);
-      int i = 0, wctr = 0;
+      const uint32_t plane16 = static_cast<uint32_t>(p.in_bytes) >> 4;
+      const uint32_t row16 = static_cast<uint32_t>(p.P) * 8u;   // one raster row in 16-byte units (128-byte pixels)
+      const uint32_t w_lo0 = lo0 + (sW >> 4);
+      int i = 0;
+      uint32_t slot = 0, wphase = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int ab = acc_bufs == 2 ? (i & 1) : 0;
         const int use = acc_bufs == 2 ? (i >> 1) : i;  // how often accumulator set `ab` has been used before
-        mbar_wait(smem_u32(&s_infull), i & 1);
+        const int is = in_bufs == 2 ? (i & 1) : 0;
+        const int iuse = in_bufs == 2 ? (i >> 1) : i;
+        mbar_wait(smem_u32(&s_infull[is]), iuse & 1);
         if (use >= 1) mbar_wait(smem_u32(&s_accempty[ab]), (use - 1) & 1);
         tc_fence_after();
         const uint32_t acc0 = tmem_base + ab * acc_stride;
-#pragma unroll 1
-        for (int st = 0; st < Md::kStages; ++st, ++wctr) {
-          const int s = wctr % ws;
-          mbar_wait(smem_u32(&s_wfull[s]), (wctr / ws) & 1);
-          tc_fence_after();
-          int wsel, koff, tap, pa, pb;
-          Md::stage(st, wsel, koff, tap, pa, pb);
-          const uint32_t tap_off = static_cast<uint32_t>((tap / 3) * p.P + (tap % 3)) * 8u;
-          const uint32_t a_lo = lo0 + ((sIn + pa * p.in_bytes) >> 4) + tap_off;
-          const uint32_t b_lo = lo0 + ((sW + s * kWStage) >> 4);
-          for (int t = 0; t < n_tiles; ++t) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_f16_lohi(acc0 + t * N, a_lo + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc,
-                              (st | k) != 0 ? 1u : 0u);
-          }
-          if (Md::kSplit && pb >= 0) {  // the residual raster against the same (value) weight stage
-            const uint32_t a2 = lo0 + ((sIn + pb * p.in_bytes) >> 4) + tap_off;
-            for (int t = 0; t < n_tiles; ++t) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_f16_lohi(acc0 + t * N, a2 + static_cast<uint32_t>(t * 128 * 8) + 2 * k, b_lo + 2 * k, hi, idesc, 1u);
-            }
-          }
-          tc_commit(smem_u32(&s_wempty[s]));
+        const uint32_t in_lo = lo0 + ((sIn0 + is * in_slot) >> 4);
+        switch (n_tiles) {
+          case 1: r128_issue_unit<N, MODE, 1>(acc0, in_lo, plane16, row16, w_lo0, hi, idesc, s_wfull, s_wempty, ws, slot, wphase); break;
+          case 2: r128_issue_unit<N, MODE, 2>(acc0, in_lo, plane16, row16, w_lo0, hi, idesc, s_wfull, s_wempty, ws, slot, wphase); break;
+          default: r128_issue_unit<N, MODE, 3>(acc0, in_lo, plane16, row16, w_lo0, hi, idesc, s_wfull, s_wempty, ws, slot, wphase); break;
         }
         tc_commit(smem_u32(&s_accfull[ab]));
-        tc_commit(smem_u32(&s_inempty));
+        tc_commit(smem_u32(&s_inempty[is]));
       }
     }
     __syncwarp();
@@ -360,23 +464,31 @@ static bool raster128_plan(const ConvArgs& a, Raster128Args& r, int& smem_bytes,
     if (n_tiles > 3) break;
     const int positions = std::max(rows_in * P, n_tiles * 128 + 2 * P + 2);
     const int in_bytes = (positions * 128 + 1023) & ~1023;
-    const int stages = std::min(8, (smem_limit - planes * in_bytes) / w_stage);
+    int in_bufs = 1;
+    int stages = std::min(8, (smem_limit - planes * in_bytes) / w_stage);
     if (stages < 3) break;
+    static const bool allow2 = !(getenv("PNVO_R128_INBUFS") && atoi(getenv("PNVO_R128_INBUFS")) == 1);
+    if (allow2 && (smem_limit - 2 * planes * in_bytes) / w_stage >= 4) {
+      in_bufs = 2;
+      stages = std::min(8, (smem_limit - 2 * planes * in_bytes) / w_stage);
+    }
     const int upi = ceil_div(a.IH, T);
     const int n_units = a.B * upi;
     const int waves = ceil_div(n_units, 148);
     const double balance = n_units >= 148 ? static_cast<double>(n_units) / (waves * 148.0) : 1.0;
+    // a single-buffered raster exposes the TMA of every unit (measured: 102 us against ~50 us of MMA time for the 64-channel
+    // split forward): weigh such geometries down
     const double eff = (static_cast<double>(a.IH) * a.IW) / (static_cast<double>(upi) * n_tiles * 128) * balance *
-                       (1.0 - 0.15 * 2.0 / (T + 2));
+                       (1.0 - 0.15 * 2.0 / (T + 2)) * ((in_bufs == 2 || !split) ? 1.0 : 0.75);
     if (eff > best + 1e-9) {
       best = eff;
       r.P = P; r.T = T; r.n_tiles = n_tiles; r.rows_in = rows_in; r.units_per_img = upi; r.n_units = n_units;
-      r.in_bytes = in_bytes; r.w_stages = stages;
+      r.in_bytes = in_bytes; r.w_stages = stages; r.in_bufs = in_bufs;
       r.acc_bufs = 2 * n_tiles * a.n_total <= 512 ? 2 : 1;
-      smem_bytes = planes * in_bytes + stages * w_stage + 1024;
+      smem_bytes = in_bufs * planes * in_bytes + stages * w_stage + 1024;
     }
   }
-  if (best < 0.5) return false;
+  if (best < 0.5 * 0.75) return false;
   r.y = a.y; r.y_lo = a.y_lo; r.add = a.add; r.stats = a.stats;
   r.B = a.B; r.H = a.IH; r.W = a.IW; r.cpg = a.cpg; r.G = a.G;
   return true;

@@ -225,25 +225,32 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const WgradArgs p, cons
       // =============================== MMA issuer ===============================
       if (elect_one()) {
         const uint32_t idesc = umma_idesc_f16(128, p.N, 1, 1);
+        // MN-major operands: LBO = distance between successive M/N blocks (64 pixel rows), SBO = 8 pixel rows.  The
+        // descriptors are split into loop-invariant (lo, hi) words: per MMA one add per operand (the first version rebuilt
+        // the 64-bit A descriptor inside the innermost loop and the issuing thread, not the tensor pipe, set the pace).
+        const uint64_t da0 = umma_desc(0, kPix * a_row, 8 * a_row, a_row);
+        const uint64_t db0 = umma_desc(0, kPix * b_row, 8 * b_row, b_row);
+        const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), b_hi = static_cast<uint32_t>(db0 >> 32);
+        const uint32_t a_lo0 = static_cast<uint32_t>(da0) + (smem_base >> 4), b_lo0 = static_cast<uint32_t>(db0) + ((smem_base + a_bytes) >> 4);
+        const uint32_t stage16 = stage_bytes >> 4;
+        const uint32_t ka = static_cast<uint32_t>(16 * a_row) >> 4, kb16 = static_cast<uint32_t>(16 * b_row) >> 4;
+        uint32_t slot = 0, phase = 0;
         for (int it = 0; it < n_chunks; ++it) {
-          const int s = it % stages;
-          mbar_wait(smem_u32(&s_full[s]), (it / stages) & 1);
+          mbar_wait(smem_u32(&s_full[slot]), phase);
           tc_fence_after();
-          const uint32_t sA = smem_base + s * stage_bytes;
-          // MN-major operands: LBO = distance between successive M/N blocks (64 pixel rows), SBO = 8 pixel rows
-          const uint64_t bdesc = umma_desc(sA + a_bytes, kPix * b_row, 8 * b_row, b_row);
+          const uint32_t a_lo = a_lo0 + slot * stage16, b_lo = b_lo0 + slot * stage16;
 #pragma unroll
           for (int k = 0; k < kPix / 16; ++k) {
             // 16 pixels of GEMM-K = 16 rows of each block
-            const uint64_t koff_a = static_cast<uint64_t>((k * 16 * a_row) >> 4);
-            const uint64_t koff_b = static_cast<uint64_t>((k * 16 * b_row) >> 4);
-            for (int i = 0; i < mt; ++i) {
-              const uint64_t adesc = umma_desc(sA + static_cast<uint32_t>(i) * 16384, kPix * a_row, 8 * a_row, a_row);
-              tc_mma_f16(tmem_base + static_cast<uint32_t>(i * p.N), adesc + koff_a, bdesc + koff_b, idesc,
-                         (it | k) != 0 ? 1u : 0u);
-            }
+            for (int i = 0; i < mt; ++i)
+              tc_mma_f16_parts(tmem_base + static_cast<uint32_t>(i * p.N), a_lo + static_cast<uint32_t>(i) * 1024u + k * ka, a_hi,
+                               b_lo + k * kb16, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
           }
-          tc_commit(smem_u32(&s_empty[s]));
+          tc_commit(smem_u32(&s_empty[slot]));
+          if (++slot == static_cast<uint32_t>(stages)) {
+            slot = 0;
+            phase ^= 1u;
+          }
         }
         tc_commit(smem_u32(&s_accum));
       }

@@ -12,7 +12,8 @@ def main(path, thresh_us=60.0):
     names = [r["Kernel Name"].split("(")[0].replace("pnvo::", "").replace("void ", "") for r in rows]
     vals = [float(r["Metric Value"].replace(",", "")) for r in rows]
     idx = [i for i, n in enumerate(names) if "adam" in n]
-    a, b = idx[-2] + 1, idx[-1] + 1
+    # (a capture of exactly one step -- PNVO_PROFILE_STEP=1 with ncu --profile-from-start off -- has a single marker)
+    a, b = (idx[-2] + 1 if len(idx) >= 2 else 0), (idx[-1] + 1 if idx else len(names))
     by = collections.defaultdict(lambda: [0, 0.0])
     for n, v in zip(names[a:b], vals[a:b]):
         by[n][0] += 1
