@@ -117,6 +117,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.x_lo = static_cast<const __half*>(p[5]);
       a.w_lo = static_cast<const __half*>(p[6]);
       a.y_lo = static_cast<__half*>(p[7]);
+      a.x_c = static_cast<const float*>(p[8]);   // compact fp32 image of a one-channel stem (nullable)
       a.x = static_cast<const __half*>(p[0]);
       a.w = static_cast<const __half*>(p[1]);
       a.y = p[2];
@@ -137,6 +138,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.x = static_cast<const __half*>(p[0]);
       a.dy = static_cast<const __half*>(p[1]);
       a.dw = static_cast<float*>(p[2]);
+      a.x_c = static_cast<const float*>(p[3]);
       a.B = i[0]; a.IH = i[1]; a.IW = i[2]; a.Cin = i[3]; a.OH = i[4]; a.OW = i[5]; a.R = i[6]; a.S = i[7];
       a.mul = i[8]; a.pad = i[9]; a.w_ld = i[11]; a.n_total = i[12]; a.ld_dy = i[14]; a.pad_w = i[18]; a.force_generic = i[19]; a.x_row_pitch = i[20];
       a.cin_real = i[21];

@@ -32,6 +32,7 @@ static constexpr int kD1RowWords = 2 * kD1InWHalf + 2; // 72 words per staged ro
 struct Direct1Args {
   const __half* x;
   const __half* x_lo;   // nullable
+  const float* x_c;     // nullable: the image as a compact fp32 plane [B, IH, IW] (4 instead of 2 x 16 bytes per pixel read)
   const __half* w;
   const __half* w_lo;   // nullable
   void* y;
@@ -73,9 +74,13 @@ __device__ __forceinline__ void d1_stage_input(const Direct1Args& a, int b, int 
     const int ih = ih0 + row, iw = iw0 + col;
     float v = 0.f;
     if (ih >= 0 && ih < a.IH && iw >= 0 && iw < a.IW) {
-      const int64_t p = ((static_cast<int64_t>(b) * a.IH + ih) * a.IW + iw) * a.cpad;
-      v = __half2float(__ldg(a.x + p));
-      if (a.x_lo) v += __half2float(__ldg(a.x_lo + p));
+      const int64_t px = (static_cast<int64_t>(b) * a.IH + ih) * a.IW + iw;
+      if (a.x_c) {
+        v = __ldg(a.x_c + px);
+      } else {
+        v = __half2float(__ldg(a.x + px * a.cpad));
+        if (a.x_lo) v += __half2float(__ldg(a.x_lo + px * a.cpad));
+      }
     }
     s_x[row * kD1RowWords + (col & 1) * (kD1InWHalf + 1) + (col >> 1)] = v;
   }
@@ -263,7 +268,7 @@ int conv_direct1_launch(const ConvArgs& c, cudaStream_t st) {
   PNVO_REQUIRE(conv_direct1_supported(c), "conv_direct1: unsupported geometry");
   if (c.B <= 0) return 0;
   Direct1Args a{};
-  a.x = c.x; a.x_lo = c.x_lo; a.w = c.w; a.w_lo = c.w_lo; a.y = c.y; a.y_lo = c.y_lo; a.stats = c.stats;
+  a.x = c.x; a.x_lo = c.x_lo; a.x_c = c.x_c; a.w = c.w; a.w_lo = c.w_lo; a.y = c.y; a.y_lo = c.y_lo; a.stats = c.stats;
   a.B = c.B; a.IH = c.IH; a.IW = c.IW; a.OH = c.OH; a.OW = c.OW; a.cpad = c.Cin; a.w_ld = c.w_ld; a.ldo = c.ldo;
   a.out_fp32 = c.out_fp32; a.cpg = c.cpg; a.G = c.G;
   a.tiles_h = ceil_div(c.OH, kD1TileH);
@@ -286,7 +291,7 @@ int wgrad_direct1_launch(const WgradArgs& w, cudaStream_t st) {
   PNVO_REQUIRE(wgrad_direct1_supported(w), "wgrad_direct1: unsupported geometry");
   if (w.B <= 0) return 0;
   Direct1Args a{};
-  a.x = w.x; a.dy = w.dy; a.dw = w.dw;
+  a.x = w.x; a.x_c = w.x_c; a.dy = w.dy; a.dw = w.dw;
   a.B = w.B; a.IH = w.IH; a.IW = w.IW; a.OH = w.OH; a.OW = w.OW; a.cpad = w.Cin; a.w_ld = w.w_ld; a.ld_dy = w.ld_dy;
   a.tiles_h = ceil_div(w.OH, kD1TileH);
   a.tiles_w = ceil_div(w.OW, kD1TileW);

@@ -11,6 +11,7 @@ struct ConvArgs {
   __half* y_lo;       // split-fp16 mode, optional: the output as value + residual fp16 planes (y = fp16(acc), y_lo =
                       // fp16(acc - y)) instead of fp32 -- same bytes, but the backward pass can read the value plane alone
   const __half* add;  // optional [M][ldo] fp16 added before the store (dgrad accumulation)
+  const float* x_c;   // optional, direct one-channel stem only (conv_direct.cu): the image as a compact fp32 plane [B, IH, IW]
   const __half* x_lo; // split-fp16 mode (both or neither): residual planes x - fp16(x), w - fp16(w) in the same layouts;
   const __half* w_lo; //   the kernel accumulates x*w + x_lo*w + x*w_lo (3 MMAs per product, ~fp32 operand precision)
   double* stats;      // optional GroupNorm partial sums [B][G][2] (sum, sum of squares), pre-zeroed; fp64 accumulators:
@@ -47,6 +48,7 @@ int conv_launch(ConvArgs a, cudaStream_t st);
 
 struct WgradArgs {
   const __half* x;   // conv input NHWC [B, IH, IW, Cin] fp16
+  const float* x_c;  // optional, direct one-channel stem only: the image as a compact fp32 plane [B, IH, IW]
   const __half* dy;  // gradient of the conv output [M][ld_dy] fp16 (M = B*OH*OW)
   float* dw;         // packed fp32 gradient [n_total][w_ld], accumulated with atomics (pre-zeroed)
   int B, IH, IW, Cin;

@@ -88,11 +88,11 @@ class ConvLayer:
         return L.op_pack_w(w, self.wp, self.wt, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld,
                            self.cout_pad, self.wt_ld, 4 if self.s2_classes else 0)
 
-    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None, y_lo=None):
+    def op_fwd(self, x, y, B, stats=None, cpg=0, G=0, out_fp32=False, x_lo=None, y_lo=None, x_c=None):
         return L.op_conv(x, self.wp, y, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
                          self.stride, self.pad, 1, self.w_ld, self.cout_pad, self.cout_pad, self.cout_pad, None, stats,
                          cpg, G, out_fp32, x_lo=x_lo, w_lo=self.wp_lo if x_lo is not None else None, y_lo=y_lo,
-                         cin_real=self.Cin)
+                         cin_real=self.Cin, x_c=x_c)
 
     def op_dgrad(self, dy, gx, B, add=None):
         # gx[b, h, w, c] = sum_{r,s,n} dy[b, (h + pad - r)/stride, (w + pad - s)/stride, n] * W[n, c, r, s]
@@ -135,10 +135,10 @@ class ConvLayer:
                          False, pad_w=self.S - 1 - self.pad)
         return [L.op_upsample2(dy, self.up, B, self.OH, self.OW, self.IH, self.IW, self.cout_pad), conv]
 
-    def op_wgrad(self, x, dy, B, x_row_pitch=0):
+    def op_wgrad(self, x, dy, B, x_row_pitch=0, x_c=None):
         return L.op_wgrad(x, dy, self.dwp, B, self.IH, self.IW, self.cin_pad, self.OH, self.OW, self.R, self.S,
                           self.stride, self.pad, self.w_ld, self.cout_pad, self.cout_pad, x_row_pitch=x_row_pitch,
-                          cin_real=self.Cin)
+                          cin_real=self.Cin, x_c=x_c)
 
     def op_unpack(self, grad):
         return L.op_unpack_dw(self.dwp, grad, self.Cout, self.Cin, self.R, self.S, self.cin_pad, self.w_ld)
@@ -205,7 +205,8 @@ class EncoderPlan:
 
     def __init__(self, *, params, buffers, B, H, W, in_channels, sources, backbone, baseplanes, ngroups,
                  compression_channels, prefix, head=None, training=True, avgpool_input=False, device="cuda",
-                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False, exact_stem=False, grad_bucket=None):
+                 world_size=1, raw_fp32=False, dropout_p=0.0, split=False, exact_stem=False, grad_bucket=None,
+                 compact_input=False):
         """params / buffers: dict name -> CUDA fp32 tensor (reference state_dict names, stable storage).
         sources: list of (obs_key, n_channels, pre_scale) in the reference's concat order.
         head: None or dict(fc_w, fc_b, out_w, out_b, hidden, out_dim).
@@ -215,6 +216,7 @@ class EncoderPlan:
         stem / raster / implicit-GEMM kernels all have a split variant).  The backward pass of a split plan reads the
         value planes only (single-pass fp16 operands, fp32 accumulation), also of the raw conv outputs (GroupNorm backward)."""
         self._grad_bucket_arg = grad_bucket
+        self._compact_input = bool(compact_input)   # avg-pooled one-channel input as a compact fp32 plane (no normalisation ops)
         self.split = bool(split)
         if self.split:
             raw_fp32 = False  # raw conv outputs are value + residual fp16 planes: same bytes, and backward reads one plane
@@ -393,8 +395,13 @@ class EncoderPlan:
             self.x0_pitch = 0
             self.x0 = self._act(B, self.inH, self.inW, self.cin_pad)
             self.x0_img = self.x0
+        self.x0c = None
         if self.avgpool_input:
             self.x0.zero_()  # pad channels stay zero (avgpool writes only the real ones)
+            # one-channel input (the depth-only policy) without input normalisation: the direct fp32 stem kernels read the
+            # pooled image as a compact fp32 plane (4 instead of 2 x 16 bytes per pixel); x0 itself is then never written
+            if self.in_channels == 1 and self._compact_input:
+                self.x0c = torch.zeros(B, self.inH, self.inW, dtype=torch.float32, device=dev)
         self.in_stats = torch.zeros(2 * 32 + 2, dtype=torch.float64, device=dev)
         self.drop_seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
         self.in_scale = torch.ones(32, dtype=torch.float32, device=dev)
@@ -550,7 +557,7 @@ class EncoderPlan:
         else:
             assert not self.use_stem, "raw_fp32 is not supported together with the stem kernel"
             ops.append(c1.op_fwd(self.x0, self.raw1, B, g1.stats, g1.cpg, g1.G, self.raw_fp32, x_lo=self.lo(self.x0),
-                                 y_lo=self.lo(self.raw1)))
+                                 y_lo=self.lo(self.raw1), x_c=self.x0c))
         ops.append(L.op_gn_pool(self.raw1, g1.stats, self.P[g1.key + ".weight"], self.P[g1.key + ".bias"], self.pool,
                                 self.argmax, B, g1.C, g1.G, g1.cpg, c1.OH, c1.OW, self.PH, self.PW,
                                 float(g1.cpg_real * c1.OH * c1.OW), self.raw_fp32, 1e-5, g1.C_real,
@@ -610,6 +617,8 @@ class EncoderPlan:
         # the data-gradient / GroupNorm-backward chain that follows them (their inputs -- forward activations and the dx
         # buffers -- are written once per step)
         W = L.side if self.side_lane_wgrad else (lambda op: op)
+        if os.environ.get("PNVO_DIAG_SKIP_WGRAD") == "1":   # timing diagnosis only: no weight gradients at all
+            W = lambda op: None  # noqa: E731
         ops = [L.op_zero(self.bwd_arena)]
         if self.head is not None:
             hd = self.head
@@ -671,7 +680,7 @@ class EncoderPlan:
         elif self.use_stem and 96 < c1.OW <= 176:
             ops.append(W(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48)))
         else:
-            ops.append(W(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch)))
+            ops.append(W(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch, x_c=self.x0c)))
         if self.exact_stem:
             ops.append(W(L.op_stem_dy_sums(self.dx1, self.stem_S, B, c1.OH, c1.OW)))
         ops.append(L.op_join())
@@ -691,6 +700,7 @@ class EncoderPlan:
             for c in self.all_convs():
                 if not (self.exact_stem and c is c1):
                     ops.append(c.op_unpack(self.grads[c.key]))
+        ops = [o for o in ops if o is not None]
         self.bwd_ops = ops
         self.bwd_prog = L.Program(ops, graph=True)
 
@@ -747,8 +757,12 @@ class EncoderPlan:
                 ops.append(L.op_avgpool2(t, None, self.B, self.H, self.W, n, self.cin_pad, coff, scale, out32=out32,
                                          ld32=self.in_channels))
             else:
-                ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale,
-                                         out_lo=self.lo(self.x0)))
+                if self.x0c is not None:
+                    ops.append(L.op_avgpool2(t, None, self.B, self.H, self.W, n, self.cin_pad, coff, scale, out32=self.x0c,
+                                             ld32=1))
+                else:
+                    ops.append(L.op_avgpool2(t, self.x0, self.B, self.H, self.W, n, self.cin_pad, coff, scale,
+                                             out_lo=self.lo(self.x0)))
             coff += n
             keep.append(t)
         self._keepalive = keep

@@ -259,7 +259,7 @@ def op_rmv_update(stats_f64, mean, var, count, scale, shift, C, update, have_rmv
 
 def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, add=None, stats=None,
             cpg=0, G=0, out_fp32=False, pad_w=None, x_lo=None, w_lo=None, y_lo=None, cin_real=0, o_mul=0, o_off=(0, 0),
-            o_hw=(0, 0), pad_hi=None):
+            o_hw=(0, 0), pad_hi=None, x_c=None):
     """x_lo / w_lo: residual planes of the split-fp16 representation (x - fp16(x)); with them the kernel accumulates
     x*w + x_lo*w + x*w_lo, i.e. products of ~fp32-precision operands (3 MMAs per product).
     cin_real: input channels that are not zero padding (0 = unknown); 1 selects the direct fp32 stem kernel.
@@ -270,13 +270,13 @@ def op_conv(x, w, y, B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total,
     return _op(OP_CONV, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, div, w_ld, n_total, n_store, ldo, cpg, G,
                          int(out_fp32), pad if pad_w is None else pad_w, 0, 0, int(cin_real), int(o_mul),
                          o_off[0] | (o_off[1] << 8), o_hw[0], o_hw[1], asym], (),
-               [x, w, y, add, stats, x_lo, w_lo, y_lo])
+               [x, w, y, add, stats, x_lo, w_lo, y_lo, x_c])
 
 
 def op_wgrad(x, dy, dw, B, IH, IW, Cin, OH, OW, R, S, mul, pad, w_ld, n_total, ld_dy, pad_w=None, x_row_pitch=0,
-             cin_real=0):
+             cin_real=0, x_c=None):
     return _op(OP_WGRAD, [B, IH, IW, Cin, OH, OW, R, S, mul, pad, 1, w_ld, n_total, 0, ld_dy, 0, 0, 0,
-                          pad if pad_w is None else pad_w, 0, x_row_pitch, int(cin_real)], (), [x, dy, dw])
+                          pad if pad_w is None else pad_w, 0, x_row_pitch, int(cin_real)], (), [x, dy, dw, x_c])
 
 
 def op_gn_apply(x, stats, gamma, beta, y, B, C, G, cpg, HW, cnt, relu=True, res=None, x_fp32=False, eps=1e-5,

@@ -182,7 +182,7 @@ class PointNavResNetNet(Net):
                                sources=enc._sources, backbone=self._backbone_name, baseplanes=enc.baseplanes,
                                ngroups=enc.ngroups, compression_channels=enc.output_shape[0], prefix="visual_encoder",
                                head=head, training=bool(need_grad), avgpool_input=True, device=first.device,
-                               split=split)
+                               split=split, compact_input=not isinstance(rmv, RunningMeanAndVar))
             self._plans[key] = plan
         return plan
 

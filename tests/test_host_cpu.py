@@ -124,7 +124,13 @@ def test_launch_planner_covers_every_layer(lib):
             for B in (1, 256):
                 info = lib.conv_launch_info(c.op_fwd(None, None, B, None, 2, 16))
                 assert info["smem_bytes"] <= 200 * 1024 and info["tmem_cols"] <= 512
-                if c.need_dgrad:
+                if c.need_dgrad and c.s2_classes:   # 3x3 / stride 2: four parity-class convolutions of dy
+                    c.wt = torch.zeros(4 * c.nt_total, c.wt_ld, dtype=torch.float16)
+                    ops = c.ops_dgrad(None, None, B)
+                    assert len(ops) == 4
+                    for op in ops:
+                        assert lib.conv_launch_info(op)["smem_bytes"] <= 200 * 1024
+                elif c.need_dgrad:
                     assert lib.conv_launch_info(c.op_dgrad(None, None, B))["smem_bytes"] <= 200 * 1024
                 assert lib.conv_launch_info(c.op_wgrad(None, None, B))["tmem_cols"] <= 512
                 n += 1
