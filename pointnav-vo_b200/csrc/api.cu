@@ -174,6 +174,7 @@ static int run_op(const pnvo_op& op, cudaStream_t st) {
       a.sums = static_cast<float*>(p[5]); a.dx = static_cast<__half*>(p[6]); a.dy_out = static_cast<__half*>(p[7]);
       a.C = i[1]; a.G = i[2]; a.cpg = i[3]; a.HW = i[4]; a.x_fp32 = i[6]; a.C_real = i[11];
       a.cnt = f[0]; a.eps = f[1]; a.g_scale = (f[2] == 0.f) ? 1.f : f[2];
+      a.class_sums = static_cast<float*>(p[8]); a.OH = i[7]; a.OW = i[8];   // apply pass only (exact-input stem)
       if (code == PNVO_OP_GN_BWD_REDUCE) return gn_bwd_reduce_launch(a, i[0], st);
       if (code == PNVO_OP_GN_BWD_FUSED) return gn_bwd_fused_launch(a, i[0], st);
       return gn_bwd_apply_launch(a, i[0], st);

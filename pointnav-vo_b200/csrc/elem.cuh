@@ -70,6 +70,10 @@ struct GnBwdArgs {
   int C, C_real, G, cpg, HW;
   float cnt, eps;
   float g_scale;           // multiplies the incoming gradient where the ReLU mask is set (inverted dropout)
+  // apply pass, optional (exact-input stem, C == 32): border-class sums S[5][5][32] of the dx it writes, accumulated with
+  // atomics -- the sums stem_exact_unpack needs (stem_exact.cu), without a separate pass over dx
+  float* class_sums;
+  int OH, OW;
 };
 int gn_bwd_reduce_launch(const GnBwdArgs& a, int B, cudaStream_t st);
 int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st);

@@ -750,6 +750,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
 }
 
 // GN backward, pass 2: dx = rstd*(gamma*dy - (S1 + xhat*S2)/cnt); optionally also writes dy (masked g)
+template <bool CLS>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
   extern __shared__ float s_mem[];  // mean [G], rstd [G], k1 [G], k2 [G], ga [C]
   const int b = blockIdx.y;
@@ -792,6 +793,17 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
     }
   };
   if (fixed) coeffs(static_cast<int>(start % c8) * 8);
+  // border-class sums of dx (exact-input stem): interior pixels (class (2, 2): ~93 % of them) accumulate in registers, the
+  // border classes go straight to a shared-memory table
+  constexpr bool cls = CLS;                    // launcher: C == 32 and a fixed chunk per thread
+  float* s_cls = s_mem + 4 * G + C;            // [25][32]
+  float acc_in[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc_in[e] = 0.f;
+  if (cls) {
+    for (int k = threadIdx.x; k < 25 * 32; k += blockDim.x) s_cls[k] = 0.f;
+    __syncthreads();
+  }
 #pragma unroll 2
   for (int64_t i = start; i < per_sample; i += stride) {
     if (!fixed) coeffs(static_cast<int>(i % c8) * 8);
@@ -808,6 +820,37 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
     for (int e = 0; e < 8; ++e) dx[e] = fmaf(kA[e], g[e], fmaf(kC[e], x[e], kB[e]));
     store8h(a.dx, base + i, dx);
     if (a.dy_out) store8h(a.dy_out, base + i, g);
+    if (cls) {
+      // the sums are those of the STORED (fp16) gradient, as the separate pass over dx computed them
+      const int pix = static_cast<int>(i >> 2), chunk = static_cast<int>(i & 3);
+      const int oh = pix / a.OW, ow = pix - oh * a.OW;
+      const int rc = oh < 2 ? oh : (oh <= a.OH - 3 ? 2 : 3 + oh - (a.OH - 2));
+      const int sc = ow < 2 ? ow : (ow <= a.OW - 3 ? 2 : 3 + ow - (a.OW - 2));
+      if (rc == 2 && sc == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc_in[e] += __half2float(__float2half_rn(dx[e]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(s_cls + (rc * 5 + sc) * 32 + chunk * 8 + e, __half2float(__float2half_rn(dx[e])));
+      }
+    }
+  }
+  if (cls) {
+    // a thread keeps one 8-channel chunk (start % 4); lanes 4 apart share it: fold them, then one shared-memory add per value
+    const int chunk = static_cast<int>(start & 3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc_in[e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 4) atomicAdd(s_cls + 12 * 32 + chunk * 8 + e, v);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 25 * 32; k += blockDim.x) {
+      const float v = s_cls[k];
+      if (v != 0.f) atomicAdd(a.class_sums + k, v);
+    }
   }
 }
 
@@ -892,7 +935,10 @@ int gn_bwd_apply_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
   PNVO_REQUIRE(a.C % 8 == 0 && a.C <= 2048, "gn_bwd_apply: C=%d", a.C);
   if (B <= 0 || a.HW <= 0) return 0;
   const int gx = gn_grid_x(static_cast<int64_t>(a.HW) * (a.C / 8), B, a.C / 8);
-  gn_bwd_apply_kernel<<<dim3(gx, B), 256, (4 * a.G + a.C) * sizeof(float), st>>>(a);
+  PNVO_REQUIRE(!a.class_sums || (a.C == 32 && a.OH * a.OW == a.HW && a.OH >= 4 && a.OW >= 4 && (static_cast<int64_t>(gx) * 256) % 4 == 0),
+               "gn_bwd_apply: border-class sums need C == 32 and the output geometry");
+  if (a.class_sums) gn_bwd_apply_kernel<true><<<dim3(gx, B), 256, (4 * a.G + a.C + 25 * 32) * sizeof(float), st>>>(a);
+  else gn_bwd_apply_kernel<false><<<dim3(gx, B), 256, (4 * a.G + a.C) * sizeof(float), st>>>(a);
   count_launch();
   return check_launch("gn_bwd_apply");
 }

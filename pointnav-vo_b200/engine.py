@@ -493,11 +493,13 @@ class EncoderPlan:
                              float(g.cpg_real * HW), relu, res, self.raw_fp32, 1e-5, g.C_real, y_lo=self.lo(y),
                              res_lo=self.lo(res), x_lo=self.lo(x))
 
-    def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
+    def _gn_bwd(self, reduce, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0, class_sums=None, ohw=(0, 0)):
         return L.op_gn_bwd(reduce, gin, relu_ref, x, g.stats, self.P[g.key + ".weight"], g.sums, dx, dy_out, self.B,
-                           g.C, g.G, g.cpg, HW, float(g.cpg_real * HW), self.raw_fp32, 1e-5, g.C_real, g_scale)
+                           g.C, g.G, g.cpg, HW, float(g.cpg_real * HW), self.raw_fp32, 1e-5, g.C_real, g_scale,
+                           class_sums=class_sums, ohw=ohw)
 
-    def _gn_bwd_all(self, ops, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0):
+    def _gn_bwd_all(self, ops, g, gin, relu_ref, x, dx, dy_out, HW, g_scale=1.0, class_sums=None, ohw=(0, 0)):
+        assert class_sums is None or not (self.fuse_gn_bwd and L.load().pnvo_gn_bwd_fused_supported(g.C, HW, int(self.raw_fp32)))
         if self.fuse_gn_bwd and L.load().pnvo_gn_bwd_fused_supported(g.C, HW, int(self.raw_fp32)):
             # one pass: a cluster per sample keeps g / x in registers between the reduction and the apply
             ops.append(self._gn_bwd("fused", g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
@@ -509,7 +511,7 @@ class EncoderPlan:
         if not self.batch_small_ops:
             ops.append(L.op_gn_param_grad(g.sums, self.grads[g.key + ".weight"], self.grads[g.key + ".bias"], self.B, g.C,
                                           g.C_real))
-        ops.append(self._gn_bwd(False, g, gin, relu_ref, x, dx, dy_out, HW, g_scale))
+        ops.append(self._gn_bwd(False, g, gin, relu_ref, x, dx, dy_out, HW, g_scale, class_sums=class_sums, ohw=ohw))
 
     def _build_programs(self):
         B = self.B
@@ -674,14 +676,19 @@ class EncoderPlan:
         # (gathering the max-pool backward inside the two GroupNorm passes was measured slower -- 0.85 vs 0.62 ms --
         # than materialising dy1 once: the 4-window gather runs twice)
         ops.append(L.op_pool_bwd(self.g_pool, self.pool, self.argmax, self.dy1, B, g1.C, c1.OH, c1.OW, self.PH, self.PW))
-        self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW)
+        # exact-input stem: the border-class sums of dx1 (for the conv1 weight gradient) are accumulated by the apply pass of
+        # the GroupNorm backward while it writes dx1 -- unless a sample fits the one-pass cluster kernel (small inputs)
+        fuse_S = bool(self.exact_stem and c1.cout_pad == 32 and os.environ.get("PNVO_FUSED_DY_SUMS", "1") != "0"
+                      and not (self.fuse_gn_bwd and L.load().pnvo_gn_bwd_fused_supported(g1.C, c1.OH * c1.OW, int(self.raw_fp32))))
+        self._gn_bwd_all(ops, g1, self.dy1, None, self.raw1, self.dx1, None, c1.OH * c1.OW,
+                         class_sums=self.stem_S if fuse_S else None, ohw=(c1.OH, c1.OW))
         if self.use_stem and self.stem_version >= 2 and L.load().pnvo_conv_stem_wgrad2_supported(self.inH, self.inW):
             ops.append(W(L.op_wgrad_stem2(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld)))
         elif self.use_stem and 96 < c1.OW <= 176:
             ops.append(W(L.op_wgrad_stem(self.x0, self.dx1, c1.dwp, B, self.inH, self.inW, c1.w_ld, 48)))
         else:
             ops.append(W(c1.op_wgrad(self.x0_img, self.dx1, B, x_row_pitch=self.x0_pitch, x_c=self.x0c)))
-        if self.exact_stem:
+        if self.exact_stem and not fuse_S:
             ops.append(W(L.op_stem_dy_sums(self.dx1, self.stem_S, B, c1.OH, c1.OW)))
         ops.append(L.op_join())
         if self.exact_stem:

@@ -297,11 +297,12 @@ def op_pool_bwd(g, pooled, argmax, dy, B, C, H, W, PH, PW):
 
 
 def op_gn_bwd(reduce, g, relu_ref, x, stats, gamma, sums, dx, dy_out, B, C, G, cpg, HW, cnt, x_fp32=False, eps=1e-5,
-              C_real=None, g_scale=1.0):
+              C_real=None, g_scale=1.0, class_sums=None, ohw=(0, 0)):
+    """class_sums (apply pass, exact-input stem): fp32 [5][5][32] border-class sums of dx, accumulated (pre-zeroed)."""
     code = OP_GN_BWD_FUSED if reduce == "fused" else (OP_GN_BWD_REDUCE if reduce else OP_GN_BWD_APPLY)
     return _op(code,
-               [B, C, G, cpg, HW, 0, int(x_fp32), 0, 0, 0, 0, C if C_real is None else C_real], [cnt, eps, g_scale],
-               [g, relu_ref, x, stats, gamma, sums, dx, dy_out])
+               [B, C, G, cpg, HW, 0, int(x_fp32), ohw[0], ohw[1], 0, 0, C if C_real is None else C_real], [cnt, eps, g_scale],
+               [g, relu_ref, x, stats, gamma, sums, dx, dy_out, class_sums if code == OP_GN_BWD_APPLY else None])
 
 
 def op_gn_param_grad(sums, dgamma, dbeta, B, C, C_real, accumulate=False):
