@@ -687,7 +687,8 @@ __global__ void __launch_bounds__(256) pool_bwd2x2_kernel(const __half* __restri
 }
 
 // GN backward, pass 1: per (sample, channel) sums of dy and dy*xhat, dy = g * [relu_ref > 0]
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) gn_bwd_reduce_kernel(const GnBwdArgs a) {
   extern __shared__ float s_mem[];  // mean_g [G], rstd_g [G], acc [2C]
   const int b = blockIdx.y;
   const int C = a.C, G = a.G;
@@ -927,7 +928,11 @@ int gn_bwd_reduce_launch(const GnBwdArgs& a, int B, cudaStream_t st) {
   PNVO_REQUIRE(256 % c8 == 0 || c8 % 256 == 0, "gn_bwd_reduce: C/8=%d must divide or be a multiple of 256", c8);
   int gx = gn_grid_x(static_cast<int64_t>(a.HW) * c8, B, c8);
   if (c8 > 256) gx = ((gx + c8 / 256 - 1) / (c8 / 256)) * (c8 / 256);  // keep gridDim.x*256 a multiple of c8
-  gn_bwd_reduce_kernel<<<dim3(gx, B), 256, (2 * a.G + 2 * a.C) * sizeof(float), st>>>(a);
+  // capped at 80 registers (3 CTAs per SM, ~25 spilled words; uncapped: 128-168 registers): 6.75 -> 6.71 ms per ResNet-18
+  // step; PNVO_GN_REDUCE_MINB=1 selects the uncapped kernel
+  static const bool cap = !(getenv("PNVO_GN_REDUCE_MINB") && atoi(getenv("PNVO_GN_REDUCE_MINB")) == 1);
+  if (cap) gn_bwd_reduce_kernel<3><<<dim3(gx, B), 256, (2 * a.G + 2 * a.C) * sizeof(float), st>>>(a);
+  else gn_bwd_reduce_kernel<1><<<dim3(gx, B), 256, (2 * a.G + 2 * a.C) * sizeof(float), st>>>(a);
   count_launch();
   return check_launch("gn_bwd_reduce");
 }
