@@ -575,7 +575,7 @@ def run_extras(args, dev, model, obs, timed, pk):
         agent.update(rs)  # warm-up: builds the B = 8192 plan
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        reps = 2
+        reps = 4   # (2 repetitions gave 122-144 ms from run to run: the update has host-side work between its launches)
         for _ in range(reps):
             agent.update(rs)
         torch.cuda.synchronize()
