@@ -26,6 +26,14 @@ def merge_input_stats(packed, n_local, pix, group=None):
     return mean, var
 
 
+def peer_slice(n_pad, rank, world):
+    """[lo, hi) elements of a bucket of n_pad floats (multiple of 4) owned by `rank`: the slice pnvo_peer_reduce_adam reduces and
+    updates there (csrc/peer_reduce.cu: slice4 = ceil(n4 / world) float4 per rank, the last ranks may own less or nothing)."""
+    n4 = n_pad // 4
+    s4 = (n4 + world - 1) // world
+    return min(4 * s4 * rank, n_pad), min(4 * s4 * (rank + 1), n_pad)
+
+
 class _RawCuda:
     """A caller-owned device range exposed through __cuda_array_interface__ (zero-copy torch view)."""
 
@@ -147,9 +155,7 @@ class PeerBuckets(PeerRegion):
 
     def slice_range(self):
         """[lo, hi) element range of the bucket whose Adam moments live on this rank."""
-        n4 = self.n_pad // 4
-        s4 = (n4 + self.world - 1) // self.world
-        return min(4 * s4 * self.rank, self.n_pad), min(4 * s4 * (self.rank + 1), self.n_pad)
+        return peer_slice(self.n_pad, self.rank, self.world)
 
     def timed_out(self):
         return bool(self.flags[17].item() != 0)

@@ -380,3 +380,17 @@ def test_rnn_state_encoder_packed_sequences_match_stepwise_masking(rnn_type):
         g1, = torch.autograd.grad(y.sum() + hn.sum(), x, retain_graph=True)
         g2, = torch.autograd.grad(yr.sum() + hr.sum(), x)
         assert torch.allclose(g1, g2, atol=1e-6)
+
+
+def test_peer_slices_tile_the_bucket():
+    """The per-rank slices of the fused reduce-scatter + Adam + all-gather kernel (parallel_utils.peer_slice mirrors
+    csrc/peer_reduce.cu) are 16-byte aligned, disjoint and cover the padded bucket for every world size the kernel takes."""
+    from pointnav_vo_b200.parallel_utils import peer_slice
+
+    for n in (4, 8, 36, 3962308, 7235844, 1000):
+        n_pad = (n + 3) // 4 * 4
+        for world in range(2, 9):
+            spans = [peer_slice(n_pad, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n_pad
+            for (lo, hi), (lo2, _) in zip(spans, spans[1:] + [(n_pad, n_pad)]):
+                assert lo % 4 == 0 and hi % 4 == 0 and lo <= hi == lo2
